@@ -1,0 +1,144 @@
+// C-ABI glue: error plumbing, device queries and the convolution dispatchers.
+// No exception or abort crosses this boundary; see include/advoc_b200.h.
+#include "common.cuh"
+
+#include <stdarg.h>
+#include <stddef.h>
+
+// the ctypes mirror in advoc_b200/_native.py relies on these layouts (tests/test_boundary.py)
+static_assert(sizeof(advoc_conv_desc) == 56, "advoc_conv_desc layout");
+static_assert(sizeof(advoc_epilogue) == 96 && offsetof(advoc_epilogue, d_out0) == 24 &&
+                  offsetof(advoc_epilogue, d_out1) == 40 &&
+                  offsetof(advoc_epilogue, d_dropout_mask) == 64 &&
+                  offsetof(advoc_epilogue, seed) == 80,
+              "advoc_epilogue layout");
+
+namespace advoc {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int fail(advoc_status st, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return (int)st;
+}
+
+static unsigned long long g_launches = 0;
+void count_launch(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 148;
+  }
+  return n;
+}
+
+int device_arch() {
+  static int arch = -1;
+  if (arch < 0) {
+    int dev = 0, ma = 0, mi = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    cudaDeviceGetAttribute(&ma, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&mi, cudaDevAttrComputeCapabilityMinor, dev);
+    arch = ma * 10 + mi;
+  }
+  return arch;
+}
+
+// defined in conv_simt.cu / conv_tc.cu
+int check_conv_desc(const advoc_conv_desc* d);
+int conv_fwd_simt(const advoc_conv_desc* d, const float* x, int ldx, const float* w,
+                  const advoc_epilogue* ep, void* stream);
+int conv_transposed_simt(const advoc_conv_desc* d, const float* x, int ldx, const float* w,
+                         const advoc_epilogue* ep, void* stream);
+bool conv_fwd_tc_eligible(const advoc_conv_desc* d, int ldx);
+bool conv_transposed_tc_eligible(const advoc_conv_desc* d, int ldx);
+int conv_fwd_tc(const advoc_conv_desc* d, const float* x, int ldx, const float* w,
+                const advoc_epilogue* ep, void* stream);
+int conv_transposed_tc(const advoc_conv_desc* d, const float* x, int ldx, const float* w,
+                       const advoc_epilogue* ep, void* stream);
+
+}  // namespace advoc
+
+using namespace advoc;
+
+extern "C" int advoc_version(void) { return ADVOC_B200_VERSION; }
+
+extern "C" int advoc_last_error(char* buf, size_t buf_len) {
+  if (!buf || buf_len == 0) return ADVOC_BAD_ARG;
+  strncpy(buf, g_err, buf_len - 1);
+  buf[buf_len - 1] = 0;
+  return ADVOC_OK;
+}
+
+extern "C" unsigned long long advoc_launch_count(void) {
+  return __atomic_load_n(&g_launches, __ATOMIC_RELAXED);
+}
+
+extern "C" int advoc_device_arch(int* arch) {
+  ADVOC_REQUIRE(arch != nullptr, ADVOC_BAD_ARG, "arch is NULL");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(ADVOC_CUDA_ERROR, "no CUDA device: %s", cudaGetErrorString(e));
+  }
+  *arch = device_arch();
+  return ADVOC_OK;
+}
+
+static int check_conv_io(const advoc_conv_desc* d, const float* x, int ldx, int cx, const float* w,
+                         const advoc_epilogue* ep) {
+  int st = check_conv_desc(d);
+  if (st) return st;
+  ADVOC_REQUIRE(x && w && ep, ADVOC_BAD_ARG, "NULL x/w/epilogue");
+  ADVOC_REQUIRE(ldx >= cx, ADVOC_BAD_SHAPE, "ld_x %d smaller than the channel count %d", ldx, cx);
+  ADVOC_REQUIRE(d->math >= ADVOC_MATH_AUTO && d->math <= ADVOC_MATH_TF32, ADVOC_BAD_ARG,
+                "unknown math mode %d", d->math);
+  return ADVOC_OK;
+}
+
+extern "C" int advoc_conv2d_fwd(const advoc_conv_desc* d, const float* d_x, int ld_x,
+                                const float* d_w, const advoc_epilogue* ep, void* stream) {
+  int st = check_conv_io(d, d_x, ld_x, d ? d->Cin : 0, d_w, ep);
+  if (st) return st;
+  if (d->math == ADVOC_MATH_FP32) return conv_fwd_simt(d, d_x, ld_x, d_w, ep, stream);
+  const bool ok = conv_fwd_tc_eligible(d, ld_x);
+  if (d->math == ADVOC_MATH_TF32 || ok) {
+    ADVOC_REQUIRE(ok, ADVOC_UNSUPPORTED, "conv shape not eligible for the tcgen05 path");
+    return conv_fwd_tc(d, d_x, ld_x, d_w, ep, stream);
+  }
+  return conv_fwd_simt(d, d_x, ld_x, d_w, ep, stream);
+}
+
+extern "C" int advoc_conv2d_transpose_fwd(const advoc_conv_desc* d, const float* d_x, int ld_x,
+                                          const float* d_w, const advoc_epilogue* ep,
+                                          void* stream) {
+  int st = check_conv_io(d, d_x, ld_x, d ? d->Cout : 0, d_w, ep);
+  if (st) return st;
+  if (d->math == ADVOC_MATH_FP32) return conv_transposed_simt(d, d_x, ld_x, d_w, ep, stream);
+  const bool ok = conv_transposed_tc_eligible(d, ld_x);
+  if (d->math == ADVOC_MATH_TF32 || ok) {
+    ADVOC_REQUIRE(ok, ADVOC_UNSUPPORTED, "conv_transpose shape not eligible for the tcgen05 path");
+    return conv_transposed_tc(d, d_x, ld_x, d_w, ep, stream);
+  }
+  return conv_transposed_simt(d, d_x, ld_x, d_w, ep, stream);
+}
+
+extern "C" int advoc_conv2d_path(const advoc_conv_desc* d, int ld_x, int transposed) {
+  if (!d || d->math == ADVOC_MATH_FP32) return ADVOC_MATH_FP32;
+  const bool ok = transposed ? conv_transposed_tc_eligible(d, ld_x) : conv_fwd_tc_eligible(d, ld_x);
+  return ok ? ADVOC_MATH_TF32 : ADVOC_MATH_FP32;
+}

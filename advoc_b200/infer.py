@@ -1,0 +1,112 @@
+"""Batched mel -> magnitude-spectrogram inference: the reference's chunk loop
+(scripts/spectrogram_advoc.py:80-95: batch-1 `sess.run` per 256-frame chunk, host->device copy
+per chunk) as ONE batched forward on persistent buffers, replayed from a CUDA graph.
+
+Pipeline per call (all on the current stream):
+  host mel [n, T, 80] --H2D--> (dB de-normalise) x pinv(mel_fb)^T  (one fused kernel: generator
+  "layer 0", models/advoc/spectral_util.py:34-43 / scripts/spectrogram_advoc.py:15-22)
+  --> U-Net generator --> magnitude [n, T, 513] --D2H--> pinned host buffer.
+"""
+import numpy as np
+import torch
+
+from advoc_b200 import _native as N
+from advoc_b200 import nets
+from advoc_b200 import spectral
+from advoc_b200.model import SpectralUtil
+
+
+class MelToMag(object):
+  """Fixed-batch engine.  `input_kind`: 'linear' (linear-amplitude mel, the training-time
+  input of models/advoc/train_evaluate.py:53-56) or 'dbnorm' (r9y9 dB-normalised mel in [0,1],
+  the `.npy` inputs of scripts/spectrogram_advoc.py)."""
+
+  def __init__(self, model, batch, input_kind='linear', dropout='rng', use_graph=True):
+    model._check_supported()
+    self.model, self.B, self.kind, self.dropout = model, batch, input_kind, dropout
+    self.T, self.n_mels = model.subseq_len, model.n_mels
+    self.su = SpectralUtil(n_mels=model.n_mels, fs=model.audio_fs)
+    self.G = model._generator(batch)
+    self.G.prepare()
+    dev = self.G.dev
+    self.mel_d = torch.zeros((batch, self.T, self.n_mels), dtype=torch.float32, device=dev)
+    self.x_d = torch.empty((batch, self.T, 513, 1), dtype=torch.float32, device=dev)
+    self.mel_h = torch.zeros((batch, self.T, self.n_mels), dtype=torch.float32).pin_memory()
+    self.out_h = torch.empty((batch, self.T, 513), dtype=torch.float32).pin_memory()
+    self.use_graph = use_graph
+    self._graph = None
+    self._seed = 0
+    self.launches_per_step = None
+
+  # -- device-resident step (inputs already in HBM) ------------------------
+  def _launch(self, seed, n_valid=None):
+    spectral_ptr = spectral._ptr
+    N.call('advoc_matmul_lastdim_f32', spectral_ptr(self.mel_d), spectral_ptr(self.su.invmeltrans),
+           spectral_ptr(self.x_d), self.B * self.T, self.n_mels, 513,
+           1 if self.kind == 'dbnorm' else 0, spectral._stream())
+    if n_valid is not None and n_valid < self.B * self.T:
+      # the reference zero-pads in the magnitude domain, after the pinv lift
+      # (scripts/spectrogram_advoc.py:81-84)
+      self.x_d.view(self.B * self.T, 513)[n_valid:].zero_()
+    return self.G.forward(self.x_d, dropout=self.dropout, seed=seed)
+
+  def step_device(self, n_valid=None):
+    """One forward over the batch resident in `self.mel_d`; returns the device output
+    [B, T, 513, 1].  Replays a CUDA graph after the first (capturing) call; with the graph the
+    dropout stream is the captured one (seed fixed at capture), matching a frozen-graph
+    deployment; pass use_graph=False for a fresh mask per call."""
+    if not self.use_graph or n_valid is not None:
+      self._seed += 1
+      return self._launch(self._seed, n_valid)
+    if self._graph is None:
+      n0 = N.launch_count()
+      self._launch(1)  # warm-up outside capture (lazy module load, caches)
+      self.launches_per_step = N.launch_count() - n0
+      torch.cuda.synchronize()
+      g = torch.cuda.CUDAGraph()
+      with torch.cuda.graph(g):
+        self._out = self._launch(1)
+      self._graph = g
+    self._graph.replay()
+    return self._out
+
+  # -- public host API ----------------------------------------------------
+  def __call__(self, mel, n_valid=None):
+    """mel: host float32 array/tensor [B, T, n_mels] (or [B, T, n_mels, 1]); frames at flat
+    index >= n_valid are treated as the reference's zero padding.  Returns the pinned host
+    tensor [B, T, 513] (valid until the next call)."""
+    if isinstance(mel, np.ndarray):
+      mel = torch.from_numpy(mel)
+    mel = mel.reshape(self.B, self.T, self.n_mels)
+    if mel.dtype != torch.float32:
+      raise ValueError()
+    if not mel.is_pinned():
+      self.mel_h.copy_(mel)
+      mel = self.mel_h
+    self.mel_d.copy_(mel, non_blocking=True)
+    out = self.step_device(n_valid)
+    self.out_h.copy_(out.view(self.B, self.T, 513), non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return self.out_h
+
+
+def mel_to_mag(model, mel, input_kind='dbnorm', batch=None, dropout='rng'):
+  """Whole-utterance helper: mel [T_total, 80] (numpy) -> magnitude [T_total, 513] (numpy f32),
+  following the reference's pad rule (always pads to floor(T/256)*256 + 256 frames,
+  scripts/spectrogram_advoc.py:82-86) and trim (:94)."""
+  T = model.subseq_len
+  n_frames = mel.shape[0]
+  padded = n_frames - n_frames % T + T
+  buf = np.zeros((padded, mel.shape[1]), dtype=np.float32)
+  buf[:n_frames] = mel
+  chunks = buf.reshape(padded // T, T, mel.shape[1])
+  n = chunks.shape[0]
+  eng = MelToMag(model, n if batch is None else batch, input_kind, dropout, use_graph=False)
+  out = np.empty((n, T, 513), dtype=np.float32)
+  for i in range(0, n, eng.B):
+    blk = chunks[i:i + eng.B]
+    if blk.shape[0] < eng.B:
+      blk = np.concatenate([blk, np.zeros((eng.B - blk.shape[0],) + blk.shape[1:], np.float32)])
+    valid = max(0, min(eng.B * T, n_frames - i * T))
+    out[i:i + eng.B] = eng(blk, n_valid=valid).numpy()[:min(eng.B, n - i)]
+  return out.reshape(padded, 513)[:n_frames]

@@ -1,0 +1,261 @@
+"""Execution engine for the AdVoc conv stacks on B200 (generator U-Net + PatchGAN discriminator).
+
+Host side only: shape arithmetic (TensorFlow SAME/VALID rules), persistent NHWC activation
+buffers in HBM, and the per-layer launches into libadvoc_b200.so.  Everything the reference
+does between two convolutions -- bias, lrelu/relu, the skip concat, the `[:, :, :-1, :]` crop and
+dropout -- is folded into the producing kernel's epilogue (dual write into the next encoder's
+input and into the channel slice of the decoder concat buffer), so no element-wise or copy
+kernel runs between layers.
+
+reference: models/advoc/advoc_model.py:25-69 (layer primitives), :75-166 (generator),
+:168-204 (discriminator); models/advoc/advoc_model_small.py (truncated variant).
+
+Parameters are a dict keyed by the TF variable names
+(`generator/encoder_N/conv2d/{kernel,bias}`, `generator/decoder_N/conv2d_transpose/{kernel,bias}`,
+`discriminator/layer_N/conv2d/{kernel,bias}`) holding CUDA float32 tensors in the TF layouts
+(conv HWIO, conv_transpose HWOI), so reference checkpoints map 1:1.
+"""
+import ctypes as C
+
+import torch
+
+from advoc_b200 import _native as N
+
+
+def _ptr(t):
+  return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream():
+  return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def same_pads(n, k, s):
+  """TF 'SAME': out = ceil(n/s), pad_total = max((out-1)s + k - n, 0), before = total // 2."""
+  out = -(-n // s)
+  total = max((out - 1) * s + k - n, 0)
+  return out, total // 2, total - total // 2
+
+
+class GenSpec(object):
+  """Static geometry of a generator (advoc_model.py:91-158)."""
+
+  def __init__(self, ngf, n_enc, dropout_decoders, subseq_len=256, nbins=513):
+    self.ngf, self.n_enc = ngf, n_enc
+    self.dropout_decoders = tuple(dropout_decoders)
+    mult = [1, 2, 4, 8, 8, 8, 8, 8]
+    self.enc_ch = [ngf * m for m in mult[:n_enc]]
+    dmult = {8: 8, 7: 8, 6: 8, 5: 8, 4: 4, 3: 2, 2: 1}
+    # the reference keeps the LAST (n_enc - 1) decoder specs (advoc_model_small.py:134)
+    self.dec_ch = {k: ngf * dmult[k] for k in range(n_enc, 1, -1)}
+    self.dec_ch[1] = 1
+    # spatial sizes: index 0 = network input, i = output of encoder_i
+    self.H, self.W, self.sh = [subseq_len], [nbins], [None]
+    n_time = subseq_len
+    self.n_stride1 = 0
+    for i in range(1, n_enc + 1):
+      if i == 1 or n_time > 1:
+        sh = 2
+        n_time //= 2
+      else:
+        sh = 1
+        self.n_stride1 += 1
+      self.sh.append(sh)
+      self.H.append(-(-self.H[-1] // sh))
+      self.W.append(-(-self.W[-1] // 2))
+
+
+class _Conv(object):
+  """One convolution launch: geometry + operands; kind 'conv' or 'deconv'."""
+
+  def __init__(self, name, kind, desc):
+    self.name, self.kind, self.desc = name, kind, desc
+    self.n_out = 1
+
+  def run(self, x, ldx, w, ep):
+    fn = 'advoc_conv2d_fwd' if self.kind == 'conv' else 'advoc_conv2d_transpose_fwd'
+    self.n_out = 2 if ep.d_out1 else 1
+    self.store_w = ep.store_w
+    self.ldx = ldx
+    N.call(fn, C.byref(self.desc), _ptr(x), ldx, _ptr(w), C.byref(ep), _stream())
+
+  # -- accounting used by bench.py (dense MACs x 2) --------------
+  def uses_tensor_cores(self, ldx=None):
+    ldx = self.ldx if ldx is None else ldx
+    return N.lib().advoc_conv2d_path(C.byref(self.desc), ldx,
+                                     1 if self.kind == 'deconv' else 0) == N.MATH_TF32
+
+  def kernel_family(self):
+    return ('tc_' if self.uses_tensor_cores() else 'simt_') + self.kind
+
+  def flops(self):
+    d = self.desc
+    return 2.0 * d.N * d.Ho * d.Wo * d.kh * d.kw * d.Cin * d.Cout
+
+  def algorithmic_bytes(self):
+    d = self.desc
+    big, small = d.N * d.H * d.W * d.Cin, d.N * d.Ho * d.Wo * d.Cout
+    w = d.kh * d.kw * d.Cin * d.Cout
+    if self.kind == 'conv':
+      return 4.0 * (big + w + small * self.n_out)
+    ws = self.store_w or d.W
+    return 4.0 * (small + w + d.N * d.H * ws * d.Cin)
+
+
+def _desc(n, h, w, cin, cout, sh, sw, pt, pl, ho, wo, math):
+  return N.ConvDesc(n, h, w, cin, cout, 4, 4, sh, sw, pt, pl, ho, wo, math)
+
+
+def _epilogue(bias, out0, ld0, coff0, act0, out1=None, ld1=0, coff1=0, act1=N.ACT_NONE,
+              store_w=0, mask=None, keep_prob=1.0, seed=0, round_tf32=0, alpha=0.2):
+  return N.Epilogue(_ptr(bias), act0, act1, alpha, _ptr(out0), ld0, coff0, _ptr(out1), ld1, coff1,
+                    store_w, _ptr(mask), keep_prob, seed, round_tf32)
+
+
+class Generator(object):
+  """U-Net generator forward on persistent buffers.  x [B,T,513,1] -> [B,T,513,1]."""
+
+  def __init__(self, spec, params, batch, math=N.MATH_AUTO, device=None):
+    self.spec, self.P, self.B, self.math = spec, params, batch, math
+    dev = device or torch.device('cuda', torch.cuda.current_device())
+    self.dev = dev
+    s = spec
+    f32 = dict(dtype=torch.float32, device=dev)
+    n = s.n_enc
+    # lrelu(encoder_i) for i < n: the next encoder's input
+    self.E = {i: torch.empty((batch, s.H[i], s.W[i], s.enc_ch[i - 1]), **f32) for i in range(1, n)}
+    # decoder_k input = relu(concat(decoder_{k+1}[:, :, :-1], encoder_k))
+    self.Dk = {k: (s.dec_ch[k + 1] if k < n else 0) for k in range(1, n + 1)}
+    self.Cat = {k: torch.empty((batch, s.H[k], s.W[k], self.Dk[k] + s.enc_ch[k - 1]), **f32)
+                for k in range(1, n + 1)}
+    self.out = torch.empty((batch, s.H[0], s.W[0], 1), **f32)
+    self.enc, self.dec = {}, {}
+    for i in range(1, n + 1):
+      cin = 1 if i == 1 else s.enc_ch[i - 2]
+      ho, pt, _ = same_pads(s.H[i - 1], 4, s.sh[i])
+      wo, pl, _ = same_pads(s.W[i - 1], 4, 2)
+      assert ho == s.H[i] and wo == s.W[i]
+      self.enc[i] = _Conv('generator/encoder_%d/conv2d' % i, 'conv',
+                          _desc(batch, s.H[i - 1], s.W[i - 1], cin, s.enc_ch[i - 1], s.sh[i], 2, pt,
+                                pl, ho, wo, math))
+    for j, k in enumerate(range(n, 0, -1)):
+      sh = 1 if j < s.n_stride1 else 2
+      cin = self.Dk[k] + s.enc_ch[k - 1]
+      # geometry of the forward conv this deconv is the input-gradient of: big side = output
+      self.dec[k] = _Conv('generator/decoder_%d/conv2d_transpose' % k, 'deconv',
+                          _desc(batch, s.H[k] * sh, s.W[k] * 2, s.dec_ch[k], cin, sh, 2, 1, 1,
+                                s.H[k], s.W[k], math))
+      assert s.H[k] * sh == s.H[k - 1] and s.W[k] * 2 - 1 == s.W[k - 1]
+
+  def prepare(self):
+    """Refresh the derived (packed / TF32-rounded) filter copies after the parameters changed."""
+    return self
+
+  def _w(self, L):
+    return self.P[L.name + '/kernel']
+
+  def _run_layer(self, L, x, ldx, w, ep):
+    L.run(x, ldx, w, ep)
+
+  def dropout_shape(self, k):
+    """Shape of the dropout mask of decoder_k: its stored (cropped) output."""
+    s = self.spec
+    return (self.B, s.H[k - 1], s.W[k - 1], s.dec_ch[k])
+
+  def forward(self, x, out=None, out_ld=1, out_coff=0, dropout=None, seed=0):
+    """x f32 [B,T,513,1] contiguous.  dropout: None (off, parity mode) | 'rng' (counter-based
+    generator keyed by `seed`, the reference's behaviour in every mode, advoc_model.py:144-149)
+    | {decoder_index: uint8 mask tensor} (injected masks).  Returns the output buffer
+    (`out` if given: written with pixel stride out_ld at channel out_coff)."""
+    s, P, n = self.spec, self.P, self.spec.n_enc
+    assert x.is_contiguous() and tuple(x.shape) == (self.B, s.H[0], s.W[0], 1), x.shape
+    inp, ld = x, 1
+    for i in range(1, n + 1):
+      L = self.enc[i]
+      cat = self.Cat[i]
+      if i < n:
+        ep = _epilogue(P[L.name + '/bias'], self.E[i], s.enc_ch[i - 1], 0, N.ACT_LRELU,
+                       cat, cat.shape[3], self.Dk[i], N.ACT_RELU)
+      else:
+        ep = _epilogue(P[L.name + '/bias'], cat, cat.shape[3], 0, N.ACT_RELU)
+      self._run_layer(L, inp, ld, self._w(L), ep)
+      if i < n:
+        inp, ld = self.E[i], s.enc_ch[i - 1]
+    dst = self.out if out is None else out
+    for k in range(n, 0, -1):
+      L = self.dec[k]
+      cat = self.Cat[k]
+      kw = {}
+      if k in s.dropout_decoders and dropout is not None:
+        kw['keep_prob'] = 0.5
+        if dropout == 'rng':
+          kw['seed'] = (seed * 0x9E3779B1 + k) & 0xFFFFFFFFFFFFFFFF
+        else:
+          kw['mask'] = dropout[k]
+      if k > 1:
+        nxt = self.Cat[k - 1]
+        ep = _epilogue(P[L.name + '/bias'], nxt, nxt.shape[3], 0, N.ACT_RELU,
+                       store_w=s.W[k - 1], **kw)
+      else:
+        ld_o, co = (1, 0) if out is None else (out_ld, out_coff)
+        ep = _epilogue(P[L.name + '/bias'], dst, ld_o, co, N.ACT_NONE, store_w=s.W[0], **kw)
+      self._run_layer(L, cat, cat.shape[3], self._w(L), ep)
+    return dst
+
+
+class Discriminator(object):
+  """PatchGAN forward.  in_cat f32 [B,T,513,2] (cond, target-or-generated) -> sigmoid map."""
+  STRIDES = (2, 2, 2, 1, 1)
+
+  def __init__(self, ndf, params, batch, math=N.MATH_AUTO, subseq_len=256, nbins=513, device=None):
+    self.P, self.B = params, batch
+    dev = device or torch.device('cuda', torch.cuda.current_device())
+    chans = [2, ndf, ndf * 2, ndf * 4, ndf * 8, 1]
+    self.chans = chans
+    h, w = subseq_len, nbins
+    self.layers, self.act = [], []
+    for i, st in enumerate(self.STRIDES):
+      ho, wo = (h + 2 - 4) // st + 1, (w + 2 - 4) // st + 1
+      self.layers.append(_Conv('discriminator/layer_%d/conv2d' % (i + 1), 'conv',
+                               _desc(batch, h, w, chans[i], chans[i + 1], st, st, 1, 1, ho, wo,
+                                     math)))
+      self.act.append(torch.empty((batch, ho, wo, chans[i + 1]), dtype=torch.float32, device=dev))
+      h, w = ho, wo
+
+  def prepare(self):
+    return self
+
+  def forward(self, in_cat):
+    assert in_cat.is_contiguous() and in_cat.shape[3] == 2 and in_cat.shape[0] == self.B
+    x, ld = in_cat, 2
+    for i, L in enumerate(self.layers):
+      act = N.ACT_LRELU if i < 4 else N.ACT_SIGMOID
+      ep = _epilogue(self.P[L.name + '/bias'], self.act[i], self.chans[i + 1], 0, act)
+      L.run(x, ld, self.P[L.name + '/kernel'], ep)
+      x, ld = self.act[i], self.chans[i + 1]
+    return x
+
+
+def init_params(ngf, ndf, n_enc, seed=0, device='cuda'):
+  """N(0, 0.02) kernels and zero biases under the TF variable names
+  (advoc_model.py:32,36,55; tf.layers default bias initialiser)."""
+  g = torch.Generator(device='cpu').manual_seed(seed)
+  spec = GenSpec(ngf, n_enc, ())
+  P = {}
+
+  def add(name, shape, nbias):
+    P[name + '/kernel'] = (torch.randn(shape, generator=g) * 0.02).to(device)
+    P[name + '/bias'] = torch.zeros(nbias, device=device)
+
+  cin = 1
+  for i, c in enumerate(spec.enc_ch):
+    add('generator/encoder_%d/conv2d' % (i + 1), (4, 4, cin, c), c)
+    cin = c
+  for k in range(n_enc, 0, -1):
+    cin = spec.enc_ch[k - 1] + (spec.dec_ch[k + 1] if k < n_enc else 0)
+    add('generator/decoder_%d/conv2d_transpose' % k, (4, 4, spec.dec_ch[k], cin), spec.dec_ch[k])
+  cin = 2
+  for i, c in enumerate([ndf, ndf * 2, ndf * 4, ndf * 8, 1]):
+    add('discriminator/layer_%d/conv2d' % (i + 1), (4, 4, cin, c), c)
+    cin = c
+  return P

@@ -1,0 +1,270 @@
+"""Drop-in for the reference's `advoc.spectral` feature path on B200.
+
+Same function names, argument meaning, shapes, dtypes and exceptions as
+/root/reference/advoc/spectral.py; the arithmetic runs in the sm_100a kernels of
+libadvoc_b200.so (csrc/spectral.cu).  numpy entry points take/return numpy arrays (host
+buffers, copies included); the `*_tf` twins of the reference's TensorFlow graph builders take
+and return `torch.Tensor`s on the GPU (container type only) in the reference's
+[b, n, feats, ch] convention.
+
+There is no CPU fallback: without the native library or a GPU these functions raise.
+"""
+import ctypes as C
+from functools import lru_cache
+
+import numpy as np
+import torch
+
+from advoc_b200 import _native as N
+
+
+def _stream():
+  return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+  return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _device():
+  if not torch.cuda.is_available():
+    raise RuntimeError('advoc_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
+  return torch.device('cuda', torch.cuda.current_device())
+
+
+# ---------------------------------------------------------------------------
+# host-side constants (window, twiddles, mel filterbank): computed once in f64, cached
+# ---------------------------------------------------------------------------
+def lws_hann_default(nfft, nhop, dtype=np.float32):
+  """Analysis window of `lws.lws(nfft, nhop)`: sqrt(hann_offset * 2 * hop / nfft).
+
+  reference: advoc/spectral.py:44-57.  Returns a numpy array (the reference returns a TF
+  constant); `dtype` may be a numpy or torch dtype.
+  """
+  i = np.arange(nfft, dtype=np.float64) + 0.5
+  w = np.sqrt((0.5 - 0.5 * np.cos(2.0 * np.pi * i / nfft)) * (2.0 * nhop / nfft))
+  if isinstance(dtype, torch.dtype):
+    return torch.from_numpy(w).to(dtype)
+  return w.astype(dtype)
+
+
+def _slaney_hz(mels):
+  mels = np.asarray(mels, dtype=np.float64)
+  f_sp = 200.0 / 3.0
+  brk_mel = 1000.0 / f_sp
+  step = np.log(6.4) / 27.0
+  return np.where(mels < brk_mel, mels * f_sp, 1000.0 * np.exp(step * (mels - brk_mel)))
+
+
+def _slaney_mel(hz):
+  hz = np.asarray(hz, dtype=np.float64)
+  f_sp = 200.0 / 3.0
+  step = np.log(6.4) / 27.0
+  return np.where(hz < 1000.0, hz / f_sp,
+                  1000.0 / f_sp + np.log(np.maximum(hz, 1e-30) / 1000.0) / step)
+
+
+@lru_cache(maxsize=8)
+def create_mel_filterbank(fs, nfft, fmin=0.0, fmax=None, n_mels=128):
+  """Slaney-scale, area-normalised triangular filterbank, f64 [n_mels, nfft//2+1].
+
+  reference: advoc/spectral.py:86-88 (`librosa.filters.mel(sr, n_fft, n_mels, fmin, fmax)`,
+  librosa 0.6.3 defaults htk=False, norm=1).
+  """
+  fmax = fs / 2.0 if fmax is None else fmax
+  freqs = np.linspace(0.0, fs / 2.0, nfft // 2 + 1)
+  pts = _slaney_hz(np.linspace(_slaney_mel(fmin), _slaney_mel(fmax), n_mels + 2))
+  lower = (freqs[None, :] - pts[:-2, None]) / (pts[1:-1] - pts[:-2])[:, None]
+  upper = (pts[2:, None] - freqs[None, :]) / (pts[2:] - pts[1:-1])[:, None]
+  fb = np.maximum(0.0, np.minimum(lower, upper))
+  fb *= (2.0 / (pts[2:] - pts[:-2]))[:, None]
+  fb.setflags(write=False)
+  return fb
+
+
+@lru_cache(maxsize=8)
+def create_inverse_mel_filterbank(fs, nfft, fmin=0.0, fmax=None, n_mels=128):
+  """reference: advoc/spectral.py:91-94.  f64 [nfft//2+1, n_mels]."""
+  inv = np.linalg.pinv(create_mel_filterbank(fs, nfft, fmin=fmin, fmax=fmax, n_mels=n_mels))
+  inv.setflags(write=False)
+  return inv
+
+
+class _Consts(object):
+  """Device-resident window / twiddle / filterbank tables, keyed by their parameters."""
+  _cache = {}
+
+  @classmethod
+  def stft(cls, nfft, nhop, dev):
+    key = ('stft', nfft, nhop, dev)
+    if key not in cls._cache:
+      win = torch.from_numpy(lws_hann_default(nfft, nhop, np.float32)).to(dev)
+      j = np.arange(nfft, dtype=np.float64)
+      tw = np.stack([np.cos(2 * np.pi * j / nfft), -np.sin(2 * np.pi * j / nfft)], axis=1)
+      cls._cache[key] = (win, torch.from_numpy(tw.astype(np.float32)).to(dev))
+    return cls._cache[key]
+
+  @classmethod
+  def mel(cls, fs, nfft, fmin, fmax, n_mels, dev):
+    key = ('mel', fs, nfft, fmin, fmax, n_mels, dev)
+    if key not in cls._cache:
+      fb64 = create_mel_filterbank(fs, nfft, fmin=fmin, fmax=fmax, n_mels=n_mels)
+      fb = torch.from_numpy(fb64.astype(np.float32)).to(dev).contiguous()
+      ranges = torch.empty((n_mels, 2), dtype=torch.int32, device=dev)
+      N.call('advoc_mel_ranges', _ptr(fb), n_mels, nfft // 2 + 1, _ptr(ranges), _stream())
+      cls._cache[key] = (fb, ranges)
+    return cls._cache[key]
+
+  @classmethod
+  def inv_mel(cls, fs, nfft, fmin, fmax, n_mels, dev):
+    key = ('inv', fs, nfft, fmin, fmax, n_mels, dev)
+    if key not in cls._cache:
+      inv = create_inverse_mel_filterbank(fs, nfft, fmin=fmin, fmax=fmax, n_mels=n_mels)
+      cls._cache[key] = torch.from_numpy(inv.astype(np.float32)).to(dev).contiguous()
+    return cls._cache[key]
+
+
+def num_frames(nsamps, nfft, nhop, pad_end=True):
+  """Frame-count rule of advoc/spectral.py:32-39 (and lws' own, tests/test_spectral.py:35-36)."""
+  return N.lib().advoc_num_frames(int(nsamps), int(nfft), int(nhop), 1 if pad_end else 0)
+
+
+# ---------------------------------------------------------------------------
+# device-level ops on torch tensors
+# ---------------------------------------------------------------------------
+def stft_tf(x, nfft, nhop, pad_end=True):
+  """Batched STFT.  x f32 [b, nsamps, 1, nch] (cuda) -> c64 [b, frames, nfft//2+1, nch].
+
+  reference: advoc/spectral.py:60-83.
+  """
+  if x.dim() != 4 or x.shape[2] != 1:
+    raise ValueError()
+  if x.dtype != torch.float32:
+    raise ValueError()
+  x = x.contiguous()
+  b, nsamps, _, nch = x.shape
+  win, tw = _Consts.stft(nfft, nhop, x.device)
+  frames = num_frames(nsamps, nfft, nhop, pad_end)
+  out = torch.empty((b, frames, nfft // 2 + 1, nch, 2), dtype=torch.float32, device=x.device)
+  N.call('advoc_stft_f32', _ptr(x), b, nsamps, nch, nfft, nhop, 1 if pad_end else 0, _ptr(win),
+         _ptr(tw), _ptr(out), None, _stream())
+  return torch.view_as_complex(out)
+
+
+stft_batched = stft_tf
+
+
+def magspec_tf(x, nfft, nhop, pad_end=True):
+  """|stft_tf(x)| without materialising the complex spectrum (loader 'magspec' extract,
+  reference: advoc/loader.py:117-121)."""
+  if x.dim() != 4 or x.shape[2] != 1 or x.dtype != torch.float32:
+    raise ValueError()
+  x = x.contiguous()
+  b, nsamps, _, nch = x.shape
+  win, tw = _Consts.stft(nfft, nhop, x.device)
+  frames = num_frames(nsamps, nfft, nhop, pad_end)
+  out = torch.empty((b, frames, nfft // 2 + 1, nch), dtype=torch.float32, device=x.device)
+  N.call('advoc_stft_f32', _ptr(x), b, nsamps, nch, nfft, nhop, 1 if pad_end else 0, _ptr(win),
+         _ptr(tw), None, _ptr(out), _stream())
+  return out
+
+
+def waveform_to_melspec_tf(x, fs, nfft, nhop, mel_min=125, mel_max=7600, mel_num_bins=80,
+                           norm_allow_clipping=True, norm_min_level_db=-100,
+                           norm_ref_level_db=20):
+  """x f32 [b, nsamps, 1, nch] (cuda) -> dB-normalised mel f32 [b, frames, mel_num_bins, nch].
+
+  One fused kernel: frame -> window -> FFT -> |.| -> mel -> 20log10 -> clip.
+  reference: advoc/spectral.py:158-227.
+  """
+  if x.dim() != 4 or x.shape[2] != 1:
+    raise ValueError()
+  if x.dtype != torch.float32:
+    raise ValueError()
+  if not norm_allow_clipping:
+    raise NotImplementedError()  # advoc/spectral.py:220-223
+  x = x.contiguous()
+  b, nsamps, _, nch = x.shape
+  win, tw = _Consts.stft(nfft, nhop, x.device)
+  fb, ranges = _Consts.mel(fs, nfft, mel_min, mel_max, mel_num_bins, x.device)
+  frames = num_frames(nsamps, nfft, nhop, True)
+  out = torch.empty((b, frames, mel_num_bins, nch), dtype=torch.float32, device=x.device)
+  N.call('advoc_melspec_f32', _ptr(x), b, nsamps, nch, nfft, nhop, _ptr(win), _ptr(tw), _ptr(fb),
+         _ptr(ranges), mel_num_bins, float(norm_min_level_db), float(norm_ref_level_db),
+         _ptr(out), _stream())
+  return out
+
+
+def waveform_to_r9y9_melspec_tf(x, fs=22050):
+  """reference: advoc/spectral.py:272-291."""
+  return waveform_to_melspec_tf(x, fs=fs, nfft=1024, nhop=256)
+
+
+def matmul_lastdim(x, w, pow10_scale=False):
+  """y[..., n] = sum_k f(x[..., k]) * w[n, k] on the GPU (f = identity or the dB
+  de-normalisation 10^((x*100-100+20)/20)).  reference: models/advoc/spectral_util.py:29-43,
+  scripts/spectrogram_advoc.py:15-22."""
+  if x.dtype != torch.float32 or w.dtype != torch.float32:
+    raise ValueError()
+  if w.dim() != 2 or x.shape[-1] != w.shape[1]:
+    raise ValueError()
+  x = x.contiguous()
+  w = w.contiguous()
+  rows = x.numel() // x.shape[-1] if x.numel() else 0
+  y = torch.empty(x.shape[:-1] + (w.shape[0],), dtype=torch.float32, device=x.device)
+  N.call('advoc_matmul_lastdim_f32', _ptr(x), _ptr(w), _ptr(y), rows, x.shape[-1], w.shape[0],
+         1 if pow10_scale else 0, _stream())
+  return y
+
+
+# ---------------------------------------------------------------------------
+# numpy entry points (host buffers in, host buffers out) -- the reference's numpy API
+# ---------------------------------------------------------------------------
+def stft(x, nfft, nhop, pad_end=True):
+  """x f32 [n, 1, 1] -> complex128 [frames, nfft//2+1, 1].  reference: advoc/spectral.py:11-41."""
+  nsamps, nfeats, nch = x.shape
+  if nfeats != 1:
+    raise ValueError()
+  if nch != 1:
+    raise NotImplementedError('Can only take STFT of monaural signals')
+  dev = _device()
+  xd = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(dev).reshape(1, nsamps, 1, 1)
+  X = stft_tf(xd, nfft, nhop, pad_end=pad_end)
+  return X[0].cpu().numpy().astype(np.complex128)
+
+
+def waveform_to_melspec(x, fs, nfft, nhop, mel_min=125, mel_max=7600, mel_num_bins=80,
+                        norm_allow_clipping=True, norm_min_level_db=-100,
+                        norm_ref_level_db=20):
+  """x f32 [n, 1, 1] -> f64 [frames, mel_num_bins, 1].  reference: advoc/spectral.py:98-154."""
+  if x.dtype != np.float32:
+    raise ValueError()
+  nsamps, nfeats, nch = x.shape
+  if nfeats != 1:
+    raise ValueError()
+  if nch != 1:
+    raise NotImplementedError('Can only extract features from monaural signals')
+  dev = _device()
+  xd = torch.from_numpy(np.ascontiguousarray(x)).to(dev).reshape(1, nsamps, 1, 1)
+  if not norm_allow_clipping:
+    # the reference asserts on the un-clipped dB values (advoc/spectral.py:149-151)
+    mag = magspec_tf(xd, nfft, nhop)[0, :, :, 0]
+    fb, _ = _Consts.mel(fs, nfft, mel_min, mel_max, mel_num_bins, dev)
+    mel = matmul_lastdim(mag, fb).cpu().numpy().astype(np.float64)
+    min_level = np.exp(norm_min_level_db / 20 * np.log(10))
+    db = 20 * np.log10(np.maximum(min_level, mel)) - norm_ref_level_db
+    assert db.max() <= 0 and db.min() - norm_min_level_db >= 0
+    return np.clip((db - norm_min_level_db) / -norm_min_level_db, 0, 1)[:, :, np.newaxis]
+  out = waveform_to_melspec_tf(xd, fs, nfft, nhop, mel_min, mel_max, mel_num_bins, True,
+                               norm_min_level_db, norm_ref_level_db)
+  return out[0].cpu().numpy().astype(np.float64)
+
+
+def waveform_to_tacotron2_melspec(x):
+  """reference: advoc/spectral.py:230-247 (x at 24 kHz)."""
+  return waveform_to_melspec(x, fs=24000, nfft=1200, nhop=300, norm_min_level_db=-40)
+
+
+def waveform_to_r9y9_melspec(x, fs=22050):
+  """reference: advoc/spectral.py:250-269."""
+  return waveform_to_melspec(x, fs=fs, nfft=1024, nhop=256)

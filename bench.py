@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""Headline benchmark: AdVoc generator forward, mel-frames/sec (BASELINE.json configs[1]).
+
+  python bench.py --gpus N --steps K --warmup W            # this framework (sm_100a kernels)
+  python bench.py --impl reference --gpus N --steps K ...   # CPU restatement of the TF1 graph
+
+One step = one pass of the hot path over one batch of synthetic input: linear mel
+[B=32, 256, 80] -> pinv lift -> AdVoc-small U-Net -> magnitude [32, 256, 513]; dropout on
+decoder_5/4 active as in the reference (advoc_model_small.py:149-154).  `value` is measured with
+the mel batch already resident in HBM (CUDA events, L2 flushed between steps); `e2e` is the same
+metric through the public host API (`advoc_b200.infer.MelToMag.__call__`) with pinned host
+buffers, H2D and D2H copies inside the timed region.  N > 1 runs one replica per GPU (weak
+scaling, no data-path collective: inference chunks are independent).  `--workload train`
+times the G+D train step instead (BASELINE configs[2]/[3]).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+  sys.path.insert(0, ROOT)
+
+FLOP_PER_FRAME = {'small': 21.84e6, 'regular': 95.75e6}   # SURVEY.md section 8(d), G forward
+T = 256
+
+
+def _peaks():
+  try:
+    with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+      p = json.load(f)
+    return dict(hbm=p['hbm_gbs'], tensor=p['bf16_tflops'], tensor_sustained=p['bf16_tflops_sustained'],
+                source='measured')
+  except Exception:
+    return dict(hbm=6650.0, tensor=1590.0, tensor_sustained=1400.0, source='fallback')
+
+
+class ClockSampler(object):
+  """Samples SM clock + throttle reasons via NVML while the timed region runs."""
+  BAD = {0x8: 'hw_slowdown', 0x40: 'hw_thermal_slowdown', 0x20: 'sw_thermal_slowdown'}
+  NOTE = {0x4: 'sw_power_cap'}
+
+  def __init__(self, index):
+    self.samples, self.reasons, self.max_mhz = [], set(), None
+    self._stop = threading.Event()
+    self._t = None
+    try:
+      import pynvml
+      pynvml.nvmlInit()
+      self.nv = pynvml
+      self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+      self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+    except Exception:
+      self.nv = None
+
+  def _run(self):
+    nv = self.nv
+    while not self._stop.is_set():
+      try:
+        self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        for bit, name in list(self.BAD.items()) + list(self.NOTE.items()):
+          if r & bit:
+            self.reasons.add(name)
+      except Exception:
+        pass
+      time.sleep(0.005)
+
+  def __enter__(self):
+    if self.nv is not None:
+      self._t = threading.Thread(target=self._run, daemon=True)
+      self._t.start()
+    return self
+
+  def __exit__(self, *a):
+    self._stop.set()
+    if self._t is not None:
+      self._t.join()
+
+  def summary(self):
+    s = sorted(self.samples)
+    return dict(sm_mhz=(s[len(s) // 2] if s else None), sm_max_mhz=self.max_mhz,
+                reasons=sorted(self.reasons), samples=len(s))
+
+
+def _model(name):
+  from advoc_b200.model import Advoc, AdvocSmall, Modes
+  m = AdvocSmall(Modes.INFER) if name == 'small' else Advoc(Modes.INFER)
+  m.init_params(seed=0)
+  return m
+
+
+def _synthetic_mel(batch, seed=1):
+  import torch
+  g = torch.Generator().manual_seed(seed)
+  return torch.randn(batch, T, 80, generator=g).abs()
+
+
+# ---------------------------------------------------------------------------
+# CPU baseline (oracle port of the TF1 graph; bench.py's cpu_baseline leg and --impl reference)
+# ---------------------------------------------------------------------------
+def cpu_generator_frames_per_sec(model_name, sample_batch, repeats, warmup=1):
+  import numpy as np
+  import torch
+  from oracle import nets_torch as O
+  from oracle import spectral_np as OS
+  cores = os.cpu_count() or 1
+  torch.set_num_threads(cores)
+  spec = O.SMALL if model_name == 'small' else O.REGULAR
+  P = O.init_params(spec, seed=0)
+  Winv = torch.from_numpy(
+      OS.create_inverse_mel_filterbank(22050, 1024, fmin=125., fmax=7600., n_mels=80)
+      .astype(np.float32))
+  mel = _synthetic_mel(sample_batch)
+  g = torch.Generator().manual_seed(7)
+  shapes = {}
+  with torch.no_grad():
+    x = (mel @ Winv.t()).unsqueeze(-1)
+    _, layers = O.generator(P, x[:1], spec, return_layers=True)
+    n_enc = spec.num_enc_layers + 1
+    for j, k in enumerate(range(n_enc, 1, -1)):
+      if k in spec.dropout_decoders:
+        shapes[k] = (sample_batch,) + tuple(layers[n_enc + j].shape[1:])
+  times = []
+  with torch.no_grad():
+    for it in range(warmup + repeats):
+      t0 = time.perf_counter()
+      x = (mel @ Winv.t()).unsqueeze(-1)
+      masks = {k: (torch.rand(s, generator=g) < 0.5).float() for k, s in shapes.items()}
+      O.generator(P, x, spec, masks)
+      dt = time.perf_counter() - t0
+      if it >= warmup:
+        times.append(dt)
+  return sample_batch * T / min(times), sum(times) / len(times), cores
+
+
+def run_reference(args):
+  rank = int(os.environ.get('RANK', '0'))
+  if rank != 0:
+    return
+  sample = 8 if args.model == 'small' else 2
+  fps, mean_s, cores = cpu_generator_frames_per_sec(args.model, sample, max(args.steps, 1),
+                                                    max(args.warmup, 1))
+  desc = ('PyTorch-CPU fp32 restatement of the TF1 graph (oracle/nets_torch.py; TF1/lws/librosa '
+          'not installable), %d of %d samples per step' % (sample, args.batch))
+  line = {
+      'impl': 'reference', 'metric': 'mel-frames/sec generator fwd', 'value': fps,
+      'unit': 'mel-frames/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+      'ms_per_step': mean_s * 1e3 * args.batch / sample, 'higher_is_better': True,
+      'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+      'config': _config(args),
+      'cpu_baseline': {'value': fps, 'unit': 'mel-frames/s', 'cores': cores, 'kind': 'port',
+                       'sample': desc},
+      'e2e': {'value': fps, 'unit': 'mel-frames/s', 'h2d_bytes_per_step': 0,
+              'd2h_bytes_per_step': 0},
+      'gpu_launches': 0,
+  }
+  print(json.dumps(line))
+
+
+def _config(args):
+  return {'workload': 'AdVoc-%s generator forward, synthetic |N(0,1)| linear mel [%d, 80, 256] -> '
+                      'magnitude [%d, 513, 256], random N(0,0.02) weights, dropout on'
+                      % (args.model, args.batch, args.batch),
+          'batch_per_gpu': args.batch, 'frames_per_sample': T,
+          'l2': 'flushed between timed steps (256 MiB write); per-step working set %d MB > 126 MB L2'
+                % (17 * args.batch if args.model == 'small' else 33 * args.batch)}
+
+
+# ---------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------
+def run_gpu(args):
+  import torch
+  import torch.distributed as dist
+  from advoc_b200 import _native as N
+  from advoc_b200.infer import MelToMag
+
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  rank = int(os.environ.get('RANK', '0'))
+  local = int(os.environ.get('LOCAL_RANK', '0'))
+  if not torch.cuda.is_available():
+    raise RuntimeError('bench.py needs a GPU (the product path has no CPU fallback)')
+  torch.cuda.set_device(local)
+  if world > 1:
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  model = _model(args.model)
+  eng = MelToMag(model, args.batch, 'linear', dropout='rng', use_graph=not args.no_graph)
+  mel_h = _synthetic_mel(args.batch, seed=1 + rank).pin_memory()
+  eng.mel_d.copy_(mel_h)
+  flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
+  stream = torch.cuda.current_stream()
+
+  def timed(fn, steps, warmup):
+    for _ in range(warmup):
+      fn()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+           for _ in range(steps)]
+    barrier()
+    for a, b in evs:
+      flush.zero_()
+      a.record(stream)
+      fn()
+      b.record(stream)
+    barrier()
+    ms = [a.elapsed_time(b) for a, b in evs]
+    return sum(ms)
+
+  n0 = N.launch_count()
+  eng.step_device()
+  per_step = eng.launches_per_step or (N.launch_count() - n0)
+
+  with ClockSampler(local) as clk:
+    total_ms = timed(eng.step_device, args.steps, args.warmup)
+    e2e_ms = timed(lambda: eng(mel_h), args.steps, args.warmup)
+  if world > 1:
+    t = torch.tensor([total_ms, e2e_ms], device='cuda', dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = float(t[0]), float(t[1])
+
+  frames = world * args.batch * T * args.steps
+  value = frames / (total_ms * 1e-3)
+  e2e = frames / (e2e_ms * 1e-3)
+
+  # per-layer device time of one un-graphed step (CUDA events on the launching stream):
+  # the roofline is reported for the dominant kernel
+  roof = layer_roofline(eng, args, stream, flush)
+
+  line = {
+      'metric': 'mel-frames/sec generator fwd', 'value': value, 'unit': 'mel-frames/s',
+      'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+      'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+      'vs_baseline': None, 'dtype': 'tf32 (fp32 accumulate, fp32 storage)', 'data': 'synthetic',
+      'config': _config(args),
+      'e2e': {'value': e2e, 'unit': 'mel-frames/s', 'ms_per_step': e2e_ms / args.steps,
+              'h2d_bytes_per_step': int(mel_h.numel() * 4),
+              'd2h_bytes_per_step': int(eng.out_h.numel() * 4)},
+      'gpu_launches': int(per_step * args.steps * 2),
+      'launches_per_step': int(per_step),
+      'clocks': clk.summary(),
+      'roofline': roof,
+      'step_tflops': FLOP_PER_FRAME[args.model] * frames / (total_ms * 1e-3) / 1e12,
+  }
+  if rank == 0:
+    if not args.no_cpu_baseline and world == 1:
+      sample = 8 if args.model == 'small' else 2
+      fps, mean_s, cores = cpu_generator_frames_per_sec(args.model, sample, 3, 1)
+      line['cpu_baseline'] = {
+          'value': fps, 'unit': 'mel-frames/s', 'cores': cores, 'kind': 'port',
+          'sample': 'oracle/nets_torch.py (PyTorch-CPU fp32 port of the TF1 graph), %d of %d '
+                    'samples, best of 3' % (sample, args.batch)}
+    print(json.dumps(line))
+  if world > 1:
+    dist.destroy_process_group()
+
+
+def layer_roofline(eng, args, stream, flush):
+  """Times every layer launch of one step with CUDA events and reports the roofline of the
+  kernel family that takes the largest share of the step."""
+  import torch
+  G = eng.G
+  recs = []
+  orig = G._run_layer
+
+  def timed_run(L, *a):
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record(stream)
+    orig(L, *a)
+    e.record(stream)
+    recs.append((L, s, e))
+
+  peaks = _peaks()
+  acc = {}
+  reps = 5
+  G._run_layer = timed_run
+  try:
+    for _ in range(reps):
+      flush.zero_()
+      eng._launch(1)
+    torch.cuda.synchronize()
+  finally:
+    G._run_layer = orig
+  for L, s, e in recs:
+    k = L.kernel_family()
+    d = acc.setdefault(k, dict(ms=0.0, flops=0.0, bytes=0.0, launches=0))
+    d['ms'] += s.elapsed_time(e) / reps
+    d['flops'] += L.flops() / reps
+    d['bytes'] += L.algorithmic_bytes() / reps
+    d['launches'] += 1.0 / reps
+  total = sum(d['ms'] for d in acc.values())
+  top = max(acc, key=lambda k: acc[k]['ms'])
+  d = acc[top]
+  layers = {k: {'ms': round(v['ms'], 4), 'share': round(v['ms'] / total, 3),
+                'tflops': round(v['flops'] / (v['ms'] * 1e-3) / 1e12, 2),
+                'gbs': round(v['bytes'] / (v['ms'] * 1e-3) / 1e9, 1)} for k, v in acc.items()}
+  if top.startswith('tc'):
+    ach = d['flops'] / (d['ms'] * 1e-3) / 1e12
+    return {'kernel': top, 'bound': 'tensor', 'achieved': ach, 'peak': peaks['tensor'],
+            'unit': 'TFLOP/s', 'frac': ach / peaks['tensor'], 'traffic': None,
+            'peak_source': peaks['source'] + ' cuBLAS bf16 burst (kernel runs kind::tf32, whose '
+                           'nominal dense peak is half the bf16 peak)',
+            'share_of_step': d['ms'] / total, 'by_kernel': layers}
+  ach = d['bytes'] / (d['ms'] * 1e-3) / 1e9
+  return {'kernel': top, 'bound': 'hbm', 'achieved': ach, 'peak': peaks['hbm'], 'unit': 'GB/s',
+          'frac': ach / peaks['hbm'], 'traffic': None, 'peak_source': peaks['source'],
+          'share_of_step': d['ms'] / total, 'by_kernel': layers}
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument('--gpus', type=int, default=1)
+  ap.add_argument('--steps', type=int, default=50)
+  ap.add_argument('--warmup', type=int, default=5)
+  ap.add_argument('--impl', default='advoc_b200', choices=['advoc_b200', 'reference'])
+  ap.add_argument('--model', default='small', choices=['small', 'regular'])
+  ap.add_argument('--batch', type=int, default=32, help='samples per GPU')
+  ap.add_argument('--no-graph', action='store_true')
+  ap.add_argument('--no-cpu-baseline', action='store_true')
+  args = ap.parse_args()
+  args.warmup = max(args.warmup, 3) if args.impl != 'reference' else args.warmup
+  if args.impl == 'reference':
+    run_reference(args)
+  else:
+    run_gpu(args)
+
+
+if __name__ == '__main__':
+  main()

@@ -1,0 +1,176 @@
+/*
+ * advoc_b200 -- C-ABI of the B200-native adversarial-vocoder hot path.
+ *
+ * The reference (paarthneekhara/advoc) has no FFI boundary: its hot path is a
+ * TensorFlow-1 graph built from Python.  This header is the boundary a
+ * maintainer binds instead (ctypes stub in INTEGRATION.md); every entry point
+ * names the reference call site it replaces as `path:line` under the reference
+ * repository root.
+ *
+ * Conventions
+ *   - every function returns an advoc_status (0 == ADVOC_OK); the message of the
+ *     last failure on the calling thread is read with advoc_last_error().
+ *   - all pointers named d_* are DEVICE pointers owned by the caller, 16-byte
+ *     aligned and densely packed in the stated layout; the library allocates
+ *     nothing on the hot path and never synchronises the device.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - activations are NHWC float32 [batch, time(H), freq(W), channels] -- the
+ *     reference's layout.  Convolution kernels are given in the TensorFlow
+ *     layouts (conv HWIO [kh,kw,Cin,Cout]; conv_transpose HWOI [kh,kw,Cout,Cin])
+ *     and are re-packed by advoc_pack_filter into the K-major TF32 operand
+ *     layout the tensor-core kernels read.
+ *   - nothing here takes or returns a torch type.
+ */
+#ifndef ADVOC_B200_H_
+#define ADVOC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADVOC_B200_VERSION 100
+
+#if defined(__GNUC__)
+#define ADVOC_API __attribute__((visibility("default")))
+#else
+#define ADVOC_API
+#endif
+
+typedef enum advoc_status {
+  ADVOC_OK = 0,
+  ADVOC_BAD_ARG = 1,          /* -> ValueError           */
+  ADVOC_BAD_SHAPE = 2,        /* -> ValueError           */
+  ADVOC_BAD_ALIGN = 3,        /* -> ValueError           */
+  ADVOC_UNSUPPORTED = 4,      /* -> NotImplementedError  */
+  ADVOC_WORKSPACE_TOO_SMALL = 5,
+  ADVOC_CUDA_ERROR = 6        /* -> RuntimeError         */
+} advoc_status;
+
+typedef enum advoc_act {
+  ADVOC_ACT_NONE = 0,
+  ADVOC_ACT_LRELU = 1,   /* max(alpha*x, x)  models/advoc/advoc_model.py:86-87 */
+  ADVOC_ACT_RELU = 2,    /* models/advoc/advoc_model.py:138                   */
+  ADVOC_ACT_SIGMOID = 3, /* models/advoc/advoc_model.py:201                   */
+  ADVOC_ACT_TANH = 4     /* models/melspecgan/conv2d.py:141                   */
+} advoc_act;
+
+typedef enum advoc_math {
+  ADVOC_MATH_AUTO = 0,  /* tensor cores (TF32, fp32 accumulate) where the layer is eligible */
+  ADVOC_MATH_FP32 = 1,  /* CUDA-core fp32 direct kernels (exact-fp32 cross-check path)      */
+  ADVOC_MATH_TF32 = 2   /* force the tcgen05 path; ADVOC_UNSUPPORTED if not eligible        */
+} advoc_math;
+
+ADVOC_API int advoc_version(void);
+/* Copies the calling thread's last error text (NUL terminated) into buf. */
+ADVOC_API int advoc_last_error(char* buf, size_t buf_len);
+/* Number of kernels this library has launched in this process (bench.py gpu_launches). */
+ADVOC_API unsigned long long advoc_launch_count(void);
+/* Compute capability of the current device as major*10+minor (100 on B200). */
+ADVOC_API int advoc_device_arch(int* arch);
+
+/* ------------------------------------------------------------------------- *
+ * Spectral features
+ * ------------------------------------------------------------------------- */
+
+/* Frame count of the reference framing rule.
+ * replaces: advoc/spectral.py:32-39 (pad_end) and lws' own rule (tests/test_spectral.py:35-36). */
+ADVOC_API int advoc_num_frames(int nsamps, int nfft, int nhop, int pad_end);
+
+/* Framed, windowed real FFT.  d_wav [batch, nsamps, 1, nch] f32 ->
+ * d_out_c64 [batch, frames, nfft/2+1, nch] interleaved (re,im) f32 and/or
+ * d_out_mag [same] f32 magnitude (either may be NULL).  d_window [nfft] f32.
+ * d_twiddle [nfft] (cos,-sin) pairs made by advoc_fill_twiddle_host / any caller.
+ * replaces: advoc/spectral.py:11-41 (`stft`, lws C++), :60-83 (`stft_tf`). */
+ADVOC_API int advoc_stft_f32(const float* d_wav, int batch, int nsamps, int nch, int nfft, int nhop,
+                   int pad_end, const float* d_window, const float* d_twiddle,
+                   float* d_out_c64, float* d_out_mag, void* stream);
+
+/* Fused waveform -> dB-normalised mel: STFT -> |.| -> mel filterbank -> 20log10 -> clip.
+ * d_mel_fb [nmels, nfft/2+1] f32 row-major.  d_out [batch, frames, nmels, nch] f32.
+ * replaces: advoc/spectral.py:98-154 and :158-227 (`waveform_to_melspec[_tf]`). */
+ADVOC_API int advoc_melspec_f32(const float* d_wav, int batch, int nsamps, int nch, int nfft, int nhop,
+                      const float* d_window, const float* d_twiddle, const float* d_mel_fb,
+                      const int* d_mel_ranges, int nmels, float min_level_db,
+                      float ref_level_db, float* d_out, void* stream);
+
+/* d_ranges[2m], d_ranges[2m+1] = [first, last+1) non-zero bin of filter m; lets the fused
+ * kernel skip the zeros of the triangular filters (optional argument above; NULL = dense). */
+ADVOC_API int advoc_mel_ranges(const float* d_mel_fb, int nmels, int bins, int* d_ranges, void* stream);
+
+/* y[r, n] = sum_k x[r, k] * w[n, k]   (x [rows,K], w [N,K], y [rows,N], all f32).
+ * replaces: models/advoc/spectral_util.py:29-32 (mag -> linear mel, w = mel_fb) and
+ * :34-43 (linear mel -> mag, w = pinv(mel_fb)); scripts/spectrogram_advoc.py:21.
+ * If pow10_scale != 0 the input is first mapped x -> 10^((x*100-100+20)/20)
+ * (the dB de-normalisation of scripts/spectrogram_advoc.py:19-20). */
+ADVOC_API int advoc_matmul_lastdim_f32(const float* d_x, const float* d_w, float* d_y, long rows, int K,
+                             int N, int pow10_scale, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Convolution stacks
+ * ------------------------------------------------------------------------- */
+
+/* Geometry of one 2-D convolution on NHWC data.  For a transposed convolution the
+ * struct describes the *forward* convolution it is the input-gradient of
+ * (SURVEY appendix B rule 2): (N,H,W,Cin) is the big (output-of-deconv) side. */
+typedef struct advoc_conv_desc {
+  int N, H, W, Cin;     /* conv input                                          */
+  int Cout;             /* conv output channels                                */
+  int kh, kw;           /* 4x4 (AdVoc) or 5x5 (MelspecGAN)                     */
+  int sh, sw;           /* strides                                             */
+  int pad_t, pad_l;     /* leading zero padding (trailing is implied by Ho/Wo) */
+  int Ho, Wo;           /* conv output spatial size                            */
+  int math;             /* advoc_math                                          */
+} advoc_conv_desc;
+
+/* What happens to an output tile before it is stored.
+ *   y0 = act0(acc + bias) [* dropout]  -> d_out0 at channel offset c_off0 of a
+ *                                         buffer with ld0 channels per pixel
+ *   y1 = act1(acc + bias) [* dropout]  -> d_out1 (optional second consumer: the
+ *                                         reference applies lrelu for the next
+ *                                         encoder and relu for the decoder skip to
+ *                                         the same tensor, advoc_model.py:109,138)
+ * Only the first `store_w` output columns are written (the reference drops the last
+ * column of every decoder output, advoc_model.py:137,154,156); 0 = all.
+ * d_dropout_mask (optional, uint8 0/1, dense [N,Ho,Wo,Cout] of the *stored* extent)
+ * multiplies by mask/keep_prob (tf.nn.dropout, advoc_model.py:144-149); if NULL and
+ * keep_prob < 1 a counter-based generator keyed by (seed, element index) is used.
+ * round_tf32: round stored values to TF32 (RNA) so the consuming tensor-core layer
+ * reads exactly-representable operands. */
+typedef struct advoc_epilogue {
+  const float* d_bias;       /* [Cout] or NULL */
+  int act0, act1;
+  float alpha;               /* lrelu slope */
+  float* d_out0; int ld0, c_off0;
+  float* d_out1; int ld1, c_off1;   /* d_out1 may be NULL */
+  int store_w;
+  const uint8_t* d_dropout_mask;
+  float keep_prob;           /* 1.0 = no dropout */
+  uint64_t seed;
+  int round_tf32;
+} advoc_epilogue;
+
+/* y = conv2d(x, w) ; x [N,H,W,Cin] (pixel stride ld_x >= Cin, channel offset 0).
+ * d_w: ADVOC_MATH_FP32 -> TF layout HWIO; TF32 -> packed [taps, Cout, Cin].
+ * replaces: tf.layers.conv2d call sites models/advoc/advoc_model.py:27-32, :46-51. */
+ADVOC_API int advoc_conv2d_fwd(const advoc_conv_desc* d, const float* d_x, int ld_x, const float* d_w,
+                     const advoc_epilogue* ep, void* stream);
+
+/* y = conv2d_transpose(x, w); x [N,Ho,Wo,Cout] (ld_x), output [N,H,W,Cin] in desc naming.
+ * d_w: FP32 -> TF layout HWOI [kh,kw,Cin(desc),Cout(desc)]; TF32 -> packed
+ * [taps, Cin(desc), Cout(desc)].
+ * replaces: tf.layers.conv2d_transpose models/advoc/advoc_model.py:65-69. */
+ADVOC_API int advoc_conv2d_transpose_fwd(const advoc_conv_desc* d, const float* d_x, int ld_x,
+                               const float* d_w, const advoc_epilogue* ep, void* stream);
+
+/* Which kernel family a call with this geometry takes: ADVOC_MATH_TF32 (tcgen05 implicit
+ * GEMM) or ADVOC_MATH_FP32 (CUDA-core kernel).  transposed != 0 asks about
+ * advoc_conv2d_transpose_fwd.  Pure host logic. */
+ADVOC_API int advoc_conv2d_path(const advoc_conv_desc* d, int ld_x, int transposed);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADVOC_B200_H_ */
