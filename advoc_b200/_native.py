@@ -56,6 +56,8 @@ SIGNATURES = {
     'advoc_mel_ranges': (_I, [_P, _I, _I, _P, _P]),
     'advoc_matmul_lastdim_f32': (_I, [_P, _P, _P, _L, _I, _I, _I, _P]),
     'advoc_conv2d_fwd': (_I, [C.POINTER(ConvDesc), _P, _I, _P, C.POINTER(Epilogue), _P]),
+    'advoc_pack_filter': (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    'advoc_debug_flags': (_I, [C.POINTER(C.c_uint)]),
     'advoc_conv2d_path': (_I, [C.POINTER(ConvDesc), _I, _I]),
     'advoc_conv2d_transpose_fwd': (_I, [C.POINTER(ConvDesc), _P, _I, _P, C.POINTER(Epilogue), _P]),
 }
@@ -100,6 +102,12 @@ def check(status):
 
 def call(name, *args):
   check(getattr(lib(), name)(*args))
+
+
+def debug_flags():
+  v = C.c_uint(0)
+  call('advoc_debug_flags', C.byref(v))
+  return v.value
 
 
 def launch_count():

@@ -142,3 +142,41 @@ extern "C" int advoc_conv2d_path(const advoc_conv_desc* d, int ld_x, int transpo
   const bool ok = transposed ? conv_transposed_tc_eligible(d, ld_x) : conv_fwd_tc_eligible(d, ld_x);
   return ok ? ADVOC_MATH_TF32 : ADVOC_MATH_FP32;
 }
+
+// ---------------------------------------------------------------------------------------------
+// filter re-pack: [taps, A, B] -> [taps, B, A] (transpose != 0) or copy, optionally TF32-rounded
+// ---------------------------------------------------------------------------------------------
+namespace {
+__global__ void pack_filter_kernel(const float* __restrict__ in, float* __restrict__ out, int taps,
+                                   int A, int B, int transpose, int round) {
+  const long total = (long)taps * A * B;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long)gridDim.x * blockDim.x) {
+    // i indexes the OUTPUT so that writes are coalesced
+    long src = i;
+    if (transpose) {
+      const int a = (int)(i % A);
+      const long r = i / A;
+      const int b = (int)(r % B);
+      const long t = r / B;
+      src = (t * A + a) * B + b;
+    }
+    float v = __ldg(in + src);
+    if (round) v = advoc::round_tf32(v);
+    out[i] = v;
+  }
+}
+}  // namespace
+
+extern "C" int advoc_pack_filter(const float* d_w, float* d_packed, int taps, int A, int B,
+                                 int transpose, int round_tf32, void* stream) {
+  ADVOC_REQUIRE(d_w && d_packed, ADVOC_BAD_ARG, "NULL filter pointer");
+  ADVOC_REQUIRE(taps > 0 && A > 0 && B > 0, ADVOC_BAD_SHAPE, "bad filter shape");
+  const long total = (long)taps * A * B;
+  const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+  pack_filter_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      d_w, d_packed, taps, A, B, transpose, round_tf32);
+  count_launch();
+  ADVOC_CHECK_CUDA(cudaGetLastError());
+  return ADVOC_OK;
+}

@@ -33,6 +33,7 @@ int fail(advoc_status st, const char* fmt, ...);
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 int sm_count();
+int device_arch();  // major*10+minor of the current device, 0 without a device
 
 // every kernel launch of this library bumps this counter (read with advoc_launch_count);
 // bench.py reports it as `gpu_launches`

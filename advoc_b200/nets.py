@@ -112,6 +112,20 @@ def _epilogue(bias, out0, ld0, coff0, act0, out1=None, ld1=0, coff1=0, act1=N.AC
                     store_w, _ptr(mask), keep_prob, seed, round_tf32)
 
 
+def _pack_for_tc(L, kernel, ldx):
+  """Derived filter copy for the tcgen05 path (None if the layer runs on CUDA cores):
+  conv HWIO -> K-major [tap][Cout][Cin]; conv_transpose HWOI is already K-major.  Values are
+  rounded to TF32 (round-to-nearest) because the tensor core would otherwise truncate."""
+  if not L.uses_tensor_cores(ldx):
+    return None
+  kh, kw, a, b = kernel.shape
+  out = torch.empty((kh * kw, b, a) if L.kind == 'conv' else (kh * kw, a, b),
+                    dtype=torch.float32, device=kernel.device)
+  N.call('advoc_pack_filter', _ptr(kernel), _ptr(out), kh * kw, a, b, 1 if L.kind == 'conv' else 0,
+         1, _stream())
+  return out
+
+
 class Generator(object):
   """U-Net generator forward on persistent buffers.  x [B,T,513,1] -> [B,T,513,1]."""
 
@@ -147,12 +161,30 @@ class Generator(object):
                                 s.H[k], s.W[k], math))
       assert s.H[k] * sh == s.H[k - 1] and s.W[k] * 2 - 1 == s.W[k - 1]
 
+  def _ldx(self, L):
+    if L.kind == 'conv':
+      return max(L.desc.Cin, 1)
+    return L.desc.Cout
+
   def prepare(self):
-    """Refresh the derived (packed / TF32-rounded) filter copies after the parameters changed."""
+    """Refresh the derived (packed / TF32-rounded) filter copies after the parameters changed
+    and decide which stored activations must be TF32-rounded for their consumer."""
+    self.Wp = {}
+    for L in list(self.enc.values()) + list(self.dec.values()):
+      self.Wp[L.name] = _pack_for_tc(L, self.P[L.name + '/kernel'], self._ldx(L))
+    n = self.spec.n_enc
+    tc = lambda L: self.Wp[L.name] is not None
+    # encoder_i writes E[i] (read by encoder_{i+1}) and Cat[i] (read by decoder_i)
+    self.round_enc = {i: int((i < n and tc(self.enc[i + 1])) or tc(self.dec[i])) for i in range(1, n + 1)}
+    # decoder_k writes Cat[k-1] (read by decoder_{k-1})
+    self.round_dec = {k: int(k > 1 and tc(self.dec[k - 1])) for k in range(1, n + 1)}
     return self
 
   def _w(self, L):
-    return self.P[L.name + '/kernel']
+    if not hasattr(self, 'Wp'):
+      self.prepare()
+    w = self.Wp[L.name]
+    return w if w is not None else self.P[L.name + '/kernel']
 
   def _run_layer(self, L, x, ldx, w, ep):
     L.run(x, ldx, w, ep)
@@ -169,15 +201,18 @@ class Generator(object):
     (`out` if given: written with pixel stride out_ld at channel out_coff)."""
     s, P, n = self.spec, self.P, self.spec.n_enc
     assert x.is_contiguous() and tuple(x.shape) == (self.B, s.H[0], s.W[0], 1), x.shape
+    if not hasattr(self, 'Wp'):
+      self.prepare()
     inp, ld = x, 1
     for i in range(1, n + 1):
       L = self.enc[i]
       cat = self.Cat[i]
       if i < n:
         ep = _epilogue(P[L.name + '/bias'], self.E[i], s.enc_ch[i - 1], 0, N.ACT_LRELU,
-                       cat, cat.shape[3], self.Dk[i], N.ACT_RELU)
+                       cat, cat.shape[3], self.Dk[i], N.ACT_RELU, round_tf32=self.round_enc[i])
       else:
-        ep = _epilogue(P[L.name + '/bias'], cat, cat.shape[3], 0, N.ACT_RELU)
+        ep = _epilogue(P[L.name + '/bias'], cat, cat.shape[3], 0, N.ACT_RELU,
+                       round_tf32=self.round_enc[i])
       self._run_layer(L, inp, ld, self._w(L), ep)
       if i < n:
         inp, ld = self.E[i], s.enc_ch[i - 1]
@@ -195,7 +230,7 @@ class Generator(object):
       if k > 1:
         nxt = self.Cat[k - 1]
         ep = _epilogue(P[L.name + '/bias'], nxt, nxt.shape[3], 0, N.ACT_RELU,
-                       store_w=s.W[k - 1], **kw)
+                       store_w=s.W[k - 1], round_tf32=self.round_dec[k], **kw)
       else:
         ld_o, co = (1, 0) if out is None else (out_ld, out_coff)
         ep = _epilogue(P[L.name + '/bias'], dst, ld_o, co, N.ACT_NONE, store_w=s.W[0], **kw)
@@ -223,15 +258,25 @@ class Discriminator(object):
       h, w = ho, wo
 
   def prepare(self):
+    self.Wp = {L.name: _pack_for_tc(L, self.P[L.name + '/kernel'], self.chans[i])
+               for i, L in enumerate(self.layers)}
+    self.round = [int(i + 1 < 5 and self.Wp[self.layers[i + 1].name] is not None) for i in range(5)]
     return self
+
+  def _w(self, L):
+    w = self.Wp[L.name]
+    return w if w is not None else self.P[L.name + '/kernel']
 
   def forward(self, in_cat):
     assert in_cat.is_contiguous() and in_cat.shape[3] == 2 and in_cat.shape[0] == self.B
+    if not hasattr(self, 'Wp'):
+      self.prepare()
     x, ld = in_cat, 2
     for i, L in enumerate(self.layers):
       act = N.ACT_LRELU if i < 4 else N.ACT_SIGMOID
-      ep = _epilogue(self.P[L.name + '/bias'], self.act[i], self.chans[i + 1], 0, act)
-      L.run(x, ld, self.P[L.name + '/kernel'], ep)
+      ep = _epilogue(self.P[L.name + '/bias'], self.act[i], self.chans[i + 1], 0, act,
+                     round_tf32=self.round[i])
+      L.run(x, ld, self._w(L), ep)
       x, ld = self.act[i], self.chans[i + 1]
     return x
 

@@ -152,15 +152,27 @@ typedef struct advoc_epilogue {
   int round_tf32;
 } advoc_epilogue;
 
+/* Re-pack a TF-layout filter [kh*kw, A, B] (A,B = Cin,Cout for conv; Cout,Cin for
+ * conv_transpose) into [kh*kw, B, A] (transpose != 0) or copy it, optionally rounding every
+ * value to TF32 (round-to-nearest) so the tensor-core path reads exactly representable
+ * operands.  replaces: nothing in the reference (TF/cuDNN pick their own filter layouts). */
+ADVOC_API int advoc_pack_filter(const float* d_w, float* d_packed, int taps, int A, int B,
+                                int transpose, int round_tf32, void* stream);
+
+/* Reads and clears the library's device-side debug word: non-zero means a pipeline barrier of a
+ * tcgen05 kernel timed out (1 producer, 2 MMA issuer, 3 epilogue).  Synchronises the device. */
+ADVOC_API int advoc_debug_flags(unsigned int* out);
+
 /* y = conv2d(x, w) ; x [N,H,W,Cin] (pixel stride ld_x >= Cin, channel offset 0).
- * d_w: ADVOC_MATH_FP32 -> TF layout HWIO; TF32 -> packed [taps, Cout, Cin].
+ * d_w: on the CUDA-core path (advoc_conv2d_path == ADVOC_MATH_FP32) the TF layout HWIO;
+ * on the tcgen05 path the K-major pack [taps, Cout, Cin] made by advoc_pack_filter.
  * replaces: tf.layers.conv2d call sites models/advoc/advoc_model.py:27-32, :46-51. */
 ADVOC_API int advoc_conv2d_fwd(const advoc_conv_desc* d, const float* d_x, int ld_x, const float* d_w,
                      const advoc_epilogue* ep, void* stream);
 
 /* y = conv2d_transpose(x, w); x [N,Ho,Wo,Cout] (ld_x), output [N,H,W,Cin] in desc naming.
- * d_w: FP32 -> TF layout HWOI [kh,kw,Cin(desc),Cout(desc)]; TF32 -> packed
- * [taps, Cin(desc), Cout(desc)].
+ * d_w: TF layout HWOI [kh,kw,Cin(desc),Cout(desc)] on both paths (it already is K-major for
+ * this GEMM; pass a TF32-rounded copy on the tcgen05 path).
  * replaces: tf.layers.conv2d_transpose models/advoc/advoc_model.py:65-69. */
 ADVOC_API int advoc_conv2d_transpose_fwd(const advoc_conv_desc* d, const float* d_x, int ld_x,
                                const float* d_w, const advoc_epilogue* ep, void* stream);

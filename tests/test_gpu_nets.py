@@ -22,6 +22,18 @@ def _to_cuda(P):
   return {k: v.cuda().contiguous() for k, v in P.items()}
 
 
+def _tf32(x):
+  """Round to TF32 (nearest, ties away) like the producing layer's epilogue does."""
+  i = x.contiguous().view(torch.int32)
+  return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def _weights_for(L, kd, ldx):
+  from advoc_b200 import nets
+  wp = nets._pack_for_tc(L, kd, ldx)
+  return kd if wp is None else wp
+
+
 def _randomize_biases(P, seed=11):
   g = torch.Generator().manual_seed(seed)
   for k in P:
@@ -41,7 +53,7 @@ def test_single_conv_layers(math):
   g = torch.Generator().manual_seed(0)
   B = 2
   for (H, W, Cin, Cout, sh) in [(16, 33, 64, 128, 2), (8, 17, 32, 64, 2), (1, 5, 64, 32, 1)]:
-    x = torch.randn(B, H, W, Cin, generator=g)
+    x = _tf32(torch.randn(B, H, W, Cin, generator=g))
     k = torch.randn(4, 4, Cin, Cout, generator=g) * 0.05
     b = torch.randn(Cout, generator=g) * 0.1
     ref = O.conv_same(x, k, b, (sh, 2))
@@ -50,33 +62,39 @@ def test_single_conv_layers(math):
     y0 = torch.full((B, ho, wo, Cout), float('nan'), device='cuda')
     cat = torch.full((B, ho, wo, Cout + 32), float('nan'), device='cuda')
     L = nets._Conv('t', 'conv', nets._desc(B, H, W, Cin, Cout, sh, 2, pt, pl, ho, wo, mm))
-    ep = nets._epilogue(b.cuda(), y0, Cout, 0, N.ACT_LRELU, cat, Cout + 32, 32, N.ACT_RELU)
-    L.run(x.cuda(), Cin, k.cuda(), ep)
+    bd, xd, kd = b.cuda(), x.cuda(), k.cuda()   # keep alive: the epilogue holds raw pointers
+    ep = nets._epilogue(bd, y0, Cout, 0, N.ACT_LRELU, cat, Cout + 32, 32, N.ACT_RELU)
+    L.run(xd, Cin, _weights_for(L, kd, Cin), ep)
     torch.cuda.synchronize()
+    assert N.debug_flags() == 0
     assert _rel(y0, O.lrelu(ref)) < tol
     assert _rel(cat[..., 32:], torch.relu(ref)) < tol
     assert torch.isnan(cat[..., :32]).all()
   # discriminator conv: explicit pad 1, VALID, strides 2 and 1
   for (H, W, Cin, Cout, st) in [(32, 65, 32, 64, 2), (16, 32, 64, 96, 1)]:
-    x = torch.randn(B, H, W, Cin, generator=g)
+    x = _tf32(torch.randn(B, H, W, Cin, generator=g))
     k = torch.randn(4, 4, Cin, Cout, generator=g) * 0.05
     b = torch.randn(Cout, generator=g) * 0.1
     ref = torch.sigmoid(O.discrim_conv(x, k, b, st))
     ho, wo = (H + 2 - 4) // st + 1, (W + 2 - 4) // st + 1
     y = torch.empty((B, ho, wo, Cout), device='cuda')
     L = nets._Conv('t', 'conv', nets._desc(B, H, W, Cin, Cout, st, st, 1, 1, ho, wo, mm))
-    L.run(x.cuda(), Cin, k.cuda(), nets._epilogue(b.cuda(), y, Cout, 0, N.ACT_SIGMOID))
+    bd, xd, kd = b.cuda(), x.cuda(), k.cuda()
+    L.run(xd, Cin, _weights_for(L, kd, Cin), nets._epilogue(bd, y, Cout, 0, N.ACT_SIGMOID))
+    assert N.debug_flags() == 0
     assert _rel(y, ref) < tol
   # deconv k4 s2 SAME, last column cropped, relu, written at channel offset 0 of a wider buffer
   for (H, W, Cin, Cout, sh) in [(8, 17, 64, 32, 2), (1, 3, 32, 64, 1)]:
-    x = torch.relu(torch.randn(B, H, W, Cin, generator=g))
+    x = _tf32(torch.relu(torch.randn(B, H, W, Cin, generator=g)))
     k = torch.randn(4, 4, Cout, Cin, generator=g) * 0.05
     b = torch.randn(Cout, generator=g) * 0.1
     ref = torch.relu(O.deconv_same(x, k, b, (sh, 2)))[:, :, :-1, :]
     cat = torch.full((B, H * sh, 2 * W - 1, Cout + 16), float('nan'), device='cuda')
     L = nets._Conv('t', 'deconv', nets._desc(B, H * sh, 2 * W, Cout, Cin, sh, 2, 1, 1, H, W, mm))
-    ep = nets._epilogue(b.cuda(), cat, Cout + 16, 0, N.ACT_RELU, store_w=2 * W - 1)
-    L.run(x.cuda(), Cin, k.cuda(), ep)
+    bd, xd, kd = b.cuda(), x.cuda(), k.cuda()
+    ep = nets._epilogue(bd, cat, Cout + 16, 0, N.ACT_RELU, store_w=2 * W - 1)
+    L.run(xd, Cin, _weights_for(L, kd, Cin), ep)
+    assert N.debug_flags() == 0
     assert _rel(cat[..., :Cout], ref) < tol
     assert torch.isnan(cat[..., Cout:]).all()
 
