@@ -172,8 +172,17 @@ int check_conv_desc(const advoc_conv_desc* d) {
   return ADVOC_OK;
 }
 
+// conv_direct.cu
+bool conv_thin_eligible(const advoc_conv_desc* d, const advoc_epilogue* ep);
+int conv_thin(const advoc_conv_desc* d, const float* x, int ldx, const float* w, const advoc_epilogue* ep,
+              void* stream);
+bool deconv_to_one_eligible(const advoc_conv_desc* d, const float* x, int ldx, const advoc_epilogue* ep);
+int deconv_to_one(const advoc_conv_desc* d, const float* x, int ldx, const float* w, const advoc_epilogue* ep,
+                  void* stream);
+
 int conv_fwd_simt(const advoc_conv_desc* d, const float* x, int ldx, const float* w,
                   const advoc_epilogue* ep, void* stream) {
+  if (ep && ep->d_out0 && conv_thin_eligible(d, ep)) return conv_thin(d, x, ldx, w, ep, stream);
   SimtArgs a = {};
   int st = lower_epilogue(ep, d->Ho, d->Wo, d->Cout, &a.epi);
   if (st) return st;
@@ -196,6 +205,7 @@ int conv_fwd_simt(const advoc_conv_desc* d, const float* x, int ldx, const float
 // callers (deconv forward / conv dgrad) is only the naming, so one stride set serves both.
 int conv_transposed_simt(const advoc_conv_desc* d, const float* x, int ldx, const float* w,
                          const advoc_epilogue* ep, void* stream) {
+  if (ep && ep->d_out0 && deconv_to_one_eligible(d, x, ldx, ep)) return deconv_to_one(d, x, ldx, w, ep, stream);
   SimtArgs a = {};
   int st = lower_epilogue(ep, d->H, d->W, d->Cin, &a.epi);
   if (st) return st;

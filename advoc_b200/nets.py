@@ -86,7 +86,14 @@ class _Conv(object):
                                      1 if self.kind == 'deconv' else 0) == N.MATH_TF32
 
   def kernel_family(self):
-    return ('tc_' if self.uses_tensor_cores() else 'simt_') + self.kind
+    if self.uses_tensor_cores():
+      return 'tc_' + self.kind
+    d = self.desc
+    if self.kind == 'conv' and d.Cin <= 2:
+      return 'thin_conv'
+    if self.kind == 'deconv' and d.Cin == 1:
+      return 'to_one_deconv'
+    return 'simt_' + self.kind
 
   def flops(self):
     d = self.desc

@@ -146,6 +146,8 @@ def stft_tf(x, nfft, nhop, pad_end=True):
   win, tw = _Consts.stft(nfft, nhop, x.device)
   frames = num_frames(nsamps, nfft, nhop, pad_end)
   out = torch.empty((b, frames, nfft // 2 + 1, nch, 2), dtype=torch.float32, device=x.device)
+  if out.numel() == 0:
+    return torch.view_as_complex(out)
   N.call('advoc_stft_f32', _ptr(x), b, nsamps, nch, nfft, nhop, 1 if pad_end else 0, _ptr(win),
          _ptr(tw), _ptr(out), None, _stream())
   return torch.view_as_complex(out)
@@ -164,6 +166,8 @@ def magspec_tf(x, nfft, nhop, pad_end=True):
   win, tw = _Consts.stft(nfft, nhop, x.device)
   frames = num_frames(nsamps, nfft, nhop, pad_end)
   out = torch.empty((b, frames, nfft // 2 + 1, nch), dtype=torch.float32, device=x.device)
+  if out.numel() == 0:
+    return out
   N.call('advoc_stft_f32', _ptr(x), b, nsamps, nch, nfft, nhop, 1 if pad_end else 0, _ptr(win),
          _ptr(tw), None, _ptr(out), _stream())
   return out
@@ -189,6 +193,8 @@ def waveform_to_melspec_tf(x, fs, nfft, nhop, mel_min=125, mel_max=7600, mel_num
   fb, ranges = _Consts.mel(fs, nfft, mel_min, mel_max, mel_num_bins, x.device)
   frames = num_frames(nsamps, nfft, nhop, True)
   out = torch.empty((b, frames, mel_num_bins, nch), dtype=torch.float32, device=x.device)
+  if out.numel() == 0:
+    return out
   N.call('advoc_melspec_f32', _ptr(x), b, nsamps, nch, nfft, nhop, _ptr(win), _ptr(tw), _ptr(fb),
          _ptr(ranges), mel_num_bins, float(norm_min_level_db), float(norm_ref_level_db),
          _ptr(out), _stream())
