@@ -9,7 +9,7 @@
 //   B  filters, K-major [tap][n][c] fp32, fetched by a tiled TMA box.
 //   D  128 x BN fp32 accumulator in tensor memory, written by tcgen05.mma.kind::tf32.
 // A transposed convolution with stride s is run as s_h*s_w independent "parity classes"
-// (blockIdx.z): every output pixel of a class sees the same dense sub-filter (2x2 taps for
+// (interleaved in launch order): every output pixel of a class sees the same dense sub-filter (2x2 taps for
 // k4 s2), so no MAC is spent on the zeros a zero-insertion formulation would multiply.
 //
 // CTA = 6 warps: warp 0 TMA producer, warp 1 TMEM allocator + single-thread MMA issuer,
@@ -41,7 +41,7 @@ struct alignas(64) TcParams {
   int ntaps[MAX_CLASSES];
   unsigned short tap_off[MAX_CLASSES][MAX_TAPS];   // (offset_h << 8) | offset_w
   unsigned short tap_wrow[MAX_CLASSES][MAX_TAPS];  // filter tap index (row block of B)
-  int Nimg;
+  int Nimg, nclasses;
   int trav_h, trav_w;  // im2col traversal stride
   int osh, osw;        // output position stride (1 for conv, s for transposed conv)
   int Cn;              // produced channels (rows of B per tap)
@@ -202,13 +202,18 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
   __shared__ __align__(8) uint64_t tmem_full_bar;
   __shared__ uint32_t tmem_base_holder;
 
-  const int cls = blockIdx.z;
+  // CTAs that share an A tile (N tiles, then parity classes) are adjacent in launch order so
+  // the activations are fetched from HBM once and re-served from L2
+  const int n_ntiles = p.Cn / BN;
+  const int n_tile = (int)(blockIdx.x % n_ntiles);
+  const int cls = (int)((blockIdx.x / n_ntiles) % p.nclasses);
+  const long m_tile = blockIdx.x / (n_ntiles * p.nclasses);
   const int Ah = p.Ah[cls], Aw = p.Aw[cls];
   const long Mc = (long)p.Nimg * Ah * Aw;
-  const long m0 = (long)blockIdx.x * BM;
+  const long m0 = m_tile * BM;
   if (m0 >= Mc) return;  // uniform per CTA, before any barrier or allocation
   if (p.dbg && *reinterpret_cast<volatile unsigned int*>(p.dbg) != 0) return;  // aborted launch
-  const int n0 = blockIdx.y * BN;
+  const int n0 = n_tile * BN;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // operand ring, 1024-byte aligned (SWIZZLE_128B atom)
@@ -428,7 +433,9 @@ int launch(const TcParams& p, int nclasses, long max_tiles, cudaStream_t st) {
                                           smem));
     configured = true;
   }
-  dim3 grid((unsigned)max_tiles, (unsigned)(p.Cn / BN), (unsigned)nclasses);
+  const long ctas = max_tiles * (p.Cn / BN) * nclasses;
+  ADVOC_REQUIRE(ctas < 2147483647L, ADVOC_BAD_SHAPE, "too many output tiles");
+  dim3 grid((unsigned)ctas, 1, 1);
   conv_tc_kernel<BN, STAGES><<<grid, NUM_THREADS, smem, st>>>(p);
   count_launch();
   ADVOC_CHECK_CUDA(cudaGetLastError());
@@ -453,6 +460,7 @@ int run(TcParams& p, int nclasses, const ClassGeom* g, void* stream) {
   if (max_tiles == 0) return ADVOC_OK;
   ADVOC_REQUIRE(max_tiles < 2147483647L, ADVOC_BAD_SHAPE, "too many output tiles");
   p.dbg = debug_word();
+  p.nclasses = nclasses;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (pick_bn(p.Cn)) {
     case 128: return launch<128, 3>(p, nclasses, max_tiles, st);
