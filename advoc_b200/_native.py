@@ -36,6 +36,10 @@ class Epilogue(C.Structure):
       ('keep_prob', C.c_float),
       ('seed', C.c_uint64),
       ('round_tf32', C.c_int),
+      ('accumulate', C.c_int),
+      ('d_gate', C.c_void_p), ('ld_gate', C.c_int), ('c_off_gate', C.c_int),
+      ('gate_act', C.c_int), ('gate_split', C.c_int),
+      ('gate_scale0', C.c_float), ('gate_scale1', C.c_float),
   ]
 
 
@@ -58,6 +62,11 @@ SIGNATURES = {
     'advoc_conv2d_fwd': (_I, [C.POINTER(ConvDesc), _P, _I, _P, C.POINTER(Epilogue), _P]),
     'advoc_pack_filter': (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     'advoc_debug_flags': (_I, [C.POINTER(C.c_uint)]),
+    'advoc_conv2d_wgrad': (_I, [C.POINTER(ConvDesc), _P, _I, _P, _I, _P, _P]),
+    'advoc_bias_grad': (_I, [_P, _I, _L, _I, _P, _P]),
+    'advoc_gan_logloss': (_I, [_P, _P, _L, _I, _F, _P, _P, _P, _P]),
+    'advoc_l1_loss': (_I, [_P, _I, _I, _P, _L, _F, _P, _P, _I, _P]),
+    'advoc_adam_tf_step': (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _L, _F, _P]),
     'advoc_conv2d_path': (_I, [C.POINTER(ConvDesc), _I, _I]),
     'advoc_conv2d_transpose_fwd': (_I, [C.POINTER(ConvDesc), _P, _I, _P, C.POINTER(Epilogue), _P]),
 }

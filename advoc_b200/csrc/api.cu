@@ -7,7 +7,8 @@
 
 // the ctypes mirror in advoc_b200/_native.py relies on these layouts (tests/test_boundary.py)
 static_assert(sizeof(advoc_conv_desc) == 56, "advoc_conv_desc layout");
-static_assert(sizeof(advoc_epilogue) == 96 && offsetof(advoc_epilogue, d_out0) == 24 &&
+static_assert(sizeof(advoc_epilogue) == 128 && offsetof(advoc_epilogue, d_gate) == 96 &&
+                  offsetof(advoc_epilogue, gate_scale1) == 124 && offsetof(advoc_epilogue, d_out0) == 24 &&
                   offsetof(advoc_epilogue, d_out1) == 40 &&
                   offsetof(advoc_epilogue, d_dropout_mask) == 64 &&
                   offsetof(advoc_epilogue, seed) == 80,

@@ -27,7 +27,9 @@ struct ThinArgs {
   EpiDev epi;
 };
 
-template <int CIN>
+// kT: transposed form y[h,w,:] = sum_taps x[(h+pt-kh)/sh, (w+pl-kw)/sw] * w[tap][:]  (CIN == 1;
+// the input gradient of a conv to one channel, e.g. the PatchGAN head)
+template <int CIN, bool kT>
 __global__ void __launch_bounds__(256) conv_thin_in_kernel(const ThinArgs<CIN> a) {
   extern __shared__ float ws[];  // [16*CIN][Cout]
   for (int i = threadIdx.x; i < 16 * CIN * a.Cout; i += blockDim.x) ws[i] = __ldg(a.w + i);
@@ -53,11 +55,23 @@ __global__ void __launch_bounds__(256) conv_thin_in_kernel(const ThinArgs<CIN> a
     float acc[4] = {bias[0], bias[1], bias[2], bias[3]};
 #pragma unroll
     for (int kh = 0; kh < 4; ++kh) {
-      const int ih = ih0 + kh;
+      int ih;
+      if (!kT) {
+        ih = ih0 + kh;
+      } else {
+        const int q = oh + a.pt - kh;
+        ih = (q >= 0 && q % a.sh == 0) ? q / a.sh : -1;
+      }
       if (ih < 0 || ih >= a.H) continue;
 #pragma unroll
       for (int kw = 0; kw < 4; ++kw) {
-        const int iw = iw0 + kw;
+        int iw;
+        if (!kT) {
+          iw = iw0 + kw;
+        } else {
+          const int q = ow + a.pl - kw;
+          iw = (q >= 0 && q % a.sw == 0) ? q / a.sw : -1;
+        }
         if (iw < 0 || iw >= a.W) continue;
         const float* xp = xb + ((size_t)ih * a.W + iw) * a.ldx;
 #pragma unroll
@@ -73,11 +87,21 @@ __global__ void __launch_bounds__(256) conv_thin_in_kernel(const ThinArgs<CIN> a
     }
     float y[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      y[j] = apply_act(acc[j], e.act0, e.alpha);
-      if (e.round) y[j] = round_tf32(y[j]);
+    for (int j = 0; j < 4; ++j) y[j] = apply_act(acc[j], e.act0, e.alpha);
+    if (e.gate) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) y[j] *= gate_factor(e, (size_t)pix, n + j);
     }
-    *reinterpret_cast<float4*>(e.out0 + (size_t)pix * e.ld0 + e.coff0 + n) = make_float4(y[0], y[1], y[2], y[3]);
+    float4* dst0 = reinterpret_cast<float4*>(e.out0 + (size_t)pix * e.ld0 + e.coff0 + n);
+    if (e.accumulate) {
+      const float4 o = *dst0;
+      y[0] += o.x; y[1] += o.y; y[2] += o.z; y[3] += o.w;
+    }
+    if (e.round) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) y[j] = round_tf32(y[j]);
+    }
+    *dst0 = make_float4(y[0], y[1], y[2], y[3]);
     if (e.out1) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -224,11 +248,38 @@ int conv_thin(const advoc_conv_desc* d, const float* x, int ldx, const float* w,
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (d->Cin == 1) {
     ThinArgs<1> a = {x, w, d->N, d->H, d->W, ldx, d->Ho, d->Wo, d->Cout, d->sh, d->sw, d->pad_t, d->pad_l, e};
-    conv_thin_in_kernel<1><<<blocks, 256, smem, s>>>(a);
+    conv_thin_in_kernel<1, false><<<blocks, 256, smem, s>>>(a);
   } else {
     ThinArgs<2> a = {x, w, d->N, d->H, d->W, ldx, d->Ho, d->Wo, d->Cout, d->sh, d->sw, d->pad_t, d->pad_l, e};
-    conv_thin_in_kernel<2><<<blocks, 256, smem, s>>>(a);
+    conv_thin_in_kernel<2, false><<<blocks, 256, smem, s>>>(a);
   }
+  count_launch();
+  ADVOC_CHECK_CUDA(cudaGetLastError());
+  return ADVOC_OK;
+}
+
+// transposed conv FROM one channel: x [N,Ho,Wo,1] -> y [N,H,W,Cin(desc)]; w [16][Cin(desc)][1]
+bool deconv_from_one_eligible(const advoc_conv_desc* d, const advoc_epilogue* ep) {
+  auto ok = [](const float* p, int ld, int co) { return aligned16(p) && ld % 4 == 0 && co % 4 == 0; };
+  return d->Cout == 1 && d->kh == 4 && d->kw == 4 && d->Cin % 4 == 0 && d->Cin <= 256 &&
+         256 % (d->Cin / 4) == 0 && ep->keep_prob >= 1.f && ep->store_w == 0 && ep->d_out1 == nullptr &&
+         ok(ep->d_out0, ep->ld0, ep->c_off0);
+}
+
+int deconv_from_one(const advoc_conv_desc* d, const float* x, int ldx, const float* w, const advoc_epilogue* ep,
+                    void* stream) {
+  EpiDev e;
+  int st = lower_epilogue(ep, d->H, d->W, d->Cin, &e);
+  if (st) return st;
+  const long npix = (long)d->N * d->H * d->W;
+  if (npix == 0) return ADVOC_OK;
+  const int ppb = 256 / (d->Cin / 4);
+  const long want = (npix + ppb - 1) / ppb;
+  const int blocks = (int)(want < (long)sm_count() * 32 ? want : (long)sm_count() * 32);
+  // the kernel's "input" is the small side, its "output" the big side
+  ThinArgs<1> a = {x, w, d->N, d->Ho, d->Wo, ldx, d->H, d->W, d->Cin, d->sh, d->sw, d->pad_t, d->pad_l, e};
+  conv_thin_in_kernel<1, true><<<blocks, 256, (size_t)16 * d->Cin * sizeof(float),
+                                 reinterpret_cast<cudaStream_t>(stream)>>>(a);
   count_launch();
   ADVOC_CHECK_CUDA(cudaGetLastError());
   return ADVOC_OK;
@@ -236,7 +287,7 @@ int conv_thin(const advoc_conv_desc* d, const float* x, int ldx, const float* w,
 
 bool deconv_to_one_eligible(const advoc_conv_desc* d, const float* x, int ldx, const advoc_epilogue* ep) {
   return d->Cin == 1 && d->kh == 4 && d->kw == 4 && d->sh == 2 && d->sw == 2 && d->pad_t == 1 && d->pad_l == 1 &&
-         d->H == 2 * d->Ho && d->W == 2 * d->Wo && d->Cout % 4 == 0 && ldx % 4 == 0 && aligned16(x) && ep->keep_prob >= 1.f && ep->d_out1 == nullptr;
+         d->H == 2 * d->Ho && (d->W == 2 * d->Wo || (ep->accumulate && d->W > 2 * d->Wo)) && d->Cout % 4 == 0 && ldx % 4 == 0 && aligned16(x) && ep->keep_prob >= 1.f && ep->d_out1 == nullptr;
 }
 
 int deconv_to_one(const advoc_conv_desc* d, const float* x, int ldx, const float* w, const advoc_epilogue* ep,

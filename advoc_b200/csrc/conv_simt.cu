@@ -45,6 +45,18 @@ int lower_epilogue(const advoc_epilogue* ep, int Hs, int Wfull, int Cout, EpiDev
   e->alpha = ep->alpha;
   e->keep_prob = ep->keep_prob;
   e->round = ep->round_tf32;
+  e->gate = ep->d_gate;
+  e->ldg = ep->ld_gate; e->coffg = ep->c_off_gate;
+  e->gate_act = ep->gate_act; e->gate_split = ep->gate_split;
+  e->gscale0 = ep->gate_scale0; e->gscale1 = ep->gate_scale1;
+  e->accumulate = ep->accumulate;
+  if (ep->d_gate) {
+    ADVOC_REQUIRE(ep->ld_gate >= ep->c_off_gate + Cout && ep->c_off_gate >= 0, ADVOC_BAD_SHAPE,
+                  "gate channel window does not fit its ld");
+    ADVOC_REQUIRE(ep->gate_act == ADVOC_ACT_LRELU || ep->gate_act == ADVOC_ACT_RELU, ADVOC_BAD_ARG,
+                  "gate_act must be lrelu or relu");
+    ADVOC_REQUIRE(ep->d_out1 == nullptr, ADVOC_BAD_ARG, "gate is not supported with a second output");
+  }
   return ADVOC_OK;
 }
 
@@ -180,9 +192,18 @@ bool deconv_to_one_eligible(const advoc_conv_desc* d, const float* x, int ldx, c
 int deconv_to_one(const advoc_conv_desc* d, const float* x, int ldx, const float* w, const advoc_epilogue* ep,
                   void* stream);
 
+bool deconv_from_one_eligible(const advoc_conv_desc* d, const advoc_epilogue* ep);
+int deconv_from_one(const advoc_conv_desc* d, const float* x, int ldx, const float* w, const advoc_epilogue* ep,
+                    void* stream);
+// train.cu
+bool conv_to_one_eligible(const advoc_conv_desc* d, const float* x, int ldx, const advoc_epilogue* ep);
+int conv_to_one(const advoc_conv_desc* d, const float* x, int ldx, const float* w, const advoc_epilogue* ep,
+                void* stream);
+
 int conv_fwd_simt(const advoc_conv_desc* d, const float* x, int ldx, const float* w,
                   const advoc_epilogue* ep, void* stream) {
   if (ep && ep->d_out0 && conv_thin_eligible(d, ep)) return conv_thin(d, x, ldx, w, ep, stream);
+  if (ep && ep->d_out0 && conv_to_one_eligible(d, x, ldx, ep)) return conv_to_one(d, x, ldx, w, ep, stream);
   SimtArgs a = {};
   int st = lower_epilogue(ep, d->Ho, d->Wo, d->Cout, &a.epi);
   if (st) return st;
@@ -206,6 +227,7 @@ int conv_fwd_simt(const advoc_conv_desc* d, const float* x, int ldx, const float
 int conv_transposed_simt(const advoc_conv_desc* d, const float* x, int ldx, const float* w,
                          const advoc_epilogue* ep, void* stream) {
   if (ep && ep->d_out0 && deconv_to_one_eligible(d, x, ldx, ep)) return deconv_to_one(d, x, ldx, w, ep, stream);
+  if (ep && ep->d_out0 && deconv_from_one_eligible(d, ep)) return deconv_from_one(d, x, ldx, w, ep, stream);
   SimtArgs a = {};
   int st = lower_epilogue(ep, d->H, d->W, d->Cin, &a.epi);
   if (st) return st;

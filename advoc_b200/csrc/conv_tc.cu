@@ -171,11 +171,25 @@ __device__ __forceinline__ void epi_store4(const EpiDev& e, size_t pix, int n, f
   }
   float y[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    y[j] = apply_act(v[j], e.act0, e.alpha) * sc[j];
-    if (e.round) y[j] = round_tf32(y[j]);
+  for (int j = 0; j < 4; ++j) y[j] = apply_act(v[j], e.act0, e.alpha) * sc[j];
+  if (e.gate) {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(e.gate + pix * e.ldg + e.coffg + n));
+    const float gv[4] = {g.x, g.y, g.z, g.w};
+    const float neg = e.gate_act == ADVOC_ACT_LRELU ? e.alpha : 0.f;
+    const float s = n < e.gate_split ? e.gscale0 : e.gscale1;  // split is a multiple of 4
+#pragma unroll
+    for (int j = 0; j < 4; ++j) y[j] *= (gv[j] > 0.f ? 1.f : neg) * s;
   }
-  *reinterpret_cast<float4*>(e.out0 + pix * e.ld0 + e.coff0 + n) = make_float4(y[0], y[1], y[2], y[3]);
+  float4* dst = reinterpret_cast<float4*>(e.out0 + pix * e.ld0 + e.coff0 + n);
+  if (e.accumulate) {
+    const float4 o = *dst;
+    y[0] += o.x; y[1] += o.y; y[2] += o.z; y[3] += o.w;
+  }
+  if (e.round) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) y[j] = round_tf32(y[j]);
+  }
+  *dst = make_float4(y[0], y[1], y[2], y[3]);
   if (e.out1) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -443,6 +457,7 @@ int launch(const TcParams& p, int nclasses, long max_tiles, cudaStream_t st) {
 }
 
 int pick_bn(int Cn) {
+  if (Cn % 256 == 0) return 256;
   if (Cn % 128 == 0) return 128;
   if (Cn % 64 == 0) return 64;
   return 32;
@@ -463,6 +478,7 @@ int run(TcParams& p, int nclasses, const ClassGeom* g, void* stream) {
   p.nclasses = nclasses;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (pick_bn(p.Cn)) {
+    case 256: return launch<256, 2>(p, nclasses, max_tiles, st);
     case 128: return launch<128, 3>(p, nclasses, max_tiles, st);
     case 64: return launch<64, 4>(p, nclasses, max_tiles, st);
     default: return launch<32, 4>(p, nclasses, max_tiles, st);
@@ -479,6 +495,7 @@ bool epilogue_vector_ok(const advoc_epilogue* ep) {
   if (!ok(ep->d_out0, ep->ld0, ep->c_off0)) return false;
   if (ep->d_out1 && !ok(ep->d_out1, ep->ld1, ep->c_off1)) return false;
   if (ep->d_bias && !aligned16(ep->d_bias)) return false;
+  if (ep->d_gate && !(ok(ep->d_gate, ep->ld_gate, ep->c_off_gate) && ep->gate_split % 4 == 0)) return false;
   return true;
 }
 

@@ -17,7 +17,18 @@ struct EpiDev {
   float alpha;
   float keep_prob;  // 1 = no dropout
   int round;        // round stored values to tf32
+  // backward-pass extensions (out0 only)
+  const float* gate;
+  int ldg, coffg, gate_act, gate_split;
+  float gscale0, gscale1;
+  int accumulate;
 };
+
+__device__ __forceinline__ float gate_factor(const EpiDev& e, size_t pix, int n) {
+  const float g = __ldg(e.gate + pix * e.ldg + e.coffg + n);
+  const float d = g > 0.f ? 1.f : (e.gate_act == ADVOC_ACT_LRELU ? e.alpha : 0.f);
+  return d * (n < e.gate_split ? e.gscale0 : e.gscale1);
+}
 
 // Validates the user epilogue against the produced tensor [N, Hs, Wfull, Cout] and lowers it.
 int lower_epilogue(const advoc_epilogue* ep, int Hs, int Wfull, int Cout, EpiDev* out);
@@ -32,8 +43,11 @@ __device__ __forceinline__ void epi_store(const EpiDev& e, size_t pix, int n, fl
     scale = keep ? 1.f / e.keep_prob : 0.f;
   }
   float y0 = apply_act(v, e.act0, e.alpha) * scale;
+  if (e.gate) y0 *= gate_factor(e, pix, n);
+  float* dst = e.out0 + pix * e.ld0 + e.coff0 + n;
+  if (e.accumulate) y0 += *dst;
   if (e.round) y0 = round_tf32(y0);
-  e.out0[pix * e.ld0 + e.coff0 + n] = y0;
+  *dst = y0;
   if (e.out1) {
     float y1 = apply_act(v, e.act1, e.alpha) * scale;
     if (e.round) y1 = round_tf32(y1);

@@ -114,9 +114,12 @@ def _desc(n, h, w, cin, cout, sh, sw, pt, pl, ho, wo, math):
 
 
 def _epilogue(bias, out0, ld0, coff0, act0, out1=None, ld1=0, coff1=0, act1=N.ACT_NONE,
-              store_w=0, mask=None, keep_prob=1.0, seed=0, round_tf32=0, alpha=0.2):
+              store_w=0, mask=None, keep_prob=1.0, seed=0, round_tf32=0, alpha=0.2,
+              accumulate=0, gate=None, ld_gate=0, coff_gate=0, gate_act=N.ACT_NONE, gate_split=0,
+              gate_scale0=1.0, gate_scale1=1.0):
   return N.Epilogue(_ptr(bias), act0, act1, alpha, _ptr(out0), ld0, coff0, _ptr(out1), ld1, coff1,
-                    store_w, _ptr(mask), keep_prob, seed, round_tf32)
+                    store_w, _ptr(mask), keep_prob, seed, round_tf32, accumulate, _ptr(gate),
+                    ld_gate, coff_gate, gate_act, gate_split, gate_scale0, gate_scale1)
 
 
 def _pack_for_tc(L, kernel, ldx):
@@ -201,16 +204,16 @@ class Generator(object):
     s = self.spec
     return (self.B, s.H[k - 1], s.W[k - 1], s.dec_ch[k])
 
-  def forward(self, x, out=None, out_ld=1, out_coff=0, dropout=None, seed=0):
+  def forward(self, x, out=None, out_ld=1, out_coff=0, dropout=None, seed=0, x_ld=1):
     """x f32 [B,T,513,1] contiguous.  dropout: None (off, parity mode) | 'rng' (counter-based
     generator keyed by `seed`, the reference's behaviour in every mode, advoc_model.py:144-149)
     | {decoder_index: uint8 mask tensor} (injected masks).  Returns the output buffer
     (`out` if given: written with pixel stride out_ld at channel out_coff)."""
     s, P, n = self.spec, self.P, self.spec.n_enc
-    assert x.is_contiguous() and tuple(x.shape) == (self.B, s.H[0], s.W[0], 1), x.shape
+    assert x.is_contiguous() and tuple(x.shape) == (self.B, s.H[0], s.W[0], x_ld), x.shape
     if not hasattr(self, 'Wp'):
       self.prepare()
-    inp, ld = x, 1
+    inp, ld = x, x_ld   # x_ld > 1: the input is channel 0 of a wider buffer
     for i in range(1, n + 1):
       L = self.enc[i]
       cat = self.Cat[i]

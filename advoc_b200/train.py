@@ -1,0 +1,296 @@
+"""G + D train step of the adversarial vocoder on B200 (forward, backward, TF1-Adam), with
+data-parallel gradient all-reduce over NCCL.
+
+reference: models/advoc/advoc_model.py:206-257 (`__call__`: losses, variable partition, two Adam
+optimisers) and :285-289 (`train_loop`: D update on one minibatch, then G update on the next,
+through the already-updated D).  The reference gets its backward pass from TF autodiff; here it
+is laid out explicitly on the same persistent NHWC buffers as the forward pass:
+
+  * input gradients reuse the forward tcgen05 kernels (conv dgrad == transposed conv with the
+    conv's HWIO filter; deconv dgrad == conv over the big side), with the lrelu / relu / dropout
+    derivative and the U-Net skip sum fused into the epilogue (gate / accumulate);
+  * filter and bias gradients, losses and Adam are the kernels of csrc/train.cu;
+  * parameters, gradients and Adam moments are single flat fp32 buffers ([G | D]), so one
+    collective and one optimiser launch per network suffice.
+"""
+import ctypes as C
+
+import torch
+
+from advoc_b200 import _native as N
+from advoc_b200 import nets
+from advoc_b200.nets import _desc, _epilogue, _ptr, _stream
+
+
+def _view_ptr(t, coff):
+  return C.c_void_p(t.data_ptr() + 4 * coff)
+
+
+class FlatParams(object):
+  """All parameters in one flat buffer, generator first; the dict holds views."""
+
+  def __init__(self, params):
+    names = sorted(params, key=lambda n: (0 if n.startswith('generator') else 1, n))
+    self.names = names
+    self.offsets, off = {}, 0
+    for n in names:
+      self.offsets[n] = off
+      off += (params[n].numel() + 3) // 4 * 4   # keep every tensor 16-byte aligned
+    self.total = off
+    self.n_gen = min([self.offsets[n] for n in names if n.startswith('discriminator')] or [off])
+    dev = params[names[0]].device
+    self.p = torch.zeros(off, dtype=torch.float32, device=dev)
+    self.g = torch.zeros(off, dtype=torch.float32, device=dev)
+    self.m = torch.zeros(off, dtype=torch.float32, device=dev)
+    self.v = torch.zeros(off, dtype=torch.float32, device=dev)
+    self.P, self.G = {}, {}
+    for n in names:
+      o, k = self.offsets[n], params[n].numel()
+      self.P[n] = self.p[o:o + k].view(params[n].shape)
+      self.P[n].copy_(params[n])
+      self.G[n] = self.g[o:o + k].view(params[n].shape)
+
+  def gen_range(self):
+    return 0, self.n_gen
+
+  def dis_range(self):
+    return self.n_gen, self.total
+
+
+class TrainEngine(object):
+  """One replica of the AdVoc train step for a fixed per-GPU batch."""
+
+  def __init__(self, spec, ndf, params, batch, gan_weight=1.0, l1_weight=10.0, math=N.MATH_AUTO,
+               lr=2e-4, beta1=0.5, beta2=0.999, eps=1e-8, process_group=None, world_size=1):
+    self.spec, self.ndf, self.B = spec, ndf, batch
+    self.gan_weight, self.l1_weight = gan_weight, l1_weight
+    self.lr, self.b1, self.b2, self.eps = lr, beta1, beta2, eps
+    self.pg, self.world = process_group, world_size
+    self.flat = FlatParams(params)
+    P = self.flat.P
+    self.P = P
+    dev = self.flat.p.device
+    self.G = nets.Generator(spec, P, batch, math)
+    self.Dr = nets.Discriminator(ndf, P, batch, math, spec.H[0], spec.W[0])
+    self.Df = nets.Discriminator(ndf, P, batch, math, spec.H[0], spec.W[0])
+    f32 = dict(dtype=torch.float32, device=dev)
+    T, F = spec.H[0], spec.W[0]
+    self.cat_real = torch.zeros((batch, T, F, 2), **f32)   # [x, target]
+    self.cat_fake = torch.zeros((batch, T, F, 2), **f32)   # [x, generated]
+    self.g_out = torch.zeros((batch, T, F, 1), **f32)      # d loss / d generated
+    self.gCat = {k: torch.zeros_like(t) for k, t in self.G.Cat.items()}
+    self.dz = [torch.zeros_like(t) for t in self.Dr.act]
+    self.losses = torch.zeros(4, **f32)                    # d_loss, g_gan, g_l1, unused
+    self.t_d, self.t_g = 0, 0
+    self.step_count = 0
+    self._build_backward_geometry(math)
+    self.refresh_weights()
+
+  # -------------------------------------------------------------------------------------------
+  def _build_backward_geometry(self, math):
+    s, B, n = self.spec, self.B, self.spec.n_enc
+    # conv geometry whose transposed form each decoder is, over the REAL (cropped) big side
+    self.dec_b = {}
+    for j, k in enumerate(range(n, 0, -1)):
+      sh = 1 if j < s.n_stride1 else 2
+      cin_small = self.G.Dk[k] + s.enc_ch[k - 1]
+      ho, pt, _ = nets.same_pads(s.H[k - 1], 4, sh)
+      wo, pl, _ = nets.same_pads(s.W[k - 1], 4, 2)
+      assert ho == s.H[k] and wo == s.W[k]
+      self.dec_b[k] = nets._Conv('generator/decoder_%d/conv2d_transpose' % k, 'conv',
+                                 _desc(B, s.H[k - 1], s.W[k - 1], s.dec_ch[k], cin_small, sh, 2, pt, pl,
+                                       ho, wo, math))
+    # encoder / discriminator dgrad = transposed conv with the layer's own desc
+    self.enc_t = {i: nets._Conv(self.G.enc[i].name, 'deconv', self.G.enc[i].desc)
+                  for i in range(2, n + 1)}
+    self.dis_t = [nets._Conv(L.name, 'deconv', L.desc) for L in self.Dr.layers]
+    d0 = self.Dr.layers[0].desc
+    # d(generated) from discriminator layer_1: transposed conv to ONE channel (channel 1 of the
+    # 2-channel input), accumulated onto the L1 gradient
+    self.dis_t0 = nets._Conv('discriminator/layer_1/conv2d', 'deconv',
+                             _desc(B, d0.H, d0.W, 1, d0.Cout, d0.sh, d0.sw, d0.pad_t, d0.pad_l, d0.Ho,
+                                   d0.Wo, N.MATH_FP32))
+
+  def refresh_weights(self):
+    """Re-derive every packed / TF32-rounded filter copy from the flat parameters (after Adam)."""
+    P = self.P
+    self.G.prepare()
+    self.Dr.prepare()
+    self.Df.Wp, self.Df.round = self.Dr.Wp, self.Dr.round
+    self.Wb = {}
+    for k, L in self.dec_b.items():      # deconv dgrad: conv over the big side
+      self.Wb[L.name] = nets._pack_for_tc(L, P[L.name + '/kernel'], L.desc.Cin)
+    for i, L in self.enc_t.items():      # conv dgrad: HWIO is already K-major, only round
+      self.Wb[L.name] = nets._pack_for_tc(L, P[L.name + '/kernel'], L.desc.Cout)
+    for L in self.dis_t[1:]:
+      self.Wb[L.name] = nets._pack_for_tc(L, P[L.name + '/kernel'], L.desc.Cout)
+    k0 = P['discriminator/layer_1/conv2d/kernel']
+    self.w_sel = k0[:, :, 1:2, :].contiguous()   # [4,4,1,ndf]: filter slice of input channel 1
+
+  def _wb(self, L):
+    w = self.Wb.get(L.name)
+    return w if w is not None else self.P[L.name + '/kernel']
+
+  # -------------------------------------------------------------------------------------------
+  # primitives
+  # -------------------------------------------------------------------------------------------
+  def _wgrad(self, desc, big, ld_big, coff_big, small, ld_small, coff_small, name):
+    N.call('advoc_conv2d_wgrad', C.byref(desc), _view_ptr(big, coff_big), ld_big,
+           _view_ptr(small, coff_small), ld_small, _ptr(self.flat.G[name + '/kernel']), _stream())
+
+  def _bgrad(self, dy, ld, coff, pixels, channels, name):
+    N.call('advoc_bias_grad', _view_ptr(dy, coff), ld, pixels, channels,
+           _ptr(self.flat.G[name + '/bias']), _stream())
+
+  def _run(self, L, x, ldx, coff_x, w, ep):
+    fn = 'advoc_conv2d_fwd' if L.kind == 'conv' else 'advoc_conv2d_transpose_fwd'
+    N.call(fn, C.byref(L.desc), _view_ptr(x, coff_x), ldx, _ptr(w), C.byref(ep), _stream())
+
+  # -------------------------------------------------------------------------------------------
+  # discriminator backward
+  # -------------------------------------------------------------------------------------------
+  def _d_backward(self, De, in_cat, param_grads, input_grad):
+    """dz[4] holds d loss / d logits of layer_5.  Walks layers 5..1."""
+    ch = De.chans
+    for i in range(4, -1, -1):
+      L = De.layers[i]
+      d = L.desc
+      dy = self.dz[i]
+      x_in, ld_in = (in_cat, 2) if i == 0 else (De.act[i - 1], ch[i])
+      if param_grads:
+        self._wgrad(d, x_in, ld_in, 0, dy, ch[i + 1], 0, L.name)
+        self._bgrad(dy, ch[i + 1], 0, d.N * d.Ho * d.Wo, ch[i + 1], L.name)
+      if i > 0:
+        Lt = self.dis_t[i]
+        ep = _epilogue(None, self.dz[i - 1], ch[i], 0, N.ACT_NONE, gate=De.act[i - 1], ld_gate=ch[i],
+                       gate_act=N.ACT_LRELU, round_tf32=1)
+        self._run(Lt, dy, ch[i + 1], 0, self._wb(Lt), ep)
+      elif input_grad:
+        ep = _epilogue(None, self.g_out, 1, 0, N.ACT_NONE, accumulate=1)
+        self._run(self.dis_t0, dy, ch[1], 0, self.w_sel, ep)
+
+  # -------------------------------------------------------------------------------------------
+  # generator backward (g_out holds d loss / d generated)
+  # -------------------------------------------------------------------------------------------
+  def _g_backward(self, x_cat):
+    s, n, G = self.spec, self.spec.n_enc, self.G
+    keep = 0.5
+    for k in range(1, n + 1):
+      L = self.dec_b[k]
+      d = L.desc
+      if k == 1:
+        dy, ld, co = self.g_out, 1, 0
+      else:
+        dy, ld, co = self.gCat[k - 1], self.gCat[k - 1].shape[3], 0
+      cat = G.Cat[k]
+      cc = cat.shape[3]
+      self._wgrad(d, dy, ld, co, cat, cc, 0, L.name)
+      self._bgrad(dy, ld, co, d.N * d.H * d.W, d.Cin, L.name)
+      scale0 = (1.0 / keep) if (k < n and (k + 1) in s.dropout_decoders and self._dropout_on) else 1.0
+      ep = _epilogue(None, self.gCat[k], cc, 0, N.ACT_NONE, gate=cat, ld_gate=cc, gate_act=N.ACT_RELU,
+                     gate_split=G.Dk[k], gate_scale0=scale0, round_tf32=1)
+      self._run(L, dy, ld, co, self._wb(L), ep)
+    for i in range(n, 0, -1):
+      L = G.enc[i]
+      d = L.desc
+      dy, ld, co = self.gCat[i], self.gCat[i].shape[3], G.Dk[i]
+      if i == 1:
+        x_in, ld_in = x_cat, 2
+      else:
+        x_in, ld_in = G.E[i - 1], s.enc_ch[i - 2]
+      self._wgrad(d, x_in, ld_in, 0, dy, ld, co, L.name)
+      self._bgrad(dy, ld, co, d.N * d.Ho * d.Wo, d.Cout, L.name)
+      if i > 1:
+        Lt = self.enc_t[i]
+        prev = self.gCat[i - 1]
+        ep = _epilogue(None, prev, prev.shape[3], G.Dk[i - 1], N.ACT_NONE, accumulate=1,
+                       gate=G.E[i - 1], ld_gate=s.enc_ch[i - 2], gate_act=N.ACT_LRELU, round_tf32=1)
+        self._run(Lt, dy, ld, co, self._wb(Lt), ep)
+
+  # -------------------------------------------------------------------------------------------
+  # optimiser + collective
+  # -------------------------------------------------------------------------------------------
+  def _allreduce(self, lo, hi):
+    if self.world > 1:
+      import torch.distributed as dist
+      dist.all_reduce(self.flat.g[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
+
+  def _adam(self, lo, hi, t):
+    f = self.flat
+    N.call('advoc_adam_tf_step', _view_ptr(f.p, lo), _view_ptr(f.g, lo), _view_ptr(f.m, lo),
+           _view_ptr(f.v, lo), hi - lo, self.lr, self.b1, self.b2, self.eps, t, 1.0 / self.world,
+           _stream())
+
+  # -------------------------------------------------------------------------------------------
+  # the two halves of `train_loop`
+  # -------------------------------------------------------------------------------------------
+  def load_batch(self, x, target):
+    """x, target f32 [B,T,513,1] on the device -> the discriminator input buffers."""
+    self.cat_real[..., 0:1].copy_(x)
+    self.cat_real[..., 1:2].copy_(target)
+    self.cat_fake[..., 0:1].copy_(x)
+
+  def _generate(self, dropout, seed):
+    self._dropout_on = dropout is not None
+    # encoder_1 reads x as channel 0 of the 2-channel buffer; decoder_1 writes channel 1
+    return self.G.forward(self.cat_fake, out=self.cat_fake, out_ld=2, out_coff=1, dropout=dropout,
+                          seed=seed, x_ld=2)
+
+  def d_step(self, x, target, dropout='rng', apply=True):
+    """advoc_model.py:257 `D_train_op` on one minibatch."""
+    self.step_count += 1
+    lo, hi = self.flat.dis_range()
+    self.flat.g[lo:hi].zero_()
+    self.losses[0:1].zero_()
+    self.load_batch(x, target)
+    self._generate(dropout, self.step_count)
+    p_real = self.Dr.forward(self.cat_real)
+    p_fake = self.Df.forward(self.cat_fake)
+    n = p_real.numel()
+    dz_fake = torch.empty_like(self.dz[4])
+    N.call('advoc_gan_logloss', _ptr(p_real), _ptr(p_fake), n, 0, 1.0, _ptr(self.losses),
+           _ptr(self.dz[4]), _ptr(dz_fake), _stream())
+    self._d_backward(self.Dr, self.cat_real, True, False)
+    self.dz[4].copy_(dz_fake)
+    self._d_backward(self.Df, self.cat_fake, True, False)
+    self._allreduce(lo, hi)
+    if apply:
+      self.t_d += 1
+      self._adam(lo, hi, self.t_d)
+      self.refresh_weights()
+
+  def g_step(self, x, target, dropout='rng', apply=True):
+    """advoc_model.py:254-255 `G_train_op` on one minibatch (bumps the global step)."""
+    self.step_count += 1
+    lo, hi = self.flat.gen_range()
+    self.flat.g[lo:hi].zero_()
+    self.losses[1:3].zero_()
+    self.load_batch(x, target)
+    self._generate(dropout, self.step_count)
+    n_out = self.g_out.numel()
+    N.call('advoc_l1_loss', _ptr(self.cat_fake), 2, 1, _ptr(target), n_out, self.l1_weight,
+           _view_ptr(self.losses, 2), _ptr(self.g_out), 0, _stream())
+    if self.gan_weight > 0:
+      p_fake = self.Df.forward(self.cat_fake)
+      N.call('advoc_gan_logloss', None, _ptr(p_fake), p_fake.numel(), 1, self.gan_weight,
+             _view_ptr(self.losses, 1), None, _ptr(self.dz[4]), _stream())
+      self._d_backward(self.Df, self.cat_fake, False, True)
+    self._g_backward(self.cat_fake)
+    self._allreduce(lo, hi)
+    if apply:
+      self.t_g += 1
+      self._adam(lo, hi, self.t_g)
+      self.refresh_weights()
+    return self.t_g
+
+  def train_loop(self, batch_d, batch_g, dropout='rng'):
+    """One reference `train_loop` (advoc_model.py:285-289): D step (skipped when gan_weight <= 0)
+    then G step, each on its own minibatch (x, target)."""
+    if self.gan_weight > 0:
+      self.d_step(batch_d[0], batch_d[1], dropout)
+    return self.g_step(batch_g[0], batch_g[1], dropout)
+
+  def loss_values(self):
+    """(d_loss, g_loss_GAN * gan_weight, g_loss_L1 * l1_weight) of the last steps (syncs)."""
+    v = self.losses.tolist()
+    return v[0], v[1], v[2]

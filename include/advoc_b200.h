@@ -138,7 +138,15 @@ typedef struct advoc_conv_desc {
  * multiplies by mask/keep_prob (tf.nn.dropout, advoc_model.py:144-149); if NULL and
  * keep_prob < 1 a counter-based generator keyed by (seed, element index) is used.
  * round_tf32: round stored values to TF32 (RNA) so the consuming tensor-core layer
- * reads exactly-representable operands. */
+ * reads exactly-representable operands.
+ * Backward-pass extensions (apply to out0 only; leave zero in the forward pass):
+ *   d_gate != NULL: y0 *= act'(g) * (n < gate_split ? gate_scale0 : gate_scale1), where g is the
+ *     STORED ACTIVATED value of the tensor whose pre-activation gradient is being produced
+ *     (gate_act = LRELU: g > 0 ? 1 : alpha; RELU: g > 0 ? 1 : 0) -- the ReluGrad / Maximum-grad /
+ *     dropout-grad nodes autodiff adds for advoc_model.py:87,138,146-149 fused into the
+ *     input-gradient GEMM.  A dropped element stored 0, so relu's gate also gates dropout and
+ *     gate_scale0 = 1/keep_prob restores its scale on the decoder slice [0, gate_split).
+ *   accumulate != 0: out0 += y0 (second gradient contribution of a skip connection). */
 typedef struct advoc_epilogue {
   const float* d_bias;       /* [Cout] or NULL */
   int act0, act1;
@@ -150,6 +158,10 @@ typedef struct advoc_epilogue {
   float keep_prob;           /* 1.0 = no dropout */
   uint64_t seed;
   int round_tf32;
+  int accumulate;
+  const float* d_gate; int ld_gate, c_off_gate;
+  int gate_act, gate_split;
+  float gate_scale0, gate_scale1;
 } advoc_epilogue;
 
 /* Re-pack a TF-layout filter [kh*kw, A, B] (A,B = Cin,Cout for conv; Cout,Cin for
@@ -176,6 +188,53 @@ ADVOC_API int advoc_conv2d_fwd(const advoc_conv_desc* d, const float* d_x, int l
  * replaces: tf.layers.conv2d_transpose models/advoc/advoc_model.py:65-69. */
 ADVOC_API int advoc_conv2d_transpose_fwd(const advoc_conv_desc* d, const float* d_x, int ld_x,
                                const float* d_w, const advoc_epilogue* ep, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Backward pass and optimiser (the gradient graph of advoc_model.py:238-257)
+ *
+ * Input gradients reuse the two forward entry points: the input gradient of a conv is
+ * advoc_conv2d_transpose_fwd with the same desc and the conv's own HWIO filter (already
+ * K-major for that GEMM); the input gradient of a conv_transpose is advoc_conv2d_fwd over the
+ * big side.  The activation / dropout derivative and the skip-connection sum are fused into
+ * their epilogues (advoc_epilogue.d_gate / accumulate).
+ * ------------------------------------------------------------------------- */
+
+/* Filter gradient.  d_dw [kh*kw][Cin][Cout] (+=, caller zeroes it): for a conv this IS the
+ * TF layout HWIO; for a conv_transpose described by `d` (big side = its output) it is HWOI.
+ *   d_dw[tap][cb][cs] += sum_{n,oh,ow} big[n, oh*sh-pad_t+kh, ow*sw-pad_l+kw, cb] * small[n,oh,ow,cs]
+ * d_big [N,H,W,*] (pixel stride ld_big, Cin channels), d_small [N,Ho,Wo,*] (ld_small, Cout).
+ * Accumulates with fp32 atomics across pixel splits (sum order is not fixed).
+ * replaces: Conv2DBackpropFilter built by opt.minimize, advoc_model.py:254-257. */
+ADVOC_API int advoc_conv2d_wgrad(const advoc_conv_desc* d, const float* d_big, int ld_big,
+                                 const float* d_small, int ld_small, float* d_dw, void* stream);
+
+/* d_dbias[c] += sum over pixels of d_dy[pix*ld_dy + c]   (BiasAddGrad). */
+ADVOC_API int advoc_bias_grad(const float* d_dy, int ld_dy, long pixels, int channels,
+                              float* d_dbias, void* stream);
+
+/* GAN log-loss on sigmoid probabilities with gradient seeds wrt the LOGITS (eps = 1e-12).
+ * mode 0: discriminator loss  mean(-(log(p_real+eps)+log(1-p_fake+eps)))
+ * mode 1: generator GAN loss  mean(-log(p_fake+eps)) * weight
+ * d_loss[0] += loss (atomic).  p_real and the gradient outputs may be NULL.
+ * replaces: models/advoc/advoc_model.py:201,238-239 and their autodiff. */
+ADVOC_API int advoc_gan_logloss(const float* d_p_real, const float* d_p_fake, long n, int mode,
+                                float weight, float* d_loss, float* d_dlogit_real,
+                                float* d_dlogit_fake, void* stream);
+
+/* d_loss[0] += weight*mean|target-gen| ; d_dgen[i] (=|+=) weight*sign(gen-target)/n.
+ * gen is read with pixel stride ld_gen at channel c_off_gen (it lives in the discriminator's
+ * 2-channel input buffer).  replaces: models/advoc/advoc_model.py:240,243. */
+ADVOC_API int advoc_l1_loss(const float* d_gen, int ld_gen, int c_off_gen, const float* d_target,
+                            long n, float weight, float* d_loss, float* d_dgen, int accumulate,
+                            void* stream);
+
+/* TF1 Adam over one flat fp32 buffer (epsilon outside the bias correction):
+ *   m=b1*m+(1-b1)g ; v=b2*v+(1-b2)g^2 ; p -= lr*sqrt(1-b2^t)/(1-b1^t) * m/(sqrt(v)+eps)
+ * grad_scale multiplies g first (1/world_size after a sum-allreduce).
+ * replaces: tf.train.AdamOptimizer(0.0002, 0.5).minimize, advoc_model.py:250-257. */
+ADVOC_API int advoc_adam_tf_step(float* d_p, const float* d_g, float* d_m, float* d_v, long n,
+                                 float lr, float beta1, float beta2, float eps, long t,
+                                 float grad_scale, void* stream);
 
 /* Which kernel family a call with this geometry takes: ADVOC_MATH_TF32 (tcgen05 implicit
  * GEMM) or ADVOC_MATH_FP32 (CUDA-core kernel).  transposed != 0 asks about

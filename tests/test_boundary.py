@@ -62,4 +62,5 @@ def test_struct_layouts_match_the_header():
   assert C.sizeof(N.ConvDesc) == 14 * 4
   assert N.Epilogue.d_out0.offset == 24 and N.Epilogue.d_out1.offset == 40
   assert N.Epilogue.d_dropout_mask.offset == 64 and N.Epilogue.seed.offset == 80
-  assert C.sizeof(N.Epilogue) == 96
+  assert N.Epilogue.d_gate.offset == 96 and N.Epilogue.gate_scale1.offset == 124
+  assert C.sizeof(N.Epilogue) == 128
