@@ -82,6 +82,7 @@ class TrainEngine(object):
     self.dz = [torch.zeros_like(t) for t in self.Dr.act]
     self.losses = torch.zeros(4, **f32)                    # d_loss, g_gan, g_l1, unused
     self.t_d, self.t_g = 0, 0
+    self.rnd = 0 if math == N.MATH_FP32 else 1   # TF32-round stored gradients for tensor-core consumers
     self.step_count = 0
     self._build_backward_geometry(math)
     self.refresh_weights()
@@ -163,7 +164,7 @@ class TrainEngine(object):
       if i > 0:
         Lt = self.dis_t[i]
         ep = _epilogue(None, self.dz[i - 1], ch[i], 0, N.ACT_NONE, gate=De.act[i - 1], ld_gate=ch[i],
-                       gate_act=N.ACT_LRELU, round_tf32=1)
+                       gate_act=N.ACT_LRELU, round_tf32=self.rnd)
         self._run(Lt, dy, ch[i + 1], 0, self._wb(Lt), ep)
       elif input_grad:
         ep = _epilogue(None, self.g_out, 1, 0, N.ACT_NONE, accumulate=1)
@@ -188,7 +189,7 @@ class TrainEngine(object):
       self._bgrad(dy, ld, co, d.N * d.H * d.W, d.Cin, L.name)
       scale0 = (1.0 / keep) if (k < n and (k + 1) in s.dropout_decoders and self._dropout_on) else 1.0
       ep = _epilogue(None, self.gCat[k], cc, 0, N.ACT_NONE, gate=cat, ld_gate=cc, gate_act=N.ACT_RELU,
-                     gate_split=G.Dk[k], gate_scale0=scale0, round_tf32=1)
+                     gate_split=G.Dk[k], gate_scale0=scale0, round_tf32=self.rnd)
       self._run(L, dy, ld, co, self._wb(L), ep)
     for i in range(n, 0, -1):
       L = G.enc[i]
@@ -204,7 +205,7 @@ class TrainEngine(object):
         Lt = self.enc_t[i]
         prev = self.gCat[i - 1]
         ep = _epilogue(None, prev, prev.shape[3], G.Dk[i - 1], N.ACT_NONE, accumulate=1,
-                       gate=G.E[i - 1], ld_gate=s.enc_ch[i - 2], gate_act=N.ACT_LRELU, round_tf32=1)
+                       gate=G.E[i - 1], ld_gate=s.enc_ch[i - 2], gate_act=N.ACT_LRELU, round_tf32=self.rnd)
         self._run(Lt, dy, ld, co, self._wb(Lt), ep)
 
   # -------------------------------------------------------------------------------------------

@@ -316,6 +316,158 @@ def layer_roofline(eng, args, stream, flush):
           'share_of_step': d['ms'] / total, 'by_kernel': layers}
 
 
+# ---------------------------------------------------------------------------
+# train-step workload (BASELINE configs[2]/[3]): 1 step = D update on batch a + G update on
+# batch b (advoc_model.py:285-289); per sample 4*G_f + 8*D_f FLOPs
+# ---------------------------------------------------------------------------
+TRAIN_GFLOP_PER_SAMPLE = {'small': 48.0, 'regular': 199.3}
+
+
+def _train_config(args, world):
+  return {'workload': 'AdVoc-%s G+D train step (log-GAN + 10*L1, TF1 Adam), synthetic magnitude '
+                      'batches [%d, 256, 513] per GPU, two minibatches per step (D then G)'
+                      % (args.model, args.batch),
+          'batch_per_gpu': args.batch, 'global_batch': args.batch * world,
+          'l2': 'per-step working set > 1 GB >> 126 MB L2, no explicit flush',
+          'parallelism': 'dp%d' % world}
+
+
+def _synthetic_mag(batch, seed):
+  import torch
+  g = torch.Generator().manual_seed(seed)
+  return (torch.randn(batch, T, 513, 1, generator=g).abs() * 0.1)
+
+
+def run_gpu_train(args):
+  import torch
+  import torch.distributed as dist
+  from advoc_b200 import _native as N
+  from advoc_b200 import nets
+  from advoc_b200.model import SpectralUtil
+  from advoc_b200.train import TrainEngine
+
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  rank = int(os.environ.get('RANK', '0'))
+  local = int(os.environ.get('LOCAL_RANK', '0'))
+  torch.cuda.set_device(local)
+  if world > 1:
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  small = args.model == 'small'
+  spec = nets.GenSpec(32 if small else 64, 5 if small else 8, (5, 4) if small else (8, 7, 6))
+  ndf = 32 if small else 64
+  params = nets.init_params(spec.ngf, ndf, spec.n_enc, seed=0)
+  eng = TrainEngine(spec, ndf, params, args.batch, world_size=world)
+  su = SpectralUtil()
+  mags_h = [_synthetic_mag(args.batch, 100 + 2 * rank + i).pin_memory() for i in range(2)]
+  mags_d = [m.cuda() for m in mags_h]
+  stage = [torch.empty_like(m) for m in mags_d]
+  stream = torch.cuda.current_stream()
+
+  def lift(mag):
+    return su.mel_linear_to_mag_spec(su.mag_to_mel_linear_spec(mag))
+
+  def step_device():
+    xa, xb = lift(mags_d[0]), lift(mags_d[1])
+    eng.train_loop((xa, mags_d[0]), (xb, mags_d[1]))
+
+  def step_e2e():
+    for i in range(2):
+      stage[i].copy_(mags_h[i], non_blocking=True)
+    xa, xb = lift(stage[0]), lift(stage[1])
+    eng.train_loop((xa, stage[0]), (xb, stage[1]))
+    return eng.loss_values()          # D2H read of the step's losses
+
+  def timed(fn, steps, warmup):
+    for _ in range(warmup):
+      fn()
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    for _ in range(steps):
+      fn()
+    b.record(stream)
+    barrier()
+    return a.elapsed_time(b)
+
+  n0 = N.launch_count()
+  step_device()
+  torch.cuda.synchronize()
+  per_step = N.launch_count() - n0
+  with ClockSampler(local) as clk:
+    total_ms = timed(step_device, args.steps, args.warmup)
+    e2e_ms = timed(step_e2e, args.steps, args.warmup)
+  if world > 1:
+    t = torch.tensor([total_ms, e2e_ms], device='cuda', dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = float(t[0]), float(t[1])
+  samples = world * args.batch * args.steps
+  value = samples / (total_ms * 1e-3)
+  peaks = _peaks()
+  tflops = TRAIN_GFLOP_PER_SAMPLE[args.model] * 1e9 * value / 1e12
+  line = {
+      'metric': 'G+D train-step samples/sec', 'value': value, 'unit': 'samples/s', 'n_gpus': world,
+      'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total_ms / args.steps,
+      'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+      'dtype': 'tf32 fwd/dgrad (fp32 accumulate), fp32 wgrad/optimizer', 'data': 'synthetic',
+      'config': _train_config(args, world),
+      'e2e': {'value': samples / (e2e_ms * 1e-3), 'unit': 'samples/s',
+              'ms_per_step': e2e_ms / args.steps,
+              'h2d_bytes_per_step': int(2 * mags_h[0].numel() * 4), 'd2h_bytes_per_step': 16},
+      'gpu_launches': int(per_step * args.steps * 2), 'launches_per_step': int(per_step),
+      'clocks': clk.summary(),
+      'roofline': {'kernel': 'whole step (all conv GEMMs)', 'bound': 'tensor',
+                   'achieved': tflops / world, 'peak': peaks['tensor_sustained'], 'unit': 'TFLOP/s',
+                   'frac': tflops / world / peaks['tensor_sustained'], 'traffic': None,
+                   'peak_source': peaks['source'] + ' cuBLAS bf16 sustained'},
+  }
+  if rank == 0:
+    print(json.dumps(line))
+  if world > 1:
+    dist.destroy_process_group()
+
+
+def run_reference_train(args):
+  import torch
+  from oracle import nets_torch as O
+  from oracle import spectral_np as OS
+  import numpy as np
+  if int(os.environ.get('RANK', '0')) != 0:
+    return
+  cores = os.cpu_count() or 1
+  torch.set_num_threads(cores)
+  spec = O.SMALL if args.model == 'small' else O.REGULAR
+  P = O.init_params(spec, seed=0)
+  W = torch.from_numpy(OS.create_mel_filterbank(22050, 1024, fmin=125., fmax=7600., n_mels=80).astype(np.float32))
+  Winv = torch.from_numpy(OS.create_inverse_mel_filterbank(22050, 1024, fmin=125., fmax=7600., n_mels=80).astype(np.float32))
+  sample = 2 if args.model == 'small' else 1
+  mags = [_synthetic_mag(sample, 100 + i) for i in range(2)]
+  opt_d, opt_g = O.TFAdam(O.d_names(P), P), O.TFAdam(O.g_names(P), P)
+  times = []
+  for it in range(max(args.warmup, 1) + max(args.steps, 1)):
+    t0 = time.perf_counter()
+    xs = [((m[..., 0] @ W.t()) @ Winv.t()).unsqueeze(-1) for m in mags]
+    O.train_step(P, opt_d, opt_g, (xs[0], mags[0]), (xs[1], mags[1]), spec)
+    if it >= max(args.warmup, 1):
+      times.append(time.perf_counter() - t0)
+  sps = sample / (sum(times) / len(times))
+  line = {'impl': 'reference', 'metric': 'G+D train-step samples/sec', 'value': sps, 'unit': 'samples/s',
+          'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+          'ms_per_step': 1e3 * args.batch / sps, 'higher_is_better': True, 'scaling': 'weak',
+          'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': _train_config(args, 1),
+          'cpu_baseline': {'value': sps, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
+                           'sample': 'oracle/nets_torch.py train_step (PyTorch-CPU autograd + TF1 Adam), '
+                                     '%d of %d samples per step, dropout off' % (sample, args.batch)},
+          'e2e': {'value': sps, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+          'gpu_launches': 0}
+  print(json.dumps(line))
+
+
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument('--gpus', type=int, default=1)
@@ -324,11 +476,17 @@ def main():
   ap.add_argument('--impl', default='advoc_b200', choices=['advoc_b200', 'reference'])
   ap.add_argument('--model', default='small', choices=['small', 'regular'])
   ap.add_argument('--batch', type=int, default=32, help='samples per GPU')
+  ap.add_argument('--workload', default='infer', choices=['infer', 'train'])
   ap.add_argument('--no-graph', action='store_true')
   ap.add_argument('--no-cpu-baseline', action='store_true')
   args = ap.parse_args()
   args.warmup = max(args.warmup, 3) if args.impl != 'reference' else args.warmup
-  if args.impl == 'reference':
+  if args.workload == 'train':
+    if args.impl == 'reference':
+      run_reference_train(args)
+    else:
+      run_gpu_train(args)
+  elif args.impl == 'reference':
     run_reference(args)
   else:
     run_gpu(args)
