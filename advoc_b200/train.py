@@ -212,9 +212,8 @@ class TrainEngine(object):
   # optimiser + collective
   # -------------------------------------------------------------------------------------------
   def _allreduce(self, lo, hi):
-    if self.world > 1:
-      import torch.distributed as dist
-      dist.all_reduce(self.flat.g[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
+    from advoc_b200 import dist as D
+    D.allreduce_sum_(self.flat.g, lo, hi, self.pg, self.world)
 
   def _adam(self, lo, hi, t):
     f = self.flat
