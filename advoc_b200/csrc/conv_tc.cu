@@ -17,12 +17,13 @@
 // one or two NHWC destinations, channel-offset and width-cropped: advoc_epilogue).
 // smem ring of kStages {A 16 KB, B BN*128 B} slots with full/empty mbarriers.
 #include "epilogue.cuh"
-
-#include <cuda.h>
+#include "tc_ptx.cuh"
 
 namespace advoc {
 
 namespace {
+
+using namespace tc;
 
 constexpr int BM = 128;        // UMMA_M (cta_group::1)
 constexpr int BK = 32;         // fp32 elements per 128-byte swizzle row
@@ -30,7 +31,6 @@ constexpr int UMMA_K = 8;      // kind::tf32
 constexpr int MAX_CLASSES = 4;
 constexpr int MAX_TAPS = 25;
 constexpr int NUM_THREADS = 192;
-constexpr unsigned long long WAIT_TIMEOUT_CYCLES = 2000000000ull;  // ~1 s: a bug must not hang the box
 
 struct alignas(64) TcParams {
   CUtensorMap tmA[MAX_CLASSES];
@@ -49,103 +49,6 @@ struct alignas(64) TcParams {
   EpiDev epi;
   unsigned int* dbg;   // [0] != 0 after a barrier wait timed out
 };
-
-// ---------------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: on timeout raise the debug flag and fall through (results are then garbage but
-// the kernel terminates; tests read the flag).
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsigned int* dbg, unsigned code) {
-  if (mbar_try_wait(bar, parity)) return;
-  const unsigned long long t0 = clock64();
-  unsigned spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 255u) == 0) {
-      // another CTA already timed out: the launch is lost, drain quickly
-      if (dbg && *reinterpret_cast<volatile unsigned int*>(dbg) != 0) return;
-      if (clock64() - t0 > WAIT_TIMEOUT_CYCLES) {
-        if (dbg) atomicExch(dbg, code);
-        return;
-      }
-    }
-  }
-}
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_im2col_4d(const CUtensorMap* tm, uint64_t* bar, void* dst, int c, int w,
-                                                   int h, int n, uint16_t off_w, uint16_t off_h) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h),
-      "r"(n), "h"(off_w), "h"(off_h)
-      : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);  // start address, 16-byte units
-  d |= (uint64_t)1 << 16;                   // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;         // stride byte offset
-  d |= (uint64_t)1 << 46;                   // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                   // SWIZZLE_128B
-  return d;
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // instruction descriptor, kind::tf32: D fp32, A/B tf32, both K-major, M=128, N=BN
 __host__ __device__ constexpr uint32_t make_idesc(int bn) {
@@ -351,51 +254,6 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
 // ---------------------------------------------------------------------------------------------
 // host side: driver entry points (no link-time libcuda dependency), tensor maps, launch
 // ---------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
-                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-struct Driver {
-  EncodeTiledFn tiled = nullptr;
-  EncodeIm2colFn im2col = nullptr;
-  int version = 0;
-  bool ok = false;
-};
-
-const Driver& driver() {
-  static Driver d = [] {
-    Driver r;
-    cudaDriverEntryPointQueryResult q;
-    void* f = nullptr;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      r.tiled = reinterpret_cast<EncodeTiledFn>(f);
-    f = nullptr;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &f, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      r.im2col = reinterpret_cast<EncodeIm2colFn>(f);
-    cudaDriverGetVersion(&r.version);
-    cudaGetLastError();
-    r.ok = r.tiled && r.im2col;
-    return r;
-  }();
-  return d;
-}
-
-unsigned int* debug_word() {
-  static unsigned int* w = [] {
-    unsigned int* p = nullptr;
-    if (cudaMalloc(&p, 64) != cudaSuccess) return (unsigned int*)nullptr;
-    cudaMemset(p, 0, 64);
-    return p;
-  }();
-  return w;
-}
-
 struct ClassGeom {
   int Ah, Aw, ph, pw, lower_h, lower_w, upper_h, upper_w, ntaps;
   unsigned short off[MAX_TAPS], wrow[MAX_TAPS];
@@ -404,38 +262,12 @@ struct ClassGeom {
 // im2col map over activations [Nimg, Hin, Win, ld] reading `Ck` channels per pixel
 int encode_A(CUtensorMap* tm, const float* x, int Nimg, int Hin, int Win, int ld, int Ck, const ClassGeom& g,
              int trav_h, int trav_w) {
-  const Driver& drv = driver();
-  cuuint64_t dims[4] = {(cuuint64_t)Ck, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)Nimg};
-  cuuint64_t strides[3] = {(cuuint64_t)ld * 4, (cuuint64_t)Win * ld * 4, (cuuint64_t)Hin * Win * ld * 4};
-  int lower[2] = {g.lower_w, g.lower_h};
-  int upper[2] = {g.upper_w, g.upper_h};
-  cuuint32_t estr[4] = {1, (cuuint32_t)trav_w, (cuuint32_t)trav_h, 1};
-  CUresult r = drv.im2col(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, lower,
-                          upper, (cuuint32_t)BK, (cuuint32_t)BM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  ADVOC_REQUIRE(r == CUDA_SUCCESS, ADVOC_CUDA_ERROR,
-                "cuTensorMapEncodeIm2col failed (%d) dims %d,%d,%d,%d ld %d corners (%d,%d)-(%d,%d)", (int)r, Ck,
-                Win, Hin, Nimg, ld, g.lower_w, g.lower_h, g.upper_w, g.upper_h);
-  // Known driver issue (<= 13.1): the im2col encoder mis-sets a descriptor bit for tensors smaller
-  // than 128 KiB; NVIDIA's own CUTLASS applies the same correction.
-  if (drv.version <= 13010 && (size_t)Nimg * Hin * Win * ld * 4 < 131072)
-    reinterpret_cast<uint64_t*>(tm)[1] &= ~(1ull << 21);
-  return ADVOC_OK;
+  return encode_im2col(tm, x, Nimg, Hin, Win, ld, Ck, g.lower_h, g.lower_w, g.upper_h, g.upper_w, trav_h, trav_w,
+                       BK, BM);
 }
 
 int encode_B(CUtensorMap* tm, const float* w, int rows, int Ck, int bn) {
-  const Driver& drv = driver();
-  cuuint64_t dims[2] = {(cuuint64_t)Ck, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)Ck * 4};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)bn};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = drv.tiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(w), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  ADVOC_REQUIRE(r == CUDA_SUCCESS, ADVOC_CUDA_ERROR, "cuTensorMapEncodeTiled failed (%d) rows %d Ck %d", (int)r,
-                rows, Ck);
-  return ADVOC_OK;
+  return encode_tiled2d(tm, w, Ck, rows, (size_t)Ck * 4, BK, bn);
 }
 
 template <int BN, int STAGES>
@@ -478,7 +310,7 @@ int run(TcParams& p, int nclasses, const ClassGeom* g, void* stream) {
   p.nclasses = nclasses;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (pick_bn(p.Cn)) {
-    case 256: return launch<256, 2>(p, nclasses, max_tiles, st);
+    case 256: return launch<256, 4>(p, nclasses, max_tiles, st);
     case 128: return launch<128, 3>(p, nclasses, max_tiles, st);
     case 64: return launch<64, 4>(p, nclasses, max_tiles, st);
     default: return launch<32, 4>(p, nclasses, max_tiles, st);
@@ -486,7 +318,7 @@ int run(TcParams& p, int nclasses, const ClassGeom* g, void* stream) {
 }
 
 bool common_eligible(int Ck, int Cn, int ldx) {
-  return driver().ok && device_arch() == 100 && Ck % BK == 0 && Cn % 32 == 0 && ldx % 4 == 0;
+  return tma_ok() && device_arch() == 100 && Ck % BK == 0 && Cn % 32 == 0 && ldx % 4 == 0;
 }
 
 bool epilogue_vector_ok(const advoc_epilogue* ep) {

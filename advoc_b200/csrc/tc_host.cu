@@ -1,0 +1,99 @@
+// Host half of the tcgen05 kernels: TMA tensor-map encoders through driver entry points fetched at
+// run time (the library has no link-time libcuda dependency and loads on a box without a driver).
+#include "tc_ptx.cuh"
+
+namespace advoc {
+namespace tc {
+
+namespace {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct Driver {
+  EncodeTiledFn tiled = nullptr;
+  EncodeIm2colFn im2col = nullptr;
+  int version = 0;
+  bool ok = false;
+};
+
+const Driver& driver() {
+  static Driver d = [] {
+    Driver r;
+    cudaDriverEntryPointQueryResult q;
+    void* f = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      r.tiled = reinterpret_cast<EncodeTiledFn>(f);
+    f = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      r.im2col = reinterpret_cast<EncodeIm2colFn>(f);
+    cudaDriverGetVersion(&r.version);
+    cudaGetLastError();
+    r.ok = r.tiled && r.im2col;
+    return r;
+  }();
+  return d;
+}
+}  // namespace
+
+bool tma_ok() { return driver().ok; }
+
+unsigned int* debug_word() {
+  static unsigned int* w = [] {
+    unsigned int* p = nullptr;
+    if (cudaMalloc(&p, 64) != cudaSuccess) return (unsigned int*)nullptr;
+    cudaMemset(p, 0, 64);
+    return p;
+  }();
+  return w;
+}
+
+int encode_im2col(CUtensorMap* tm, const float* x, int Nimg, int Hin, int Win, int ld, int C, int lower_h,
+                  int lower_w, int upper_h, int upper_w, int trav_h, int trav_w, int box_c, int box_pix, bool atom32) {
+  const Driver& drv = driver();
+  ADVOC_REQUIRE(drv.ok, ADVOC_UNSUPPORTED, "TMA tensor-map encoders unavailable");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)Nimg};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 4, (cuuint64_t)Win * ld * 4, (cuuint64_t)Hin * Win * ld * 4};
+  int lower[2] = {lower_w, lower_h};
+  int upper[2] = {upper_w, upper_h};
+  cuuint32_t estr[4] = {1, (cuuint32_t)trav_w, (cuuint32_t)trav_h, 1};
+  CUresult r = drv.im2col(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, lower,
+                          upper, (cuuint32_t)box_c, (cuuint32_t)box_pix, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  ADVOC_REQUIRE(r == CUDA_SUCCESS, ADVOC_CUDA_ERROR,
+                "cuTensorMapEncodeIm2col failed (%d) dims %d,%d,%d,%d ld %d corners (%d,%d)-(%d,%d)", (int)r, C,
+                Win, Hin, Nimg, ld, lower_w, lower_h, upper_w, upper_h);
+  // Known driver issue (<= 13.1): the im2col encoder mis-sets a descriptor bit for tensors smaller
+  // than 128 KiB; NVIDIA's own CUTLASS applies the same correction.
+  if (drv.version <= 13010 && (size_t)Nimg * Hin * Win * ld * 4 < 131072)
+    reinterpret_cast<uint64_t*>(tm)[1] &= ~(1ull << 21);
+  return ADVOC_OK;
+}
+
+int encode_tiled2d(CUtensorMap* tm, const float* p, int inner, long rows, size_t row_stride_bytes, int box_inner,
+                   int box_rows, bool atom32) {
+  const Driver& drv = driver();
+  ADVOC_REQUIRE(drv.ok, ADVOC_UNSUPPORTED, "TMA tensor-map encoders unavailable");
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)row_stride_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = drv.tiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  ADVOC_REQUIRE(r == CUDA_SUCCESS, ADVOC_CUDA_ERROR, "cuTensorMapEncodeTiled failed (%d) inner %d rows %ld", (int)r,
+                inner, rows);
+  return ADVOC_OK;
+}
+
+}  // namespace tc
+}  // namespace advoc
