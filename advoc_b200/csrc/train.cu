@@ -172,12 +172,22 @@ __global__ void __launch_bounds__(256) wgrad_thin_kernel(const WgradThinArgs a) 
       }
     }
   }
+  // lanes l, l+groups, l+2*groups, ... of a warp hold the same channel group: fold them with
+  // shuffles first so that only `groups` lanes per warp touch the shared accumulators
+  const bool fold = groups < 32 && (groups & (groups - 1)) == 0;
+  const int lane = threadIdx.x & 31;
 #pragma unroll
   for (int t = 0; t < 16; ++t)
 #pragma unroll
     for (int c = 0; c < CT; ++c)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) atomicAdd(&dws[(t * CT + c) * a.C + n + j], acc[t][c][j]);
+      for (int j = 0; j < 4; ++j) {
+        float v = acc[t][c][j];
+        if (fold) {
+          for (int o = 16; o >= groups; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        }
+        if (!fold || lane < groups) atomicAdd(&dws[(t * CT + c) * a.C + n + j], v);
+      }
   __syncthreads();
   // dW layouts: thin-on-big  -> [tap][ct][C]   (== dws)
   //             wide-on-big  -> [tap][C][ct=1] (== dws for CT == 1)
@@ -388,7 +398,7 @@ extern "C" int advoc_conv2d_wgrad(const advoc_conv_desc* d, const float* d_big, 
     WgradThinArgs a = {d_big, d_small, d_dw, d->N, d->H, d->W, ld_big, d->Ho, d->Wo, ld_small, d->Cout,
                        d->sh, d->sw, d->pad_t, d->pad_l};
     const int ppb = 256 / (d->Cout / 4);
-    const int blocks = grid_for(M, ppb * 8);
+    const int blocks = grid_for(M, ppb * 8) < sm_count() * 2 ? grid_for(M, ppb * 8) : sm_count() * 2;
     const size_t smem = (size_t)16 * d->Cin * d->Cout * sizeof(float);
     if (d->Cin == 1) wgrad_thin_kernel<1, false><<<blocks, 256, smem, s>>>(a);
     else wgrad_thin_kernel<2, false><<<blocks, 256, smem, s>>>(a);
@@ -398,7 +408,7 @@ extern "C" int advoc_conv2d_wgrad(const advoc_conv_desc* d, const float* d_big, 
                        d->sh, d->sw, d->pad_t, d->pad_l};
     const long Mb = (long)d->N * d->H * d->W;
     const int ppb = 256 / (d->Cin / 4);
-    const int blocks = grid_for(Mb, ppb * 8);
+    const int blocks = grid_for(Mb, ppb * 8) < sm_count() * 2 ? grid_for(Mb, ppb * 8) : sm_count() * 2;
     const size_t smem = (size_t)16 * d->Cin * sizeof(float);
     wgrad_thin_kernel<1, true><<<blocks, 256, smem, s>>>(a);
   } else {

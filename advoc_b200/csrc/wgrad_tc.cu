@@ -10,8 +10,10 @@
 // Each box lands as BK rows of 128 B in the 128B/32B-atom swizzle = one column block of the
 // canonical MN-major UMMA layout for 32-bit operands (4-pixel atoms 512 B apart, 32-channel
 // blocks BK*128 B apart).
-// The side with more channels is put on the 128 TMEM lanes (M), the other on N <= 128 columns.
-// Work = (tap, M tile, N tile, pixel split); partial sums are added to dW with fp32 atomics.
+// The small side sits on the 128 TMEM lanes (M); the N axis is the concatenation (tap, big channel):
+// 16 boxes = 512 accumulator columns per CTA, so the small-side tile is fetched once for 16
+// tap/channel blocks.  Work = (M tile, N tile, pixel split); partial sums are added to dW with
+// fp32 atomics.
 #include "tc_ptx.cuh"
 
 namespace advoc {
@@ -22,17 +24,23 @@ namespace {
 
 using namespace tc;
 
-constexpr int WM = 128;     // UMMA_M
-constexpr int WBK = 32;     // pixels per pipeline stage
+constexpr int WM = 128;       // UMMA_M: small-side channels on the TMEM lanes
+constexpr int WBK = 16;       // pixels per pipeline stage (two K=8 steps)
+constexpr int WNB = 16;       // 32-channel blocks of the (tap, big-channel) axis per CTA = 512 TMEM columns
+constexpr int WSTAGES = 4;
 constexpr int W_THREADS = 192;
+constexpr int BLK_BYTES = WBK * 128;                  // one [WBK pixels][32 channels] box
+constexpr int A_BYTES = (WM / 32) * BLK_BYTES;        // small side, 128 channels
+constexpr int B_BYTES = WNB * BLK_BYTES;              // big side, 16 (tap, channel-block) boxes
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;        // 40 KB
 
 struct alignas(64) WgParams {
   CUtensorMap tmBig;    // im2col
   CUtensorMap tmSmall;  // 2-D
   float* dw;
   int Cb, Cs;
-  int big_on_m;         // 1: M = big channels, N = small channels; 0: swapped
-  int mtiles, ntiles, taps, kw;
+  int cbb;              // 32-channel blocks of the big side
+  int mtiles, ntiles, kw;
   int Ho, Wo, sh, sw, lower_h, lower_w;
   long P, chunk;        // output pixels, pixels per split (multiple of WBK)
   unsigned int* dbg;
@@ -42,56 +50,52 @@ struct alignas(64) WgParams {
 // (128-byte rows, 32-byte chunks XOR-swizzled over 4-row atoms) -- what TMA produces with
 // CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  32-channel blocks are `lbo` bytes apart, 4-pixel atoms
 // 512 bytes apart.
-__device__ __forceinline__ uint64_t make_mn_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes = 512) {
+__device__ __forceinline__ uint64_t make_mn_desc(uint32_t saddr, uint32_t lbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
   d |= (uint64_t)(lbo_bytes >> 4) << 16;
-  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)(512 >> 4) << 32;
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)1 << 61;   // SWIZZLE_128B_BASE32B
   return d;
 }
 
-// kind::tf32, D fp32, A and B MN-major, M = 128, N = bn
-__host__ __device__ constexpr uint32_t make_idesc_mn(int bn) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(bn >> 3) << 17) |
-         ((uint32_t)(WM >> 4) << 24);
-}
+// kind::tf32, D fp32, A and B MN-major, M = 128, N = 256
+constexpr uint32_t kIdescMN = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                              ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(WM >> 4) << 24);
 
-template <int BN, int STAGES>
+// D[cs, (tap, cb)] += sum_p small[p, cs] * big[p @ tap, cb]: the small-side tile is fetched once
+// per stage and shared by all 16 (tap, channel-block) boxes of the big side, which sit back to
+// back in smem so that ONE N=256 MMA spans eight of them (LBO = box size).
 __global__ void __launch_bounds__(W_THREADS) wgrad_tc_kernel(const __grid_constant__ WgParams p) {
-  constexpr int A_BYTES = WM * WBK * 4;       // 4 blocks of [WBK][128 B]
-  constexpr int B_BYTES = BN * WBK * 4;
-  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr int BLK_BYTES = WBK * 128;        // one 32-channel block
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[STAGES];
-  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t full_bar[WSTAGES];
+  __shared__ __align__(8) uint64_t empty_bar[WSTAGES];
   __shared__ __align__(8) uint64_t tmem_full_bar;
   __shared__ uint32_t tmem_base_holder;
 
-  // work decode: tap fastest, then M tile, N tile, pixel split (CTAs of one split share operands in L2)
+  // work decode: N tile fastest, then M tile, then pixel split (CTAs of one split share L2 lines)
   unsigned id = blockIdx.x;
-  const int tap = id % p.taps; id /= p.taps;
-  const int mt = id % p.mtiles; id /= p.mtiles;
   const int nt = id % p.ntiles; id /= p.ntiles;
+  const int mt = id % p.mtiles; id /= p.mtiles;
   const long p0 = (long)id * p.chunk;
   if (p0 >= p.P) return;
   const long p1 = p0 + p.chunk < p.P ? p0 + p.chunk : p.P;
   const int iters = (int)((p1 - p0 + WBK - 1) / WBK);
   if (p.dbg && *reinterpret_cast<volatile unsigned int*>(p.dbg) != 0) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = mt * WM, n0 = nt * BN;
+  const int m0 = mt * WM;
+  const int gb0 = nt * WNB;   // first (tap, channel-block) index of this CTA
 
   const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* ring_ptr = smem_raw + (ring - smem_u32(smem_raw));
-  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  constexpr uint32_t TMEM_COLS = 512;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.tmBig);
     prefetch_tmap(&p.tmSmall);
 #pragma unroll
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < WSTAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
@@ -111,36 +115,42 @@ __global__ void __launch_bounds__(W_THREADS) wgrad_tc_kernel(const __grid_consta
   const uint32_t tmem_base = tmem_base_holder;
 
   if (warp == 0) {
-    if (lane == 0) {
-      const int kh = tap / p.kw, kwi = tap - kh * p.kw;
-      const int big_c0 = p.big_on_m ? m0 : n0, small_c0 = p.big_on_m ? n0 : m0;
-      const int big_blocks = p.big_on_m ? WM / 32 : BN / 32;
-      const int small_blocks = p.big_on_m ? BN / 32 : WM / 32;
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int it = 0; it < iters; ++it) {
-        const long pix = p0 + (long)it * WBK;
-        const int ow = (int)(pix % p.Wo);
-        const long r = pix / p.Wo;
-        const int oh = (int)(r % p.Ho);
-        const int img = (int)(r / p.Ho);
+    // ===== TMA producer: 20 boxes per stage, one per lane (lanes 0-3 small side, 4-19 big side) =====
+    int my_c = 0;
+    uint16_t my_kw = 0, my_kh = 0;
+    if (lane < WM / 32) {
+      my_c = m0 + 32 * lane;
+    } else if (lane < WM / 32 + WNB) {
+      const int gb = gb0 + (lane - WM / 32);
+      const int tap = gb / p.cbb, cblk = gb - tap * p.cbb;
+      my_c = 32 * cblk;
+      my_kh = (uint16_t)(tap / p.kw);
+      my_kw = (uint16_t)(tap - (tap / p.kw) * p.kw);
+    }
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int it = 0; it < iters; ++it) {
+      const long pix = p0 + (long)it * WBK;
+      const int ow = (int)(pix % p.Wo);
+      const long r = pix / p.Wo;
+      const int oh = (int)(r % p.Ho);
+      const int img = (int)(r / p.Ho);
+      if (lane == 0) {
         mbar_wait(&empty_bar[stage], phase ^ 1u, p.dbg, 11u);
-        uint8_t* a_dst = ring_ptr + stage * STAGE_BYTES;
-        uint8_t* b_dst = a_dst + A_BYTES;
-        uint8_t* big_dst = p.big_on_m ? a_dst : b_dst;
-        uint8_t* small_dst = p.big_on_m ? b_dst : a_dst;
         mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-        for (int j = 0; j < big_blocks; ++j)
-          tma_load_im2col_4d(&p.tmBig, &full_bar[stage], big_dst + j * BLK_BYTES, big_c0 + 32 * j,
-                             ow * p.sw + p.lower_w, oh * p.sh + p.lower_h, img, (uint16_t)kwi, (uint16_t)kh);
-        for (int j = 0; j < small_blocks; ++j)
-          tma_load_2d(&p.tmSmall, &full_bar[stage], small_dst + j * BLK_BYTES, small_c0 + 32 * j, (int)pix);
-        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
+      __syncwarp();
+      uint8_t* dst = ring_ptr + stage * STAGE_BYTES + lane * BLK_BYTES;
+      if (lane < WM / 32) {
+        tma_load_2d(&p.tmSmall, &full_bar[stage], dst, my_c, (int)pix);
+      } else if (lane < WM / 32 + WNB) {
+        tma_load_im2col_4d(&p.tmBig, &full_bar[stage], dst, my_c, ow * p.sw + p.lower_w, oh * p.sh + p.lower_h,
+                           img, my_kw, my_kh);
+      }
+      if (++stage == WSTAGES) { stage = 0; phase ^= 1u; }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_mn(BN);
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < iters; ++it) {
@@ -148,36 +158,37 @@ __global__ void __launch_bounds__(W_THREADS) wgrad_tc_kernel(const __grid_consta
         tc_fence_after();
         const uint32_t a_addr = ring + stage * STAGE_BYTES;
         const uint64_t da = make_mn_desc(a_addr, BLK_BYTES);
-        const uint64_t db = make_mn_desc(a_addr + A_BYTES, BLK_BYTES);
+        const uint64_t db0 = make_mn_desc(a_addr + A_BYTES, BLK_BYTES);
+        const uint64_t db1 = make_mn_desc(a_addr + A_BYTES + 8 * BLK_BYTES, BLK_BYTES);
 #pragma unroll
         for (int k = 0; k < WBK / 8; ++k) {
-          // 8 pixels = one 1024-byte swizzle atom along K
-          umma_tf32(tmem_base, da + (uint64_t)(64 * k), db + (uint64_t)(64 * k), idesc, (it | k) != 0 ? 1u : 0u);
+          // 8 pixels = 1024 bytes along K inside every box
+          const uint32_t acc = (it | k) != 0 ? 1u : 0u;
+          umma_tf32(tmem_base, da + (uint64_t)(64 * k), db0 + (uint64_t)(64 * k), kIdescMN, acc);
+          umma_tf32(tmem_base + 256u, da + (uint64_t)(64 * k), db1 + (uint64_t)(64 * k), kIdescMN, acc);
         }
         umma_commit(&empty_bar[stage]);
-        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        if (++stage == WSTAGES) { stage = 0; phase ^= 1u; }
       }
       umma_commit(&tmem_full_bar);
     }
   } else {
     const int q = warp & 3;
-    const int m = m0 + q * 32 + lane;
-    const int CM = p.big_on_m ? p.Cb : p.Cs, CN = p.big_on_m ? p.Cs : p.Cb;
+    const int cs = m0 + q * 32 + lane;
     mbar_wait(&tmem_full_bar, 0u, p.dbg, 13u);
     tc_fence_after();
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+    for (int b = 0; b < WNB; ++b) {
       uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * 32), v);
       tmem_ld_wait();
-      if (m < CM) {
+      const int gb = gb0 + b;
+      const int tap = gb / p.cbb, cblk = gb - tap * p.cbb;
+      if (cs < p.Cs) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const int n = n0 + c0 + j;
-          if (n < CN) {
-            const size_t idx = p.big_on_m ? ((size_t)tap * p.Cb + m) * p.Cs + n : ((size_t)tap * p.Cb + n) * p.Cs + m;
-            atomicAdd(p.dw + idx, __uint_as_float(v[j]));
-          }
+          const int cb = cblk * 32 + j;
+          if (cb < p.Cb) atomicAdd(p.dw + ((size_t)tap * p.Cb + cb) * p.Cs + cs, __uint_as_float(v[j]));
         }
       }
     }
@@ -191,27 +202,14 @@ __global__ void __launch_bounds__(W_THREADS) wgrad_tc_kernel(const __grid_consta
   }
 }
 
-template <int BN, int STAGES>
-int launch_wg(const WgParams& p, long ctas, cudaStream_t st) {
-  constexpr int smem = STAGES * (WM * WBK * 4 + BN * WBK * 4) + 1024;
-  static bool configured = false;
-  if (!configured) {
-    ADVOC_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          smem));
-    configured = true;
-  }
-  wgrad_tc_kernel<BN, STAGES><<<(unsigned)ctas, W_THREADS, smem, st>>>(p);
-  count_launch();
-  ADVOC_CHECK_CUDA(cudaGetLastError());
-  return ADVOC_OK;
-}
-
 }  // namespace
 
 bool wgrad_tc_eligible(const advoc_conv_desc* d, const float* big, int ld_big, const float* small, int ld_small) {
+  const int cbb = (d->Cin + 31) / 32;
   return d->math != ADVOC_MATH_FP32 && tc::tma_ok() && device_arch() == 100 && d->Cin >= 32 && d->Cout >= 32 &&
          d->Cin % 4 == 0 && d->Cout % 4 == 0 && ld_big % 4 == 0 && ld_small % 4 == 0 && aligned16(big) &&
-         aligned16(small) && d->kh * d->kw <= 255 && d->pad_t <= 127 && d->pad_l <= 127;
+         aligned16(small) && d->kh * d->kw <= 255 && d->pad_t <= 127 && d->pad_l <= 127 &&
+         (d->kh * d->kw * cbb) % WNB == 0;
 }
 
 int wgrad_tc(const advoc_conv_desc* d, const float* big, int ld_big, const float* small, int ld_small, float* dw,
@@ -231,17 +229,15 @@ int wgrad_tc(const advoc_conv_desc* d, const float* big, int ld_big, const float
   st = encode_tiled2d(&p.tmSmall, small, d->Cout, P, (size_t)ld_small * 4, 32, WBK, true);
   if (st) return st;
   p.dw = dw; p.Cb = d->Cin; p.Cs = d->Cout;
-  p.big_on_m = d->Cin >= d->Cout ? 1 : 0;
-  const int CM = p.big_on_m ? p.Cb : p.Cs, CN = p.big_on_m ? p.Cs : p.Cb;
-  const int bn = CN > 64 ? 128 : (CN > 32 ? 64 : 32);
-  p.mtiles = (CM + WM - 1) / WM;
-  p.ntiles = (CN + bn - 1) / bn;
-  p.taps = d->kh * d->kw; p.kw = d->kw;
+  p.cbb = (d->Cin + 31) / 32;
+  p.mtiles = (d->Cout + WM - 1) / WM;
+  p.ntiles = d->kh * d->kw * p.cbb / WNB;
+  p.kw = d->kw;
   p.Ho = d->Ho; p.Wo = d->Wo; p.sh = d->sh; p.sw = d->sw; p.lower_h = lower_h; p.lower_w = lower_w;
   p.P = P;
-  const long tiles = (long)p.taps * p.mtiles * p.ntiles;
+  const long tiles = (long)p.mtiles * p.ntiles;
   long splits = ((long)sm_count() * 2 + tiles - 1) / tiles;
-  const long max_splits = (P + 4 * WBK - 1) / (4 * WBK);
+  const long max_splits = (P + 8 * WBK - 1) / (8 * WBK);
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   p.chunk = ((P + splits - 1) / splits + WBK - 1) / WBK * WBK;
@@ -249,12 +245,16 @@ int wgrad_tc(const advoc_conv_desc* d, const float* big, int ld_big, const float
   const long ctas = tiles * splits;
   ADVOC_REQUIRE(ctas < 2147483647L, ADVOC_BAD_SHAPE, "too many wgrad CTAs");
   p.dbg = debug_word();
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  switch (bn) {
-    case 128: return launch_wg<128, 6>(p, ctas, s);
-    case 64: return launch_wg<64, 8>(p, ctas, s);
-    default: return launch_wg<32, 8>(p, ctas, s);
+  constexpr int smem = WSTAGES * STAGE_BYTES + 1024;
+  static bool configured = false;
+  if (!configured) {
+    ADVOC_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
   }
+  wgrad_tc_kernel<<<(unsigned)ctas, W_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  count_launch();
+  ADVOC_CHECK_CUDA(cudaGetLastError());
+  return ADVOC_OK;
 }
 
 }  // namespace advoc
