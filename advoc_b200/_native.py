@@ -62,6 +62,9 @@ SIGNATURES = {
     'advoc_conv2d_fwd': (_I, [C.POINTER(ConvDesc), _P, _I, _P, C.POINTER(Epilogue), _P]),
     'advoc_pack_filter': (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     'advoc_debug_flags': (_I, [C.POINTER(C.c_uint)]),
+    'advoc_istft_frames_f32': (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P]),
+    'advoc_overlap_add_f32': (_I, [_P, _I, _I, _I, _I, _P, _P]),
+    'advoc_griffin_lim_iter_f32': (_I, [_P, _L, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
     'advoc_conv2d_wgrad': (_I, [C.POINTER(ConvDesc), _P, _I, _P, _I, _P, _P]),
     'advoc_bias_grad': (_I, [_P, _I, _L, _I, _P, _P]),
     'advoc_gan_logloss': (_I, [_P, _P, _L, _I, _F, _P, _P, _P, _P]),

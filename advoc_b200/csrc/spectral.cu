@@ -33,6 +33,7 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
 
 // Complex in-smem Stockham autosort FFT, radix 4 with one trailing radix-2 pass when
 // log2(N) is odd.  `a` holds the input, result pointer is returned (a or b).
+template <bool kInv>
 __device__ float2* stockham_fft(float2* a, float2* b, const float2* __restrict__ tw, int N) {
   int n = N, s = 1;
   while (n >= 4) {
@@ -48,14 +49,16 @@ __device__ float2* stockham_fft(float2* a, float2* b, const float2* __restrict__
       const float2 amc = make_float2(A.x - C.x, A.y - C.y);
       const float2 bpd = make_float2(B.x + D.x, B.y + D.y);
       const float2 jbmd = make_float2(-(B.y - D.y), B.x - D.x);  // i * (B - D)
-      const float2 w1 = __ldg(tw + p * tws);
-      const float2 w2 = __ldg(tw + 2 * p * tws);
-      const float2 w3 = __ldg(tw + 3 * p * tws);
+      float2 w1 = __ldg(tw + p * tws);
+      float2 w2 = __ldg(tw + 2 * p * tws);
+      float2 w3 = __ldg(tw + 3 * p * tws);
+      if (kInv) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; }
       const int o = q + s * 4 * p;
+      const float sg = kInv ? -1.f : 1.f;   // inverse transform: +i instead of -i rotations
       b[o] = make_float2(apc.x + bpd.x, apc.y + bpd.y);
-      b[o + s] = cmul(w1, make_float2(amc.x - jbmd.x, amc.y - jbmd.y));
+      b[o + s] = cmul(w1, make_float2(amc.x - sg * jbmd.x, amc.y - sg * jbmd.y));
       b[o + 2 * s] = cmul(w2, make_float2(apc.x - bpd.x, apc.y - bpd.y));
-      b[o + 3 * s] = cmul(w3, make_float2(amc.x + jbmd.x, amc.y + jbmd.y));
+      b[o + 3 * s] = cmul(w3, make_float2(amc.x + sg * jbmd.x, amc.y + sg * jbmd.y));
     }
     __syncthreads();
     float2* t2 = a; a = b; b = t2;
@@ -103,7 +106,7 @@ __global__ void __launch_bounds__(256) stft_pair_kernel(const StftArgs g) {
 
   const float2* Z;
   if (kPow2) {
-    Z = stockham_fft(bufa, bufb, g.tw, g.nfft);
+    Z = stockham_fft<false>(bufa, bufb, g.tw, g.nfft);
   } else {
     // generic length: direct DFT (tacotron2 preset nfft=1200); O(N^2), correctness path
     for (int k = threadIdx.x; k < g.nfft; k += blockDim.x) {
@@ -234,6 +237,106 @@ __global__ void __launch_bounds__(256) matmul_lastdim_kernel(const float* __rest
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Inversion: windowed inverse frames of two consecutive frames per CTA (z = Xa + i Xb, both
+// Hermitian, so ifft(z) = xa + i xb), optionally preceded by a Griffin-Lim phase update
+//   S = stft(wave) ; angle = S / |S| ; X = mag * angle            (advoc/spectral.py:304-307)
+// and a separate atomics-free overlap-add.  lws istft with perfectrec=False: synthesis window ==
+// analysis window, output length (frames-1)*hop + nfft (advoc/spectral.py:300-311).
+// ---------------------------------------------------------------------------------------------
+struct IstftArgs {
+  const float2* spec;   // [batch, frames, bins] complex, or null (Griffin-Lim mode)
+  const float* mag;     // [batch, frames, bins] (Griffin-Lim mode)
+  const float* wave;    // [batch, nwave] current estimate (Griffin-Lim mode)
+  const float* window;
+  const float2* tw;
+  float* frames_out;    // [batch, frames, nfft]
+  int batch, frames, bins, nfft, nhop;
+  long nwave;
+};
+
+__global__ void __launch_bounds__(256) istft_pair_kernel(const IstftArgs g) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* bufa = reinterpret_cast<float2*>(smem_raw);
+  float2* bufb = bufa + g.nfft;
+  const int pairs = (g.frames + 1) >> 1;
+  const int pair = blockIdx.x % pairs;
+  const int b = blockIdx.x / pairs;
+  const int f0 = pair * 2;
+  const bool has_b = (f0 + 1) < g.frames;
+  const size_t sbase = ((size_t)b * g.frames + f0) * g.bins;
+
+  if (g.spec == nullptr) {
+    // Griffin-Lim: analysis of the current waveform estimate (lws stft: no end padding needed,
+    // the estimate is exactly (frames-1)*hop + nfft long)
+    const float* x = g.wave + (size_t)b * g.nwave;
+    for (int i = threadIdx.x; i < g.nfft; i += blockDim.x) {
+      const float w = __ldg(g.window + i);
+      const long ia = (long)f0 * g.nhop + i, ib = ia + g.nhop;
+      const float va = ia < g.nwave ? __ldg(x + ia) * w : 0.f;
+      const float vb = (has_b && ib < g.nwave) ? __ldg(x + ib) * w : 0.f;
+      bufa[i] = make_float2(va, vb);
+    }
+    __syncthreads();
+    float2* Z = stockham_fft<false>(bufa, bufb, g.tw, g.nfft);
+    float2* O = (Z == bufa) ? bufb : bufa;
+    // split the two spectra, replace the magnitude, re-pack z = Xa + i Xb over the full circle
+    for (int k = threadIdx.x; k < g.bins; k += blockDim.x) {
+      const float2 zk = Z[k];
+      const float2 zn = Z[k == 0 ? 0 : g.nfft - k];
+      float2 xa = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
+      float2 xb = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));
+      const float na = sqrtf(xa.x * xa.x + xa.y * xa.y), nb = sqrtf(xb.x * xb.x + xb.y * xb.y);
+      const float ma = __ldg(g.mag + sbase + k);
+      const float mb = has_b ? __ldg(g.mag + sbase + g.bins + k) : 0.f;
+      xa = na > 0.f ? make_float2(xa.x / na * ma, xa.y / na * ma) : make_float2(ma, 0.f);   // angle(0) = 0
+      xb = nb > 0.f ? make_float2(xb.x / nb * mb, xb.y / nb * mb) : make_float2(mb, 0.f);
+      if (k == 0 || k == g.nfft / 2) { xa.y = 0.f; xb.y = 0.f; }   // irfft ignores these imaginary parts
+      O[k] = make_float2(xa.x - xb.y, xa.y + xb.x);
+      if (k != 0 && k != g.nfft / 2) O[g.nfft - k] = make_float2(xa.x + xb.y, -xa.y + xb.x);  // conj(Xa) + i conj(Xb)
+    }
+    __syncthreads();
+    float2* other = (O == bufa) ? bufb : bufa;
+    bufa = O; bufb = other;
+  } else {
+    for (int k = threadIdx.x; k < g.bins; k += blockDim.x) {
+      float2 xa = __ldg(g.spec + sbase + k);
+      float2 xb = has_b ? __ldg(g.spec + sbase + g.bins + k) : make_float2(0.f, 0.f);
+      if (k == 0 || k == g.nfft / 2) { xa.y = 0.f; xb.y = 0.f; }
+      bufa[k] = make_float2(xa.x - xb.y, xa.y + xb.x);
+      if (k != 0 && k != g.nfft / 2) bufa[g.nfft - k] = make_float2(xa.x + xb.y, -xa.y + xb.x);
+    }
+    __syncthreads();
+  }
+  const float2* Y = stockham_fft<true>(bufa, bufb, g.tw, g.nfft);
+  const float scale = 1.f / (float)g.nfft;
+  float* oa = g.frames_out + ((size_t)b * g.frames + f0) * g.nfft;
+  for (int i = threadIdx.x; i < g.nfft; i += blockDim.x) {
+    const float w = __ldg(g.window + i) * scale;
+    oa[i] = Y[i].x * w;
+    if (has_b) oa[g.nfft + i] = Y[i].y * w;
+  }
+}
+
+// out[b, i] = sum over frames m with 0 <= i - m*hop < nfft of frames[b, m, i - m*hop]
+__global__ void __launch_bounds__(256) overlap_add_kernel(const float* __restrict__ fr, float* __restrict__ out,
+                                                          int batch, int frames, int nfft, int nhop, long nout) {
+  const long total = (long)batch * nout;
+  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const long b = t / nout, i = t - b * nout;
+    long m_hi = i / nhop;
+    if (m_hi > frames - 1) m_hi = frames - 1;
+    long m_lo = (i - nfft + nhop) / nhop;   // smallest m with i - m*hop < nfft
+    if (i - nfft + 1 <= 0) m_lo = 0;
+    float s = 0.f;
+    for (long m = m_lo; m <= m_hi; ++m) {
+      const long j = i - m * nhop;
+      if (j >= 0 && j < nfft) s += __ldg(fr + ((size_t)b * frames + m) * nfft + j);
+    }
+    out[t] = s;
+  }
+}
+
 int launch_stft(StftArgs& g, void* stream) {
   if (g.frames == 0 || g.batch == 0 || g.nch == 0) return ADVOC_OK;
   const bool pow2 = (g.nfft & (g.nfft - 1)) == 0;
@@ -335,6 +438,72 @@ extern "C" int advoc_matmul_lastdim_f32(const float* d_x, const float* d_w, floa
   dim3 grid((unsigned)((rows + 63) / 64), (unsigned)((N + 63) / 64));
   matmul_lastdim_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d_x, d_w, d_y, rows,
                                                                                 K, N, pow10_scale);
+  count_launch();
+  ADVOC_CHECK_CUDA(cudaGetLastError());
+  return ADVOC_OK;
+}
+
+static int check_inv_common(int batch, int frames, int nfft, int nhop, const float* d_window, const float* d_twiddle,
+                            float* d_frames) {
+  ADVOC_REQUIRE(batch >= 0 && frames >= 0, ADVOC_BAD_SHAPE, "bad spectrogram shape [%d,%d]", batch, frames);
+  ADVOC_REQUIRE(nfft >= 8 && (nfft & (nfft - 1)) == 0 && nhop >= 1 && nhop <= nfft, ADVOC_UNSUPPORTED,
+                "inverse transform needs a power-of-two nfft (got %d) and 1 <= nhop <= nfft", nfft);
+  ADVOC_REQUIRE(d_window && d_twiddle && d_frames, ADVOC_BAD_ARG, "NULL window / twiddle / frames pointer");
+  ADVOC_REQUIRE((size_t)2 * nfft * sizeof(float2) <= 200 * 1024, ADVOC_UNSUPPORTED, "nfft too large");
+  return ADVOC_OK;
+}
+
+static int launch_istft(IstftArgs& g, void* stream) {
+  if (g.batch == 0 || g.frames == 0) return ADVOC_OK;
+  const size_t smem = (size_t)2 * g.nfft * sizeof(float2);
+  if (smem > 48 * 1024)
+    ADVOC_CHECK_CUDA(cudaFuncSetAttribute(istft_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long grid = (long)g.batch * ((g.frames + 1) / 2);
+  ADVOC_REQUIRE(grid < 2147483647L, ADVOC_BAD_SHAPE, "too many frames for one launch");
+  istft_pair_kernel<<<(unsigned)grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(g);
+  count_launch();
+  ADVOC_CHECK_CUDA(cudaGetLastError());
+  return ADVOC_OK;
+}
+
+extern "C" int advoc_istft_frames_f32(const float* d_spec_c64, int batch, int frames, int nfft, int nhop,
+                                      const float* d_window, const float* d_twiddle, float* d_frames,
+                                      void* stream) {
+  int st = check_inv_common(batch, frames, nfft, nhop, d_window, d_twiddle, d_frames);
+  if (st) return st;
+  ADVOC_REQUIRE(d_spec_c64 || batch * frames == 0, ADVOC_BAD_ARG, "spectrum pointer is NULL");
+  IstftArgs g = {};
+  g.spec = reinterpret_cast<const float2*>(d_spec_c64);
+  g.window = d_window; g.tw = reinterpret_cast<const float2*>(d_twiddle); g.frames_out = d_frames;
+  g.batch = batch; g.frames = frames; g.bins = nfft / 2 + 1; g.nfft = nfft; g.nhop = nhop;
+  return launch_istft(g, stream);
+}
+
+extern "C" int advoc_griffin_lim_iter_f32(const float* d_wave, long nwave, const float* d_mag, int batch,
+                                          int frames, int nfft, int nhop, const float* d_window,
+                                          const float* d_twiddle, float* d_frames, void* stream) {
+  int st = check_inv_common(batch, frames, nfft, nhop, d_window, d_twiddle, d_frames);
+  if (st) return st;
+  ADVOC_REQUIRE((d_wave && d_mag) || batch * frames == 0, ADVOC_BAD_ARG, "wave / mag pointer is NULL");
+  ADVOC_REQUIRE(nwave == (long)(frames - 1) * nhop + nfft || frames == 0, ADVOC_BAD_SHAPE,
+                "waveform estimate must be (frames-1)*hop + nfft samples long");
+  IstftArgs g = {};
+  g.mag = d_mag; g.wave = d_wave; g.nwave = nwave;
+  g.window = d_window; g.tw = reinterpret_cast<const float2*>(d_twiddle); g.frames_out = d_frames;
+  g.batch = batch; g.frames = frames; g.bins = nfft / 2 + 1; g.nfft = nfft; g.nhop = nhop;
+  return launch_istft(g, stream);
+}
+
+extern "C" int advoc_overlap_add_f32(const float* d_frames, int batch, int frames, int nfft, int nhop,
+                                     float* d_out, void* stream) {
+  ADVOC_REQUIRE(batch >= 0 && frames >= 0 && nfft >= 1 && nhop >= 1, ADVOC_BAD_SHAPE, "bad overlap-add shape");
+  if (batch == 0 || frames == 0) return ADVOC_OK;
+  ADVOC_REQUIRE(d_frames && d_out, ADVOC_BAD_ARG, "NULL pointer");
+  const long nout = (long)(frames - 1) * nhop + nfft;
+  const long total = (long)batch * nout;
+  const long blocks = (total + 255) / 256;
+  overlap_add_kernel<<<(unsigned)(blocks < 65535 * 16 ? blocks : 65535 * 16), 256, 0,
+                       reinterpret_cast<cudaStream_t>(stream)>>>(d_frames, d_out, batch, frames, nfft, nhop, nout);
   count_launch();
   ADVOC_CHECK_CUDA(cudaGetLastError());
   return ADVOC_OK;

@@ -274,3 +274,115 @@ def waveform_to_tacotron2_melspec(x):
 def waveform_to_r9y9_melspec(x, fs=22050):
   """reference: advoc/spectral.py:250-269."""
   return waveform_to_melspec(x, fs=fs, nfft=1024, nhop=256)
+
+
+# ---------------------------------------------------------------------------
+# inversion (SURVEY.md section 8(f) "next" row): ISTFT and Griffin-Lim on the GPU
+# ---------------------------------------------------------------------------
+def istft_tf(X, nfft, nhop):
+  """Batched inverse STFT.  X c64 [b, frames, nfft//2+1] (cuda) -> f32 [b, (frames-1)*nhop + nfft].
+  lws istft with perfectrec=False (synthesis window == analysis window).
+  reference: advoc/spectral.py:303,307,322 (`lws_proc.istft`)."""
+  if X.dim() != 3 or X.shape[2] != nfft // 2 + 1 or X.dtype != torch.complex64:
+    raise ValueError()
+  b, frames, _ = X.shape
+  win, tw = _Consts.stft(nfft, nhop, X.device)
+  nout = (frames - 1) * nhop + nfft if frames > 0 else 0
+  out = torch.zeros((b, nout), dtype=torch.float32, device=X.device)
+  if out.numel() == 0:
+    return out
+  spec = torch.view_as_real(X.contiguous())
+  fr = torch.empty((b, frames, nfft), dtype=torch.float32, device=X.device)
+  N.call('advoc_istft_frames_f32', _ptr(spec), b, frames, nfft, nhop, _ptr(win), _ptr(tw), _ptr(fr),
+         _stream())
+  N.call('advoc_overlap_add_f32', _ptr(fr), b, frames, nfft, nhop, _ptr(out), _stream())
+  return out
+
+
+def griffin_lim_tf(X_mag, nfft, nhop, ngl=60, init_phase=None, generator=None):
+  """Batched Griffin-Lim.  X_mag f32 [b, frames, nfft//2+1] (cuda) -> f32 [b, (frames-1)*nhop+nfft].
+  Each iteration is two kernels (fused stft -> phase -> istft frames, then overlap-add).
+  `init_phase` (radians, same shape) replaces the reference's `2*pi*np.random.rand` start."""
+  if X_mag.dim() != 3 or X_mag.shape[2] != nfft // 2 + 1 or X_mag.dtype != torch.float32:
+    raise ValueError()
+  b, frames, bins = X_mag.shape
+  mag = X_mag.abs().contiguous()
+  if init_phase is None:
+    init_phase = 2 * np.pi * torch.rand(mag.shape, device=mag.device, generator=generator)
+  x = istft_tf(torch.polar(mag, init_phase.to(torch.float32)), nfft, nhop)
+  if frames == 0:
+    return x
+  win, tw = _Consts.stft(nfft, nhop, mag.device)
+  fr = torch.empty((b, frames, nfft), dtype=torch.float32, device=mag.device)
+  for _ in range(ngl):
+    N.call('advoc_griffin_lim_iter_f32', _ptr(x), x.shape[1], _ptr(mag), b, frames, nfft, nhop,
+           _ptr(win), _ptr(tw), _ptr(fr), _stream())
+    N.call('advoc_overlap_add_f32', _ptr(fr), b, frames, nfft, nhop, _ptr(x), _stream())
+  return x
+
+
+def magspec_to_waveform_griffin_lim(X_mag, nfft, nhop, ngl=60, init_phase=None):
+  """X_mag [frames, bins, 1] -> f32 [n, 1, 1].  reference: advoc/spectral.py:294-311."""
+  nsamps, nbins, nch = X_mag.shape
+  if nch != 1:
+    raise NotImplementedError('Can only invert monaural signals')
+  dev = _device()
+  mag = torch.from_numpy(np.ascontiguousarray(np.abs(X_mag[:, :, 0]), dtype=np.float32)).to(dev)[None]
+  ph = None
+  if init_phase is not None:
+    ph = torch.from_numpy(np.ascontiguousarray(init_phase, dtype=np.float32)).to(dev)[None]
+  x = griffin_lim_tf(mag, nfft, nhop, ngl=ngl, init_phase=ph)
+  return x[0].cpu().numpy()[:, np.newaxis, np.newaxis].astype(np.float32)
+
+
+def magspec_to_waveform_lws(X_mag, nfft, nhop):
+  """reference: advoc/spectral.py:314-326 (`lws.run_lws`, mode='speech').  The LWS phase
+  reconstruction lives in the third-party `lws` C++ package whose source is not part of the
+  reference and whose goldens cannot be reproduced here, so it is not restated; use
+  `magspec_to_waveform_griffin_lim` / phase_estimation='gl60'."""
+  nsamps, nbins, nch = X_mag.shape
+  if nch != 1:
+    raise NotImplementedError('Can only invert monaural signals')
+  raise NotImplementedError('LWS phase reconstruction is not available; use phase_estimation="gl60"')
+
+
+def melspec_to_waveform(X_mel_dbnorm, fs, nfft, nhop, mel_min=125, mel_max=7600,
+                        norm_min_level_db=-100, norm_ref_level_db=20, phase_estimation='lws',
+                        waveform_len=None):
+  """dB-normalised mel f64 [frames, mels, 1] -> waveform f32 [n, 1, 1]: dB de-normalise, pinv mel
+  (one fused kernel), clamp at 0, phase estimation.  reference: advoc/spectral.py:330-395."""
+  if X_mel_dbnorm.dtype != np.float64:
+    raise ValueError()
+  nsamps, mel_num_bins, nch = X_mel_dbnorm.shape
+  if nch != 1:
+    raise NotImplementedError('Can only invert monaural signals')
+  if phase_estimation != 'lws':
+    if phase_estimation[:2] != 'gl':
+      raise ValueError()
+    try:
+      ngl = int(phase_estimation[2:])
+    except Exception:
+      raise ValueError()
+  if norm_min_level_db != -100 or norm_ref_level_db != 20:
+    raise NotImplementedError('only the reference default dB normalisation is fused')
+  dev = _device()
+  inv = _Consts.inv_mel(fs, nfft, mel_min, mel_max, mel_num_bins, dev)
+  mel = torch.from_numpy(np.ascontiguousarray(X_mel_dbnorm[:, :, 0], dtype=np.float32)).to(dev)
+  X_mag = torch.clamp_min(matmul_lastdim(mel, inv, pow10_scale=True), 0.)
+  if phase_estimation == 'lws':
+    x = magspec_to_waveform_lws(X_mag.cpu().numpy()[:, :, np.newaxis], nfft, nhop)
+  else:
+    x = griffin_lim_tf(X_mag[None], nfft, nhop, ngl=ngl)[0].cpu().numpy()[:, np.newaxis, np.newaxis]
+  if waveform_len is not None:
+    x_len = x.shape[0]
+    if x_len < waveform_len:
+      x = np.pad(x, [[0, waveform_len - x_len], [0, 0], [0, 0]], 'constant')
+    elif x_len > waveform_len:
+      x = x[:waveform_len]
+  return x.astype(np.float32)
+
+
+def r9y9_melspec_to_waveform(X_mel_dbnorm, fs=22050, phase_estimation='lws', waveform_len=None):
+  """reference: advoc/spectral.py:398-420."""
+  return melspec_to_waveform(X_mel_dbnorm, fs=fs, nfft=1024, nhop=256,
+                             phase_estimation=phase_estimation, waveform_len=waveform_len)

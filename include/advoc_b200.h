@@ -108,6 +108,25 @@ ADVOC_API int advoc_mel_ranges(const float* d_mel_fb, int nmels, int bins, int* 
 ADVOC_API int advoc_matmul_lastdim_f32(const float* d_x, const float* d_w, float* d_y, long rows, int K,
                              int N, int pow10_scale, void* stream);
 
+/* Spectrogram inversion ("next" rows of SURVEY.md section 8(f)).  lws istft with
+ * perfectrec=False: out = overlap-add( irfft(X[m]) * window ), length (frames-1)*hop + nfft.
+ * Step 1: windowed inverse frames, d_spec_c64 [batch, frames, nfft/2+1] interleaved (re,im) ->
+ * d_frames [batch, frames, nfft].  nfft must be a power of two.
+ * replaces: lws istft, advoc/spectral.py:303,307,322. */
+ADVOC_API int advoc_istft_frames_f32(const float* d_spec_c64, int batch, int frames, int nfft, int nhop,
+                                     const float* d_window, const float* d_twiddle, float* d_frames,
+                                     void* stream);
+/* Step 2: atomics-free overlap-add, d_out [batch, (frames-1)*nhop + nfft]. */
+ADVOC_API int advoc_overlap_add_f32(const float* d_frames, int batch, int frames, int nfft, int nhop,
+                                    float* d_out, void* stream);
+/* One Griffin-Lim iteration fused in one kernel: S = stft(d_wave); X = d_mag * S/|S|; windowed
+ * inverse frames of X -> d_frames (follow with advoc_overlap_add_f32 to get the next estimate).
+ * d_wave [batch, nwave], nwave == (frames-1)*nhop + nfft; d_mag [batch, frames, nfft/2+1].
+ * replaces: the loop body of advoc/spectral.py:304-307. */
+ADVOC_API int advoc_griffin_lim_iter_f32(const float* d_wave, long nwave, const float* d_mag, int batch,
+                                         int frames, int nfft, int nhop, const float* d_window,
+                                         const float* d_twiddle, float* d_frames, void* stream);
+
 /* ------------------------------------------------------------------------- *
  * Convolution stacks
  * ------------------------------------------------------------------------- */
