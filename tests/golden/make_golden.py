@@ -2,6 +2,7 @@
 /root/reference does not exist on the GPU box).
 
   sc09.wav               <- /root/reference/tests/audio/sc09.wav (byte copy, test data)
+  mono.wav               <- /root/reference/tests/audio/mono.wav (byte copy, test data)
   mono_22k_r9y9_mel.npy  <- /root/reference/tests/audio/mono_22k_r9y9.pkl (pickle -> npy)
 """
 import os
@@ -15,6 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 if __name__ == '__main__':
   shutil.copyfile(os.path.join(REF, 'sc09.wav'), os.path.join(HERE, 'sc09.wav'))
+  shutil.copyfile(os.path.join(REF, 'mono.wav'), os.path.join(HERE, 'mono.wav'))
   with open(os.path.join(REF, 'mono_22k_r9y9.pkl'), 'rb') as f:
     mel = pickle.load(f, encoding='latin1')
   np.save(os.path.join(HERE, 'mono_22k_r9y9_mel.npy'), np.asarray(mel, dtype=np.float64))

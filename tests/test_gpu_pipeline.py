@@ -1,0 +1,124 @@
+"""GPU tests of the pieces around the nets: loader extract stage, batched inference with the
+reference's pad/trim rule, checkpoints, the CLI entry points, and data-parallel equivalence."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _rel(a, b):
+  a = torch.as_tensor(a).detach().double().cpu()
+  b = torch.as_tensor(b).detach().double().cpu()
+  return float((a - b).norm() / b.norm().clamp_min(1e-300))
+
+
+def test_loader_extract_slices_follow_reference_framing():
+  # advoc/loader.py:133-186 semantics on the magnitude STFT of a whole file
+  from advoc_b200 import loader
+  from oracle import spectral_np as O
+  rng = np.random.RandomState(0)
+  wav = rng.uniform(-1, 1, (100000, 1, 1)).astype(np.float32)
+  mag = O.magspec_f32(wav[np.newaxis], 1024, 256)[0]                 # [391, 513, 1]
+  s = loader.extract_magspec_slices(wav, slice_len=256, slice_overlap_ratio=0.25)
+  hop = 192
+  n = -(-391 // hop)
+  assert s.shape == (n, 256, 513, 1)
+  ref = np.zeros(((n - 1) * hop + 256, 513, 1), np.float32)
+  ref[:391] = mag
+  for i in range(n):
+    assert _rel(s[i], ref[i * hop:i * hop + 256]) < 1e-4
+  s2 = loader.extract_magspec_slices(wav, slice_len=256, slice_overlap_ratio=0., slice_pad_end=False)
+  assert s2.shape == (1, 256, 513, 1)
+  assert loader.extract_magspec_slices(wav, slice_first_only=True).shape[0] == 1
+  with pytest.raises(ValueError):
+    loader.extract_magspec_slices(wav, slice_overlap_ratio=1.0)
+  assert len(list(loader.batches(s, 2))) == n // 2
+
+
+def test_batched_inference_pad_and_trim_rule(golden_dir):
+  # scripts/spectrogram_advoc.py:80-95: pad to floor(T/256)*256 + 256 frames in the MAGNITUDE
+  # domain, run 256-frame chunks, concatenate, trim -- here as one batched forward
+  from advoc_b200 import infer
+  from advoc_b200.model import AdvocSmall, Modes
+  from oracle import nets_torch as O
+  from oracle import spectral_np as OS
+  P = O.init_params(O.SMALL, seed=0)
+  model = AdvocSmall(Modes.INFER, params={k: v.cuda() for k, v in P.items()})
+  mel = np.load(os.path.join(golden_dir, 'mono_22k_r9y9_mel.npy')).T.copy()        # [325, 80]
+  got = infer.mel_to_mag(model, mel.astype(np.float32), input_kind='dbnorm', dropout=None)
+  assert got.shape == (325, 513)
+  Winv = OS.create_inverse_mel_filterbank(22050, 1024, fmin=125., fmax=7600., n_mels=80)
+  X = OS.tacotron_mel_to_mag(mel, Winv).astype(np.float32)
+  X = np.pad(X, ([0, 512 - 325], [0, 0]), 'constant').reshape(2, 256, 513, 1)
+  ref = O.generator(P, torch.from_numpy(X), O.SMALL).reshape(512, 513)[:325]
+  assert _rel(got, ref) < 1e-3
+
+
+def test_checkpoint_roundtrip_and_cli(tmp_path, golden_dir):
+  from advoc_b200 import checkpoint, nets
+  P = nets.init_params(32, 32, 5, seed=3)
+  ck = str(tmp_path / 'model.npz')
+  checkpoint.save_params(ck, P, step=123)
+  Q, step = checkpoint.load_params(ck)
+  assert step == 123 and sorted(Q) == sorted(P)
+  assert all(torch.equal(P[k], Q[k]) for k in P)
+  assert checkpoint.infer_model_type(Q) == 'small'
+  # the inference entry point, with and without a checkpoint
+  spec_dir, out_dir = tmp_path / 'specs', tmp_path / 'wavs'
+  spec_dir.mkdir()
+  mel = np.load(os.path.join(golden_dir, 'mono_22k_r9y9_mel.npy')).T[:100, :, np.newaxis]
+  np.save(str(spec_dir / 'utt.npy'), mel)
+  for extra in ([], ['--model_ckpt', ck, '--meta_fp', 'ignored.meta']):
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'scripts', 'spectrogram_advoc.py'),
+                        '--spec_dir', str(spec_dir), '--out_dir', str(out_dir), '--ngl', '3'] + extra,
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, universal_newlines=True)
+    assert r.returncode == 0, r.stdout
+    from scipy.io import wavfile
+    fs, w = wavfile.read(str(out_dir / 'utt.wav'))
+    assert fs == 22050 and w.dtype == np.int16 and w.shape == (99 * 256 + 1024,)
+  # wav -> mel CLI
+  wdir, sdir = tmp_path / 'w', tmp_path / 's'
+  wdir.mkdir()
+  import shutil
+  shutil.copyfile(os.path.join(golden_dir, 'sc09.wav'), str(wdir / 'a.wav'))
+  r = subprocess.run([sys.executable, os.path.join(ROOT, 'scripts', 'audio_to_spectrogram.py'),
+                      '--wave_dir', str(wdir), '--out_dir', str(sdir), '--data_fast_wav'],
+                     stdout=subprocess.PIPE, stderr=subprocess.STDOUT, universal_newlines=True)
+  assert r.returncode == 0, r.stdout
+  m = np.load(str(sdir / 'a.npy'))
+  assert m.shape == (63, 80, 1) and m.dtype == np.float64 and 0 <= m.min() and m.max() <= 1
+
+
+def test_data_parallel_gradient_equivalence():
+  """the mean of per-rank gradients over equal shards == the gradient of the
+  global batch.  Emulated on one GPU: two engines on the two halves (summed, x 1/2) vs one engine
+  on the whole batch, exact-fp32 math, injected dropout masks."""
+  from advoc_b200 import _native as N
+  from advoc_b200 import nets
+  from advoc_b200.train import TrainEngine
+  P = nets.init_params(32, 32, 5, seed=0)
+  spec = nets.GenSpec(32, 5, (5, 4))
+  g = torch.Generator().manual_seed(0)
+  target = (torch.randn(2, 256, 513, 1, generator=g).abs() * 0.1).cuda()
+  x = (target + torch.randn(2, 256, 513, 1, generator=g).cuda() * 0.02)
+  full = TrainEngine(spec, 32, {k: v.clone() for k, v in P.items()}, 2, math=N.MATH_FP32)
+  masks = {k: (torch.rand(full.G.dropout_shape(k), generator=g) < 0.5).to(torch.uint8).cuda()
+           for k in (5, 4)}
+  halves = [TrainEngine(spec, 32, {k: v.clone() for k, v in P.items()}, 1, math=N.MATH_FP32)
+            for _ in range(2)]
+  for step in ('d_step', 'g_step'):
+    getattr(full, step)(x, target, dropout=masks, apply=False)
+    acc = None
+    for r, eng in enumerate(halves):
+      m = {k: v[r:r + 1].contiguous() for k, v in masks.items()}
+      getattr(eng, step)(x[r:r + 1].contiguous(), target[r:r + 1].contiguous(), dropout=m, apply=False)
+      acc = eng.flat.g.clone() if acc is None else acc + eng.flat.g
+    lo, hi = full.flat.dis_range() if step == 'd_step' else full.flat.gen_range()
+    assert _rel(acc[lo:hi] * 0.5, full.flat.g[lo:hi]) < 1e-4
