@@ -70,6 +70,10 @@ int conv_fwd_tc(const advoc_conv_desc* d, const float* x, int ldx, const float* 
                 const advoc_epilogue* ep, void* stream);
 int conv_transposed_tc(const advoc_conv_desc* d, const float* x, int ldx, const float* w,
                        const advoc_epilogue* ep, void* stream);
+bool conv_transposed_patch_eligible(const advoc_conv_desc* d, int ldx, int store_w);
+int conv_transposed_patch(const advoc_conv_desc* d, const float* x, int ldx, const float* w,
+                          const advoc_epilogue* ep, void* stream);
+bool tc_epilogue_ok(const advoc_epilogue* ep);
 
 }  // namespace advoc
 
@@ -133,6 +137,12 @@ extern "C" int advoc_conv2d_transpose_fwd(const advoc_conv_desc* d, const float*
   const bool ok = conv_transposed_tc_eligible(d, ld_x);
   if (d->math == ADVOC_MATH_TF32 || ok) {
     ADVOC_REQUIRE(ok, ADVOC_UNSUPPORTED, "conv_transpose shape not eligible for the tcgen05 path");
+    if (conv_transposed_patch_eligible(d, ld_x, ep->store_w)) {
+      ADVOC_REQUIRE(aligned16(d_x) && aligned16(d_w), ADVOC_BAD_ALIGN, "x / w must be 16-byte aligned");
+      ADVOC_REQUIRE(tc_epilogue_ok(ep), ADVOC_BAD_ALIGN,
+                    "tcgen05 path needs 16-byte aligned outputs with ld and channel offset multiples of 4");
+      return conv_transposed_patch(d, d_x, ld_x, d_w, ep, stream);
+    }
     return conv_transposed_tc(d, d_x, ld_x, d_w, ep, stream);
   }
   return conv_transposed_simt(d, d_x, ld_x, d_w, ep, stream);

@@ -333,6 +333,8 @@ bool epilogue_vector_ok(const advoc_epilogue* ep) {
 
 }  // namespace
 
+bool tc_epilogue_ok(const advoc_epilogue* ep) { return epilogue_vector_ok(ep); }
+
 bool conv_fwd_tc_eligible(const advoc_conv_desc* d, int ldx) {
   return common_eligible(d->Cin, d->Cout, ldx) && d->kh * d->kw <= MAX_TAPS && d->pad_t <= 127 && d->pad_l <= 127;
 }
