@@ -70,9 +70,9 @@ int conv_fwd_tc(const advoc_conv_desc* d, const float* x, int ldx, const float* 
                 const advoc_epilogue* ep, void* stream);
 int conv_transposed_tc(const advoc_conv_desc* d, const float* x, int ldx, const float* w,
                        const advoc_epilogue* ep, void* stream);
-bool conv_transposed_patch_eligible(const advoc_conv_desc* d, int ldx, int store_w);
-int conv_transposed_patch(const advoc_conv_desc* d, const float* x, int ldx, const float* w,
-                          const advoc_epilogue* ep, void* stream);
+bool conv_p2d_eligible(const advoc_conv_desc* d, int ldx, int transposed, int store_w);
+int conv_p2d(const advoc_conv_desc* d, int transposed, const float* x, int ldx, const float* w,
+             const advoc_epilogue* ep, void* stream);
 bool tc_epilogue_ok(const advoc_epilogue* ep);
 
 }  // namespace advoc
@@ -123,6 +123,12 @@ extern "C" int advoc_conv2d_fwd(const advoc_conv_desc* d, const float* d_x, int 
   const bool ok = conv_fwd_tc_eligible(d, ld_x);
   if (d->math == ADVOC_MATH_TF32 || ok) {
     ADVOC_REQUIRE(ok, ADVOC_UNSUPPORTED, "conv shape not eligible for the tcgen05 path");
+    if (conv_p2d_eligible(d, ld_x, 0, 0)) {
+      ADVOC_REQUIRE(aligned16(d_x) && aligned16(d_w), ADVOC_BAD_ALIGN, "x / w must be 16-byte aligned");
+      ADVOC_REQUIRE(tc_epilogue_ok(ep), ADVOC_BAD_ALIGN,
+                    "tcgen05 path needs 16-byte aligned outputs with ld and channel offset multiples of 4");
+      return conv_p2d(d, 0, d_x, ld_x, d_w, ep, stream);
+    }
     return conv_fwd_tc(d, d_x, ld_x, d_w, ep, stream);
   }
   return conv_fwd_simt(d, d_x, ld_x, d_w, ep, stream);
@@ -137,11 +143,11 @@ extern "C" int advoc_conv2d_transpose_fwd(const advoc_conv_desc* d, const float*
   const bool ok = conv_transposed_tc_eligible(d, ld_x);
   if (d->math == ADVOC_MATH_TF32 || ok) {
     ADVOC_REQUIRE(ok, ADVOC_UNSUPPORTED, "conv_transpose shape not eligible for the tcgen05 path");
-    if (conv_transposed_patch_eligible(d, ld_x, ep->store_w)) {
+    if (conv_p2d_eligible(d, ld_x, 1, ep->store_w)) {
       ADVOC_REQUIRE(aligned16(d_x) && aligned16(d_w), ADVOC_BAD_ALIGN, "x / w must be 16-byte aligned");
       ADVOC_REQUIRE(tc_epilogue_ok(ep), ADVOC_BAD_ALIGN,
                     "tcgen05 path needs 16-byte aligned outputs with ld and channel offset multiples of 4");
-      return conv_transposed_patch(d, d_x, ld_x, d_w, ep, stream);
+      return conv_p2d(d, 1, d_x, ld_x, d_w, ep, stream);
     }
     return conv_transposed_tc(d, d_x, ld_x, d_w, ep, stream);
   }

@@ -48,6 +48,21 @@ __device__ __forceinline__ float round_tf32(float x) {
   return __uint_as_float(r);
 }
 
+// none / lrelu / relu as straight-line code: y = max(max(v, slope*v), floor).  The generic
+// apply_act() switch below gets if-converted by the compiler (tanhf and expf evaluated for every
+// element and then selected), which made the conv epilogues instruction-bound.
+struct ActLin {
+  float slope, floor;
+};
+__device__ __forceinline__ bool act_is_linear(int act) { return act < ADVOC_ACT_SIGMOID; }
+__device__ __forceinline__ ActLin act_linear(int act, float alpha) {
+  ActLin a;
+  a.slope = act == ADVOC_ACT_LRELU ? alpha : 1.f;
+  a.floor = act == ADVOC_ACT_RELU ? 0.f : __int_as_float(0xff800000);   // -inf
+  return a;
+}
+__device__ __forceinline__ float apply_lin(float v, const ActLin& a) { return fmaxf(fmaxf(v, a.slope * v), a.floor); }
+
 __device__ __forceinline__ float apply_act(float v, int act, float alpha) {
   switch (act) {
     case ADVOC_ACT_LRELU: return fmaxf(alpha * v, v);

@@ -1,0 +1,772 @@
+// Persistent tcgen05 convolution / transposed convolution over 2-D shared-memory PATCHES (sm_100a,
+// TF32 operands, fp32 accumulators in TMEM).
+//
+// conv_tc.cu re-fetches the im2col operand from L2 once per filter tap (16x for k4) and runs one
+// output tile per CTA with no overlap between tiles; ncu shows it bound by neither DRAM, L2 nor the
+// tensor pipe (profiles/r01b_*).  Here:
+//   * the CTA is persistent (grid = #SMs, tiles strided over CTAs); TMA producers, the MMA issuer and
+//     the epilogue warps run decoupled through mbarrier rings, and the accumulator is double-buffered
+//     in TMEM whenever it fits, so tile i's epilogue overlaps tile i+1's main loop;
+//   * the activation operand of a tile is ONE tiled-mode TMA box per 32-channel block and input
+//     "plane": a (th + halo) x (tw + halo) patch of pixels, zero-filled outside the image by TMA.
+//     GEMM row m = r*PW + c is patch position (r, c); every filter tap is the same patch seen through
+//     a UMMA descriptor whose start address is advanced by (dr*PW + dc) rows of 128 bytes (the 128B
+//     swizzle is a function of the absolute smem address, so a row-shifted view de-swizzles
+//     correctly; probed on B200 by csrc/selftest.cu);
+//   * stride-s convolution: the input is split into s*s parity planes (one strided tensor map each),
+//     tap (kh, kw) reads plane ((kh-pad) mod s, (kw-pad) mod s) at unit shift floor((k-pad)/s);
+//   * stride-s transposed convolution: the s*s output parity classes of a position share the patch
+//     and accumulate side by side in TMEM (class z in columns [z*BN, z*BN+BN)); each class sees a
+//     dense sub-filter, no MAC is spent on inserted zeros.
+// Patch traffic is ~1.3-1.6x the activation bytes instead of 16x; filter tiles stream through their
+// own ring, or stay resident in smem when the whole filter of the layer fits.
+//
+// replaces: tf.layers.conv2d / conv2d_transpose (models/advoc/advoc_model.py:27-32,46-51,65-69) and,
+// in the backward pass, their input gradients.
+#include "epilogue.cuh"
+#include "tc_ptx.cuh"
+
+#include <stdlib.h>
+
+namespace advoc {
+
+int lower_epilogue(const advoc_epilogue* ep, int Hs, int Wfull, int Cout, EpiDev* out);
+
+namespace {
+
+using namespace tc;
+
+constexpr int QM = 128;         // UMMA_M: patch positions per tile
+constexpr int QK = 32;          // channels per k-block (one 128-byte swizzle row)
+constexpr int Q_MAXT = 36;      // filter taps
+constexpr int Q_MAXP = 4;       // input planes
+constexpr int Q_MAXC = 4;       // output parity classes
+constexpr int Q_MAXA = 8;       // patch ring depth
+constexpr int Q_MAXB = 32;      // filter-tile ring depth
+constexpr int Q_THREADS = 224;  // warp 0 patch producer, 1 MMA issuer, 2 filter producer, 3-6 epilogue
+constexpr size_t Q_SMEM_BUDGET = 216 * 1024;   // operand rings + output staging
+constexpr uint32_t Q_STAGE_BYTES = QM * 128;   // one staged output chunk: <=128 pixels x 32 channels
+
+struct alignas(64) P2dParams {
+  CUtensorMap tmA[Q_MAXP];  // tiled 4-D {c, w, h, n}, box {32, PW, PH, 1}
+  CUtensorMap tmB;          // filter [taps * Cn][Ck], box {32, BN}
+  CUtensorMap tmO[2][Q_MAXC];  // output stores per destination and parity class, box {32, tw, th, 1}
+  int tma_store, n_out, stage_bufs;
+  uint32_t stage_off;
+  int nplanes, ntaps, ncls;
+  int plane_tap0[Q_MAXP + 1];  // taps are sorted by plane: plane p owns [plane_tap0[p], plane_tap0[p+1])
+  int plane_oh[Q_MAXP], plane_ow[Q_MAXP];  // patch origin relative to the tile origin (plane coordinates)
+  unsigned char tap_cls[Q_MAXT];
+  unsigned short tap_wrow[Q_MAXT];   // row block of the filter matrix
+  unsigned short tap_shift[Q_MAXT];  // rows from the patch start
+  int cls_ph[Q_MAXC], cls_pw[Q_MAXC];
+  int PW, PH, th, tw;          // patch box and useful tile extent (positions)
+  int tiles_h, tiles_w, n_ntiles;
+  long total_tiles;
+  int Hc, Wc;                  // position grid per image
+  int osh, osw;                // output pixel = position * os + class offset
+  int Cn, kblocks;
+  uint32_t a_slot_bytes, a_box_bytes, tmem_cols;
+  int a_stages, b_stages, acc_bufs, b_resident;
+  int exp_flags;               // timing experiments (ADVOC_P2D_EXP): 1 skip staging stores, 2 skip epilogue math
+  int G;                       // filter taps per ring slot (one barrier pair per group; divides every plane's tap count)
+  EpiDev epi;
+  unsigned int* dbg;
+  unsigned long long* prof;   // optional [gridDim.x][16] cycle counters (ADVOC_P2D_PROFILE)
+};
+
+// profiling wait: like mbar_wait, adds the stalled cycles to `acc` when profiling
+__device__ __forceinline__ void mbar_wait_p(uint64_t* bar, uint32_t parity, unsigned int* dbg, unsigned code,
+                                            const unsigned long long* prof, unsigned long long& acc) {
+  if (prof == nullptr) { mbar_wait(bar, parity, dbg, code); return; }
+  const long long t0 = clock64();
+  mbar_wait(bar, parity, dbg, code);
+  acc += (unsigned long long)(clock64() - t0);
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, uint32_t src, int c, int w, int h, int n) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tm)),
+               "r"(src), "r"(c), "r"(w), "r"(h), "r"(n)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// One staged chunk: 32 accumulator columns of this thread's pixel -> bias, dropout, activation(s),
+// TF32 rounding -> swizzled staging row(s).  kLin: both activations are none / relu / lrelu.
+template <bool kLin, bool kDrop>
+__device__ __forceinline__ void stage_chunk(const EpiDev& e, const uint32_t (&v)[32], const float4 (&bias4)[8],
+                                            uint32_t dst_row, uint32_t sx, int n_out, size_t idx0) {
+  const ActLin a0 = act_linear(e.act0, e.alpha), a1 = act_linear(e.act1, e.alpha);
+  const float inv_keep = 1.f / e.keep_prob;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float x[4] = {__uint_as_float(v[4 * j]) + bias4[j].x, __uint_as_float(v[4 * j + 1]) + bias4[j].y,
+                        __uint_as_float(v[4 * j + 2]) + bias4[j].z, __uint_as_float(v[4 * j + 3]) + bias4[j].w};
+    float sc[4] = {1.f, 1.f, 1.f, 1.f};
+    if (kDrop) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const size_t idx = idx0 + 4 * j + u;
+        const bool keep = e.mask ? (__ldg(e.mask + idx) != 0) : dropout_keep(e.seed, idx, e.keep_prob);
+        sc[u] = keep ? inv_keep : 0.f;
+      }
+    }
+    float y[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      y[u] = (kLin ? apply_lin(x[u], a0) : apply_act(x[u], e.act0, e.alpha)) * sc[u];
+      if (e.round) y[u] = round_tf32(y[u]);
+    }
+    const uint32_t dst = dst_row + (((uint32_t)j ^ sx) << 4);
+    st_shared_v4(dst, y[0], y[1], y[2], y[3]);
+    if (n_out == 2) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        y[u] = (kLin ? apply_lin(x[u], a1) : apply_act(x[u], e.act1, e.alpha)) * sc[u];
+        if (e.round) y[u] = round_tf32(y[u]);
+      }
+      st_shared_v4(dst + Q_STAGE_BYTES, y[0], y[1], y[2], y[3]);
+    }
+  }
+}
+
+struct TileCoord {
+  int n_tile, img, h0, w0;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const P2dParams& p, long t) {
+  TileCoord c;
+  c.n_tile = (int)(t % p.n_ntiles);
+  long s = t / p.n_ntiles;
+  c.w0 = (int)(s % p.tiles_w) * p.tw;
+  s /= p.tiles_w;
+  c.h0 = (int)(s % p.tiles_h) * p.th;
+  c.img = (int)(s / p.tiles_h);
+  return c;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(Q_THREADS, 1) conv_p2d_kernel(const __grid_constant__ P2dParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t a_full[Q_MAXA], a_empty[Q_MAXA];
+  __shared__ __align__(8) uint64_t b_full[Q_MAXB], b_empty[Q_MAXB];
+  __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_base_holder;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* ring_ptr = smem_raw + (ring - smem_u32(smem_raw));
+  const uint32_t b_off = (uint32_t)p.a_stages * p.a_slot_bytes;
+  constexpr uint32_t B_BYTES = BN * 128;
+  const uint32_t acc_cols = (uint32_t)p.ncls * BN;
+  const long ntl = p.total_tiles;
+  __shared__ uint32_t s_tap[Q_MAXT];   // (cls << 24) | byte offset of the tap's view into the patch
+  if (threadIdx.x < p.ntaps)
+    s_tap[threadIdx.x] = ((uint32_t)p.tap_cls[threadIdx.x] << 24) | ((uint32_t)p.tap_shift[threadIdx.x] * 128u);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.a_stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < p.b_stages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < p.nplanes; ++i) prefetch_tmap(&p.tmA[i]);
+    prefetch_tmap(&p.tmB);
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(&tmem_base_holder)),
+                 "r"(p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_holder;
+  const bool aborted = p.dbg && *reinterpret_cast<volatile unsigned int*>(p.dbg) != 0;
+
+  if (aborted) {
+    // a previous launch timed out: do nothing
+  } else if (warp == 0) {
+    // ===== patch producer: warp-uniform loop, TMA issued by one elected lane =====
+    int as = 0;
+    uint32_t aph = 0;
+    unsigned long long w_a = 0;
+    const long long t_start = clock64();
+    for (long t = blockIdx.x; t < ntl; t += gridDim.x) {
+      const TileCoord tc_ = decode_tile(p, t);
+      for (int kb = 0; kb < p.kblocks; ++kb) {
+        for (int pl = 0; pl < p.nplanes; ++pl) {
+          mbar_wait_p(&a_empty[as], aph ^ 1u, p.dbg, 31u, p.prof, w_a);
+          __syncwarp();
+          if (elect_one()) {
+            mbar_expect_tx(&a_full[as], p.a_box_bytes);
+            tma_load_4d(&p.tmA[pl], &a_full[as], ring_ptr + (size_t)as * p.a_slot_bytes, kb * QK,
+                        tc_.w0 + p.plane_ow[pl], tc_.h0 + p.plane_oh[pl], tc_.img);
+          }
+          __syncwarp();
+          if (++as == p.a_stages) { as = 0; aph ^= 1u; }
+        }
+      }
+    }
+    if (p.prof && lane == 0) {
+      p.prof[blockIdx.x * 16 + 0] = (unsigned long long)(clock64() - t_start);
+      p.prof[blockIdx.x * 16 + 1] = w_a;
+    }
+  } else if (warp == 2) {
+    // ===== filter producer: one ring slot = G consecutive taps (G loads, one barrier) =====
+    const int G = p.G;
+    const uint32_t slot_bytes = (uint32_t)G * B_BYTES;
+    if (p.b_resident) {
+      if ((long)blockIdx.x < ntl) {
+        // everything once: lane l loads tap tile l, l+32, ... of slot (kb, group)
+        const int ngroups = p.ntaps / G;
+        for (int s = 0; s < p.kblocks * ngroups; ++s) {
+          const int kb = s / ngroups, g = s - kb * ngroups;
+          if (lane == 0) mbar_expect_tx(&b_full[s], slot_bytes);
+          __syncwarp();
+          if (lane < G)
+            tma_load_2d(&p.tmB, &b_full[s], ring_ptr + b_off + (size_t)s * slot_bytes + (size_t)lane * B_BYTES, kb * QK,
+                        (int)p.tap_wrow[g * G + lane] * p.Cn);
+        }
+      }
+    } else {
+      int bs = 0;
+      uint32_t bph = 0;
+      unsigned long long w_b = 0;
+      const long long t_start = clock64();
+      for (long t = blockIdx.x; t < ntl; t += gridDim.x) {
+        const int n0 = (int)(t % p.n_ntiles) * BN;
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          for (int t0 = 0; t0 < p.ntaps; t0 += G) {
+            mbar_wait_p(&b_empty[bs], bph ^ 1u, p.dbg, 32u, p.prof, w_b);
+            if (lane == 0) mbar_expect_tx(&b_full[bs], slot_bytes);
+            __syncwarp();
+            if (lane < G)
+              tma_load_2d(&p.tmB, &b_full[bs], ring_ptr + b_off + (size_t)bs * slot_bytes + (size_t)lane * B_BYTES,
+                          kb * QK, (int)p.tap_wrow[t0 + lane] * p.Cn + n0);
+            __syncwarp();
+            if (++bs == p.b_stages) { bs = 0; bph ^= 1u; }
+          }
+        }
+      }
+      if (p.prof && lane == 0) {
+        p.prof[blockIdx.x * 16 + 2] = (unsigned long long)(clock64() - t_start);
+        p.prof[blockIdx.x * 16 + 3] = w_b;
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: warp-uniform loop; the tcgen05.mma / commit instructions of one filter group
+    // are issued back to back by one elected lane (descriptors in uniform registers, see elect_one) =====
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                               ((uint32_t)(QM >> 4) << 24);
+    const int G = p.G;
+    const uint32_t slot_bytes = (uint32_t)G * B_BYTES;
+    const int ngroups = p.ntaps / G;
+    int as = 0, bs = 0;
+    uint32_t aph = 0, bph = 0;
+    long i = 0;
+    unsigned long long w_acc = 0, w_a = 0, w_b = 0;
+    const long long t_start = clock64();
+    for (long t = blockIdx.x; t < ntl; t += gridDim.x, ++i) {
+      const int buf = (int)(i % p.acc_bufs);
+      const uint32_t use = (uint32_t)(i / p.acc_bufs);
+      mbar_wait_p(&acc_empty[buf], (use & 1u) ^ 1u, p.dbg, 33u, p.prof, w_acc);
+      tc_fence_after();
+      const uint32_t d_base = tmem_base + (uint32_t)buf * acc_cols;
+      uint32_t started = 0;
+      for (int kb = 0; kb < p.kblocks; ++kb) {
+        int tp = 0;
+        for (int pl = 0; pl < p.nplanes; ++pl) {
+          mbar_wait_p(&a_full[as], aph, p.dbg, 34u, p.prof, w_a);
+          const uint32_t a_addr = ring + (uint32_t)as * p.a_slot_bytes;
+          const int t_end = p.plane_tap0[pl + 1];
+          for (; tp < t_end; tp += G) {
+            uint32_t b_addr;
+            if (p.b_resident) {
+              const int slot = kb * ngroups + tp / G;
+              if (i == 0) mbar_wait(&b_full[slot], 0u, p.dbg, 35u);
+              b_addr = ring + b_off + (uint32_t)slot * slot_bytes;
+            } else {
+              mbar_wait_p(&b_full[bs], bph, p.dbg, 35u, p.prof, w_b);
+              b_addr = ring + b_off + (uint32_t)bs * slot_bytes;
+            }
+            tc_fence_after();
+            const bool last_of_plane = tp + G >= t_end;
+            __syncwarp();
+            if (elect_one()) {
+              uint32_t st = started;
+              for (int u = 0; u < G; ++u) {
+                const uint32_t info = s_tap[tp + u];
+                const uint32_t cls = info >> 24;
+                const uint64_t da = make_smem_desc(a_addr + (info & 0xFFFFFFu));
+                const uint64_t db = make_smem_desc(b_addr + (uint32_t)u * B_BYTES);
+                const uint32_t d_tmem = d_base + cls * BN;
+                const uint32_t acc0 = (st >> cls) & 1u;
+                st |= 1u << cls;
+#pragma unroll
+                for (int k = 0; k < QK / 8; ++k)
+                  umma_tf32(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, acc0 | (uint32_t)(k != 0));
+              }
+              if (!p.b_resident) umma_commit(&b_empty[bs]);
+              if (last_of_plane) umma_commit(&a_empty[as]);
+            }
+            __syncwarp();
+            // every lane tracks `started` (the elected lane may differ between groups)
+            for (int u = 0; u < G; ++u) started |= 1u << (s_tap[tp + u] >> 24);
+            if (!p.b_resident) {
+              if (++bs == p.b_stages) { bs = 0; bph ^= 1u; }
+            }
+          }
+          if (++as == p.a_stages) { as = 0; aph ^= 1u; }
+        }
+      }
+      if (elect_one()) umma_commit(&acc_full[buf]);
+      __syncwarp();
+    }
+    if (p.prof && lane == 0) {
+      p.prof[blockIdx.x * 16 + 4] = (unsigned long long)(clock64() - t_start);
+      p.prof[blockIdx.x * 16 + 5] = w_acc;
+      p.prof[blockIdx.x * 16 + 6] = w_a;
+      p.prof[blockIdx.x * 16 + 7] = w_b;
+      p.prof[blockIdx.x * 16 + 8] = (unsigned long long)i;
+    }
+  } else {
+    // ===== epilogue: warp w may only touch TMEM lanes [32*(w%4), +32) =====
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int r = m / p.PW, c = m - r * p.PW;
+    const bool in_tile = r < p.th && c < p.tw;
+    const EpiDev& e = p.epi;
+    const bool issuer = warp == 3 && lane == 0;
+    // staging row of this position inside the dense {tw x th} store box; 16-byte chunk j of a row
+    // lives at chunk (j ^ row%8): the SWIZZLE_128B pattern the store tensor map expects, and
+    // conflict-free for the 8 rows of a quarter-warp
+    const uint32_t srow = (uint32_t)(r * p.tw + c);
+    const uint32_t s_row_addr = ring + p.stage_off + srow * 128u;
+    const uint32_t sx = srow & 7u;
+    const bool lin_acts = act_is_linear(e.act0) && act_is_linear(e.act1);
+    uint32_t chunk_ctr = 0;
+    long i = 0;
+    unsigned long long w_full = 0, w_bar = 0, w_ld = 0, w_math = 0, w_fence = 0, w_issue = 0;
+    const long long t_start = clock64();
+    for (long t = blockIdx.x; t < ntl; t += gridDim.x, ++i) {
+      const int buf = (int)(i % p.acc_bufs);
+      const uint32_t use = (uint32_t)(i / p.acc_bufs);
+      const TileCoord tc_ = decode_tile(p, t);
+      const int a = tc_.h0 + r, b = tc_.w0 + c;
+      const bool row_ok = in_tile && a < p.Hc && b < p.Wc;
+      const int n0 = tc_.n_tile * BN;
+      mbar_wait_p(&acc_full[buf], use & 1u, p.dbg, 36u, p.prof, w_full);
+      tc_fence_after();
+      const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * acc_cols;
+#pragma unroll 1
+      for (int z = 0; z < p.ncls; ++z) {
+        const int oh = a * p.osh + p.cls_ph[z], ow = b * p.osw + p.cls_pw[z];
+        const bool valid = row_ok && oh < e.Hs && ow < e.Ws;
+        const size_t pix = valid ? ((size_t)tc_.img * e.Hs + oh) * e.Ws + ow : 0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t v[32];
+          const long long tl0 = p.prof ? clock64() : 0;
+          tmem_ld32(t_base + (uint32_t)(z * BN + c0), v);
+          if (!p.tma_store) {
+            tmem_ld_wait();
+            if (valid) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                epi_store_vec4(e, pix, n0 + c0 + j,
+                               make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                           __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
+            }
+            continue;
+          }
+          // ---- staged path: registers -> swizzled smem -> one TMA store per destination ----
+          float4 bias4[8];
+          if (e.bias) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bias4[j] = __ldg(reinterpret_cast<const float4*>(e.bias + n0 + c0) + j);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bias4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          tmem_ld_wait();
+          if (p.prof) w_ld += (unsigned long long)(clock64() - tl0);
+          const uint32_t sbuf = (p.stage_bufs == 2 ? (chunk_ctr & 1u) : 0u) * (uint32_t)p.n_out * Q_STAGE_BYTES;
+          const long long tb0 = p.prof ? clock64() : 0;
+          if (issuer) {   // the store that last read this staging buffer is done with it
+            if (p.stage_bufs == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
+          }
+          epi_bar(1);
+          if (p.prof) w_bar += (unsigned long long)(clock64() - tb0);
+          const long long tm0 = p.prof ? clock64() : 0;
+          if (in_tile && !(p.exp_flags & 2)) {
+            const uint32_t dst_row = s_row_addr + sbuf;
+            const bool drop = e.keep_prob < 1.f && valid;
+            const size_t idx0 = pix * e.Cout + n0 + c0;
+            if (lin_acts) {
+              if (drop) stage_chunk<true, true>(e, v, bias4, dst_row, sx, p.n_out, idx0);
+              else stage_chunk<true, false>(e, v, bias4, dst_row, sx, p.n_out, idx0);
+            } else {
+              if (drop) stage_chunk<false, true>(e, v, bias4, dst_row, sx, p.n_out, idx0);
+              else stage_chunk<false, false>(e, v, bias4, dst_row, sx, p.n_out, idx0);
+            }
+          }
+          const long long tf0 = p.prof ? clock64() : 0;
+          if (p.prof) w_math += (unsigned long long)(tf0 - tm0);
+          fence_async_smem();
+          epi_bar(2);
+          const long long ti0 = p.prof ? clock64() : 0;
+          if (p.prof) w_fence += (unsigned long long)(ti0 - tf0);
+          if (issuer) {
+            tma_store_4d(&p.tmO[0][z], ring + p.stage_off + sbuf, n0 + c0, tc_.w0, tc_.h0, tc_.img);
+            if (p.n_out == 2)
+              tma_store_4d(&p.tmO[1][z], ring + p.stage_off + sbuf + Q_STAGE_BYTES, n0 + c0, tc_.w0, tc_.h0, tc_.img);
+            bulk_commit();
+          }
+          if (p.prof) w_issue += (unsigned long long)(clock64() - ti0);
+          ++chunk_ctr;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    }
+    if (issuer) bulk_wait_all();
+    if (p.prof && issuer) {
+      p.prof[blockIdx.x * 16 + 9] = (unsigned long long)(clock64() - t_start);
+      p.prof[blockIdx.x * 16 + 10] = w_full;
+      p.prof[blockIdx.x * 16 + 11] = w_bar;
+      p.prof[blockIdx.x * 16 + 12] = w_ld;
+      p.prof[blockIdx.x * 16 + 13] = w_math;
+      p.prof[blockIdx.x * 16 + 14] = w_fence;
+      p.prof[blockIdx.x * 16 + 15] = w_issue;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: geometry
+// ---------------------------------------------------------------------------------------------
+struct Plan {
+  P2dParams p;
+  int bn;
+  size_t smem;
+  double efficiency;  // useful positions / GEMM rows
+  // plane views of the contraction-side tensor
+  int plane_ph[Q_MAXP], plane_pw[Q_MAXP];
+  int plane_sh, plane_sw;
+};
+
+struct TapT { int plane, cls, wrow, fh, fw; };
+
+inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
+// transposed == false: y[N,Ho,Wo,Cout] = conv(x[N,H,W,Cin]);  Cn = Cout, Ck = Cin
+// transposed == true : y[N,H,Wstored,Cin] = conv_transpose(x[N,Ho,Wo,Cout]);  Cn = Cin, Ck = Cout
+bool make_plan(const advoc_conv_desc* d, bool transposed, int Wstored, int n_out, bool tma_store, Plan* pl) {
+  P2dParams& p = pl->p;
+  TapT taps[Q_MAXT];
+  int nt = 0, ncls = 0, nplanes = 0;
+  int smin_h[Q_MAXP], smax_h[Q_MAXP], smin_w[Q_MAXP], smax_w[Q_MAXP];
+  bool used[Q_MAXP] = {false, false, false, false};
+  int Hc, Wc;
+  if (!transposed) {
+    if (d->sh * d->sw > Q_MAXP || d->kh * d->kw > Q_MAXT) return false;
+    Hc = d->Ho; Wc = d->Wo;
+    ncls = 1;
+    p.cls_ph[0] = 0; p.cls_pw[0] = 0;
+    p.osh = 1; p.osw = 1;
+    pl->plane_sh = d->sh; pl->plane_sw = d->sw;
+    for (int kh = 0; kh < d->kh; ++kh) {
+      const int eh = kh - d->pad_t, ph = ((eh % d->sh) + d->sh) % d->sh, fh = floordiv(eh - ph, d->sh);
+      for (int kw = 0; kw < d->kw; ++kw) {
+        const int ew = kw - d->pad_l, pw = ((ew % d->sw) + d->sw) % d->sw, fw = floordiv(ew - pw, d->sw);
+        taps[nt++] = {ph * d->sw + pw, 0, kh * d->kw + kw, fh, fw};
+      }
+    }
+  } else {
+    if (d->sh * d->sw > Q_MAXC || d->kh * d->kw > Q_MAXT) return false;
+    Hc = (d->H + d->sh - 1) / d->sh;
+    Wc = (Wstored + d->sw - 1) / d->sw;
+    p.osh = d->sh; p.osw = d->sw;
+    pl->plane_sh = 1; pl->plane_sw = 1;
+    for (int ph = 0; ph < d->sh; ++ph)
+      for (int pw = 0; pw < d->sw; ++pw) {
+        if (ph >= d->H || pw >= Wstored) continue;
+        const int z = ncls++;
+        p.cls_ph[z] = ph; p.cls_pw[z] = pw;
+        for (int kh = 0; kh < d->kh; ++kh) {
+          if ((ph + d->pad_t - kh) % d->sh != 0) continue;
+          const int dr = (ph + d->pad_t - kh) / d->sh;
+          for (int kw = 0; kw < d->kw; ++kw) {
+            if ((pw + d->pad_l - kw) % d->sw != 0) continue;
+            const int dc = (pw + d->pad_l - kw) / d->sw;
+            if (nt >= Q_MAXT) return false;
+            taps[nt++] = {0, z, kh * d->kw + kw, dr, dc};
+          }
+        }
+      }
+  }
+  if (nt == 0 || ncls == 0) return false;
+  for (int t = 0; t < nt; ++t) {
+    const int q = taps[t].plane;
+    if (!used[q]) { used[q] = true; smin_h[q] = smax_h[q] = taps[t].fh; smin_w[q] = smax_w[q] = taps[t].fw; }
+    if (taps[t].fh < smin_h[q]) smin_h[q] = taps[t].fh;
+    if (taps[t].fh > smax_h[q]) smax_h[q] = taps[t].fh;
+    if (taps[t].fw < smin_w[q]) smin_w[q] = taps[t].fw;
+    if (taps[t].fw > smax_w[q]) smax_w[q] = taps[t].fw;
+  }
+  int halo_h = 0, halo_w = 0, remap[Q_MAXP];
+  for (int q = 0; q < Q_MAXP; ++q) {
+    remap[q] = -1;
+    if (!used[q]) continue;
+    remap[q] = nplanes;
+    pl->plane_ph[nplanes] = q / (transposed ? 1 : d->sw);
+    pl->plane_pw[nplanes] = q % (transposed ? 1 : d->sw);
+    p.plane_oh[nplanes] = smin_h[q];
+    p.plane_ow[nplanes] = smin_w[q];
+    if (smax_h[q] - smin_h[q] > halo_h) halo_h = smax_h[q] - smin_h[q];
+    if (smax_w[q] - smin_w[q] > halo_w) halo_w = smax_w[q] - smin_w[q];
+    ++nplanes;
+  }
+  // tile shape: fewest tiles, then smallest patch
+  long best_tiles = -1;
+  int best_tw = 0, best_th = 0;
+  for (int tw = 1; tw <= Wc && tw + halo_w <= QM; ++tw) {
+    const int PW = tw + halo_w;
+    int th = QM / PW;
+    if (th > Hc) th = Hc;
+    if (th < 1 || PW > 256 || th + halo_h > 256) continue;
+    const long tiles = (long)((Hc + th - 1) / th) * ((Wc + tw - 1) / tw);
+    if (best_tiles < 0 || tiles < best_tiles ||
+        (tiles == best_tiles && (long)(th + halo_h) * PW < (long)(best_th + halo_h) * (best_tw + halo_w))) {
+      best_tiles = tiles; best_tw = tw; best_th = th;
+    }
+  }
+  if (best_tiles < 0) return false;
+  p.th = best_th; p.tw = best_tw;
+  p.PW = best_tw + halo_w; p.PH = best_th + halo_h;
+  p.tiles_h = (Hc + p.th - 1) / p.th;
+  p.tiles_w = (Wc + p.tw - 1) / p.tw;
+  p.Hc = Hc; p.Wc = Wc;
+  pl->efficiency = (double)Hc * Wc / ((double)best_tiles * QM);
+  // taps sorted by plane
+  int k = 0;
+  for (int q = 0; q < nplanes; ++q) {
+    p.plane_tap0[q] = k;
+    for (int t = 0; t < nt; ++t) {
+      if (remap[taps[t].plane] != q) continue;
+      const int orig = taps[t].plane;
+      p.tap_cls[k] = (unsigned char)taps[t].cls;
+      p.tap_wrow[k] = (unsigned short)taps[t].wrow;
+      p.tap_shift[k] = (unsigned short)((taps[t].fh - smin_h[orig]) * p.PW + (taps[t].fw - smin_w[orig]));
+      ++k;
+    }
+  }
+  p.plane_tap0[nplanes] = k;
+  if (getenv("ADVOC_P2D_NOSHIFT"))   // timing experiment only (wrong results): every tap reads the aligned patch start
+    for (int t = 0; t < k; ++t) p.tap_shift[t] = 0;
+  if (getenv("ADVOC_P2D_SHIFT8"))    // timing experiment only: shifts rounded down to whole 1 KB swizzle atoms
+    for (int t = 0; t < k; ++t) p.tap_shift[t] &= ~7;
+  p.nplanes = nplanes; p.ntaps = nt; p.ncls = ncls;
+  const int Cn = transposed ? d->Cin : d->Cout, Ck = transposed ? d->Cout : d->Cin;
+  if (Ck % QK != 0 || Cn % 32 != 0) return false;
+  int bn = Cn % 256 == 0 ? 256 : (Cn % 128 == 0 ? 128 : (Cn % 64 == 0 ? 64 : 32));
+  while (ncls * bn > 512) bn >>= 1;
+  pl->bn = bn;
+  p.Cn = Cn; p.kblocks = Ck / QK;
+  p.n_ntiles = Cn / bn;
+  p.total_tiles = (long)d->N * best_tiles * p.n_ntiles;
+  p.acc_bufs = (2 * ncls * bn <= 512) ? 2 : 1;
+  uint32_t cols = (uint32_t)(p.acc_bufs * ncls * bn), pow2 = 32;
+  while (pow2 < cols) pow2 <<= 1;
+  p.tmem_cols = pow2;
+  // shared memory: patch slots hold the box and every 128-row shifted window into it
+  const int max_shift = halo_h * p.PW + halo_w;
+  int rows = p.PH * p.PW;
+  if (max_shift + QM > rows) rows = max_shift + QM;
+  p.a_box_bytes = (uint32_t)p.PH * p.PW * 128u;
+  p.a_slot_bytes = ((uint32_t)rows * 128u + 1023u) & ~1023u;
+  // filter ring slot = G taps (<= 32 KB), G divides every plane's tap count
+  int G = 1;
+  for (int g = 2; g <= 8 && g * bn * 128 <= 32 * 1024; g *= 2) {
+    bool ok = true;
+    for (int q = 0; q < nplanes; ++q) ok = ok && ((p.plane_tap0[q + 1] - p.plane_tap0[q]) % g == 0);
+    if (ok) G = g;
+  }
+  p.G = G;
+  const size_t b_tile = (size_t)G * bn * 128;
+  const int nslots_all = nt / G * p.kblocks;
+  const size_t all_b = (size_t)nslots_all * b_tile;
+  p.tma_store = tma_store ? 1 : 0;
+  p.n_out = n_out;
+  const size_t stage1 = tma_store ? (size_t)n_out * Q_STAGE_BYTES : 0;
+  int a_need = nplanes + 1 > 3 ? nplanes + 1 : 3;   // patches in flight cover the TMA latency
+  while (a_need > 2 && (size_t)a_need * p.a_slot_bytes + 4 * b_tile + stage1 > Q_SMEM_BUDGET) --a_need;
+  if ((size_t)a_need * p.a_slot_bytes + 3 * b_tile + stage1 > Q_SMEM_BUDGET) return false;
+  size_t left = Q_SMEM_BUDGET - stage1 - (size_t)a_need * p.a_slot_bytes;
+  p.a_stages = a_need;
+  if (p.n_ntiles == 1 && nslots_all <= Q_MAXB && all_b <= left) {
+    p.b_resident = 1;
+    p.b_stages = nslots_all;
+    left -= all_b;
+  } else {
+    p.b_resident = 0;
+    long bs = (long)(left / b_tile);
+    const long want = (long)((96 * 1024) / b_tile) > 4 ? (long)((96 * 1024) / b_tile) : 4;   // ~96 KB of filter tiles in flight
+    if (bs > want) bs = want;
+    if (bs > Q_MAXB) bs = Q_MAXB;
+    p.b_stages = (int)bs;
+    left -= (size_t)bs * b_tile;
+  }
+  p.stage_bufs = 1;
+  if (tma_store && left >= stage1) { p.stage_bufs = 2; left -= stage1; }
+  while (p.a_stages < Q_MAXA && left >= p.a_slot_bytes) { ++p.a_stages; left -= p.a_slot_bytes; }
+  const size_t staging = stage1 * p.stage_bufs;
+  p.stage_off = (uint32_t)((size_t)p.a_stages * p.a_slot_bytes + (size_t)p.b_stages * b_tile);
+  pl->smem = (size_t)p.stage_off + staging + 1024;
+  if (pl->smem < 120 * 1024) pl->smem = 120 * 1024;  // one CTA per SM: TMEM is not shared between CTAs here
+  return p.total_tiles > 0;
+}
+
+template <int BN>
+int launch_p2d(const Plan& pl, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    ADVOC_CHECK_CUDA(cudaFuncSetAttribute(conv_p2d_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)(Q_SMEM_BUDGET + 1024)));
+    configured = true;
+  }
+  long ctas = pl.p.total_tiles < (long)sm_count() ? pl.p.total_tiles : (long)sm_count();
+  conv_p2d_kernel<BN><<<(unsigned)ctas, Q_THREADS, pl.smem, st>>>(pl.p);
+  count_launch();
+  ADVOC_CHECK_CUDA(cudaGetLastError());
+  return ADVOC_OK;
+}
+
+unsigned long long* prof_buffer() {
+  static unsigned long long* buf = [] {
+    unsigned long long* b = nullptr;
+    if (getenv("ADVOC_P2D_PROFILE") == nullptr) return b;
+    if (cudaMalloc(&b, 256 * 16 * sizeof(unsigned long long)) != cudaSuccess) return (unsigned long long*)nullptr;
+    cudaMemset(b, 0, 256 * 16 * sizeof(unsigned long long));
+    return b;
+  }();
+  return buf;
+}
+
+double min_efficiency() {
+  static const double v = [] {
+    const char* s = getenv("ADVOC_P2D_MIN_EFF");
+    return s ? atof(s) : 0.45;
+  }();
+  return v;
+}
+
+}  // namespace
+
+bool conv_p2d_eligible(const advoc_conv_desc* d, int ldx, int transposed, int store_w) {
+  static const bool disabled = getenv("ADVOC_NO_P2D") != nullptr;  // A/B switch for benchmarking
+  if (disabled || !(tc::tma_ok() && device_arch() == 100 && ldx % 4 == 0)) return false;
+  Plan pl = {};
+  if (!make_plan(d, transposed != 0, store_w ? store_w : d->W, 2, true, &pl)) return false;
+  return pl.efficiency >= min_efficiency();
+}
+
+int conv_p2d(const advoc_conv_desc* d, int transposed, const float* x, int ldx, const float* w,
+             const advoc_epilogue* ep, void* stream) {
+  Plan pl = {};
+  int st = transposed ? lower_epilogue(ep, d->H, d->W, d->Cin, &pl.p.epi)
+                      : lower_epilogue(ep, d->Ho, d->Wo, d->Cout, &pl.p.epi);
+  if (st) return st;
+  if (!transposed)
+    ADVOC_REQUIRE(pl.p.epi.Ws == d->Wo, ADVOC_UNSUPPORTED, "store_w crop is only supported on conv_transpose");
+  static const bool no_tma_store = getenv("ADVOC_P2D_DIRECT_STORE") != nullptr;   // A/B switch
+  const bool tma_store = !no_tma_store && !ep->d_gate && !ep->accumulate;
+  ADVOC_REQUIRE(make_plan(d, transposed != 0, pl.p.epi.Ws, ep->d_out1 ? 2 : 1, tma_store, &pl), ADVOC_UNSUPPORTED,
+                "layer does not fit the patch kernel");
+  P2dParams& p = pl.p;
+  if (tma_store) {
+    const EpiDev& e = p.epi;
+    for (int o = 0; o < p.n_out; ++o) {
+      float* base = o == 0 ? e.out0 + e.coff0 : e.out1 + e.coff1;
+      const long ld = o == 0 ? e.ld0 : e.ld1;
+      for (int z = 0; z < p.ncls; ++z) {
+        const int ph = p.cls_ph[z], pw = p.cls_pw[z];
+        const int Hz = (e.Hs - ph + p.osh - 1) / p.osh, Wz = (e.Ws - pw + p.osw - 1) / p.osw;
+        st = encode_tiled4d(&p.tmO[o][z], base + ((size_t)ph * e.Ws + pw) * ld, p.Cn, Wz, Hz, d->N, p.osw * ld,
+                            (long)p.osh * e.Ws * ld, (long)e.Hs * e.Ws * ld, 32, p.tw, p.th);
+        if (st) return st;
+      }
+    }
+  }
+  const int Hin = transposed ? d->Ho : d->H, Win = transposed ? d->Wo : d->W;
+  const int Ck = transposed ? d->Cout : d->Cin;
+  for (int q = 0; q < p.nplanes; ++q) {
+    const int ph = pl.plane_ph[q], pw = pl.plane_pw[q], sh = pl.plane_sh, sw = pl.plane_sw;
+    const int Hp = Hin > ph ? (Hin - ph + sh - 1) / sh : 0, Wp = Win > pw ? (Win - pw + sw - 1) / sw : 0;
+    ADVOC_REQUIRE(Hp > 0 && Wp > 0, ADVOC_UNSUPPORTED, "empty input plane");
+    st = encode_tiled4d(&p.tmA[q], x + ((size_t)ph * Win + pw) * ldx, Ck, Wp, Hp, d->N, (long)sw * ldx,
+                        (long)sh * Win * ldx, (long)Hin * Win * ldx, QK, p.PW, p.PH);
+    if (st) return st;
+  }
+  st = encode_tiled2d(&p.tmB, w, Ck, (long)d->kh * d->kw * p.Cn, (size_t)Ck * 4, QK, pl.bn);
+  if (st) return st;
+  p.dbg = debug_word();
+  p.prof = prof_buffer();
+  static const int exp_flags = getenv("ADVOC_P2D_EXP") ? atoi(getenv("ADVOC_P2D_EXP")) : 0;
+  p.exp_flags = exp_flags;
+  static const bool verbose = getenv("ADVOC_P2D_VERBOSE") != nullptr;
+  if (verbose)
+    fprintf(stderr,
+            "p2d %s N%d %dx%dx%d->%d k%d s%d | tile %dx%d patch %dx%d planes %d taps %d cls %d | bn %d ntiles %d "
+            "tiles %ld eff %.2f | A %d x %u B %d x %d %s stage %d x %d smem %zu tmem %u\n",
+            transposed ? "deconv" : "conv", d->N, Hin, Win, Ck, p.Cn, d->kh, d->sh, p.th, p.tw, p.PH, p.PW, p.nplanes,
+            p.ntaps, p.ncls, pl.bn, p.n_ntiles, p.total_tiles, pl.efficiency, p.a_stages, p.a_slot_bytes, p.b_stages,
+            p.G * pl.bn * 128, p.b_resident ? "resident" : "ring", p.stage_bufs, p.n_out, pl.smem, p.tmem_cols);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  switch (pl.bn) {
+    case 256: return launch_p2d<256>(pl, s);
+    case 128: return launch_p2d<128>(pl, s);
+    case 64: return launch_p2d<64>(pl, s);
+    default: return launch_p2d<32>(pl, s);
+  }
+}
+
+}  // namespace advoc
+
+// Developer hook (ADVOC_P2D_PROFILE=1): copies the per-CTA cycle counters of the last patch-kernel
+// launches to the host ([256][16] u64) and clears them.  Synchronises the device.
+extern "C" __attribute__((visibility("default"))) int advoc_p2d_profile_read(unsigned long long* out) {
+  using namespace advoc;
+  unsigned long long* b = prof_buffer();
+  ADVOC_REQUIRE(b != nullptr && out != nullptr, ADVOC_UNSUPPORTED, "profiling is off (set ADVOC_P2D_PROFILE=1)");
+  ADVOC_CHECK_CUDA(cudaMemcpy(out, b, 256 * 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  ADVOC_CHECK_CUDA(cudaMemset(b, 0, 256 * 16 * sizeof(unsigned long long)));
+  return ADVOC_OK;
+}

@@ -55,54 +55,6 @@ __host__ __device__ constexpr uint32_t make_idesc(int bn) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
-// Four consecutive channels of one stored pixel (the vector form of epi_store).
-__device__ __forceinline__ void epi_store4(const EpiDev& e, size_t pix, int n, float4 acc) {
-  float v[4] = {acc.x, acc.y, acc.z, acc.w};
-  if (e.bias) {
-    const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + n));
-    v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
-  }
-  float sc[4] = {1.f, 1.f, 1.f, 1.f};
-  if (e.keep_prob < 1.f) {
-    const size_t idx = pix * e.Cout + n;
-    const float inv = 1.f / e.keep_prob;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const bool keep = e.mask ? (__ldg(e.mask + idx + j) != 0) : dropout_keep(e.seed, idx + j, e.keep_prob);
-      sc[j] = keep ? inv : 0.f;
-    }
-  }
-  float y[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) y[j] = apply_act(v[j], e.act0, e.alpha) * sc[j];
-  if (e.gate) {
-    const float4 g = __ldg(reinterpret_cast<const float4*>(e.gate + pix * e.ldg + e.coffg + n));
-    const float gv[4] = {g.x, g.y, g.z, g.w};
-    const float neg = e.gate_act == ADVOC_ACT_LRELU ? e.alpha : 0.f;
-    const float s = n < e.gate_split ? e.gscale0 : e.gscale1;  // split is a multiple of 4
-#pragma unroll
-    for (int j = 0; j < 4; ++j) y[j] *= (gv[j] > 0.f ? 1.f : neg) * s;
-  }
-  float4* dst = reinterpret_cast<float4*>(e.out0 + pix * e.ld0 + e.coff0 + n);
-  if (e.accumulate) {
-    const float4 o = *dst;
-    y[0] += o.x; y[1] += o.y; y[2] += o.z; y[3] += o.w;
-  }
-  if (e.round) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) y[j] = round_tf32(y[j]);
-  }
-  *dst = make_float4(y[0], y[1], y[2], y[3]);
-  if (e.out1) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      y[j] = apply_act(v[j], e.act1, e.alpha) * sc[j];
-      if (e.round) y[j] = round_tf32(y[j]);
-    }
-    *reinterpret_cast<float4*>(e.out1 + pix * e.ld1 + e.coff1 + n) = make_float4(y[0], y[1], y[2], y[3]);
-  }
-}
-
 template <int BN>
 struct SmemLayout {
   static constexpr int A_BYTES = BM * BK * 4;  // 16 KB
@@ -235,7 +187,7 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
       if (valid) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-          epi_store4(p.epi, pix, n0 + c0 + j,
+          epi_store_vec4(p.epi, pix, n0 + c0 + j,
                      make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
                                  __uint_as_float(v[j + 3])));
         }

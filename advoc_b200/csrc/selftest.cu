@@ -64,8 +64,138 @@ __global__ void __launch_bounds__(128) desc_shift_probe(float* out, int shift, i
   if (threadIdx.x < 32)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(32u) : "memory");
 }
+// Tensor-pipe issue-rate probe: one thread issues `reps` MMAs (M=128, N=n, K=8 tf32 or K=16 f16)
+// over uninitialised shared memory and reports cycles from first issue to completion.
+//   mode 0: tf32, one accumulator      mode 1: tf32, accumulators alternate between two TMEM regions
+//   mode 2: kind::f16 (same bytes per operand row)   mode 3: tf32 + tcgen05.commit after every 4 MMAs
+//   mode 4: tf32, A descriptor start shifted by 3 rows (un-aligned view)
+//   mode 5: tf32 issued from a warp-uniform loop under elect.sync (instead of `if (thread == 0)`)
+__global__ void __launch_bounds__(128) mma_rate_probe(unsigned long long* out, int n, int reps, int mode) {
+  extern __shared__ uint8_t raw[];
+  __shared__ __align__(8) uint64_t bar, bar2;
+  __shared__ uint32_t tmem_holder;
+  const uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    mbar_init(&bar2, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_holder;
+  if (mode >= 16) {
+    // bit flags under elect.sync issue: 1 shifted A view, 2 four accumulators in rotation, 4 commit after
+    // every 4 MMAs, 8 the other three warps poll an mbarrier meanwhile, 32 per-step descriptor rebuild
+    const int fl = mode - 16;
+    if (threadIdx.x < 32) {
+      const uint32_t idesc_tf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const long long t0 = clock64();
+      for (int i = 0; i < reps; i += 4) {
+        const int step = i >> 2;
+        const uint32_t a_addr = base + ((fl & 1) ? (uint32_t)(1 + (step % 5) * 13) * 128u : 0u);
+        const uint64_t da = make_smem_desc(a_addr);
+        const uint64_t db = make_smem_desc(base + 64 * 1024 + ((fl & 32) ? (uint32_t)(step & 3) * 8192u : 0u));
+        const uint32_t d = tmem + ((fl & 2) ? (uint32_t)(step & 3) * (uint32_t)(n > 128 ? 128 : n) : 0u);
+        __syncwarp();
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_tf32(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_tf32, (i | k) ? 1u : 0u);
+          if (fl & 4) umma_commit(&bar2);
+        }
+        __syncwarp();
+      }
+      const long long t1 = clock64();
+      if (elect_one()) umma_commit(&bar);
+      __syncwarp();
+      mbar_wait(&bar, 0u, nullptr, 0u);
+      const long long t2 = clock64();
+      if (threadIdx.x == 0) {
+        out[blockIdx.x * 2 + 0] = (unsigned long long)(t1 - t0);
+        out[blockIdx.x * 2 + 1] = (unsigned long long)(t2 - t0);
+      }
+    } else if (fl & 8) {
+      while (!mbar_try_wait(&bar, 0u)) {}
+    }
+  } else if (mode == 5) {
+    if (threadIdx.x < 32) {
+      const uint64_t da = make_smem_desc(base);
+      const uint64_t db = make_smem_desc(base + 64 * 1024);
+      const uint32_t idesc_tf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const long long t0 = clock64();
+      for (int i = 0; i < reps; ++i) {
+        const uint64_t adv = (uint64_t)(2 * (i & 3));
+        if (elect_one()) umma_tf32(tmem, da + adv, db + adv, idesc_tf32, i ? 1u : 0u);
+        __syncwarp();
+      }
+      const long long t1 = clock64();
+      if (elect_one()) umma_commit(&bar);
+      __syncwarp();
+      mbar_wait(&bar, 0u, nullptr, 0u);
+      const long long t2 = clock64();
+      if (threadIdx.x == 0) {
+        out[blockIdx.x * 2 + 0] = (unsigned long long)(t1 - t0);
+        out[blockIdx.x * 2 + 1] = (unsigned long long)(t2 - t0);
+      }
+    }
+  } else if (threadIdx.x == 0) {
+    const uint32_t a_addr = base + (mode == 4 ? 3u * 128u : 0u);
+    const uint64_t da = make_smem_desc(a_addr);
+    const uint64_t db = make_smem_desc(base + 64 * 1024);
+    const uint32_t idesc_tf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t idesc_f16 = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const long long t0 = clock64();
+    for (int i = 0; i < reps; ++i) {
+      const uint64_t adv = (uint64_t)(2 * (i & 3));
+      const uint32_t d = tmem + ((mode == 1 && (i & 4)) ? 256u : 0u);
+      if (mode == 2) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d),
+            "l"(da + adv), "l"(db + adv), "r"(idesc_f16), "r"(i ? 1u : 0u)
+            : "memory");
+      } else {
+        umma_tf32(d, da + adv, db + adv, idesc_tf32, i ? 1u : 0u);
+      }
+      if (mode == 3 && (i & 3) == 3) umma_commit(&bar2);
+    }
+    const long long t1 = clock64();
+    umma_commit(&bar);
+    mbar_wait(&bar, 0u, nullptr, 0u);
+    const long long t2 = clock64();
+    out[blockIdx.x * 2 + 0] = (unsigned long long)(t1 - t0);
+    out[blockIdx.x * 2 + 1] = (unsigned long long)(t2 - t0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
 }  // namespace
 }  // namespace advoc
+
+// h_out [ctas*2] u64: cycles to issue / to complete `reps` MMAs on each CTA.
+extern "C" __attribute__((visibility("default"))) int advoc_selftest_mma_rate(unsigned long long* h_out, int ctas,
+                                                                              int n, int reps, int mode) {
+  using namespace advoc;
+  ADVOC_REQUIRE(h_out && ctas > 0 && ctas <= 1024 && n >= 8 && n <= 256 && n % 8 == 0, ADVOC_BAD_ARG, "bad arguments");
+  unsigned long long* d = nullptr;
+  ADVOC_CHECK_CUDA(cudaMalloc(&d, ctas * 2 * sizeof(unsigned long long)));
+  const int smem = 64 * 1024 + 64 * 1024 + 1024;
+  ADVOC_CHECK_CUDA(cudaFuncSetAttribute(mma_rate_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  mma_rate_probe<<<ctas, 128, smem>>>(d, n, reps, mode);
+  ADVOC_CHECK_CUDA(cudaGetLastError());
+  ADVOC_CHECK_CUDA(cudaDeviceSynchronize());
+  ADVOC_CHECK_CUDA(cudaMemcpy(h_out, d, ctas * 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  return ADVOC_OK;
+}
 
 // d_out [128*32] floats.  Returns the rows the MMA actually read as out[m*32+n] = (row & 63)*32 + n.
 extern "C" __attribute__((visibility("default"))) int advoc_selftest_desc_shift(float* d_out, int shift, int mode) {

@@ -95,5 +95,22 @@ int encode_tiled2d(CUtensorMap* tm, const float* p, int inner, long rows, size_t
   return ADVOC_OK;
 }
 
+int encode_tiled4d(CUtensorMap* tm, const float* x, int C, int W, int H, int Nimg, long stride_w, long stride_h,
+                   long stride_n, int box_c, int box_w, int box_h) {
+  const Driver& drv = driver();
+  ADVOC_REQUIRE(drv.ok, ADVOC_UNSUPPORTED, "TMA tensor-map encoders unavailable");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Nimg};
+  cuuint64_t strides[3] = {(cuuint64_t)stride_w * 4, (cuuint64_t)stride_h * 4, (cuuint64_t)stride_n * 4};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = drv.tiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  ADVOC_REQUIRE(r == CUDA_SUCCESS, ADVOC_CUDA_ERROR,
+                "cuTensorMapEncodeTiled(4d) failed (%d) dims %d,%d,%d,%d strides %ld,%ld,%ld box %d,%d,%d", (int)r, C,
+                W, H, Nimg, stride_w, stride_h, stride_n, box_c, box_w, box_h);
+  return ADVOC_OK;
+}
+
 }  // namespace tc
 }  // namespace advoc

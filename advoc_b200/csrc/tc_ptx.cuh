@@ -56,6 +56,14 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, uint64_t* bar
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// tiled-mode 4-D box {c, w, h, n}; out-of-range coordinates (negative included) read as zero
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* tm, uint64_t* bar, void* dst, int c, int w, int h,
+                                            int n) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_im2col_4d(const CUtensorMap* tm, uint64_t* bar, void* dst, int c, int w,
                                                    int h, int n, uint16_t off_w, uint16_t off_h) {
   asm volatile(
@@ -89,6 +97,18 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t
       ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc)
       : "memory");
 }
+// One lane of a converged warp (elect.sync).  Issuing tcgen05 / TMA instructions under this predicate
+// from warp-uniform code lets the compiler keep their operands in uniform registers; a plain
+// `if (lane == 0)` region makes it wrap every UTCMMA in an ELECT/BRA.U.ANY loop (~140 cycles each).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
@@ -119,6 +139,10 @@ int encode_im2col(CUtensorMap* tm, const float* x, int Nimg, int Hin, int Win, i
 // plain 2-D map: `rows` rows of `inner` floats, row stride in bytes; box = box_inner x box_rows
 int encode_tiled2d(CUtensorMap* tm, const float* p, int inner, long rows, size_t row_stride_bytes, int box_inner,
                    int box_rows, bool atom32 = false);
+// tiled 4-D map over a strided NHWC view: dims {C, W, H, N} with pixel / row / image strides in
+// floats; box {box_c, box_w, box_h, 1}, 128-byte swizzle
+int encode_tiled4d(CUtensorMap* tm, const float* x, int C, int W, int H, int Nimg, long stride_w, long stride_h,
+                   long stride_n, int box_c, int box_w, int box_h);
 // atom32: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B (32-byte chunks swizzled over 4 rows) -- the only
 // layout tcgen05 accepts for MN-major 32-bit (tf32) operands; default is SWIZZLE_128B.
 

@@ -1,0 +1,22 @@
+"""Developer probe: tcgen05.mma issue / completion rate per instruction (see csrc/selftest.cu)."""
+import ctypes as C
+import os
+import sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from advoc_b200 import _native as N
+torch.zeros(1, device='cuda')
+lib = N.lib()
+fn = lib.advoc_selftest_mma_rate
+fn.restype = C.c_int
+fn.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+for mode, name in [(16, 'elect step4'), (20, '+commit/4'),
+                   (24, '+3 polling warps'), (48, '+B desc varies'), (16 + 1 + 2 + 4 + 8 + 32, 'all')]:
+  for n in (32, 64, 128, 256):
+    ctas, reps = 148, 2048
+    out = np.zeros((ctas, 2), dtype=np.uint64)
+    st = fn(out.ctypes.data, ctas, n, reps, mode)
+    assert st == 0, st
+    print('%-18s N=%3d  issue %.1f cyc/MMA  complete %.1f cyc/MMA (ideal %d)'
+          % (name, n, out[:, 0].mean() / reps, out[:, 1].mean() / reps, 128 * n // 256))
