@@ -71,6 +71,7 @@ SIGNATURES = {
     'advoc_l1_loss': (_I, [_P, _I, _I, _P, _L, _F, _P, _P, _I, _P]),
     'advoc_adam_tf_step': (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _L, _F, _P]),
     'advoc_conv2d_path': (_I, [C.POINTER(ConvDesc), _I, _I]),
+    'advoc_conv2d_kernel': (_I, [C.POINTER(ConvDesc), _I, _I, _I]),
     'advoc_conv2d_transpose_fwd': (_I, [C.POINTER(ConvDesc), _P, _I, _P, C.POINTER(Epilogue), _P]),
 }
 

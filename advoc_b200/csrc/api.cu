@@ -160,6 +160,11 @@ extern "C" int advoc_conv2d_path(const advoc_conv_desc* d, int ld_x, int transpo
   return ok ? ADVOC_MATH_TF32 : ADVOC_MATH_FP32;
 }
 
+extern "C" int advoc_conv2d_kernel(const advoc_conv_desc* d, int ld_x, int transposed, int store_w) {
+  if (advoc_conv2d_path(d, ld_x, transposed) != ADVOC_MATH_TF32) return 0;
+  return conv_p2d_eligible(d, ld_x, transposed, store_w) ? 2 : 1;
+}
+
 // ---------------------------------------------------------------------------------------------
 // filter re-pack: [taps, A, B] -> [taps, B, A] (transpose != 0) or copy, optionally TF32-rounded
 // ---------------------------------------------------------------------------------------------

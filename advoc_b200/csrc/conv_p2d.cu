@@ -477,6 +477,7 @@ struct Plan {
   int bn;
   size_t smem;
   double efficiency;  // useful positions / GEMM rows
+  size_t filter_bytes_per_tile;  // filter bytes one output tile streams through shared memory
   // plane views of the contraction-side tensor
   int plane_ph[Q_MAXP], plane_pw[Q_MAXP];
   int plane_sh, plane_sw;
@@ -620,6 +621,7 @@ bool make_plan(const advoc_conv_desc* d, bool transposed, int Wstored, int n_out
     if (ok) G = g;
   }
   p.G = G;
+  pl->filter_bytes_per_tile = (size_t)nt * p.kblocks * bn * 128;
   const size_t b_tile = (size_t)G * bn * 128;
   const int nslots_all = nt / G * p.kblocks;
   const size_t all_b = (size_t)nslots_all * b_tile;
@@ -695,7 +697,13 @@ bool conv_p2d_eligible(const advoc_conv_desc* d, int ldx, int transposed, int st
   if (disabled || !(tc::tma_ok() && device_arch() == 100 && ldx % 4 == 0)) return false;
   Plan pl = {};
   if (!make_plan(d, transposed != 0, store_w ? store_w : d->W, 2, true, &pl)) return false;
-  return pl.efficiency >= min_efficiency();
+  if (pl.efficiency < min_efficiency()) return false;
+  // Measured on B200 (profiles/README.md, r01c): the patch kernel wins where the layer has several
+  // tiles per SM and an output tile streams little filter data (it re-reads the filter once per
+  // 128-position tile); deep, filter-heavy layers stay on the per-tap kernel of conv_tc.cu.
+  static const bool force = getenv("ADVOC_P2D_FORCE") != nullptr;
+  if (force) return true;
+  return pl.p.total_tiles >= 3L * sm_count() && pl.filter_bytes_per_tile <= 512 * 1024;
 }
 
 int conv_p2d(const advoc_conv_desc* d, int transposed, const float* x, int ldx, const float* w,

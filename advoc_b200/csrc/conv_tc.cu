@@ -116,51 +116,58 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
   const int iters = p.ntaps[cls] * p.kblocks;
 
   if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
-      const int a_w = (int)(m0 % Aw);
-      const long r = m0 / Aw;
-      const int a_h = (int)(r % Ah);
-      const int img = (int)(r / Ah);
-      const int cw = a_w * p.trav_w + p.base_w[cls];
-      const int ch = a_h * p.trav_h + p.base_h[cls];
-      int stage = 0;
-      uint32_t phase = 0;
-      int tap = 0, kb = 0;
-      for (int it = 0; it < iters; ++it) {
-        mbar_wait(&empty_bar[stage], phase ^ 1u, p.dbg, 1u);
-        uint8_t* a_dst = ring_ptr + stage * L::STAGE_BYTES;
-        uint8_t* b_dst = a_dst + L::A_BYTES;
+    // ===== TMA producer: warp-uniform loop, loads issued by one elected lane =====
+    const int a_w = (int)(m0 % Aw);
+    const long r = m0 / Aw;
+    const int a_h = (int)(r % Ah);
+    const int img = (int)(r / Ah);
+    const int cw = a_w * p.trav_w + p.base_w[cls];
+    const int ch = a_h * p.trav_h + p.base_h[cls];
+    int stage = 0;
+    uint32_t phase = 0;
+    int tap = 0, kb = 0;
+    for (int it = 0; it < iters; ++it) {
+      mbar_wait(&empty_bar[stage], phase ^ 1u, p.dbg, 1u);
+      uint8_t* a_dst = ring_ptr + stage * L::STAGE_BYTES;
+      uint8_t* b_dst = a_dst + L::A_BYTES;
+      const unsigned off = p.tap_off[cls][tap];
+      const int wrow = (int)p.tap_wrow[cls][tap] * p.Cn + n0;
+      __syncwarp();
+      if (elect_one()) {
         mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-        const unsigned off = p.tap_off[cls][tap];
         tma_load_im2col_4d(&p.tmA[cls], &full_bar[stage], a_dst, kb * BK, cw, ch, img, (uint16_t)(off & 0xFF),
                            (uint16_t)(off >> 8));
-        tma_load_2d(&p.tmB, &full_bar[stage], b_dst, kb * BK, (int)p.tap_wrow[cls][tap] * p.Cn + n0);
-        if (++kb == p.kblocks) { kb = 0; ++tap; }
-        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        tma_load_2d(&p.tmB, &full_bar[stage], b_dst, kb * BK, wrow);
       }
+      __syncwarp();
+      if (++kb == p.kblocks) { kb = 0; ++tap; }
+      if (++stage == STAGES) { stage = 0; phase ^= 1u; }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (one thread) =====
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BN);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int it = 0; it < iters; ++it) {
-        mbar_wait(&full_bar[stage], phase, p.dbg, 2u);
-        tc_fence_after();
-        const uint32_t a_addr = ring + stage * L::STAGE_BYTES;
-        const uint64_t da = make_smem_desc(a_addr);
-        const uint64_t db = make_smem_desc(a_addr + L::A_BYTES);
+    // ===== MMA issuer: warp-uniform loop, tcgen05.mma issued by one elected lane (a plain
+    // `if (lane == 0)` region makes the compiler wrap every UTCMMA in an ELECT/BRA.U.ANY loop that
+    // costs ~140 cycles per instruction: scripts/dev_mma_rate.py) =====
+    constexpr uint32_t idesc = make_idesc(BN);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int it = 0; it < iters; ++it) {
+      mbar_wait(&full_bar[stage], phase, p.dbg, 2u);
+      tc_fence_after();
+      const uint32_t a_addr = ring + stage * L::STAGE_BYTES;
+      const uint64_t da = make_smem_desc(a_addr);
+      const uint64_t db = make_smem_desc(a_addr + L::A_BYTES);
+      __syncwarp();
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < BK / UMMA_K; ++k) {
           // advance 32 bytes (= 2 x 16-byte units) along K inside the swizzle atom
           umma_tf32(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (it | k) != 0 ? 1u : 0u);
         }
         umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
-        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        if (it == iters - 1) umma_commit(&tmem_full_bar);  // accumulator complete -> epilogue
       }
-      umma_commit(&tmem_full_bar);       // accumulator complete -> epilogue
+      __syncwarp();
+      if (++stage == STAGES) { stage = 0; phase ^= 1u; }
     }
   } else {
     // ===== epilogue: warp q may only touch TMEM lanes [32q, 32q+32) =====

@@ -1,0 +1,322 @@
+// Kernels the MelspecGAN stacks need beyond the convolutions (models/melspecgan/conv2d.py,
+// models/melspecgan/train.py): dense layers, batch normalisation with batch statistics (forward
+// and backward, the ReLU / leaky-ReLU that follows it fused in), tanh backward and the GAN losses
+// on the critic's logits.  All exact fp32 on CUDA cores: these ops are small next to the 5x5
+// convolutions ([64, 4..32, 5..40, 64..512] activations).
+#include "common.cuh"
+
+namespace advoc {
+
+int grid_for(long n, int per_block);
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// C[M,N] (+)= op(A) * op(B) (+ bias[N]);  row-major, op = identity or transpose.
+// 64x64 tile, 16-deep slabs, 4x4 register tile per thread.
+// ---------------------------------------------------------------------------------------------
+constexpr int GT = 64, GK = 16;
+
+__global__ void __launch_bounds__(256) gemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B,
+                                                   int ldb, float* __restrict__ C, int ldc, int M, int N, int K,
+                                                   int tA, int tB, int accumulate, const float* __restrict__ bias) {
+  __shared__ float As[GK][GT + 4];
+  __shared__ float Bs[GK][GT + 4];
+  const int m0 = blockIdx.y * GT, n0 = blockIdx.x * GT;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += GK) {
+    for (int i = threadIdx.x; i < GT * GK; i += 256) {
+      // A slab: element (m, k)
+      const int k = tA ? i / GT : i % GK, m = tA ? i % GT : i / GK;
+      const int gm = m0 + m, gk = k0 + k;
+      float v = 0.f;
+      if (gm < M && gk < K) v = tA ? __ldg(A + (size_t)gk * lda + gm) : __ldg(A + (size_t)gm * lda + gk);
+      As[k][m] = v;
+    }
+    for (int i = threadIdx.x; i < GT * GK; i += 256) {
+      // B slab: element (k, n)
+      const int k = tB ? i % GK : i / GT, n = tB ? i / GK : i % GT;
+      const int gn = n0 + n, gk = k0 + k;
+      float v = 0.f;
+      if (gn < N && gk < K) v = tB ? __ldg(B + (size_t)gn * ldb + gk) : __ldg(B + (size_t)gk * ldb + gn);
+      Bs[k][n] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < GK; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx + 16 * j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx + 16 * j;
+      if (n >= N) continue;
+      float v = acc[i][j] + (bias ? __ldg(bias + n) : 0.f);
+      float* dst = C + (size_t)m * ldc + n;
+      if (accumulate) v += *dst;
+      *dst = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// batch normalisation over [pixels, C] (pixel stride ld), batch statistics
+// ---------------------------------------------------------------------------------------------
+// stats[0:C] += sum x, stats[C:2C] += sum x^2   (caller zeroes stats)
+__global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ x, int ld, long pixels, int C,
+                                                       float* __restrict__ stats) {
+  extern __shared__ float part[];  // [2C]
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) part[i] = 0.f;
+  __syncthreads();
+  const int lanes = C < 256 ? C : 256;            // threads per pixel row
+  const int ppb = 256 / lanes;
+  const int c0 = threadIdx.x % lanes;
+  if ((int)(threadIdx.x / lanes) < ppb) {
+    for (int c = c0; c < C; c += lanes) {
+      float s = 0.f, q = 0.f;
+      for (long p = (long)blockIdx.x * ppb + threadIdx.x / lanes; p < pixels; p += (long)gridDim.x * ppb) {
+        const float v = __ldg(x + (size_t)p * ld + c);
+        s += v;
+        q = fmaf(v, v, q);
+      }
+      atomicAdd(&part[c], s);
+      atomicAdd(&part[C + c], q);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(stats + i, part[i]);
+}
+
+__device__ __forceinline__ void bn_moments(const float* stats, int C, int c, float inv_m, float eps, float* mean,
+                                           float* invstd) {
+  const float m = __ldg(stats + c) * inv_m;
+  const float var = fmaxf(__ldg(stats + C + c) * inv_m - m * m, 0.f);
+  *mean = m;
+  *invstd = rsqrtf(var + eps);
+}
+
+// y = act(gamma * (x - mean) * invstd + beta)
+__global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__ x, int ldx, long pixels, int C,
+                                                       const float* __restrict__ stats, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, float eps, int act, float alpha,
+                                                       float* __restrict__ y, int ldy, int round) {
+  const long total = pixels * C;
+  const float inv_m = 1.f / (float)pixels;
+  const ActLin a = act_linear(act, alpha);
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long p = i / C;
+    const int c = (int)(i - p * C);
+    float mean, invstd;
+    bn_moments(stats, C, c, inv_m, eps, &mean, &invstd);
+    float v = (__ldg(x + (size_t)p * ldx + c) - mean) * invstd * __ldg(gamma + c) + __ldg(beta + c);
+    v = apply_lin(v, a);
+    if (round) v = round_tf32(v);
+    y[(size_t)p * ldy + c] = v;
+  }
+}
+
+// g = dy * act'(y);  red[0:C] += sum g (= dbeta), red[C:2C] += sum g * xhat (= dgamma)
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restrict__ dy, int lddy,
+                                                            const float* __restrict__ y, int ldy,
+                                                            const float* __restrict__ x, int ldx, long pixels, int C,
+                                                            const float* __restrict__ stats, float eps, int act,
+                                                            float alpha, float* __restrict__ red) {
+  extern __shared__ float part[];  // [2C]
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) part[i] = 0.f;
+  __syncthreads();
+  const float inv_m = 1.f / (float)pixels;
+  const float neg = act == ADVOC_ACT_LRELU ? alpha : (act == ADVOC_ACT_RELU ? 0.f : 1.f);
+  const int lanes = C < 256 ? C : 256;
+  const int ppb = 256 / lanes;
+  const int c0 = threadIdx.x % lanes;
+  if ((int)(threadIdx.x / lanes) < ppb) {
+    for (int c = c0; c < C; c += lanes) {
+      float mean, invstd;
+      bn_moments(stats, C, c, inv_m, eps, &mean, &invstd);
+      float s = 0.f, q = 0.f;
+      for (long p = (long)blockIdx.x * ppb + threadIdx.x / lanes; p < pixels; p += (long)gridDim.x * ppb) {
+        float g = __ldg(dy + (size_t)p * lddy + c);
+        if (!(__ldg(y + (size_t)p * ldy + c) > 0.f)) g *= neg;
+        const float xh = (__ldg(x + (size_t)p * ldx + c) - mean) * invstd;
+        s += g;
+        q = fmaf(g, xh, q);
+      }
+      atomicAdd(&part[c], s);
+      atomicAdd(&part[C + c], q);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(red + i, part[i]);
+}
+
+// dx = gamma * invstd * (g - dbeta/M - xhat * dgamma/M)
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restrict__ dy, int lddy,
+                                                           const float* __restrict__ y, int ldy,
+                                                           const float* __restrict__ x, int ldx, long pixels, int C,
+                                                           const float* __restrict__ stats,
+                                                           const float* __restrict__ gamma, float eps, int act,
+                                                           float alpha, const float* __restrict__ red,
+                                                           float* __restrict__ dx, int lddx, int round) {
+  const long total = pixels * C;
+  const float inv_m = 1.f / (float)pixels;
+  const float neg = act == ADVOC_ACT_LRELU ? alpha : (act == ADVOC_ACT_RELU ? 0.f : 1.f);
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long p = i / C;
+    const int c = (int)(i - p * C);
+    float mean, invstd;
+    bn_moments(stats, C, c, inv_m, eps, &mean, &invstd);
+    float g = __ldg(dy + (size_t)p * lddy + c);
+    if (!(__ldg(y + (size_t)p * ldy + c) > 0.f)) g *= neg;
+    const float xh = (__ldg(x + (size_t)p * ldx + c) - mean) * invstd;
+    float v = __ldg(gamma + c) * invstd * (g - __ldg(red + c) * inv_m - xh * __ldg(red + C + c) * inv_m);
+    if (round) v = round_tf32(v);
+    dx[(size_t)p * lddx + c] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256) tanh_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                                                       float* __restrict__ dx, long n) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const float t = __ldg(y + i);
+    dx[i] = __ldg(dy + i) * (1.f - t * t);
+  }
+}
+
+// losses on logits (one block).  mode 0 dcgan D, 1 dcgan G, 2 wgan D (without the penalty), 3 wgan G
+__device__ __forceinline__ float softplus(float v) { return fmaxf(v, 0.f) + log1pf(__expf(-fabsf(v))); }
+
+__global__ void __launch_bounds__(256) gan_logit_loss_kernel(const float* __restrict__ real,
+                                                             const float* __restrict__ fake, int n, int mode,
+                                                             float* __restrict__ loss, float* __restrict__ dreal,
+                                                             float* __restrict__ dfake) {
+  __shared__ float red[256];
+  float s = 0.f;
+  const float inv = 1.f / (float)n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float f = __ldg(fake + i);
+    const float sf = 1.f / (1.f + __expf(-f));
+    if (mode == 0) {
+      // (xent(fake, 0) + xent(real, 1)) / 2 ;  xent(l, 0) = softplus(l), xent(l, 1) = softplus(-l)
+      const float r = __ldg(real + i);
+      const float sr = 1.f / (1.f + __expf(-r));
+      s += 0.5f * (softplus(f) + softplus(-r));
+      dfake[i] = 0.5f * sf * inv;
+      dreal[i] = 0.5f * (sr - 1.f) * inv;
+    } else if (mode == 1) {
+      s += softplus(-f);
+      dfake[i] = (sf - 1.f) * inv;
+    } else if (mode == 2) {
+      const float r = __ldg(real + i);
+      s += f - r;
+      dfake[i] = inv;
+      dreal[i] = -inv;
+    } else {
+      s -= f;
+      dfake[i] = -inv;
+    }
+  }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) loss[0] = red[0] * inv;
+}
+
+}  // namespace
+}  // namespace advoc
+
+using namespace advoc;
+
+extern "C" int advoc_gemm_f32(const float* d_a, int lda, const float* d_b, int ldb, float* d_c, int ldc, int M,
+                              int N, int K, int trans_a, int trans_b, int accumulate, const float* d_bias,
+                              void* stream) {
+  ADVOC_REQUIRE(d_a && d_b && d_c, ADVOC_BAD_ARG, "NULL matrix");
+  ADVOC_REQUIRE(M > 0 && N > 0 && K > 0 && lda > 0 && ldb > 0 && ldc >= N, ADVOC_BAD_SHAPE, "bad gemm shape");
+  dim3 grid((N + GT - 1) / GT, (M + GT - 1) / GT, 1);
+  gemm_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d_a, lda, d_b, ldb, d_c, ldc, M, N, K,
+                                                                        trans_a, trans_b, accumulate, d_bias);
+  count_launch();
+  ADVOC_CHECK_CUDA(cudaGetLastError());
+  return ADVOC_OK;
+}
+
+extern "C" int advoc_bn_stats(const float* d_x, int ld, long pixels, int C, float* d_stats, void* stream) {
+  ADVOC_REQUIRE(d_x && d_stats && pixels > 0 && C > 0 && C <= 4096 && ld >= C, ADVOC_BAD_ARG, "bad bn_stats arguments");
+  const int ppb = 256 / (C < 256 ? C : 256);
+  int blocks = grid_for(pixels, ppb * 8);
+  if (blocks > sm_count() * 4) blocks = sm_count() * 4;
+  bn_stats_kernel<<<blocks, 256, 2 * C * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(d_x, ld, pixels, C,
+                                                                                                 d_stats);
+  count_launch();
+  ADVOC_CHECK_CUDA(cudaGetLastError());
+  return ADVOC_OK;
+}
+
+extern "C" int advoc_bn_apply(const float* d_x, int ldx, long pixels, int C, const float* d_stats,
+                              const float* d_gamma, const float* d_beta, float eps, int act, float alpha, float* d_y,
+                              int ldy, int round_tf32, void* stream) {
+  ADVOC_REQUIRE(d_x && d_stats && d_gamma && d_beta && d_y && pixels > 0 && C > 0, ADVOC_BAD_ARG, "bad bn_apply arguments");
+  ADVOC_REQUIRE(act >= ADVOC_ACT_NONE && act <= ADVOC_ACT_RELU, ADVOC_BAD_ARG, "bn_apply fuses none / lrelu / relu only");
+  int blocks = grid_for(pixels * C, 256 * 4);
+  bn_apply_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d_x, ldx, pixels, C, d_stats, d_gamma,
+                                                                             d_beta, eps, act, alpha, d_y, ldy,
+                                                                             round_tf32);
+  count_launch();
+  ADVOC_CHECK_CUDA(cudaGetLastError());
+  return ADVOC_OK;
+}
+
+extern "C" int advoc_bn_backward(const float* d_dy, int lddy, const float* d_y, int ldy, const float* d_x, int ldx,
+                                 long pixels, int C, const float* d_stats, const float* d_gamma, float eps, int act,
+                                 float alpha, float* d_red, float* d_dx, int lddx, int round_tf32, void* stream) {
+  ADVOC_REQUIRE(d_dy && d_y && d_x && d_stats && d_gamma && d_red && d_dx && pixels > 0 && C > 0 && C <= 4096,
+                ADVOC_BAD_ARG, "bad bn_backward arguments");
+  ADVOC_REQUIRE(act >= ADVOC_ACT_NONE && act <= ADVOC_ACT_RELU, ADVOC_BAD_ARG, "bn_backward handles none / lrelu / relu");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int ppb = 256 / (C < 256 ? C : 256);
+  int blocks = grid_for(pixels, ppb * 8);
+  if (blocks > sm_count() * 4) blocks = sm_count() * 4;
+  bn_bwd_reduce_kernel<<<blocks, 256, 2 * C * sizeof(float), s>>>(d_dy, lddy, d_y, ldy, d_x, ldx, pixels, C, d_stats,
+                                                                  eps, act, alpha, d_red);
+  bn_bwd_apply_kernel<<<grid_for(pixels * C, 256 * 4), 256, 0, s>>>(d_dy, lddy, d_y, ldy, d_x, ldx, pixels, C, d_stats,
+                                                                    d_gamma, eps, act, alpha, d_red, d_dx, lddx,
+                                                                    round_tf32);
+  count_launch(2);
+  ADVOC_CHECK_CUDA(cudaGetLastError());
+  return ADVOC_OK;
+}
+
+extern "C" int advoc_tanh_backward(const float* d_dy, const float* d_y, float* d_dx, long n, void* stream) {
+  ADVOC_REQUIRE(d_dy && d_y && d_dx && n > 0, ADVOC_BAD_ARG, "bad tanh_backward arguments");
+  tanh_bwd_kernel<<<grid_for(n, 256 * 4), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d_dy, d_y, d_dx, n);
+  count_launch();
+  ADVOC_CHECK_CUDA(cudaGetLastError());
+  return ADVOC_OK;
+}
+
+extern "C" int advoc_gan_logit_loss(const float* d_real, const float* d_fake, int n, int mode, float* d_loss,
+                                    float* d_dreal, float* d_dfake, void* stream) {
+  ADVOC_REQUIRE(d_fake && d_loss && d_dfake && n > 0 && mode >= 0 && mode <= 3, ADVOC_BAD_ARG, "bad loss arguments");
+  ADVOC_REQUIRE((mode & 1) || (d_real && d_dreal), ADVOC_BAD_ARG, "the critic losses need the real logits");
+  gan_logit_loss_kernel<<<1, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d_real, d_fake, n, mode, d_loss,
+                                                                              d_dreal, d_dfake);
+  count_launch();
+  ADVOC_CHECK_CUDA(cudaGetLastError());
+  return ADVOC_OK;
+}

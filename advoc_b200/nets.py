@@ -86,8 +86,13 @@ class _Conv(object):
                                      1 if self.kind == 'deconv' else 0) == N.MATH_TF32
 
   def kernel_family(self):
-    if self.uses_tensor_cores():
-      return 'tc_' + self.kind
+    """Kernel that runs this layer (bench.py attributes time by it)."""
+    k = N.lib().advoc_conv2d_kernel(C.byref(self.desc), self.ldx, 1 if self.kind == 'deconv' else 0,
+                                    getattr(self, 'store_w', 0) or 0)
+    if k == 2:
+      return 'conv_p2d_kernel/' + self.kind
+    if k == 1:
+      return 'conv_tc_kernel/' + self.kind
     d = self.desc
     if self.kind == 'conv' and d.Cin <= 2:
       return 'thin_conv'

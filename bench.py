@@ -264,9 +264,49 @@ def run_gpu(args):
     dist.destroy_process_group()
 
 
+def _tf32_peak():
+  """Dense TF32 tensor-core peak measured live the way MEASURED_PEAKS.json measures bf16
+  (cuBLAS 8192^3, best of 10, CUDA events): the conv kernels compute in kind::tf32, so this is
+  the roofline denominator BASELINE.md section 2 asks for."""
+  import torch
+  old = torch.backends.cuda.matmul.allow_tf32
+  torch.backends.cuda.matmul.allow_tf32 = True
+  try:
+    n = 8192
+    a = torch.randn(n, n, device='cuda')
+    b = torch.randn(n, n, device='cuda')
+    c = torch.empty(n, n, device='cuda')
+    best = float('inf')
+    for i in range(12):
+      s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      s.record()
+      torch.matmul(a, b, out=c)
+      e.record()
+      torch.cuda.synchronize()
+      if i >= 2:
+        best = min(best, s.elapsed_time(e))
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+  finally:
+    torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def _ncu_traffic(model, batch):
+  """DRAM bytes per launch from the committed `ncu --set full` capture of this workload
+  (profiles/*_traffic.json: {"model/batch": {layer name: dram read+write bytes}})."""
+  import glob
+  best = {}
+  for fn in sorted(glob.glob(os.path.join(ROOT, 'profiles', '*_traffic.json'))):
+    try:
+      with open(fn) as f:
+        best = json.load(f).get('%s/%d' % (model, batch), best)
+    except Exception:
+      pass
+  return best
+
+
 def layer_roofline(eng, args, stream, flush):
-  """Times every layer launch of one step with CUDA events and reports the roofline of the
-  kernel family that takes the largest share of the step."""
+  """Times every layer launch of one step with CUDA events on the launching stream (L2 flushed
+  before each step) and reports the roofline of the kernel with the largest share of the step."""
   import torch
   G = eng.G
   recs = []
@@ -280,7 +320,7 @@ def layer_roofline(eng, args, stream, flush):
     recs.append((L, s, e))
 
   peaks = _peaks()
-  acc = {}
+  acc, per_layer = {}, {}
   reps = 5
   G._run_layer = timed_run
   try:
@@ -291,29 +331,48 @@ def layer_roofline(eng, args, stream, flush):
   finally:
     G._run_layer = orig
   for L, s, e in recs:
-    k = L.kernel_family()
-    d = acc.setdefault(k, dict(ms=0.0, flops=0.0, bytes=0.0, launches=0))
-    d['ms'] += s.elapsed_time(e) / reps
+    k = L.kernel_family().split('/')[0]
+    ms = s.elapsed_time(e) / reps
+    d = acc.setdefault(k, dict(ms=0.0, flops=0.0, bytes=0.0, launches=0.0, layers=[]))
+    d['ms'] += ms
     d['flops'] += L.flops() / reps
     d['bytes'] += L.algorithmic_bytes() / reps
     d['launches'] += 1.0 / reps
+    if L.name not in d['layers']:
+      d['layers'].append(L.name)
+    pl = per_layer.setdefault(L.name, dict(kernel=k, ms=0.0, gflop=L.flops() / 1e9,
+                                           mbytes=L.algorithmic_bytes() / 1e6))
+    pl['ms'] += ms
   total = sum(d['ms'] for d in acc.values())
   top = max(acc, key=lambda k: acc[k]['ms'])
   d = acc[top]
-  layers = {k: {'ms': round(v['ms'], 4), 'share': round(v['ms'] / total, 3),
-                'tflops': round(v['flops'] / (v['ms'] * 1e-3) / 1e12, 2),
-                'gbs': round(v['bytes'] / (v['ms'] * 1e-3) / 1e9, 1)} for k, v in acc.items()}
-  if top.startswith('tc'):
+  kernels = {k: {'ms': round(v['ms'], 4), 'share': round(v['ms'] / total, 3),
+                 'launches_per_step': int(round(v['launches'])),
+                 'tflops': round(v['flops'] / (v['ms'] * 1e-3) / 1e12, 2),
+                 'gbs': round(v['bytes'] / (v['ms'] * 1e-3) / 1e9, 1)} for k, v in acc.items()}
+  layers = {n.replace('generator/', '').split('/')[0]:
+                {'kernel': v['kernel'], 'us': round(v['ms'] * 1e3, 1),
+                 'tflops': round(v['gflop'] / v['ms'], 2), 'gbs': round(v['mbytes'] / v['ms'], 1)}
+            for n, v in per_layer.items()}
+  traffic_by_layer = _ncu_traffic(args.model, args.batch)
+  traffic = [traffic_by_layer[n] for n in d['layers'] if n in traffic_by_layer]
+  traffic = (sum(traffic) / len(traffic)) if len(traffic) == len(d['layers']) and traffic else None
+  n_launch = max(d['launches'], 1.0)
+  if top.startswith('conv_p2d') or top.startswith('conv_tc'):
+    tf32 = _tf32_peak()
     ach = d['flops'] / (d['ms'] * 1e-3) / 1e12
-    return {'kernel': top, 'bound': 'tensor', 'achieved': ach, 'peak': peaks['tensor'],
-            'unit': 'TFLOP/s', 'frac': ach / peaks['tensor'], 'traffic': None,
-            'peak_source': peaks['source'] + ' cuBLAS bf16 burst (kernel runs kind::tf32, whose '
-                           'nominal dense peak is half the bf16 peak)',
-            'share_of_step': d['ms'] / total, 'by_kernel': layers}
+    return {'kernel': top, 'bound': 'tensor', 'achieved': ach, 'peak': tf32, 'unit': 'TFLOP/s',
+            'frac': ach / tf32, 'traffic': traffic,
+            'peak_source': 'cuBLAS TF32 8192^3 measured in this run (the kernel computes in '
+                           'kind::tf32); MEASURED_PEAKS.json bf16 burst = %.1f' % peaks['tensor'],
+            'frac_of_bf16_peak': ach / peaks['tensor'],
+            'flops_per_launch': d['flops'] / n_launch, 'ms_per_launch': d['ms'] / n_launch,
+            'share_of_step': d['ms'] / total, 'by_kernel': kernels, 'by_layer': layers}
   ach = d['bytes'] / (d['ms'] * 1e-3) / 1e9
   return {'kernel': top, 'bound': 'hbm', 'achieved': ach, 'peak': peaks['hbm'], 'unit': 'GB/s',
-          'frac': ach / peaks['hbm'], 'traffic': None, 'peak_source': peaks['source'],
-          'share_of_step': d['ms'] / total, 'by_kernel': layers}
+          'frac': ach / peaks['hbm'], 'traffic': traffic, 'peak_source': peaks['source'] + ' copy bandwidth',
+          'bytes_per_launch': d['bytes'] / n_launch, 'ms_per_launch': d['ms'] / n_launch,
+          'share_of_step': d['ms'] / total, 'by_kernel': kernels, 'by_layer': layers}
 
 
 # ---------------------------------------------------------------------------
@@ -409,6 +468,7 @@ def run_gpu_train(args):
   samples = world * args.batch * args.steps
   value = samples / (total_ms * 1e-3)
   peaks = _peaks()
+  tf32_peak = _tf32_peak()
   tflops = TRAIN_GFLOP_PER_SAMPLE[args.model] * 1e9 * value / 1e12
   line = {
       'metric': 'G+D train-step samples/sec', 'value': value, 'unit': 'samples/s', 'n_gpus': world,
@@ -422,9 +482,10 @@ def run_gpu_train(args):
       'gpu_launches': int(per_step * args.steps * 2), 'launches_per_step': int(per_step),
       'clocks': clk.summary(),
       'roofline': {'kernel': 'whole step (all conv GEMMs)', 'bound': 'tensor',
-                   'achieved': tflops / world, 'peak': peaks['tensor_sustained'], 'unit': 'TFLOP/s',
-                   'frac': tflops / world / peaks['tensor_sustained'], 'traffic': None,
-                   'peak_source': peaks['source'] + ' cuBLAS bf16 sustained'},
+                   'achieved': tflops / world, 'peak': tf32_peak, 'unit': 'TFLOP/s',
+                   'frac': tflops / world / tf32_peak, 'traffic': None,
+                   'peak_source': 'cuBLAS TF32 8192^3 measured in this run (convs compute in kind::tf32); '
+                                  'MEASURED_PEAKS.json bf16 sustained = %.1f' % peaks['tensor_sustained']},
   }
   if rank == 0:
     print(json.dumps(line))

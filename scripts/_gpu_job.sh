@@ -1,10 +1,16 @@
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_nets.py tests/test_gpu_train.py -x -q > gpurun_out/s15_pytest.log 2>&1; tail -3 gpurun_out/s15_pytest.log
-ADVOC_P2D_PROFILE=1 python scripts/dev_p2d_prof.py small 32 2>&1 | tail -11 | sed 's/generator.//' | cut -c1-150,330-500 > gpurun_out/s15_prof.txt
-cat gpurun_out/s15_prof.txt
-timeout 200 python bench.py --no-cpu-baseline > gpurun_out/s15_bench.json 2> gpurun_out/s15_bench.err; tail -3 gpurun_out/s15_bench.err
-python -c "
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/s18_pytest.log 2>&1; tail -3 gpurun_out/s18_pytest.log
+timeout 300 python bench.py > gpurun_out/s18_bench.json 2> gpurun_out/s18_bench.err; tail -3 gpurun_out/s18_bench.err
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 3 > gpurun_out/s18_bench_n2.json 2> gpurun_out/s18_bench_n2.err; tail -3 gpurun_out/s18_bench_n2.err
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --workload train --steps 5 --warmup 3 > gpurun_out/s18_bench_train_n2.json 2> gpurun_out/s18_bench_train_n2.err; tail -3 gpurun_out/s18_bench_train_n2.err
+timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/s18_bench_ref.json 2> gpurun_out/s18_bench_ref.err
+python - <<'PY'
 import json
-d=json.loads(open('gpurun_out/s15_bench.json').read())
-print(d['value'], d['ms_per_step']); print(d['roofline']['by_kernel'])"
-ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/s15_launches.csv python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/s15_l.log 2>&1
+for f in ['s18_bench','s18_bench_n2','s18_bench_train_n2','s18_bench_ref']:
+    try:
+        d=json.loads(open('gpurun_out/%s.json'%f).read().strip().splitlines()[-1])
+        r=d.get('roofline') or {}
+        print(f, d['value'], d['ms_per_step'], d.get('e2e'), {k:v for k,v in r.items() if k not in ('by_kernel','by_layer')})
+        for k,v in (r.get('by_layer') or {}).items(): print('   ',k,v)
+    except Exception as e: print(f, 'ERR', e)
+PY
