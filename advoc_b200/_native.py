@@ -72,6 +72,12 @@ SIGNATURES = {
     'advoc_adam_tf_step': (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _L, _F, _P]),
     'advoc_conv2d_path': (_I, [C.POINTER(ConvDesc), _I, _I]),
     'advoc_conv2d_kernel': (_I, [C.POINTER(ConvDesc), _I, _I, _I]),
+    'advoc_gemm_f32': (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
+    'advoc_bn_stats': (_I, [_P, _I, _L, _I, _P, _P]),
+    'advoc_bn_apply': (_I, [_P, _I, _L, _I, _P, _P, _P, _F, _I, _F, _P, _I, _I, _P]),
+    'advoc_bn_backward': (_I, [_P, _I, _P, _I, _P, _I, _L, _I, _P, _P, _F, _I, _F, _P, _P, _I, _I, _P]),
+    'advoc_tanh_backward': (_I, [_P, _P, _P, _L, _P]),
+    'advoc_gan_logit_loss': (_I, [_P, _P, _I, _I, _P, _P, _P, _P]),
     'advoc_conv2d_transpose_fwd': (_I, [C.POINTER(ConvDesc), _P, _I, _P, C.POINTER(Epilogue), _P]),
 }
 

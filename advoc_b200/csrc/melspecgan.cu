@@ -7,9 +7,13 @@
 
 namespace advoc {
 
-int grid_for(long n, int per_block);
-
 namespace {
+
+int grid_for(long n, int per_block) {
+  long b = (n + per_block - 1) / per_block;
+  const long cap = (long)sm_count() * 16;
+  return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
 
 // ---------------------------------------------------------------------------------------------
 // C[M,N] (+)= op(A) * op(B) (+ bias[N]);  row-major, op = identity or transpose.

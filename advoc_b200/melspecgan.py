@@ -1,0 +1,401 @@
+"""MelspecGAN on B200: DCGAN-style generator / discriminator over 64 x 80 mel patches, forward,
+backward and TF1-Adam, data-parallel like the AdVoc train step.
+
+reference: models/melspecgan/conv2d.py (`dense_layer` :4-14, `conv2d_transpose_layer` :17-52,
+`conv2d_layer` :55-79, `MelspecGANGenerator.__call__` :95-150, `MelspecGANDiscriminator.__call__`
+:166-219) and models/melspecgan/train.py (:44-57 z / G, :64-72 D on real and fake, :74-111 losses,
+:117-153 optimisers and the D:G schedule).
+
+Every op is a launch into libadvoc_b200.so on persistent NHWC buffers: the 5x5 stride-2
+convolutions through the same conv entry points as AdVoc (tcgen05 TF32 where the channel counts
+allow it), dense layers / batch normalisation / tanh' / logit losses through csrc/melspecgan.cu.
+Batch normalisation uses batch statistics (`training=True`, the only mode the reference trains
+in) over each discriminator call's own batch, as the reference's three separate `D(...)` graphs do.
+
+Parameters are a dict keyed by the reference's variable names (`G/z_proj/{W,b}`,
+`G/upconv_{1..4}/{W,b}`, `G/batch_normalization{,_1,_2,_3}/{gamma,beta}`, `D/conv_{0..3}/{W,b}`,
+`D/batch_normalization{,_1,_2}/{gamma,beta}`, `D/out/{W,b}`), weights in the TF layouts.
+
+Not built: the gradient-penalty term of `TRAIN_LOSS = 'wgangp'` (train.py:99-109) needs the second
+derivative of the discriminator (double backward through conv + batch-norm + leaky-ReLU);
+`train_loss='wgangp'` raises NotImplementedError, 'dcgan' (train.py:76-94) is complete and
+'wgan' runs the critic losses of :96-97 without the penalty.
+"""
+import ctypes as C
+
+import torch
+
+from advoc_b200 import _native as N
+from advoc_b200 import nets
+from advoc_b200.nets import _epilogue, _ptr, _stream
+from advoc_b200.train import FlatParams
+
+BN_EPS = 1e-3   # tf.layers.batch_normalization default
+Z_DIM = 100     # train.py:15
+G_BN = ['G/batch_normalization', 'G/batch_normalization_1', 'G/batch_normalization_2',
+        'G/batch_normalization_3']
+D_BN = ['D/batch_normalization', 'D/batch_normalization_1', 'D/batch_normalization_2']
+
+
+def init_params(seed=0, dim=64, device='cuda'):
+  """N(0, 0.02) weights, zero biases, gamma 1 / beta 0 (conv2d.py:7-12,38-48,68-75)."""
+  g = torch.Generator(device='cpu').manual_seed(seed)
+  P = {}
+
+  def w(name, shape, nb):
+    P[name + '/W'] = (torch.randn(shape, generator=g) * 0.02).to(device)
+    P[name + '/b'] = torch.zeros(nb, device=device)
+
+  def bn(name, c):
+    P[name + '/gamma'] = torch.ones(c, device=device)
+    P[name + '/beta'] = torch.zeros(c, device=device)
+
+  w('G/z_proj', (Z_DIM, 4 * 5 * dim * 8), 4 * 5 * dim * 8)
+  bn(G_BN[0], dim * 8)
+  ch = [dim * 8, dim * 4, dim * 2, dim, 1]
+  for i in range(4):
+    w('G/upconv_%d' % (i + 1), (5, 5, ch[i + 1], ch[i]), ch[i + 1])
+    if i < 3:
+      bn(G_BN[i + 1], ch[i + 1])
+  dch = [1, dim, dim * 2, dim * 4, dim * 8]
+  for i in range(4):
+    w('D/conv_%d' % i, (5, 5, dch[i], dch[i + 1]), dch[i + 1])
+    if i > 0:
+      bn(D_BN[i - 1], dch[i + 1])
+  w('D/out', (4 * 5 * dim * 8, 1), 1)
+  return P
+
+
+def _desc5(n, h, w, cin, cout, math):
+  """5x5 stride-2 SAME conv on even sizes: TF pads (1, 2) on both axes."""
+  return N.ConvDesc(n, h, w, cin, cout, 5, 5, 2, 2, 1, 1, h // 2, w // 2, math)
+
+
+class _DBufs(object):
+  """Activations of one discriminator call (real or fake batch)."""
+
+  def __init__(self, B, dch, dev):
+    f32 = dict(dtype=torch.float32, device=dev)
+    h, w = 64, 80
+    self.X, self.Y, self.dX, self.dY, self.stats, self.red = {}, {}, {}, {}, {}, {}
+    for i in range(4):
+      h, w = h // 2, w // 2
+      shape = (B, h, w, dch[i + 1])
+      self.Y[i] = torch.empty(shape, **f32)
+      self.dY[i] = torch.empty(shape, **f32)
+      self.dX[i] = torch.empty(shape, **f32)
+      if i > 0:
+        self.X[i] = torch.empty(shape, **f32)
+        self.stats[i] = torch.zeros(2 * dch[i + 1], **f32)
+        self.red[i] = torch.zeros(2 * dch[i + 1], **f32)
+    self.logits = torch.empty(B, **f32)
+    self.dlogits = torch.empty(B, **f32)
+
+
+class MelspecGAN(object):
+  """One replica of the MelspecGAN train step for a fixed per-GPU batch."""
+
+  def __init__(self, params, batch, dim=64, train_loss='dcgan', math=N.MATH_AUTO, process_group=None,
+               world_size=1):
+    if train_loss == 'wgangp':
+      raise NotImplementedError('the WGAN-GP gradient penalty (models/melspecgan/train.py:99-109) needs a '
+                                'double backward through the discriminator, which is not built; use '
+                                "train_loss='dcgan' (train.py:76-94) or 'wgan' (critic terms only)")
+    if train_loss not in ('dcgan', 'wgan'):
+      raise ValueError()
+    self.loss_kind, self.B, self.dim, self.math = train_loss, batch, dim, math
+    self.pg, self.world = process_group, world_size
+    # optimiser settings of train.py:117-135
+    if train_loss == 'dcgan':
+      self.lr, self.b1, self.b2 = 2e-4, 0.5, 0.999
+    else:
+      self.lr, self.b1, self.b2 = 1e-4, 0.5, 0.9
+    self.eps = 1e-8
+    self.flat = FlatParams(params, gen_prefix='G/', dis_prefix='D/')
+    P = self.P = self.flat.P
+    dev = self.flat.p.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    B = batch
+    self.rnd = 0 if math == N.MATH_FP32 else 1
+    # ---- generator buffers: X[i] pre-BN, Y[i] = relu(BN(X[i])); level 0 is the projected z
+    self.gch = [dim * 8, dim * 4, dim * 2, dim, 1]
+    self.z = torch.zeros((B, Z_DIM), **f32)
+    self.ones = torch.ones((1, B), **f32)
+    self.gX, self.gY, self.gdX, self.gdY, self.gstats, self.gred = {}, {}, {}, {}, {}, {}
+    h, w = 4, 5
+    for i in range(4):
+      shape = (B, h, w, self.gch[i])
+      self.gX[i], self.gY[i] = torch.empty(shape, **f32), torch.empty(shape, **f32)
+      self.gdX[i], self.gdY[i] = torch.empty(shape, **f32), torch.empty(shape, **f32)
+      self.gstats[i] = torch.zeros(2 * self.gch[i], **f32)
+      self.gred[i] = torch.zeros(2 * self.gch[i], **f32)
+      h, w = h * 2, w * 2
+    self.G_z = torch.empty((B, 64, 80, 1), **f32)
+    self.dG_z = torch.empty((B, 64, 80, 1), **f32)
+    self.dX4 = torch.empty((B, 64, 80, 1), **f32)
+    # upconv_i (i = 1..4): transposed conv == input gradient of a conv from the big side to the small
+    self.up, self.up_b = {}, {}
+    h, w = 4, 5
+    for i in range(1, 5):
+      d = _desc5(B, 2 * h, 2 * w, self.gch[i], self.gch[i - 1], math)
+      self.up[i] = nets._Conv('G/upconv_%d' % i, 'deconv', d)     # forward
+      self.up_b[i] = nets._Conv('G/upconv_%d' % i, 'conv', d)     # its input gradient
+      h, w = 2 * h, 2 * w
+    # ---- discriminator
+    self.dch = [1, dim, dim * 2, dim * 4, dim * 8]
+    self.conv, self.conv_t = {}, {}
+    h, w = 64, 80
+    for i in range(4):
+      d = _desc5(B, h, w, self.dch[i], self.dch[i + 1], math)
+      self.conv[i] = nets._Conv('D/conv_%d' % i, 'conv', d)
+      self.conv_t[i] = nets._Conv('D/conv_%d' % i, 'deconv', d)
+      h, w = h // 2, w // 2
+    self.real, self.fake = _DBufs(B, self.dch, dev), _DBufs(B, self.dch, dev)
+    self.x_real = torch.zeros((B, 64, 80, 1), **f32)
+    self.losses = torch.zeros(2, **f32)     # D_loss, G_loss
+    self.t_d = self.t_g = 0
+    self.refresh_weights()
+
+  # -------------------------------------------------------------------------------------------
+  def refresh_weights(self):
+    """Derived (packed / TF32-rounded) filter copies for the tcgen05 path, after every Adam step."""
+    P = self.P
+    self.Wf, self.Wb = {}, {}
+    for i in range(1, 5):
+      k = P['G/upconv_%d/W' % i]
+      self.Wf[self.up[i].name] = nets._pack_for_tc(self.up[i], k, self.gch[i - 1])
+      self.Wb[self.up_b[i].name] = nets._pack_for_tc(self.up_b[i], k, self.gch[i])
+    for i in range(4):
+      k = P['D/conv_%d/W' % i]
+      self.Wf[self.conv[i].name] = nets._pack_for_tc(self.conv[i], k, self.dch[i])
+      self.Wb[self.conv_t[i].name] = nets._pack_for_tc(self.conv_t[i], k, self.dch[i + 1])
+    self.WoutT = None
+
+  def _w(self, table, L, key):
+    w = table.get(L.name)
+    return w if w is not None else self.P[key]
+
+  # -------------------------------------------------------------------------------------------
+  # primitives
+  # -------------------------------------------------------------------------------------------
+  def _gemm(self, a, lda, b, ldb, c, ldc, M, Nn, K, ta=0, tb=0, acc=0, bias=None):
+    N.call('advoc_gemm_f32', _ptr(a), lda, _ptr(b), ldb, _ptr(c), ldc, M, Nn, K, ta, tb, acc, _ptr(bias),
+           _stream())
+
+  def _bn_fwd(self, x, stats, gamma, beta, act, y):
+    Cc = x.shape[-1]
+    pixels = x.numel() // Cc
+    stats.zero_()
+    N.call('advoc_bn_stats', _ptr(x), Cc, pixels, Cc, _ptr(stats), _stream())
+    N.call('advoc_bn_apply', _ptr(x), Cc, pixels, Cc, _ptr(stats), _ptr(gamma), _ptr(beta), BN_EPS, act, 0.2,
+           _ptr(y), Cc, self.rnd, _stream())
+
+  def _bn_bwd(self, dy, y, x, stats, gamma, act, red, dx, bn_name, param_grads):
+    Cc = x.shape[-1]
+    pixels = x.numel() // Cc
+    red.zero_()
+    N.call('advoc_bn_backward', _ptr(dy), Cc, _ptr(y), Cc, _ptr(x), Cc, pixels, Cc, _ptr(stats), _ptr(gamma),
+           BN_EPS, act, 0.2, _ptr(red), _ptr(dx), Cc, self.rnd, _stream())
+    if param_grads:
+      self.flat.G[bn_name + '/beta'].add_(red[:Cc])
+      self.flat.G[bn_name + '/gamma'].add_(red[Cc:])
+
+  def _conv(self, L, x, ldx, w, ep):
+    fn = 'advoc_conv2d_fwd' if L.kind == 'conv' else 'advoc_conv2d_transpose_fwd'
+    N.call(fn, C.byref(L.desc), _ptr(x), ldx, _ptr(w), C.byref(ep), _stream())
+
+  def _wgrad(self, desc, big, ld_big, small, ld_small, name):
+    N.call('advoc_conv2d_wgrad', C.byref(desc), _ptr(big), ld_big, _ptr(small), ld_small,
+           _ptr(self.flat.G[name + '/W']), _stream())
+
+  def _bgrad(self, dy, channels, name):
+    N.call('advoc_bias_grad', _ptr(dy), channels, dy.numel() // channels, channels,
+           _ptr(self.flat.G[name + '/b']), _stream())
+
+  # -------------------------------------------------------------------------------------------
+  # generator  (conv2d.py:95-150)
+  # -------------------------------------------------------------------------------------------
+  def generate(self, z):
+    """z [B, 100] on the device -> G_z [B, 64, 80, 1] in (-1, 1)."""
+    P, B = self.P, self.B
+    self.z.copy_(z)
+    n0 = 4 * 5 * self.gch[0]
+    self._gemm(self.z, Z_DIM, P['G/z_proj/W'], n0, self.gX[0], n0, B, n0, Z_DIM, bias=P['G/z_proj/b'])
+    self._bn_fwd(self.gX[0], self.gstats[0], P[G_BN[0] + '/gamma'], P[G_BN[0] + '/beta'], N.ACT_RELU, self.gY[0])
+    for i in range(1, 5):
+      L = self.up[i]
+      w = self._w(self.Wf, L, L.name + '/W')
+      if i < 4:
+        ep = _epilogue(P[L.name + '/b'], self.gX[i], self.gch[i], 0, N.ACT_NONE)
+        self._conv(L, self.gY[i - 1], self.gch[i - 1], w, ep)
+        self._bn_fwd(self.gX[i], self.gstats[i], P[G_BN[i] + '/gamma'], P[G_BN[i] + '/beta'], N.ACT_RELU,
+                     self.gY[i])
+      else:
+        ep = _epilogue(P[L.name + '/b'], self.G_z, 1, 0, N.ACT_TANH)
+        self._conv(L, self.gY[3], self.gch[3], w, ep)
+    return self.G_z
+
+  def _g_backward(self):
+    """dG_z holds d loss / d G_z."""
+    P, B = self.P, self.B
+    N.call('advoc_tanh_backward', _ptr(self.dG_z), _ptr(self.G_z), _ptr(self.dX4), self.dX4.numel(), _stream())
+    dX = self.dX4
+    for i in range(4, 0, -1):
+      L = self.up_b[i]
+      c_big, c_small = self.gch[i], self.gch[i - 1]
+      self._wgrad(L.desc, dX, c_big, self.gY[i - 1], c_small, L.name)
+      self._bgrad(dX, c_big, L.name)
+      ep = _epilogue(None, self.gdY[i - 1], c_small, 0, N.ACT_NONE)
+      self._conv(L, dX, c_big, self._w(self.Wb, L, L.name + '/W'), ep)
+      self._bn_bwd(self.gdY[i - 1], self.gY[i - 1], self.gX[i - 1], self.gstats[i - 1], P[G_BN[i - 1] + '/gamma'],
+                   N.ACT_RELU, self.gred[i - 1], self.gdX[i - 1], G_BN[i - 1], True)
+      dX = self.gdX[i - 1]
+    n0 = 4 * 5 * self.gch[0]
+    G = self.flat.G
+    # dW = z^T dX0 ; db = 1^T dX0
+    self._gemm(self.z, Z_DIM, dX, n0, G['G/z_proj/W'], n0, Z_DIM, n0, B, ta=1, acc=1)
+    self._gemm(self.ones, B, dX, n0, G['G/z_proj/b'], n0, 1, n0, B, acc=1)
+
+  # -------------------------------------------------------------------------------------------
+  # discriminator  (conv2d.py:166-219)
+  # -------------------------------------------------------------------------------------------
+  def discriminate(self, x, bufs):
+    """x [B, 64, 80, 1] -> logits [B] (kept in bufs.logits)."""
+    P, B = self.P, self.B
+    L = self.conv[0]
+    ep = _epilogue(P[L.name + '/b'], bufs.Y[0], self.dch[1], 0, N.ACT_LRELU, round_tf32=self.rnd)
+    self._conv(L, x, 1, self._w(self.Wf, L, L.name + '/W'), ep)
+    for i in range(1, 4):
+      L = self.conv[i]
+      ep = _epilogue(P[L.name + '/b'], bufs.X[i], self.dch[i + 1], 0, N.ACT_NONE)
+      self._conv(L, bufs.Y[i - 1], self.dch[i], self._w(self.Wf, L, L.name + '/W'), ep)
+      self._bn_fwd(bufs.X[i], bufs.stats[i], P[D_BN[i - 1] + '/gamma'], P[D_BN[i - 1] + '/beta'], N.ACT_LRELU,
+                   bufs.Y[i])
+    k = 4 * 5 * self.dch[4]
+    self._gemm(bufs.Y[3], k, P['D/out/W'], 1, bufs.logits, 1, B, 1, k, bias=P['D/out/b'])
+    return bufs.logits
+
+  def _d_backward(self, x, bufs, param_grads, input_grad):
+    """bufs.dlogits holds d loss / d logits."""
+    P, B, G = self.P, self.B, self.flat.G
+    k = 4 * 5 * self.dch[4]
+    if param_grads:
+      self._gemm(bufs.Y[3], k, bufs.dlogits, 1, G['D/out/W'], 1, k, 1, B, ta=1, acc=1)
+      self._gemm(self.ones, B, bufs.dlogits, 1, G['D/out/b'], 1, 1, 1, B, acc=1)
+    # dY3 = dlogits (x) W^T
+    self._gemm(bufs.dlogits, 1, P['D/out/W'], 1, bufs.dY[3], k, B, k, 1, tb=1)
+    for i in range(3, 0, -1):
+      L = self.conv[i]
+      self._bn_bwd(bufs.dY[i], bufs.Y[i], bufs.X[i], bufs.stats[i], P[D_BN[i - 1] + '/gamma'], N.ACT_LRELU,
+                   bufs.red[i], bufs.dX[i], D_BN[i - 1], param_grads)
+      if param_grads:
+        self._wgrad(L.desc, bufs.Y[i - 1], self.dch[i], bufs.dX[i], self.dch[i + 1], L.name)
+        self._bgrad(bufs.dX[i], self.dch[i + 1], L.name)
+      Lt = self.conv_t[i]
+      if i > 1:
+        ep = _epilogue(None, bufs.dY[i - 1], self.dch[i], 0, N.ACT_NONE)
+      else:   # conv_0 has no batch norm: fold its leaky-ReLU derivative into this epilogue
+        ep = _epilogue(None, bufs.dX[0], self.dch[1], 0, N.ACT_NONE, gate=bufs.Y[0], ld_gate=self.dch[1],
+                       gate_act=N.ACT_LRELU, round_tf32=self.rnd)
+      self._conv(Lt, bufs.dX[i], self.dch[i + 1], self._w(self.Wb, Lt, Lt.name + '/W'), ep)
+    L = self.conv[0]
+    if param_grads:
+      self._wgrad(L.desc, x, 1, bufs.dX[0], self.dch[1], L.name)
+      self._bgrad(bufs.dX[0], self.dch[1], L.name)
+    if input_grad:
+      Lt = self.conv_t[0]
+      ep = _epilogue(None, self.dG_z, 1, 0, N.ACT_NONE)
+      self._conv(Lt, bufs.dX[0], self.dch[1], self._w(self.Wb, Lt, Lt.name + '/W'), ep)
+
+  # -------------------------------------------------------------------------------------------
+  # optimiser + collective
+  # -------------------------------------------------------------------------------------------
+  def _finish(self, lo, hi, t, apply):
+    from advoc_b200 import dist as D
+    D.allreduce_sum_(self.flat.g, lo, hi, self.pg, self.world)
+    if apply:
+      f = self.flat
+      o = lambda t_: C.c_void_p(t_.data_ptr() + 4 * lo)
+      N.call('advoc_adam_tf_step', o(f.p), o(f.g), o(f.m), o(f.v), hi - lo, self.lr, self.b1, self.b2, self.eps,
+             t, 1.0 / self.world, _stream())
+      self.refresh_weights()
+
+  def d_step(self, x, z, apply=True):
+    """`D_train_op` on one minibatch (train.py:139,151): x [B,64,80,1] in [-1,1], z [B,100]."""
+    lo, hi = self.flat.dis_range()
+    self.flat.g[lo:hi].zero_()
+    self.x_real.copy_(x)
+    G_z = self.generate(z)
+    self.discriminate(self.x_real, self.real)
+    self.discriminate(G_z, self.fake)
+    N.call('advoc_gan_logit_loss', _ptr(self.real.logits), _ptr(self.fake.logits), self.B,
+           0 if self.loss_kind == 'dcgan' else 2, _ptr(self.losses), _ptr(self.real.dlogits),
+           _ptr(self.fake.dlogits), _stream())
+    self._d_backward(self.x_real, self.real, True, False)
+    self._d_backward(G_z, self.fake, True, False)
+    if apply:
+      self.t_d += 1
+    self._finish(lo, hi, self.t_d, apply)
+
+  def g_step(self, z, apply=True):
+    """`G_train_op` on one draw of z (train.py:137-138,153)."""
+    lo, hi = self.flat.gen_range()
+    self.flat.g[lo:hi].zero_()
+    G_z = self.generate(z)
+    self.discriminate(G_z, self.fake)
+    N.call('advoc_gan_logit_loss', None, _ptr(self.fake.logits), self.B, 1 if self.loss_kind == 'dcgan' else 3,
+           C.c_void_p(self.losses.data_ptr() + 4), None, _ptr(self.fake.dlogits), _stream())
+    self._d_backward(G_z, self.fake, False, True)
+    self._g_backward()
+    if apply:
+      self.t_g += 1
+    self._finish(lo, hi, self.t_g, apply)
+    return self.t_g
+
+  def train_loop(self, batches, zs_d, z_g):
+    """One outer iteration of train.py:149-153: `num_disc_updates_per_genr` D steps (1 for dcgan,
+    5 for the WGAN losses), each on a fresh minibatch and a fresh z, then one G step."""
+    for x, z in zip(batches, zs_d):
+      self.d_step(x, z)
+    return self.g_step(z_g)
+
+  def loss_values(self):
+    v = self.losses.tolist()
+    return v[0], v[1]
+
+
+# ---------------------------------------------------------------------------------------------
+# Callable mirrors of the reference classes (models/melspecgan/conv2d.py:82-95,153-166): same
+# names, constructor arguments and call signature; tensors are CUDA float32 in the reference's
+# shapes.  `training=False` would need BatchNorm moving averages, which the reference only uses
+# in its `infer` / `incept` graphs (train.py:163,192); they are not tracked here.
+# ---------------------------------------------------------------------------------------------
+class _Net(object):
+  def __init__(self, dim=64, kernel_len=5, batchnorm=True, params=None):
+    if kernel_len != 5 or not batchnorm:
+      raise NotImplementedError()
+    self.dim, self.kernel_len, self.stride, self.batchnorm = dim, kernel_len, 2, batchnorm
+    self.params = params
+    self._eng = None
+
+  def _engine(self, batch):
+    if self._eng is None or self._eng.B != batch:
+      if self.params is None:
+        self.params = init_params(dim=self.dim)
+      self._eng = MelspecGAN(self.params, batch, dim=self.dim)
+    return self._eng
+
+
+class MelspecGANGenerator(_Net):
+  def __call__(self, z, training=False):
+    if not training:
+      raise NotImplementedError('moving-average batch norm (inference graphs) is not tracked')
+    return self._engine(z.shape[0]).generate(z)
+
+
+class MelspecGANDiscriminator(_Net):
+  def __call__(self, x, training=False):
+    if not training:
+      raise NotImplementedError('moving-average batch norm (inference graphs) is not tracked')
+    eng = self._engine(x.shape[0])
+    return eng.discriminate(x.contiguous(), eng.real)

@@ -29,15 +29,15 @@ def _view_ptr(t, coff):
 class FlatParams(object):
   """All parameters in one flat buffer, generator first; the dict holds views."""
 
-  def __init__(self, params):
-    names = sorted(params, key=lambda n: (0 if n.startswith('generator') else 1, n))
+  def __init__(self, params, gen_prefix='generator', dis_prefix='discriminator'):
+    names = sorted(params, key=lambda n: (0 if n.startswith(gen_prefix) else 1, n))
     self.names = names
     self.offsets, off = {}, 0
     for n in names:
       self.offsets[n] = off
       off += (params[n].numel() + 3) // 4 * 4   # keep every tensor 16-byte aligned
     self.total = off
-    self.n_gen = min([self.offsets[n] for n in names if n.startswith('discriminator')] or [off])
+    self.n_gen = min([self.offsets[n] for n in names if n.startswith(dis_prefix)] or [off])
     dev = params[names[0]].device
     self.p = torch.zeros(off, dtype=torch.float32, device=dev)
     self.g = torch.zeros(off, dtype=torch.float32, device=dev)

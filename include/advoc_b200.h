@@ -266,6 +266,47 @@ ADVOC_API int advoc_conv2d_path(const advoc_conv_desc* d, int ld_x, int transpos
  * to attribute time to kernels.  replaces: nothing in the reference. */
 ADVOC_API int advoc_conv2d_kernel(const advoc_conv_desc* d, int ld_x, int transposed, int store_w);
 
+/* ------------------------------------------------------------------------- *
+ * MelspecGAN building blocks (models/melspecgan/conv2d.py, models/melspecgan/train.py).
+ * The 5x5 stride-2 convolutions go through advoc_conv2d_fwd / _transpose_fwd / _wgrad.
+ * ------------------------------------------------------------------------- */
+
+/* C[M,N] (+)= op(A) * op(B) (+ bias[N]); row-major fp32, op = identity or transpose (trans_* != 0
+ * means the operand is stored transposed: A as [K,M], B as [N,K]).
+ * replaces: tf.matmul + tf.nn.bias_add of dense_layer (conv2d.py:4-14) and their gradients. */
+ADVOC_API int advoc_gemm_f32(const float* d_a, int lda, const float* d_b, int ldb, float* d_c, int ldc,
+                             int M, int N, int K, int trans_a, int trans_b, int accumulate,
+                             const float* d_bias, void* stream);
+
+/* d_stats[0:C] += sum_pixels x, d_stats[C:2C] += sum_pixels x^2 (caller zeroes d_stats).
+ * replaces: the batch moments of tf.layers.batch_normalization(training=True), conv2d.py:108,178. */
+ADVOC_API int advoc_bn_stats(const float* d_x, int ld, long pixels, int C, float* d_stats, void* stream);
+
+/* y = act(gamma * (x - mean) / sqrt(var + eps) + beta), act in {none, lrelu, relu}; mean / biased
+ * var from d_stats.  replaces: tf.layers.batch_normalization + tf.nn.relu / leaky_relu,
+ * conv2d.py:116-137,186-201. */
+ADVOC_API int advoc_bn_apply(const float* d_x, int ldx, long pixels, int C, const float* d_stats,
+                             const float* d_gamma, const float* d_beta, float eps, int act, float alpha,
+                             float* d_y, int ldy, int round_tf32, void* stream);
+
+/* Backward of advoc_bn_apply: g = dy * act'(y); d_red[0:C] += sum g (dbeta), d_red[C:2C] += sum g*xhat
+ * (dgamma) (caller zeroes d_red); dx = gamma/sqrt(var+eps) * (g - dbeta/M - xhat*dgamma/M).
+ * replaces: the autodiff of the same ops (opt.minimize, train.py:137-139). */
+ADVOC_API int advoc_bn_backward(const float* d_dy, int lddy, const float* d_y, int ldy, const float* d_x,
+                                int ldx, long pixels, int C, const float* d_stats, const float* d_gamma,
+                                float eps, int act, float alpha, float* d_red, float* d_dx, int lddx,
+                                int round_tf32, void* stream);
+
+/* dx = dy * (1 - y^2).  replaces: the gradient of tf.nn.tanh, conv2d.py:141. */
+ADVOC_API int advoc_tanh_backward(const float* d_dy, const float* d_y, float* d_dx, long n, void* stream);
+
+/* Losses on the critic's logits with gradient seeds (mean over n):
+ *   mode 0 dcgan D: (xent(fake,0) + xent(real,1)) / 2     mode 1 dcgan G: xent(fake,1)
+ *   mode 2 wgan  D: mean(fake) - mean(real) (penalty term not included)   mode 3 wgan G: -mean(fake)
+ * replaces: models/melspecgan/train.py:76-97. */
+ADVOC_API int advoc_gan_logit_loss(const float* d_real, const float* d_fake, int n, int mode, float* d_loss,
+                                   float* d_dreal, float* d_dfake, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -95,7 +95,7 @@ def generator(P, z, dim=DIM, return_layers=False):
   return (x, layers) if return_layers else x
 
 
-def discriminator(P, x, return_layers=False):
+def discriminator(P, x, return_layers=False, dim=None):
   """x [b, 64, 80, 1] -> logits [b]  (conv2d.py:166-219, training=True)."""
   layers = []
   for i in range(4):
@@ -111,7 +111,11 @@ def discriminator(P, x, return_layers=False):
 
 def losses(P, z, x, train_loss='wgangp', alpha=None):
   """G_loss, D_loss of train.py:74-111.  `alpha` [b,1,1,1] = the interpolation draw of :100."""
-  G_z = generator(P, z)
+  return losses_dim(P, z, x, P['G/upconv_4/W'].shape[3], train_loss, alpha)
+
+
+def losses_dim(P, z, x, dim, train_loss='wgangp', alpha=None):
+  G_z = generator(P, z, dim)
   D_x = discriminator(P, x)
   D_G_z = discriminator(P, G_z)
   if train_loss == 'dcgan':

@@ -1,0 +1,104 @@
+"""GPU parity of the MelspecGAN stacks and train step (through the C-ABI) against the PyTorch-CPU
+oracle (oracle/melspecgan_torch.py; parity unpinned by the reference).  Tolerances: forward 1e-3
+relative L2 on the TF32 tensor-core path (BASELINE.json north_star), 1e-4 on the exact-fp32 path
+(batch-norm divides by small per-channel deviations, which amplifies fp32 summation-order noise);
+gradients 6e-3 (fp32: the deepest ones pass through eight batch-normalised layers at batch 6, where ReLU gates of near-zero activations flip with summation order) / 6e-2 (TF32 operands through sixteen layer passes)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+  a = a.detach().double().cpu()
+  b = b.detach().double().cpu()
+  return float((a - b).norm() / b.norm().clamp_min(1e-300))
+
+
+# a bias added right before a batch normalisation has an exactly zero gradient (the mean
+# subtraction removes it): both sides hold rounding noise there, so compare absolutely
+_DEAD_BIAS = ('D/conv_1/b', 'D/conv_2/b', 'D/conv_3/b', 'G/upconv_1/b', 'G/upconv_2/b',
+              'G/upconv_3/b')
+
+
+def _check_grads(eng, ref, names, gtol):
+  for n in names:
+    if n in _DEAD_BIAS:
+      scale = float(ref[n[:-2] + '/W'].norm())
+      assert float(eng.flat.G[n].norm()) < 1e-3 * scale and float(ref[n].norm()) < 1e-3 * scale, n
+    else:
+      # bias / beta gradients are plain sums over the batch with heavy cancellation: TF32 operand
+      # rounding upstream shows up ~3x larger in them than in the filter gradients
+      tol = 3 * gtol if (gtol > 1e-2 and (n.endswith('/b') or n.endswith('/beta'))) else gtol
+      assert _rel(eng.flat.G[n], ref[n]) < tol, n
+
+
+def _setup(math, dim, batch, loss='dcgan', seed=0):
+  from advoc_b200 import _native as N
+  from advoc_b200.melspecgan import MelspecGAN
+  from oracle import melspecgan_torch as M
+  P = M.init_params(seed=seed, dim=dim)
+  g = torch.Generator().manual_seed(5)
+  for n in P:   # make biases / BN parameters non-trivial
+    if n.endswith('/b') or n.endswith('/beta'):
+      P[n] = torch.randn(P[n].shape, generator=g) * 0.05
+    if n.endswith('/gamma'):
+      P[n] = 1 + torch.randn(P[n].shape, generator=g) * 0.1
+  eng = MelspecGAN({k: v.cuda() for k, v in P.items()}, batch, dim=dim, train_loss=loss,
+                   math=N.MATH_FP32 if math == 'fp32' else N.MATH_AUTO)
+  z = torch.randn(batch, M.Z_DIM, generator=g)
+  x = torch.rand(batch, 64, 80, 1, generator=g) * 2 - 1
+  return M, P, eng, z, x
+
+
+@pytest.mark.parametrize('math,tol', [('fp32', 1e-4), ('auto', 1e-3)])
+def test_forward_matches_oracle(math, tol):
+  M, P, eng, z, x = _setup(math, 64, 8)
+  G_z = eng.generate(z.cuda())
+  ref, layers = M.generator(P, z, 64, return_layers=True)
+  assert G_z.shape == ref.shape == (8, 64, 80, 1)
+  for i in range(4):
+    assert _rel(eng.gY[i], layers[i]) < tol, i
+  assert _rel(G_z, ref) < tol
+  logits = eng.discriminate(x.cuda().contiguous(), eng.real)
+  want, dl = M.discriminator(P, x, return_layers=True)
+  for i in range(4):
+    assert _rel(eng.real.Y[i], dl[i]) < tol, i
+  assert _rel(logits, want) < 5 * tol     # one 10240-term dot product of the activations above
+
+
+@pytest.mark.parametrize('math,gtol', [('fp32', 6e-3), ('auto', 6e-2)])
+@pytest.mark.parametrize('loss', ['dcgan', 'wgan'])
+def test_train_step_gradients(math, gtol, loss):
+  M, P, eng, z, x = _setup(math, 32, 6, loss)
+  Pr = {n: t.clone().requires_grad_(True) for n, t in P.items()}
+  G_z = M.generator(Pr, z, 32)
+  D_x, D_G_z = M.discriminator(Pr, x), M.discriminator(Pr, G_z)
+  if loss == 'dcgan':
+    l = M.losses_dim(Pr, z, x, 32, 'dcgan')
+    D_loss, G_loss = l['D_loss'], l['G_loss']
+  else:
+    D_loss, G_loss = D_G_z.mean() - D_x.mean(), -D_G_z.mean()
+  dn, gn = M.d_names(P), M.g_names(P)
+  ref_d = dict(zip(dn, torch.autograd.grad(D_loss, [Pr[n] for n in dn], retain_graph=True)))
+  ref_g = dict(zip(gn, torch.autograd.grad(G_loss, [Pr[n] for n in gn])))
+  eng.d_step(x.cuda(), z.cuda(), apply=False)
+  assert abs(eng.loss_values()[0] - float(D_loss)) < 2e-3 * max(abs(float(D_loss)), 1e-2)
+  _check_grads(eng, ref_d, dn, gtol)
+  eng.g_step(z.cuda(), apply=False)
+  assert abs(eng.loss_values()[1] - float(G_loss)) < 2e-3 * max(abs(float(G_loss)), 1e-2)
+  _check_grads(eng, ref_g, gn, gtol)
+
+
+def test_adam_updates_and_wgangp_is_loud():
+  from advoc_b200.melspecgan import MelspecGAN
+  M, P, eng, z, x = _setup('auto', 32, 4)
+  before = eng.flat.p.clone()
+  eng.train_loop([x.cuda()], [z.cuda()], z.cuda())
+  delta = (eng.flat.p - before).abs()
+  assert eng.t_d == 1 and eng.t_g == 1 and torch.isfinite(eng.flat.p).all()
+  lo, hi = eng.flat.dis_range()
+  assert float(delta[lo:hi].max()) > 0 and float(delta[:lo].max()) > 0
+  assert float(delta.max()) <= 2.1e-4      # |Adam step| <= lr at t = 1
+  with pytest.raises(NotImplementedError):
+    MelspecGAN({k: v.cuda() for k, v in P.items()}, 4, dim=32, train_loss='wgangp')
