@@ -74,6 +74,10 @@ bool conv_p2d_eligible(const advoc_conv_desc* d, int ldx, int transposed, int st
 int conv_p2d(const advoc_conv_desc* d, int transposed, const float* x, int ldx, const float* w,
              const advoc_epilogue* ep, void* stream);
 bool tc_epilogue_ok(const advoc_epilogue* ep);
+bool deconv_one_tc_geometry(const advoc_conv_desc* d, int ldx);
+bool deconv_one_tc_eligible(const advoc_conv_desc* d, const float* x, int ldx, const advoc_epilogue* ep);
+int deconv_one_tc(const advoc_conv_desc* d, const float* x, int ldx, const float* w, const advoc_epilogue* ep,
+                  void* stream);
 
 }  // namespace advoc
 
@@ -140,6 +144,7 @@ extern "C" int advoc_conv2d_transpose_fwd(const advoc_conv_desc* d, const float*
   int st = check_conv_io(d, d_x, ld_x, d ? d->Cout : 0, d_w, ep);
   if (st) return st;
   if (d->math == ADVOC_MATH_FP32) return conv_transposed_simt(d, d_x, ld_x, d_w, ep, stream);
+  if (deconv_one_tc_eligible(d, d_x, ld_x, ep)) return deconv_one_tc(d, d_x, ld_x, d_w, ep, stream);
   const bool ok = conv_transposed_tc_eligible(d, ld_x);
   if (d->math == ADVOC_MATH_TF32 || ok) {
     ADVOC_REQUIRE(ok, ADVOC_UNSUPPORTED, "conv_transpose shape not eligible for the tcgen05 path");
@@ -156,12 +161,14 @@ extern "C" int advoc_conv2d_transpose_fwd(const advoc_conv_desc* d, const float*
 
 extern "C" int advoc_conv2d_path(const advoc_conv_desc* d, int ld_x, int transposed) {
   if (!d || d->math == ADVOC_MATH_FP32) return ADVOC_MATH_FP32;
+  if (transposed && deconv_one_tc_geometry(d, ld_x)) return ADVOC_MATH_TF32;
   const bool ok = transposed ? conv_transposed_tc_eligible(d, ld_x) : conv_fwd_tc_eligible(d, ld_x);
   return ok ? ADVOC_MATH_TF32 : ADVOC_MATH_FP32;
 }
 
 extern "C" int advoc_conv2d_kernel(const advoc_conv_desc* d, int ld_x, int transposed, int store_w) {
   if (advoc_conv2d_path(d, ld_x, transposed) != ADVOC_MATH_TF32) return 0;
+  if (transposed && deconv_one_tc_geometry(d, ld_x)) return 3;
   return conv_p2d_eligible(d, ld_x, transposed, store_w) ? 2 : 1;
 }
 

@@ -137,13 +137,14 @@ __global__ void __launch_bounds__(128) conv_thin_px_kernel(const ThinArgs<CIN> a
   __syncthreads();
   const long pix = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned pix_in_img = a.Ho * a.Wo;
-  if (pix >= (long)a.N * pix_in_img) return;
+  const bool valid = pix < (long)a.N * pix_in_img;
+  float4 acc[COUT / 4];
+  if (valid) {
   const unsigned img = (unsigned)(pix / pix_in_img);
   const unsigned rem = (unsigned)(pix - (long)img * pix_in_img);
   const int oh = rem / a.Wo, ow = rem - oh * a.Wo;
   const float* xb = a.x + (size_t)img * a.H * a.W * a.ldx;
   const int ih0 = oh * a.sh - a.pt, iw0 = ow * a.sw - a.pl;
-  float4 acc[COUT / 4];
 #pragma unroll
   for (int j = 0; j < COUT / 4; ++j) acc[j] = bs4[j];
 #pragma unroll
@@ -170,21 +171,40 @@ __global__ void __launch_bounds__(128) conv_thin_px_kernel(const ThinArgs<CIN> a
       }
     }
   }
-  const float s0 = act_slope(e.act0, e.alpha), s1 = act_slope(e.act1, e.alpha);
-  float4* o0 = reinterpret_cast<float4*>(e.out0 + (size_t)pix * e.ld0 + e.coff0);
-  float4* o1 = e.out1 ? reinterpret_cast<float4*>(e.out1 + (size_t)pix * e.ld1 + e.coff1) : nullptr;
+  }   // valid pixel
+  // Stores: a thread-per-pixel store touches 32 different 128-byte lines per instruction.  Stage the
+  // raw accumulators in shared memory (16-byte chunk j of pixel p at chunk j ^ (p & 7): conflict
+  // free both ways) and write them out cooperatively, 8 consecutive lanes per pixel row, so every
+  // store instruction covers whole lines; both activations are applied on the way out.
+  {
+    __shared__ float4 stage[128 * (COUT / 4)];
+    constexpr int Q = COUT / 4;
+    static_assert(Q == 8 || Q == 16, "staging layout assumes 32 or 64 output channels");
+    if (valid) {
 #pragma unroll
-  for (int j = 0; j < COUT / 4; ++j) {
-    const float4 v = acc[j];
-    float4 y = make_float4(v.x > 0.f ? v.x : s0 * v.x, v.y > 0.f ? v.y : s0 * v.y,
-                           v.z > 0.f ? v.z : s0 * v.z, v.w > 0.f ? v.w : s0 * v.w);
-    if (e.round) y = make_float4(round_tf32(y.x), round_tf32(y.y), round_tf32(y.z), round_tf32(y.w));
-    o0[j] = y;
-    if (o1) {
-      float4 z = make_float4(v.x > 0.f ? v.x : s1 * v.x, v.y > 0.f ? v.y : s1 * v.y,
-                             v.z > 0.f ? v.z : s1 * v.z, v.w > 0.f ? v.w : s1 * v.w);
-      if (e.round) z = make_float4(round_tf32(z.x), round_tf32(z.y), round_tf32(z.z), round_tf32(z.w));
-      o1[j] = z;
+      for (int j = 0; j < Q; ++j) stage[threadIdx.x * Q + (j ^ (threadIdx.x & 7))] = acc[j];
+    }
+    __syncthreads();
+    const float s0 = act_slope(e.act0, e.alpha), s1 = act_slope(e.act1, e.alpha);
+    const long pix0 = (long)blockIdx.x * blockDim.x;
+    const long npix = (long)a.N * pix_in_img;
+#pragma unroll
+    for (int k = 0; k < Q; ++k) {
+      const int i = threadIdx.x + 128 * k;
+      const int p = i / Q, j = i % Q;
+      const long gp = pix0 + p;
+      if (gp >= npix) continue;
+      const float4 v = stage[p * Q + (j ^ (p & 7))];
+      float4 y = make_float4(v.x > 0.f ? v.x : s0 * v.x, v.y > 0.f ? v.y : s0 * v.y,
+                             v.z > 0.f ? v.z : s0 * v.z, v.w > 0.f ? v.w : s0 * v.w);
+      if (e.round) y = make_float4(round_tf32(y.x), round_tf32(y.y), round_tf32(y.z), round_tf32(y.w));
+      reinterpret_cast<float4*>(e.out0 + (size_t)gp * e.ld0 + e.coff0)[j] = y;
+      if (e.out1) {
+        float4 z = make_float4(v.x > 0.f ? v.x : s1 * v.x, v.y > 0.f ? v.y : s1 * v.y,
+                               v.z > 0.f ? v.z : s1 * v.z, v.w > 0.f ? v.w : s1 * v.w);
+        if (e.round) z = make_float4(round_tf32(z.x), round_tf32(z.y), round_tf32(z.z), round_tf32(z.w));
+        reinterpret_cast<float4*>(e.out1 + (size_t)gp * e.ld1 + e.coff1)[j] = z;
+      }
     }
   }
 }
@@ -222,6 +242,7 @@ __global__ void __launch_bounds__(256) deconv_to_one_kernel(const ToOneArgs a) {
 
   // phase 1: thread t owns positions t and t + 256 (tile rows r and r + 8, same column)
   {
+
     const int col = threadIdx.x & (T1_TW - 1), row = threadIdx.x >> 5;
     const int bc = b0 + col, ar0 = a0 + row, ar1 = ar0 + T1_TH / 2;
     const bool okc = bc >= 0 && bc < a.Ws;
@@ -328,7 +349,7 @@ int conv_thin(const advoc_conv_desc* d, const float* x, int ldx, const float* w,
 // transposed conv FROM one channel: x [N,Ho,Wo,1] -> y [N,H,W,Cin(desc)]; w [16][Cin(desc)][1]
 bool deconv_from_one_eligible(const advoc_conv_desc* d, const advoc_epilogue* ep) {
   auto ok = [](const float* p, int ld, int co) { return aligned16(p) && ld % 4 == 0 && co % 4 == 0; };
-  return d->Cout == 1 && d->kh == 4 && d->kw == 4 && d->Cin % 4 == 0 && d->Cin <= 256 &&
+  return d->Cout == 1 && d->kh == 4 && d->kw == 4 && d->Cin % 4 == 0 && d->Cin <= 512 &&
          256 % (d->Cin / 4) == 0 && ep->keep_prob >= 1.f && ep->store_w == 0 && ep->d_out1 == nullptr &&
          ok(ep->d_out0, ep->ld0, ep->c_off0);
 }

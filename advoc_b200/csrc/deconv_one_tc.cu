@@ -1,0 +1,249 @@
+// k4 s2 transposed convolution to ONE output channel on the tensor cores (generator decoder_1,
+// models/advoc/advoc_model.py:153-158; also the input gradient of the discriminator's layer_1).
+//
+// The layer is bound by reading its [N, Hs, Ws, Cs] input once (269 MB at B = 32 for AdVoc-small).
+// The CUDA-core kernel (conv_direct.cu) reads it with thread-per-pixel 16-byte loads (1.8 TB/s); here
+// TMA streams 8 x 16-pixel patches (halo included) into 128B-swizzled shared memory and one
+// M = 128, N = 16 tcgen05.mma chain per patch computes the 16 tap dot products of every position,
+//     T[pos, tap] = <x[pos, :], w[tap, :]>          (TF32 operands, fp32 accumulate in TMEM),
+// which the epilogue warps fold into output pixels without atomics (col2im in shared memory):
+//     out[2a+ph, 2b+pw] = sum_{dr,dc} T(a+dr, b+dc)[ph+1-2dr, pw+1-2dc]      for the 6 x 14 interior.
+// Persistent CTAs; warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue; the accumulator
+// and the T staging buffer are double-buffered so the epilogue of a patch overlaps the next.
+#include "epilogue.cuh"
+#include "tc_ptx.cuh"
+
+#include <stdlib.h>
+
+namespace advoc {
+
+int lower_epilogue(const advoc_epilogue* ep, int Hs, int Wfull, int Cout, EpiDev* out);
+
+namespace {
+
+using namespace tc;
+
+constexpr int O_PH = 8, O_PW = 16;            // patch (GEMM rows = O_PH * O_PW = 128)
+constexpr int O_IH = O_PH - 2, O_IW = O_PW - 2;
+constexpr int O_STAGES = 8;                   // 16 KB patch slots
+constexpr int O_THREADS = 192;
+constexpr int O_MAXKB = 8;                    // Cs <= 256
+
+struct alignas(64) OneParams {
+  CUtensorMap tmA;   // tiled 4-D {c, w, h, n}, box {32, 16, 8, 1}
+  CUtensorMap tmB;   // taps [16][Cs], box {32, 16}
+  int N, Hs, Ws, kblocks, tiles_h, tiles_w;
+  long total_tiles;
+  EpiDev epi;
+  unsigned int* dbg;
+};
+
+__device__ __forceinline__ void mbar_arrive1(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+
+__global__ void __launch_bounds__(O_THREADS, 1) deconv_one_tc_kernel(const __grid_constant__ OneParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t a_full[O_STAGES], a_empty[O_STAGES];
+  __shared__ __align__(8) uint64_t b_full, acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_base_holder;
+  __shared__ float tsm[2][O_PH * O_PW][17];   // T[pos][tap], +1 pad: conflict-free column access
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* ring_ptr = smem_raw + (ring - smem_u32(smem_raw));
+  constexpr uint32_t A_BYTES = O_PH * O_PW * 128;   // one k-block of one patch
+  constexpr uint32_t B_BYTES = 16 * 128;            // one k-block of the 16 taps
+  const uint32_t b_off = O_STAGES * A_BYTES;
+  const long ntl = p.total_tiles;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < O_STAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    mbar_init(&b_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    prefetch_tmap(&p.tmA);
+    prefetch_tmap(&p.tmB);
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(&tmem_base_holder)),
+                 "r"(32u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_holder;
+  const bool aborted = p.dbg && *reinterpret_cast<volatile unsigned int*>(p.dbg) != 0;
+  const int per_img = p.tiles_h * p.tiles_w;
+
+  if (aborted) {
+  } else if (warp == 0) {
+    // ===== TMA producer: the resident tap matrix once, then one box per (patch, k-block) =====
+    if ((long)blockIdx.x < ntl) {
+      if (elect_one()) {
+        mbar_expect_tx(&b_full, (uint32_t)p.kblocks * B_BYTES);
+        for (int kb = 0; kb < p.kblocks; ++kb)
+          tma_load_2d(&p.tmB, &b_full, ring_ptr + b_off + (size_t)kb * B_BYTES, kb * 32, 0);
+      }
+      __syncwarp();
+    }
+    int as = 0;
+    uint32_t aph = 0;
+    for (long t = blockIdx.x; t < ntl; t += gridDim.x) {
+      const int img = (int)(t / per_img);
+      const int r = (int)(t - (long)img * per_img);
+      const int a0 = (r / p.tiles_w) * O_IH - 1, b0 = (r % p.tiles_w) * O_IW - 1;
+      for (int kb = 0; kb < p.kblocks; ++kb) {
+        mbar_wait(&a_empty[as], aph ^ 1u, p.dbg, 41u);
+        __syncwarp();
+        if (elect_one()) {
+          mbar_expect_tx(&a_full[as], A_BYTES);
+          tma_load_4d(&p.tmA, &a_full[as], ring_ptr + (size_t)as * A_BYTES, kb * 32, b0, a0, img);
+        }
+        __syncwarp();
+        if (++as == O_STAGES) { as = 0; aph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: M = 128 positions, N = 16 taps, K = Cs =====
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(16 >> 3) << 17) |
+                               ((uint32_t)(128 >> 4) << 24);
+    int as = 0;
+    uint32_t aph = 0;
+    long i = 0;
+    if ((long)blockIdx.x < ntl) mbar_wait(&b_full, 0u, p.dbg, 42u);
+    for (long t = blockIdx.x; t < ntl; t += gridDim.x, ++i) {
+      const int buf = (int)(i & 1);
+      const uint32_t use = (uint32_t)(i >> 1);
+      mbar_wait(&acc_empty[buf], (use & 1u) ^ 1u, p.dbg, 43u);
+      tc_fence_after();
+      for (int kb = 0; kb < p.kblocks; ++kb) {
+        mbar_wait(&a_full[as], aph, p.dbg, 44u);
+        tc_fence_after();
+        const uint64_t da = make_smem_desc(ring + (uint32_t)as * A_BYTES);
+        const uint64_t db = make_smem_desc(ring + b_off + (uint32_t)kb * B_BYTES);
+        __syncwarp();
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_tf32(tmem_base + (uint32_t)buf * 16u, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                      (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&a_empty[as]);
+          if (kb == p.kblocks - 1) umma_commit(&acc_full[buf]);
+        }
+        __syncwarp();
+        if (++as == O_STAGES) { as = 0; aph ^= 1u; }
+      }
+    }
+  } else {
+    // ===== epilogue: TMEM -> T[pos][tap] in smem -> col2im -> output pixels =====
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int tid = (warp - 2) * 32 + lane;    // 0..127
+    long i = 0;
+    for (long t = blockIdx.x; t < ntl; t += gridDim.x, ++i) {
+      const int buf = (int)(i & 1);
+      const uint32_t use = (uint32_t)(i >> 1);
+      const int img = (int)(t / per_img);
+      const int r = (int)(t - (long)img * per_img);
+      const int a0 = (r / p.tiles_w) * O_IH - 1, b0 = (r % p.tiles_w) * O_IW - 1;
+      mbar_wait(&acc_full[buf], use & 1u, p.dbg, 45u);
+      tc_fence_after();
+      uint32_t v[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * 16u, v);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive1(&acc_empty[buf]);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) tsm[buf][row][k] = __uint_as_float(v[k]);
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // T of this patch complete (the buffer of two
+                                                      // patches ago was consumed before this point)
+      constexpr int OWT = 2 * O_IW;
+      for (int o = tid; o < 2 * O_IH * OWT; o += 128) {
+        const int orow = o / OWT, ocol = o - orow * OWT;
+        const int ai = 1 + (orow >> 1), bi = 1 + (ocol >> 1);
+        const int ph = orow & 1, pw = ocol & 1;
+        const int ar = a0 + ai, bc = b0 + bi;
+        const int oh = 2 * ar + ph, ow = 2 * bc + pw;
+        if (ar >= p.Hs || bc >= p.Ws || ow >= p.epi.Ws) continue;
+        float acc = 0.f;
+#pragma unroll
+        for (int jr = 0; jr < 2; ++jr)
+#pragma unroll
+          for (int jc = 0; jc < 2; ++jc) {
+            const int dr = ph - 1 + jr, dc = pw - 1 + jc;
+            const int kh = ph + 1 - 2 * dr, kw = pw + 1 - 2 * dc;
+            acc += tsm[buf][(ai + dr) * O_PW + (bi + dc)][kh * 4 + kw];
+          }
+        const size_t pix = ((size_t)img * p.epi.Hs + oh) * p.epi.Ws + ow;
+        epi_store(p.epi, pix, 0, acc);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(32u) : "memory");
+  }
+}
+
+}  // namespace
+
+// geometry test (no epilogue): the same layer family as conv_direct.cu's deconv_to_one
+bool deconv_one_tc_geometry(const advoc_conv_desc* d, int ldx) {
+  static const bool disabled = getenv("ADVOC_NO_ONE_TC") != nullptr;   // A/B switch for benchmarking
+  return !disabled && d->math != ADVOC_MATH_FP32 && tc::tma_ok() && device_arch() == 100 && d->Cin == 1 &&
+         d->kh == 4 && d->kw == 4 && d->sh == 2 && d->sw == 2 && d->pad_t == 1 && d->pad_l == 1 && d->H == 2 * d->Ho &&
+         d->W == 2 * d->Wo && d->Cout % 32 == 0 && d->Cout <= 32 * O_MAXKB && ldx % 4 == 0;
+}
+
+bool deconv_one_tc_eligible(const advoc_conv_desc* d, const float* x, int ldx, const advoc_epilogue* ep) {
+  return deconv_one_tc_geometry(d, ldx) && aligned16(x) && ep->keep_prob >= 1.f && ep->d_out1 == nullptr;
+}
+
+// w: [16 taps][Cs] fp32 (the HWOI filter of a conv_transpose to one channel), TF32-rounded by the caller
+int deconv_one_tc(const advoc_conv_desc* d, const float* x, int ldx, const float* w, const advoc_epilogue* ep,
+                  void* stream) {
+  OneParams p = {};
+  int st = lower_epilogue(ep, d->H, d->W, 1, &p.epi);
+  if (st) return st;
+  ADVOC_REQUIRE(aligned16(w), ADVOC_BAD_ALIGN, "filter must be 16-byte aligned");
+  p.N = d->N; p.Hs = d->Ho; p.Ws = d->Wo; p.kblocks = d->Cout / 32;
+  p.tiles_h = (p.Hs + O_IH - 1) / O_IH;
+  p.tiles_w = (p.Ws + O_IW - 1) / O_IW;
+  p.total_tiles = (long)p.N * p.tiles_h * p.tiles_w;
+  if (p.total_tiles == 0) return ADVOC_OK;
+  st = encode_tiled4d(&p.tmA, x, d->Cout, p.Ws, p.Hs, p.N, ldx, (long)p.Ws * ldx, (long)p.Hs * p.Ws * ldx, 32, O_PW,
+                      O_PH);
+  if (st) return st;
+  st = encode_tiled2d(&p.tmB, w, d->Cout, 16, (size_t)d->Cout * 4, 32, 16);
+  if (st) return st;
+  p.dbg = debug_word();
+  const int smem = O_STAGES * O_PH * O_PW * 128 + O_MAXKB * 16 * 128 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    ADVOC_CHECK_CUDA(cudaFuncSetAttribute(deconv_one_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  const long ctas = p.total_tiles < (long)sm_count() ? p.total_tiles : (long)sm_count();
+  deconv_one_tc_kernel<<<(unsigned)ctas, O_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  count_launch();
+  ADVOC_CHECK_CUDA(cudaGetLastError());
+  return ADVOC_OK;
+}
+
+}  // namespace advoc

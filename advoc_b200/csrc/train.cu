@@ -391,7 +391,7 @@ extern "C" int advoc_conv2d_wgrad(const advoc_conv_desc* d, const float* d_big, 
   const bool k4 = d->kh == 4 && d->kw == 4;
   const bool vec_small = d->Cout % 4 == 0 && ld_small % 4 == 0 && aligned16(d_small) && d->Cout <= 256 &&
                          256 % (d->Cout / 4 > 0 ? d->Cout / 4 : 1) == 0;
-  const bool vec_big = d->Cin % 4 == 0 && ld_big % 4 == 0 && aligned16(d_big) && d->Cin <= 256 &&
+  const bool vec_big = d->Cin % 4 == 0 && ld_big % 4 == 0 && aligned16(d_big) && d->Cin <= 512 &&
                        256 % (d->Cin / 4 > 0 ? d->Cin / 4 : 1) == 0;
   if (k4 && (d->Cin == 1 || d->Cin == 2) && vec_small) {
     // thin side = conv input (big), wide = conv output (small)

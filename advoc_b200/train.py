@@ -112,21 +112,25 @@ class TrainEngine(object):
                              _desc(B, d0.H, d0.W, 1, d0.Cout, d0.sh, d0.sw, d0.pad_t, d0.pad_l, d0.Ho,
                                    d0.Wo, N.MATH_FP32))
 
-  def refresh_weights(self):
-    """Re-derive every packed / TF32-rounded filter copy from the flat parameters (after Adam)."""
+  def refresh_weights(self, which='GD'):
+    """Re-derive the packed / TF32-rounded filter copies from the flat parameters after an Adam
+    step; `which` names the network(s) whose parameters changed ('G', 'D' or 'GD')."""
     P = self.P
-    self.G.prepare()
-    self.Dr.prepare()
-    self.Df.Wp, self.Df.round = self.Dr.Wp, self.Dr.round
-    self.Wb = {}
-    for k, L in self.dec_b.items():      # deconv dgrad: conv over the big side
-      self.Wb[L.name] = nets._pack_for_tc(L, P[L.name + '/kernel'], L.desc.Cin)
-    for i, L in self.enc_t.items():      # conv dgrad: HWIO is already K-major, only round
-      self.Wb[L.name] = nets._pack_for_tc(L, P[L.name + '/kernel'], L.desc.Cout)
-    for L in self.dis_t[1:]:
-      self.Wb[L.name] = nets._pack_for_tc(L, P[L.name + '/kernel'], L.desc.Cout)
-    k0 = P['discriminator/layer_1/conv2d/kernel']
-    self.w_sel = k0[:, :, 1:2, :].contiguous()   # [4,4,1,ndf]: filter slice of input channel 1
+    if not hasattr(self, 'Wb'):
+      self.Wb = {}
+    if 'G' in which:
+      self.G.prepare()
+      for k, L in self.dec_b.items():      # deconv dgrad: conv over the big side
+        self.Wb[L.name] = nets._pack_for_tc(L, P[L.name + '/kernel'], L.desc.Cin)
+      for i, L in self.enc_t.items():      # conv dgrad: HWIO is already K-major, only round
+        self.Wb[L.name] = nets._pack_for_tc(L, P[L.name + '/kernel'], L.desc.Cout)
+    if 'D' in which:
+      self.Dr.prepare()
+      self.Df.Wp, self.Df.round = self.Dr.Wp, self.Dr.round
+      for L in self.dis_t[1:]:
+        self.Wb[L.name] = nets._pack_for_tc(L, P[L.name + '/kernel'], L.desc.Cout)
+      k0 = P['discriminator/layer_1/conv2d/kernel']
+      self.w_sel = k0[:, :, 1:2, :].contiguous()   # [4,4,1,ndf]: filter slice of input channel 1
 
   def _wb(self, L):
     w = self.Wb.get(L.name)
@@ -257,7 +261,7 @@ class TrainEngine(object):
     if apply:
       self.t_d += 1
       self._adam(lo, hi, self.t_d)
-      self.refresh_weights()
+      self.refresh_weights('D')
 
   def g_step(self, x, target, dropout='rng', apply=True):
     """advoc_model.py:254-255 `G_train_op` on one minibatch (bumps the global step)."""
@@ -280,7 +284,7 @@ class TrainEngine(object):
     if apply:
       self.t_g += 1
       self._adam(lo, hi, self.t_g)
-      self.refresh_weights()
+      self.refresh_weights('G')
     return self.t_g
 
   def train_loop(self, batch_d, batch_g, dropout='rng'):
