@@ -51,8 +51,10 @@ struct alignas(64) P2dParams {
   CUtensorMap tmA[Q_MAXP];  // tiled 4-D {c, w, h, n}, box {32, PW, PH, 1}
   CUtensorMap tmB;          // filter [taps * Cn][Ck], box {32, BN}
   CUtensorMap tmO[2][Q_MAXC];  // output stores per destination and parity class, box {32, tw, th, 1}
+  CUtensorMap tmG[Q_MAXC];     // backward pass: the activation whose derivative gates the output, same boxes
   int tma_store, n_out, stage_bufs;
-  uint32_t stage_off;
+  int use_gate, reduce_add;    // gate tiles come in by TMA; accumulate = TMA reduce-add store
+  uint32_t stage_off, gate_off;
   int nplanes, ntaps, ncls;
   int plane_tap0[Q_MAXP + 1];  // taps are sorted by plane: plane p owns [plane_tap0[p], plane_tap0[p+1])
   int plane_oh[Q_MAXP], plane_ow[Q_MAXP];  // patch origin relative to the tile origin (plane coordinates)
@@ -94,6 +96,17 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, uint32_t src
                "r"(src), "r"(c), "r"(w), "r"(h), "r"(n)
                : "memory");
 }
+__device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* tm, uint32_t src, int c, int w, int h, int n) {
+  asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tm)),
+               "r"(src), "r"(c), "r"(w), "r"(h), "r"(n)
+               : "memory");
+}
+__device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() {
@@ -108,6 +121,27 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, float a, float b, fl
 
 // One staged chunk: 32 accumulator columns of this thread's pixel -> bias, dropout, activation(s),
 // TF32 rounding -> swizzled staging row(s).  kLin: both activations are none / relu / lrelu.
+// Backward-pass chunk: out = acc * act'(gate) * scale, gate row read from its swizzled smem tile.
+__device__ __forceinline__ void stage_chunk_gated(const EpiDev& e, const uint32_t (&v)[32], uint32_t dst_row,
+                                                  uint32_t gate_row, uint32_t sx, int n) {
+  const float neg = e.gate_act == ADVOC_ACT_LRELU ? e.alpha : 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint32_t off = ((uint32_t)j ^ sx) << 4;
+    const float4 g = ld_shared_v4(gate_row + off);
+    const float s = (n + 4 * j) < e.gate_split ? e.gscale0 : e.gscale1;   // split is a multiple of 4
+    float y[4] = {__uint_as_float(v[4 * j]) * ((g.x > 0.f ? 1.f : neg) * s),
+                  __uint_as_float(v[4 * j + 1]) * ((g.y > 0.f ? 1.f : neg) * s),
+                  __uint_as_float(v[4 * j + 2]) * ((g.z > 0.f ? 1.f : neg) * s),
+                  __uint_as_float(v[4 * j + 3]) * ((g.w > 0.f ? 1.f : neg) * s)};
+    if (e.round) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) y[u] = round_tf32(y[u]);
+    }
+    st_shared_v4(dst_row + off, y[0], y[1], y[2], y[3]);
+  }
+}
+
 template <bool kLin, bool kDrop>
 __device__ __forceinline__ void stage_chunk(const EpiDev& e, const uint32_t (&v)[32], const float4 (&bias4)[8],
                                             uint32_t dst_row, uint32_t sx, int n_out, size_t idx0) {
@@ -165,7 +199,7 @@ __global__ void __launch_bounds__(Q_THREADS, 1) conv_p2d_kernel(const __grid_con
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[Q_MAXA], a_empty[Q_MAXA];
   __shared__ __align__(8) uint64_t b_full[Q_MAXB], b_empty[Q_MAXB];
-  __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
+  __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2], g_full[2];
   __shared__ uint32_t tmem_base_holder;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -182,7 +216,7 @@ __global__ void __launch_bounds__(Q_THREADS, 1) conv_p2d_kernel(const __grid_con
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.a_stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < p.b_stages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); mbar_init(&g_full[s], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0 && lane == 0) {
@@ -363,6 +397,22 @@ __global__ void __launch_bounds__(Q_THREADS, 1) conv_p2d_kernel(const __grid_con
     const uint32_t s_row_addr = ring + p.stage_off + srow * 128u;
     const uint32_t sx = srow & 7u;
     const bool lin_acts = act_is_linear(e.act0) && act_is_linear(e.act1);
+    // gate tiles: chunk g of this CTA (tile-major, then class, then 32-channel block) lands in gate
+    // buffer g & 1; the issuer keeps the loads two chunks ahead of the math
+    constexpr int CPC = BN / 32;
+    const int cpt = p.ncls * CPC;
+    auto gate_load = [&](uint32_t g) {
+      const long gi = g / cpt;
+      const int rem = (int)(g - gi * cpt);
+      const long gt = blockIdx.x + gi * (long)gridDim.x;
+      if (gt >= ntl) return;
+      const int gz = rem / CPC, gc0 = (rem - gz * CPC) * 32;
+      const TileCoord gc = decode_tile(p, gt);
+      mbar_expect_tx(&g_full[g & 1u], (uint32_t)p.th * p.tw * 128u);
+      tma_load_4d(&p.tmG[gz], &g_full[g & 1u], ring_ptr + p.gate_off + (g & 1u) * Q_STAGE_BYTES, gc.n_tile * BN + gc0,
+                  gc.w0, gc.h0, gc.img);
+    };
+    if (p.use_gate && issuer) { gate_load(0); gate_load(1); }
     uint32_t chunk_ctr = 0;
     long i = 0;
     unsigned long long w_full = 0, w_bar = 0, w_ld = 0, w_math = 0, w_fence = 0, w_issue = 0;
@@ -417,11 +467,15 @@ __global__ void __launch_bounds__(Q_THREADS, 1) conv_p2d_kernel(const __grid_con
           epi_bar(1);
           if (p.prof) w_bar += (unsigned long long)(clock64() - tb0);
           const long long tm0 = p.prof ? clock64() : 0;
+          if (p.use_gate) mbar_wait(&g_full[chunk_ctr & 1u], (chunk_ctr >> 1) & 1u, p.dbg, 37u);
           if (in_tile && !(p.exp_flags & 2)) {
             const uint32_t dst_row = s_row_addr + sbuf;
             const bool drop = e.keep_prob < 1.f && valid;
             const size_t idx0 = pix * e.Cout + n0 + c0;
-            if (lin_acts) {
+            if (p.use_gate) {
+              stage_chunk_gated(e, v, dst_row, ring + p.gate_off + (chunk_ctr & 1u) * Q_STAGE_BYTES + srow * 128u, sx,
+                                n0 + c0);
+            } else if (lin_acts) {
               if (drop) stage_chunk<true, true>(e, v, bias4, dst_row, sx, p.n_out, idx0);
               else stage_chunk<true, false>(e, v, bias4, dst_row, sx, p.n_out, idx0);
             } else {
@@ -436,10 +490,14 @@ __global__ void __launch_bounds__(Q_THREADS, 1) conv_p2d_kernel(const __grid_con
           const long long ti0 = p.prof ? clock64() : 0;
           if (p.prof) w_fence += (unsigned long long)(ti0 - tf0);
           if (issuer) {
-            tma_store_4d(&p.tmO[0][z], ring + p.stage_off + sbuf, n0 + c0, tc_.w0, tc_.h0, tc_.img);
+            if (p.reduce_add)
+              tma_reduce_add_4d(&p.tmO[0][z], ring + p.stage_off + sbuf, n0 + c0, tc_.w0, tc_.h0, tc_.img);
+            else
+              tma_store_4d(&p.tmO[0][z], ring + p.stage_off + sbuf, n0 + c0, tc_.w0, tc_.h0, tc_.img);
             if (p.n_out == 2)
               tma_store_4d(&p.tmO[1][z], ring + p.stage_off + sbuf + Q_STAGE_BYTES, n0 + c0, tc_.w0, tc_.h0, tc_.img);
             bulk_commit();
+            if (p.use_gate) gate_load(chunk_ctr + 2);   // this chunk's gate buffer was consumed before bar 2
           }
           if (p.prof) w_issue += (unsigned long long)(clock64() - ti0);
           ++chunk_ctr;
@@ -489,7 +547,8 @@ inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b
 
 // transposed == false: y[N,Ho,Wo,Cout] = conv(x[N,H,W,Cin]);  Cn = Cout, Ck = Cin
 // transposed == true : y[N,H,Wstored,Cin] = conv_transpose(x[N,Ho,Wo,Cout]);  Cn = Cin, Ck = Cout
-bool make_plan(const advoc_conv_desc* d, bool transposed, int Wstored, int n_out, bool tma_store, Plan* pl) {
+bool make_plan(const advoc_conv_desc* d, bool transposed, int Wstored, int n_out, bool tma_store, bool gate,
+               Plan* pl) {
   P2dParams& p = pl->p;
   TapT taps[Q_MAXT];
   int nt = 0, ncls = 0, nplanes = 0;
@@ -627,7 +686,8 @@ bool make_plan(const advoc_conv_desc* d, bool transposed, int Wstored, int n_out
   const size_t all_b = (size_t)nslots_all * b_tile;
   p.tma_store = tma_store ? 1 : 0;
   p.n_out = n_out;
-  const size_t stage1 = tma_store ? (size_t)n_out * Q_STAGE_BYTES : 0;
+  const size_t gate_bytes = (tma_store && gate) ? (size_t)2 * Q_STAGE_BYTES : 0;
+  const size_t stage1 = (tma_store ? (size_t)n_out * Q_STAGE_BYTES : 0) + gate_bytes;
   int a_need = nplanes + 1 > 3 ? nplanes + 1 : 3;   // patches in flight cover the TMA latency
   while (a_need > 2 && (size_t)a_need * p.a_slot_bytes + 4 * b_tile + stage1 > Q_SMEM_BUDGET) --a_need;
   if ((size_t)a_need * p.a_slot_bytes + 3 * b_tile + stage1 > Q_SMEM_BUDGET) return false;
@@ -647,10 +707,13 @@ bool make_plan(const advoc_conv_desc* d, bool transposed, int Wstored, int n_out
     left -= (size_t)bs * b_tile;
   }
   p.stage_bufs = 1;
-  if (tma_store && left >= stage1) { p.stage_bufs = 2; left -= stage1; }
+  const size_t stage_only = stage1 - gate_bytes;
+  if (tma_store && left >= stage_only) { p.stage_bufs = 2; left -= stage_only; }
   while (p.a_stages < Q_MAXA && left >= p.a_slot_bytes) { ++p.a_stages; left -= p.a_slot_bytes; }
-  const size_t staging = stage1 * p.stage_bufs;
+  const size_t staging = stage_only * p.stage_bufs + gate_bytes;
   p.stage_off = (uint32_t)((size_t)p.a_stages * p.a_slot_bytes + (size_t)p.b_stages * b_tile);
+  p.gate_off = p.stage_off + (uint32_t)(stage_only * p.stage_bufs);
+  p.use_gate = gate_bytes ? 1 : 0;
   pl->smem = (size_t)p.stage_off + staging + 1024;
   if (pl->smem < 120 * 1024) pl->smem = 120 * 1024;  // one CTA per SM: TMEM is not shared between CTAs here
   return p.total_tiles > 0;
@@ -696,7 +759,7 @@ bool conv_p2d_eligible(const advoc_conv_desc* d, int ldx, int transposed, int st
   static const bool disabled = getenv("ADVOC_NO_P2D") != nullptr;  // A/B switch for benchmarking
   if (disabled || !(tc::tma_ok() && device_arch() == 100 && ldx % 4 == 0)) return false;
   Plan pl = {};
-  if (!make_plan(d, transposed != 0, store_w ? store_w : d->W, 2, true, &pl)) return false;
+  if (!make_plan(d, transposed != 0, store_w ? store_w : d->W, 2, true, true, &pl)) return false;
   if (pl.efficiency < min_efficiency()) return false;
   // Measured on B200 (profiles/README.md, r01c): the patch kernel wins where the layer has several
   // tiles per SM and an output tile streams little filter data (it re-reads the filter once per
@@ -715,12 +778,27 @@ int conv_p2d(const advoc_conv_desc* d, int transposed, const float* x, int ldx, 
   if (!transposed)
     ADVOC_REQUIRE(pl.p.epi.Ws == d->Wo, ADVOC_UNSUPPORTED, "store_w crop is only supported on conv_transpose");
   static const bool no_tma_store = getenv("ADVOC_P2D_DIRECT_STORE") != nullptr;   // A/B switch
-  const bool tma_store = !no_tma_store && !ep->d_gate && !ep->accumulate;
-  ADVOC_REQUIRE(make_plan(d, transposed != 0, pl.p.epi.Ws, ep->d_out1 ? 2 : 1, tma_store, &pl), ADVOC_UNSUPPORTED,
-                "layer does not fit the patch kernel");
+  // backward-pass epilogues: the gate tile arrives by TMA and the skip-connection sum is a TMA
+  // reduce-add; they carry no bias, activation, dropout or second output
+  const bool bwd = ep->d_gate || ep->accumulate;
+  const bool bwd_ok = !ep->d_bias && ep->act0 == ADVOC_ACT_NONE && ep->keep_prob >= 1.f && !ep->d_out1;
+  const bool tma_store = !no_tma_store && (!bwd || bwd_ok);
+  ADVOC_REQUIRE(make_plan(d, transposed != 0, pl.p.epi.Ws, ep->d_out1 ? 2 : 1, tma_store, tma_store && ep->d_gate,
+                          &pl),
+                ADVOC_UNSUPPORTED, "layer does not fit the patch kernel");
   P2dParams& p = pl.p;
+  p.reduce_add = (tma_store && ep->accumulate) ? 1 : 0;
   if (tma_store) {
     const EpiDev& e = p.epi;
+    if (p.use_gate) {
+      for (int z = 0; z < p.ncls; ++z) {
+        const int ph = p.cls_ph[z], pw = p.cls_pw[z];
+        const int Hz = (e.Hs - ph + p.osh - 1) / p.osh, Wz = (e.Ws - pw + p.osw - 1) / p.osw;
+        st = encode_tiled4d(&p.tmG[z], e.gate + e.coffg + ((size_t)ph * e.Ws + pw) * e.ldg, p.Cn, Wz, Hz, d->N,
+                            (long)p.osw * e.ldg, (long)p.osh * e.Ws * e.ldg, (long)e.Hs * e.Ws * e.ldg, 32, p.tw, p.th);
+        if (st) return st;
+      }
+    }
     for (int o = 0; o < p.n_out; ++o) {
       float* base = o == 0 ? e.out0 + e.coff0 : e.out1 + e.coff1;
       const long ld = o == 0 ? e.ld0 : e.ld1;

@@ -42,14 +42,19 @@ __device__ __forceinline__ void epi_store(const EpiDev& e, size_t pix, int n, fl
     const bool keep = e.mask ? (__ldg(e.mask + idx) != 0) : dropout_keep(e.seed, idx, e.keep_prob);
     scale = keep ? 1.f / e.keep_prob : 0.f;
   }
-  float y0 = apply_act(v, e.act0, e.alpha) * scale;
+  const bool lin = act_is_linear(e.act0) && act_is_linear(e.act1);   // real branch: see ActLin
+  float y0;
+  if (lin) y0 = apply_lin(v, act_linear(e.act0, e.alpha)) * scale;
+  else y0 = apply_act(v, e.act0, e.alpha) * scale;
   if (e.gate) y0 *= gate_factor(e, pix, n);
   float* dst = e.out0 + pix * e.ld0 + e.coff0 + n;
   if (e.accumulate) y0 += *dst;
   if (e.round) y0 = round_tf32(y0);
   *dst = y0;
   if (e.out1) {
-    float y1 = apply_act(v, e.act1, e.alpha) * scale;
+    float y1;
+    if (lin) y1 = apply_lin(v, act_linear(e.act1, e.alpha)) * scale;
+    else y1 = apply_act(v, e.act1, e.alpha) * scale;
     if (e.round) y1 = round_tf32(y1);
     e.out1[pix * e.ld1 + e.coff1 + n] = y1;
   }
