@@ -51,18 +51,22 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
       : "r"(taddr));
 }
 
+// KS = filter size (4: AdVoc decoder_1; 5: MelspecGAN upconv_4, models/melspecgan/conv2d.py:139-141);
+// the tap axis is padded to NP = 16 / 32 accumulator columns (TMA zero-fills the missing filter rows)
+template <int KS>
 __global__ void __launch_bounds__(O_THREADS, 1) deconv_one_tc_kernel(const __grid_constant__ OneParams p) {
+  constexpr int NP = KS == 4 ? 16 : 32;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[O_STAGES], a_empty[O_STAGES];
   __shared__ __align__(8) uint64_t b_full, acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_holder;
-  __shared__ float tsm[2][O_PH * O_PW][17];   // T[pos][tap], +1 pad: conflict-free column access
+  __shared__ float tsm[2][O_PH * O_PW][NP + 1];   // T[pos][tap], +1 pad: conflict-free column access
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* ring_ptr = smem_raw + (ring - smem_u32(smem_raw));
   constexpr uint32_t A_BYTES = O_PH * O_PW * 128;   // one k-block of one patch
-  constexpr uint32_t B_BYTES = 16 * 128;            // one k-block of the 16 taps
+  constexpr uint32_t B_BYTES = NP * 128;            // one k-block of the taps
   const uint32_t b_off = O_STAGES * A_BYTES;
   const long ntl = p.total_tiles;
 
@@ -77,7 +81,7 @@ __global__ void __launch_bounds__(O_THREADS, 1) deconv_one_tc_kernel(const __gri
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32(&tmem_base_holder)),
-                 "r"(32u)
+                 "r"((uint32_t)(2 * NP))
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -117,8 +121,8 @@ __global__ void __launch_bounds__(O_THREADS, 1) deconv_one_tc_kernel(const __gri
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer: M = 128 positions, N = 16 taps, K = Cs =====
-    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(16 >> 3) << 17) |
+    // ===== MMA issuer: M = 128 positions, N = NP taps, K = Cs =====
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NP >> 3) << 17) |
                                ((uint32_t)(128 >> 4) << 24);
     int as = 0;
     uint32_t aph = 0;
@@ -138,7 +142,7 @@ __global__ void __launch_bounds__(O_THREADS, 1) deconv_one_tc_kernel(const __gri
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_tf32(tmem_base + (uint32_t)buf * 16u, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+            umma_tf32(tmem_base + (uint32_t)buf * NP, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
                       (kb | k) != 0 ? 1u : 0u);
           umma_commit(&a_empty[as]);
           if (kb == p.kblocks - 1) umma_commit(&acc_full[buf]);
@@ -161,14 +165,15 @@ __global__ void __launch_bounds__(O_THREADS, 1) deconv_one_tc_kernel(const __gri
       const int a0 = (r / p.tiles_w) * O_IH - 1, b0 = (r % p.tiles_w) * O_IW - 1;
       mbar_wait(&acc_full[buf], use & 1u, p.dbg, 45u);
       tc_fence_after();
-      uint32_t v[16];
-      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * 16u, v);
+      uint32_t v[NP];
+      if (NP == 16) tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * NP, v);
+      else tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * NP, v);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive1(&acc_empty[buf]);
 #pragma unroll
-      for (int k = 0; k < 16; ++k) tsm[buf][row][k] = __uint_as_float(v[k]);
+      for (int k = 0; k < KS * KS; ++k) tsm[buf][row][k] = __uint_as_float(v[k]);
       asm volatile("bar.sync 1, 128;" ::: "memory");   // T of this patch complete (the buffer of two
                                                       // patches ago was consumed before this point)
       constexpr int OWT = 2 * O_IW;
@@ -179,15 +184,19 @@ __global__ void __launch_bounds__(O_THREADS, 1) deconv_one_tc_kernel(const __gri
         const int ar = a0 + ai, bc = b0 + bi;
         const int oh = 2 * ar + ph, ow = 2 * bc + pw;
         if (ar >= p.Hs || bc >= p.Ws || ow >= p.epi.Ws) continue;
+        // out[oh, ow] = sum over taps with (oh + 1 - kh) even of T[(oh + 1 - kh) / 2, ...][kh, kw] (pad 1, stride 2)
         float acc = 0.f;
 #pragma unroll
-        for (int jr = 0; jr < 2; ++jr)
+        for (int kh = 0; kh < KS; ++kh) {
+          if (((ph + 1 - kh) & 1) != 0) continue;
+          const int dr = (ph + 1 - kh) >> 1;          // -1, 0 or +1
 #pragma unroll
-          for (int jc = 0; jc < 2; ++jc) {
-            const int dr = ph - 1 + jr, dc = pw - 1 + jc;
-            const int kh = ph + 1 - 2 * dr, kw = pw + 1 - 2 * dc;
-            acc += tsm[buf][(ai + dr) * O_PW + (bi + dc)][kh * 4 + kw];
+          for (int kw = 0; kw < KS; ++kw) {
+            if (((pw + 1 - kw) & 1) != 0) continue;
+            const int dc = (pw + 1 - kw) >> 1;
+            acc += tsm[buf][(ai + dr) * O_PW + (bi + dc)][kh * KS + kw];
           }
+        }
         const size_t pix = ((size_t)img * p.epi.Hs + oh) * p.epi.Ws + ow;
         epi_store(p.epi, pix, 0, acc);
       }
@@ -197,7 +206,8 @@ __global__ void __launch_bounds__(O_THREADS, 1) deconv_one_tc_kernel(const __gri
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(32u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * NP))
+                 : "memory");
   }
 }
 
@@ -207,7 +217,7 @@ __global__ void __launch_bounds__(O_THREADS, 1) deconv_one_tc_kernel(const __gri
 bool deconv_one_tc_geometry(const advoc_conv_desc* d, int ldx) {
   static const bool disabled = getenv("ADVOC_NO_ONE_TC") != nullptr;   // A/B switch for benchmarking
   return !disabled && d->math != ADVOC_MATH_FP32 && tc::tma_ok() && device_arch() == 100 && d->Cin == 1 &&
-         d->kh == 4 && d->kw == 4 && d->sh == 2 && d->sw == 2 && d->pad_t == 1 && d->pad_l == 1 && d->H == 2 * d->Ho &&
+         (d->kh == 4 || d->kh == 5) && d->kw == d->kh && d->sh == 2 && d->sw == 2 && d->pad_t == 1 && d->pad_l == 1 && d->H == 2 * d->Ho &&
          d->W == 2 * d->Wo && d->Cout % 32 == 0 && d->Cout <= 32 * O_MAXKB && ldx % 4 == 0;
 }
 
@@ -230,17 +240,22 @@ int deconv_one_tc(const advoc_conv_desc* d, const float* x, int ldx, const float
   st = encode_tiled4d(&p.tmA, x, d->Cout, p.Ws, p.Hs, p.N, ldx, (long)p.Ws * ldx, (long)p.Hs * p.Ws * ldx, 32, O_PW,
                       O_PH);
   if (st) return st;
-  st = encode_tiled2d(&p.tmB, w, d->Cout, 16, (size_t)d->Cout * 4, 32, 16);
+  const int np = d->kh == 4 ? 16 : 32;
+  st = encode_tiled2d(&p.tmB, w, d->Cout, d->kh * d->kw, (size_t)d->Cout * 4, 32, np);
   if (st) return st;
   p.dbg = debug_word();
-  const int smem = O_STAGES * O_PH * O_PW * 128 + O_MAXKB * 16 * 128 + 1024;
+  const int smem = O_STAGES * O_PH * O_PW * 128 + O_MAXKB * 32 * 128 + 1024;
   static bool configured = false;
   if (!configured) {
-    ADVOC_CHECK_CUDA(cudaFuncSetAttribute(deconv_one_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ADVOC_CHECK_CUDA(cudaFuncSetAttribute(deconv_one_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ADVOC_CHECK_CUDA(cudaFuncSetAttribute(deconv_one_tc_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   const long ctas = p.total_tiles < (long)sm_count() ? p.total_tiles : (long)sm_count();
-  deconv_one_tc_kernel<<<(unsigned)ctas, O_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  if (d->kh == 4)
+    deconv_one_tc_kernel<4><<<(unsigned)ctas, O_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  else
+    deconv_one_tc_kernel<5><<<(unsigned)ctas, O_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   count_launch();
   ADVOC_CHECK_CUDA(cudaGetLastError());
   return ADVOC_OK;

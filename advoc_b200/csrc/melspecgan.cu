@@ -77,6 +77,25 @@ __global__ void __launch_bounds__(256) gemm_kernel(const float* __restrict__ A, 
   }
 }
 
+// N == 1 (the critic's output layer): one warp per row of A, lanes across K.
+__global__ void __launch_bounds__(256) gemv_kernel(const float* __restrict__ A, int lda, const float* __restrict__ b,
+                                                   int ldb, float* __restrict__ c, int ldc, int M, int K,
+                                                   int accumulate, const float* __restrict__ bias) {
+  const int lane = threadIdx.x & 31;
+  const int m = (int)(((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (m >= M) return;
+  const float* a = A + (size_t)m * lda;
+  float s = 0.f;
+  for (int k = lane; k < K; k += 32) s = fmaf(__ldg(a + k), __ldg(b + (size_t)k * ldb), s);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) {
+    float v = s + (bias ? __ldg(bias) : 0.f);
+    if (accumulate) v += c[(size_t)m * ldc];
+    c[(size_t)m * ldc] = v;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // batch normalisation over [pixels, C] (pixel stride ld), batch statistics
 // ---------------------------------------------------------------------------------------------
@@ -252,6 +271,14 @@ extern "C" int advoc_gemm_f32(const float* d_a, int lda, const float* d_b, int l
                               void* stream) {
   ADVOC_REQUIRE(d_a && d_b && d_c, ADVOC_BAD_ARG, "NULL matrix");
   ADVOC_REQUIRE(M > 0 && N > 0 && K > 0 && lda > 0 && ldb > 0 && ldc >= N, ADVOC_BAD_SHAPE, "bad gemm shape");
+  if (N == 1 && !trans_a && K >= 256) {
+    // b[k] = B[k][0] (ldb) or, stored transposed [1][K], B[0][k]
+    gemv_kernel<<<(M * 32 + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        d_a, lda, d_b, trans_b ? 1 : ldb, d_c, ldc, M, K, accumulate, d_bias);
+    count_launch();
+    ADVOC_CHECK_CUDA(cudaGetLastError());
+    return ADVOC_OK;
+  }
   dim3 grid((N + GT - 1) / GT, (M + GT - 1) / GT, 1);
   gemm_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d_a, lda, d_b, ldb, d_c, ldc, M, N, K,
                                                                         trans_a, trans_b, accumulate, d_bias);

@@ -40,6 +40,7 @@ struct alignas(64) WgParams {
   float* dw;
   int Cb, Cs;
   int cbb;              // 32-channel blocks of the big side
+  int nboxes;           // taps * cbb: (tap, channel-block) boxes; the last N tile may be partial
   int mtiles, ntiles, kw;
   int Ho, Wo, sh, sw, lower_h, lower_w;
   long P, chunk;        // output pixels, pixels per split (multiple of WBK)
@@ -137,13 +138,14 @@ __global__ void __launch_bounds__(W_THREADS) wgrad_tc_kernel(const __grid_consta
       const int img = (int)(r / p.Ho);
       if (lane == 0) {
         mbar_wait(&empty_bar[stage], phase ^ 1u, p.dbg, 11u);
-        mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+        const int nb = p.nboxes - gb0 < WNB ? p.nboxes - gb0 : WNB;   // boxes of a partial last tile are
+        mbar_expect_tx(&full_bar[stage], A_BYTES + nb * BLK_BYTES);   // not loaded (their columns are skipped)
       }
       __syncwarp();
       uint8_t* dst = ring_ptr + stage * STAGE_BYTES + lane * BLK_BYTES;
       if (lane < WM / 32) {
         tma_load_2d(&p.tmSmall, &full_bar[stage], dst, my_c, (int)pix);
-      } else if (lane < WM / 32 + WNB) {
+      } else if (lane < WM / 32 + WNB && gb0 + (lane - WM / 32) < p.nboxes) {
         tma_load_im2col_4d(&p.tmBig, &full_bar[stage], dst, my_c, ow * p.sw + p.lower_w, oh * p.sh + p.lower_h,
                            img, my_kw, my_kh);
       }
@@ -187,7 +189,7 @@ __global__ void __launch_bounds__(W_THREADS) wgrad_tc_kernel(const __grid_consta
       tmem_ld_wait();
       const int gb = gb0 + b;
       const int tap = gb / p.cbb, cblk = gb - tap * p.cbb;
-      if (cs < p.Cs) {
+      if (cs < p.Cs && gb < p.nboxes) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int cb = cblk * 32 + j;
@@ -211,8 +213,7 @@ bool wgrad_tc_eligible(const advoc_conv_desc* d, const float* big, int ld_big, c
   const int cbb = (d->Cin + 31) / 32;
   return d->math != ADVOC_MATH_FP32 && tc::tma_ok() && device_arch() == 100 && d->Cin >= 32 && d->Cout >= 32 &&
          d->Cin % 4 == 0 && d->Cout % 4 == 0 && ld_big % 4 == 0 && ld_small % 4 == 0 && aligned16(big) &&
-         aligned16(small) && d->kh * d->kw <= 255 && d->pad_t <= 127 && d->pad_l <= 127 &&
-         (d->kh * d->kw * cbb) % WNB == 0;
+         aligned16(small) && d->kh * d->kw <= 255 && d->pad_t <= 127 && d->pad_l <= 127 && cbb > 0;
 }
 
 int wgrad_tc(const advoc_conv_desc* d, const float* big, int ld_big, const float* small, int ld_small, float* dw,
@@ -234,7 +235,8 @@ int wgrad_tc(const advoc_conv_desc* d, const float* big, int ld_big, const float
   p.dw = dw; p.Cb = d->Cin; p.Cs = d->Cout;
   p.cbb = (d->Cin + 31) / 32;
   p.mtiles = (d->Cout + WM - 1) / WM;
-  p.ntiles = d->kh * d->kw * p.cbb / WNB;
+  p.nboxes = d->kh * d->kw * p.cbb;
+  p.ntiles = (p.nboxes + WNB - 1) / WNB;
   p.kw = d->kw;
   p.Ho = d->Ho; p.Wo = d->Wo; p.sh = d->sh; p.sw = d->sw; p.lower_h = lower_h; p.lower_w = lower_w;
   p.P = P;

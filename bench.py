@@ -529,6 +529,175 @@ def run_reference_train(args):
   print(json.dumps(line))
 
 
+# ---------------------------------------------------------------------------
+# spectral workload (BASELINE configs[0] + SURVEY 8(d) config 1): waveform -> r9y9 mel
+# ---------------------------------------------------------------------------
+def run_gpu_spectral(args):
+  """value: mel frames/s of the fused STFT->|.|->mel->dB kernel on a resident batch of
+  [B, 65536] waveforms (HBM-bound regime); e2e: the numpy entry point `waveform_to_r9y9_melspec` on
+  the reference's own case (1 s of 22.05 kHz audio -> 87 frames, launch-bound), host buffers."""
+  import numpy as np
+  import torch
+  from advoc_b200 import _native as N
+  from advoc_b200 import spectral
+  from oracle import spectral_np as OS
+  torch.cuda.set_device(0)
+  B, n = args.batch, 65536
+  g = torch.Generator().manual_seed(3)
+  wav = (torch.rand(B, n, 1, 1, generator=g) * 2 - 1).cuda()
+  flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
+  stream = torch.cuda.current_stream()
+  n0 = N.launch_count()
+  out = spectral.waveform_to_r9y9_melspec_tf(wav)
+  per_step = N.launch_count() - n0
+  frames = out.shape[0] * out.shape[1]
+
+  def timed(fn, steps, warmup):
+    for _ in range(warmup):
+      fn()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    torch.cuda.synchronize()
+    for a, b in evs:
+      flush.zero_()
+      a.record(stream)
+      fn()
+      b.record(stream)
+    torch.cuda.synchronize()
+    return sum(a.elapsed_time(b) for a, b in evs)
+
+  with ClockSampler(0) as clk:
+    total_ms = timed(lambda: spectral.waveform_to_r9y9_melspec_tf(wav), args.steps, args.warmup)
+  value = frames * args.steps / (total_ms * 1e-3)
+  rng = np.random.RandomState(0)
+  x1 = rng.uniform(-1, 1, 22050).astype(np.float32).reshape(-1, 1, 1)
+  for _ in range(3):
+    spectral.waveform_to_r9y9_melspec(x1)
+  t0 = time.perf_counter()
+  reps = 50
+  for _ in range(reps):
+    y1 = spectral.waveform_to_r9y9_melspec(x1)
+  e2e_s = (time.perf_counter() - t0) / reps
+  t0 = time.perf_counter()
+  for _ in range(5):
+    ref = OS.waveform_to_r9y9_melspec(x1)
+  cpu_s = (time.perf_counter() - t0) / 5
+  peaks = _peaks()
+  bytes_per_step = 4.0 * B * n + 4.0 * 80 * frames
+  ach = bytes_per_step * args.steps / (total_ms * 1e-3) / 1e9
+  line = {
+      'metric': 'mel-frames/sec STFT+mel', 'value': value, 'unit': 'mel-frames/s', 'n_gpus': 1, 'steps': args.steps,
+      'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+      'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+      'config': {'workload': 'advoc.spectral r9y9 mel (nfft 1024, hop 256, 80 mels) on uniform noise [%d, 65536]; '
+                             'e2e = the reference case 1x22050 samples -> (87, 80, 1) through the numpy API' % B,
+                 'l2': 'flushed between timed steps'},
+      'e2e': {'value': 87 / e2e_s, 'unit': 'mel-frames/s', 'us_per_call': e2e_s * 1e6,
+              'h2d_bytes_per_step': 88200, 'd2h_bytes_per_step': 87 * 80 * 8},
+      'gpu_launches': int(per_step * args.steps), 'launches_per_step': int(per_step), 'clocks': clk.summary(),
+      'roofline': {'kernel': 'stft_pair_kernel', 'bound': 'hbm', 'achieved': ach, 'peak': peaks['hbm'], 'unit': 'GB/s',
+                   'frac': ach / peaks['hbm'], 'traffic': None, 'peak_source': peaks['source'] + ' copy bandwidth',
+                   'bytes_per_launch': bytes_per_step},
+      'cpu_baseline': {'value': 87 / cpu_s, 'unit': 'mel-frames/s', 'cores': 1, 'kind': 'port',
+                       'sample': 'oracle/spectral_np.py on the 22050-sample case, mean of 5 (us/call %.0f)' % (cpu_s * 1e6)},
+      'parity_rel_l2': float(np.linalg.norm(y1 - ref) / np.linalg.norm(ref)),
+  }
+  print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------
+# MelspecGAN workload (BASELINE configs[4]): one outer iteration of models/melspecgan/train.py:149-153
+# ---------------------------------------------------------------------------
+MELSPECGAN_GFLOP = {'G_f': 0.3994, 'D_f': 0.3973}
+
+
+def run_gpu_melspecgan(args):
+  import torch
+  import torch.distributed as dist
+  from advoc_b200 import _native as N
+  from advoc_b200 import melspecgan as MG
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  rank = int(os.environ.get('RANK', '0'))
+  local = int(os.environ.get('LOCAL_RANK', '0'))
+  torch.cuda.set_device(local)
+  if world > 1:
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+  B = args.batch
+  eng = MG.MelspecGAN(MG.init_params(seed=0), B, train_loss=args.melspecgan_loss, world_size=world)
+  n_d = 1 if args.melspecgan_loss == 'dcgan' else 5
+  g = torch.Generator().manual_seed(10 + rank)
+  xs_h = [(torch.rand(B, 64, 80, 1, generator=g) * 2 - 1).pin_memory() for _ in range(n_d)]
+  xs_d = [x.cuda() for x in xs_h]
+  stage = [torch.empty_like(x) for x in xs_d]
+  zs = [torch.randn(B, MG.Z_DIM, generator=g).cuda() for _ in range(n_d + 1)]
+  stream = torch.cuda.current_stream()
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  def step_device():
+    eng.train_loop(xs_d, zs[:n_d], zs[n_d])
+
+  def step_e2e():
+    for s, h in zip(stage, xs_h):
+      s.copy_(h, non_blocking=True)
+    eng.train_loop(stage, zs[:n_d], zs[n_d])
+    return eng.loss_values()
+
+  def timed(fn, steps, warmup):
+    for _ in range(warmup):
+      fn()
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    for _ in range(steps):
+      fn()
+    b.record(stream)
+    barrier()
+    return a.elapsed_time(b)
+
+  n0 = N.launch_count()
+  step_device()
+  torch.cuda.synchronize()
+  per_step = N.launch_count() - n0
+  with ClockSampler(local) as clk:
+    total_ms = timed(step_device, args.steps, args.warmup)
+    e2e_ms = timed(step_e2e, args.steps, args.warmup)
+  if world > 1:
+    t = torch.tensor([total_ms, e2e_ms], device='cuda', dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = float(t[0]), float(t[1])
+  samples = world * B * args.steps
+  value = samples / (total_ms * 1e-3)
+  # first-order passes only: D step = G_f + 2 D_f + 2 (2 D_f); G step = 3 G_f + 2 D_f (SURVEY 8(d) accounting)
+  gf, df = MELSPECGAN_GFLOP['G_f'], MELSPECGAN_GFLOP['D_f']
+  gflop = n_d * (gf + 6 * df) + (3 * gf + 2 * df)
+  tf32_peak = _tf32_peak()
+  tflops = gflop * 1e9 * value / 1e12
+  line = {
+      'metric': 'MelspecGAN outer-iteration samples/sec', 'value': value, 'unit': 'samples/s', 'n_gpus': world,
+      'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
+      'scaling': 'weak', 'vs_baseline': None, 'dtype': 'tf32 convs (fp32 accumulate), fp32 elsewhere',
+      'data': 'synthetic',
+      'config': {'workload': 'MelspecGAN 64x80 train iteration, train_loss=%s (%d D steps + 1 G step, '
+                             'models/melspecgan/train.py:149-153), batch %d per GPU; the WGAN-GP penalty term is '
+                             'not built' % (args.melspecgan_loss, n_d, B),
+                 'batch_per_gpu': B, 'global_batch': B * world, 'parallelism': 'dp%d' % world,
+                 'l2': 'working set per iteration exceeds L2; no explicit flush'},
+      'e2e': {'value': samples / (e2e_ms * 1e-3), 'unit': 'samples/s', 'ms_per_step': e2e_ms / args.steps,
+              'h2d_bytes_per_step': int(n_d * xs_h[0].numel() * 4), 'd2h_bytes_per_step': 8},
+      'gpu_launches': int(per_step * args.steps * 2), 'launches_per_step': int(per_step), 'clocks': clk.summary(),
+      'roofline': {'kernel': 'whole iteration (conv GEMMs)', 'bound': 'tensor', 'achieved': tflops / world,
+                   'peak': tf32_peak, 'unit': 'TFLOP/s', 'frac': tflops / world / tf32_peak, 'traffic': None,
+                   'peak_source': 'cuBLAS TF32 8192^3 measured in this run'},
+  }
+  if rank == 0:
+    print(json.dumps(line))
+  if world > 1:
+    dist.destroy_process_group()
+
+
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument('--gpus', type=int, default=1)
@@ -537,12 +706,19 @@ def main():
   ap.add_argument('--impl', default='advoc_b200', choices=['advoc_b200', 'reference'])
   ap.add_argument('--model', default='small', choices=['small', 'regular'])
   ap.add_argument('--batch', type=int, default=32, help='samples per GPU')
-  ap.add_argument('--workload', default='infer', choices=['infer', 'train'])
+  ap.add_argument('--workload', default='infer', choices=['infer', 'train', 'spectral', 'melspecgan'])
+  ap.add_argument('--melspecgan-loss', default='dcgan', choices=['dcgan', 'wgan'])
   ap.add_argument('--no-graph', action='store_true')
   ap.add_argument('--no-cpu-baseline', action='store_true')
   args = ap.parse_args()
   args.warmup = max(args.warmup, 3) if args.impl != 'reference' else args.warmup
-  if args.workload == 'train':
+  if args.workload == 'spectral':
+    run_gpu_spectral(args)
+  elif args.workload == 'melspecgan':
+    if args.batch == 32:
+      args.batch = 64          # models/melspecgan/train.py:13
+    run_gpu_melspecgan(args)
+  elif args.workload == 'train':
     if args.impl == 'reference':
       run_reference_train(args)
     else:
