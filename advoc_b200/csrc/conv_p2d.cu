@@ -307,81 +307,77 @@ __global__ void __launch_bounds__(Q_THREADS, 1) conv_p2d_kernel(const __grid_con
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer: warp-uniform loop; the tcgen05.mma / commit instructions of one filter group
-    // are issued back to back by one elected lane (descriptors in uniform registers, see elect_one) =====
-    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
-                               ((uint32_t)(QM >> 4) << 24);
-    const int G = p.G;
-    const uint32_t slot_bytes = (uint32_t)G * B_BYTES;
-    const int ngroups = p.ntaps / G;
-    int as = 0, bs = 0;
-    uint32_t aph = 0, bph = 0;
-    long i = 0;
-    unsigned long long w_acc = 0, w_a = 0, w_b = 0;
-    const long long t_start = clock64();
-    for (long t = blockIdx.x; t < ntl; t += gridDim.x, ++i) {
-      const int buf = (int)(i % p.acc_bufs);
-      const uint32_t use = (uint32_t)(i / p.acc_bufs);
-      mbar_wait_p(&acc_empty[buf], (use & 1u) ^ 1u, p.dbg, 33u, p.prof, w_acc);
-      tc_fence_after();
-      const uint32_t d_base = tmem_base + (uint32_t)buf * acc_cols;
-      uint32_t started = 0;
-      for (int kb = 0; kb < p.kblocks; ++kb) {
-        int tp = 0;
-        for (int pl = 0; pl < p.nplanes; ++pl) {
-          mbar_wait_p(&a_full[as], aph, p.dbg, 34u, p.prof, w_a);
-          const uint32_t a_addr = ring + (uint32_t)as * p.a_slot_bytes;
-          const int t_end = p.plane_tap0[pl + 1];
-          for (; tp < t_end; tp += G) {
-            uint32_t b_addr;
-            if (p.b_resident) {
-              const int slot = kb * ngroups + tp / G;
-              if (i == 0) mbar_wait(&b_full[slot], 0u, p.dbg, 35u);
-              b_addr = ring + b_off + (uint32_t)slot * slot_bytes;
-            } else {
-              mbar_wait_p(&b_full[bs], bph, p.dbg, 35u, p.prof, w_b);
-              b_addr = ring + b_off + (uint32_t)bs * slot_bytes;
-            }
-            tc_fence_after();
-            const bool last_of_plane = tp + G >= t_end;
-            __syncwarp();
-            if (elect_one()) {
-              uint32_t st = started;
+    // ===== MMA issuer: the whole loop runs inside ONE elect.sync region -- a single thread waits and
+    // issues, and because the region is entered through elect.sync the compiler keeps the descriptors
+    // in uniform registers (no per-instruction ELECT/BRA.U.ANY wrapper, no warp-wide polling) =====
+    if (elect_one()) {
+      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                                 ((uint32_t)(QM >> 4) << 24);
+      const int G = p.G;
+      const uint32_t slot_bytes = (uint32_t)G * B_BYTES;
+      const int ngroups = p.ntaps / G;
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      long i = 0;
+      unsigned long long w_acc = 0, w_a = 0, w_b = 0;
+      const long long t_start = clock64();
+      for (long t = blockIdx.x; t < ntl; t += gridDim.x, ++i) {
+        const int buf = (int)(i % p.acc_bufs);
+        const uint32_t use = (uint32_t)(i / p.acc_bufs);
+        mbar_wait_p(&acc_empty[buf], (use & 1u) ^ 1u, p.dbg, 33u, p.prof, w_acc);
+        tc_fence_after();
+        const uint32_t d_base = tmem_base + (uint32_t)buf * acc_cols;
+        uint32_t started = 0;
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          int tp = 0;
+          for (int pl = 0; pl < p.nplanes; ++pl) {
+            mbar_wait_p(&a_full[as], aph, p.dbg, 34u, p.prof, w_a);
+            const uint32_t a_addr = ring + (uint32_t)as * p.a_slot_bytes;
+            const int t_end = p.plane_tap0[pl + 1];
+            for (; tp < t_end; tp += G) {
+              uint32_t b_addr;
+              if (p.b_resident) {
+                const int slot = kb * ngroups + tp / G;
+                if (i == 0) mbar_wait(&b_full[slot], 0u, p.dbg, 35u);
+                b_addr = ring + b_off + (uint32_t)slot * slot_bytes;
+              } else {
+                mbar_wait_p(&b_full[bs], bph, p.dbg, 35u, p.prof, w_b);
+                b_addr = ring + b_off + (uint32_t)bs * slot_bytes;
+              }
+              // no tcgen05.fence here: the operands were written by TMA (async proxy) and their
+              // arrival is ordered by the mbarrier; the fence is only needed for the TMEM hand-off above
               for (int u = 0; u < G; ++u) {
                 const uint32_t info = s_tap[tp + u];
                 const uint32_t cls = info >> 24;
                 const uint64_t da = make_smem_desc(a_addr + (info & 0xFFFFFFu));
                 const uint64_t db = make_smem_desc(b_addr + (uint32_t)u * B_BYTES);
                 const uint32_t d_tmem = d_base + cls * BN;
-                const uint32_t acc0 = (st >> cls) & 1u;
-                st |= 1u << cls;
+                const uint32_t acc0 = (started >> cls) & 1u;
+                started |= 1u << cls;
 #pragma unroll
                 for (int k = 0; k < QK / 8; ++k)
                   umma_tf32(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, acc0 | (uint32_t)(k != 0));
               }
-              if (!p.b_resident) umma_commit(&b_empty[bs]);
-              if (last_of_plane) umma_commit(&a_empty[as]);
+              if (!p.b_resident) {
+                umma_commit(&b_empty[bs]);
+                if (++bs == p.b_stages) { bs = 0; bph ^= 1u; }
+              }
             }
-            __syncwarp();
-            // every lane tracks `started` (the elected lane may differ between groups)
-            for (int u = 0; u < G; ++u) started |= 1u << (s_tap[tp + u] >> 24);
-            if (!p.b_resident) {
-              if (++bs == p.b_stages) { bs = 0; bph ^= 1u; }
-            }
+            umma_commit(&a_empty[as]);
+            if (++as == p.a_stages) { as = 0; aph ^= 1u; }
           }
-          if (++as == p.a_stages) { as = 0; aph ^= 1u; }
         }
+        umma_commit(&acc_full[buf]);
       }
-      if (elect_one()) umma_commit(&acc_full[buf]);
-      __syncwarp();
+      if (p.prof) {
+        p.prof[blockIdx.x * 16 + 4] = (unsigned long long)(clock64() - t_start);
+        p.prof[blockIdx.x * 16 + 5] = w_acc;
+        p.prof[blockIdx.x * 16 + 6] = w_a;
+        p.prof[blockIdx.x * 16 + 7] = w_b;
+        p.prof[blockIdx.x * 16 + 8] = (unsigned long long)i;
+      }
     }
-    if (p.prof && lane == 0) {
-      p.prof[blockIdx.x * 16 + 4] = (unsigned long long)(clock64() - t_start);
-      p.prof[blockIdx.x * 16 + 5] = w_acc;
-      p.prof[blockIdx.x * 16 + 6] = w_a;
-      p.prof[blockIdx.x * 16 + 7] = w_b;
-      p.prof[blockIdx.x * 16 + 8] = (unsigned long long)i;
-    }
+    __syncwarp();
   } else {
     // ===== epilogue: warp w may only touch TMEM lanes [32*(w%4), +32) =====
     const int q = warp & 3;

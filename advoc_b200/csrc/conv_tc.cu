@@ -19,6 +19,8 @@
 #include "epilogue.cuh"
 #include "tc_ptx.cuh"
 
+#include <stdlib.h>
+
 namespace advoc {
 
 namespace {
@@ -148,27 +150,25 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
     // `if (lane == 0)` region makes the compiler wrap every UTCMMA in an ELECT/BRA.U.ANY loop that
     // costs ~140 cycles per instruction: scripts/dev_mma_rate.py) =====
     constexpr uint32_t idesc = make_idesc(BN);
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int it = 0; it < iters; ++it) {
-      mbar_wait(&full_bar[stage], phase, p.dbg, 2u);
-      tc_fence_after();
-      const uint32_t a_addr = ring + stage * L::STAGE_BYTES;
-      const uint64_t da = make_smem_desc(a_addr);
-      const uint64_t db = make_smem_desc(a_addr + L::A_BYTES);
-      __syncwarp();
-      if (elect_one()) {
+    if (elect_one()) {   // one thread waits and issues; entered through elect.sync (see tc::elect_one)
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < iters; ++it) {
+        mbar_wait(&full_bar[stage], phase, p.dbg, 2u);
+        const uint32_t a_addr = ring + stage * L::STAGE_BYTES;
+        const uint64_t da = make_smem_desc(a_addr);
+        const uint64_t db = make_smem_desc(a_addr + L::A_BYTES);
 #pragma unroll
         for (int k = 0; k < BK / UMMA_K; ++k) {
           // advance 32 bytes (= 2 x 16-byte units) along K inside the swizzle atom
           umma_tf32(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (it | k) != 0 ? 1u : 0u);
         }
         umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
-        if (it == iters - 1) umma_commit(&tmem_full_bar);  // accumulator complete -> epilogue
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
-      __syncwarp();
-      if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      umma_commit(&tmem_full_bar);       // accumulator complete -> epilogue
     }
+    __syncwarp();
   } else {
     // ===== epilogue: warp q may only touch TMEM lanes [32q, 32q+32) =====
     const int q = warp & 3;
@@ -247,11 +247,24 @@ int launch(const TcParams& p, int nclasses, long max_tiles, cudaStream_t st) {
   return ADVOC_OK;
 }
 
-int pick_bn(int Cn) {
-  if (Cn % 256 == 0) return 256;
-  if (Cn % 128 == 0) return 128;
-  if (Cn % 64 == 0) return 64;
-  return 32;
+// Widest N tile that still leaves about two waves of CTAs: a layer with few output pixels and
+// many channels (encoder_5: 34 M tiles x 256 channels) otherwise runs on a fraction of the SMs
+// with one long serial K loop per CTA.  `m_ctas` = M tiles x parity classes.
+int pick_bn(int Cn, long m_ctas) {
+  static const bool fixed = getenv("ADVOC_TC_WIDE_N") != nullptr;   // A/B switch: always the widest tile
+  int bn = Cn % 256 == 0 ? 256 : (Cn % 128 == 0 ? 128 : (Cn % 64 == 0 ? 64 : 32));
+  if (fixed) return bn;
+  while (bn > 64 && m_ctas * (Cn / bn) < 2L * sm_count()) bn >>= 1;
+  return bn;
+}
+
+long m_ctas_of(int Nimg, const ClassGeom* g, int nclasses) {
+  long tiles = 0;
+  for (int c = 0; c < nclasses; ++c) {
+    const long t = ((long)Nimg * g[c].Ah * g[c].Aw + BM - 1) / BM;
+    if (t > tiles) tiles = t;
+  }
+  return tiles * nclasses;
 }
 
 int run(TcParams& p, int nclasses, const ClassGeom* g, void* stream) {
@@ -268,7 +281,7 @@ int run(TcParams& p, int nclasses, const ClassGeom* g, void* stream) {
   p.dbg = debug_word();
   p.nclasses = nclasses;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  switch (pick_bn(p.Cn)) {
+  switch (pick_bn(p.Cn, m_ctas_of(p.Nimg, g, nclasses))) {
     case 256: return launch<256, 4>(p, nclasses, max_tiles, st);
     case 128: return launch<128, 3>(p, nclasses, max_tiles, st);
     case 64: return launch<64, 4>(p, nclasses, max_tiles, st);
@@ -327,7 +340,7 @@ int conv_fwd_tc(const advoc_conv_desc* d, const float* x, int ldx, const float* 
                 "im2col corner out of range");
   st = encode_A(&p.tmA[0], x, d->N, d->H, d->W, ldx, d->Cin, g, d->sh, d->sw);
   if (st) return st;
-  st = encode_B(&p.tmB, w, g.ntaps * d->Cout, d->Cin, pick_bn(d->Cout));
+  st = encode_B(&p.tmB, w, g.ntaps * d->Cout, d->Cin, pick_bn(d->Cout, m_ctas_of(d->N, &g, 1)));
   if (st) return st;
   p.Nimg = d->N; p.trav_h = d->sh; p.trav_w = d->sw; p.osh = 1; p.osw = 1;
   p.Cn = d->Cout; p.kblocks = d->Cin / BK;
@@ -377,7 +390,7 @@ int conv_transposed_tc(const advoc_conv_desc* d, const float* x, int ldx, const 
       ++nc;
     }
   }
-  st = encode_B(&p.tmB, w, d->kh * d->kw * d->Cin, d->Cout, pick_bn(d->Cin));
+  st = encode_B(&p.tmB, w, d->kh * d->kw * d->Cin, d->Cout, pick_bn(d->Cin, m_ctas_of(d->N, g, nc)));
   if (st) return st;
   p.Nimg = d->N; p.trav_h = 1; p.trav_w = 1; p.osh = d->sh; p.osw = d->sw;
   p.Cn = d->Cin; p.kblocks = d->Cout / BK;

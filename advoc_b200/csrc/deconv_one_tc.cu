@@ -156,6 +156,19 @@ __global__ void __launch_bounds__(O_THREADS, 1) deconv_one_tc_kernel(const __gri
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int tid = (warp - 2) * 32 + lane;    // 0..127
+    // the (up to O_NOUT) output pixels of this thread inside a patch are the same for every patch
+    constexpr int OWT = 2 * O_IW;
+    constexpr int O_NOUT = (2 * O_IH * OWT + 127) / 128;
+    int o_ai[O_NOUT], o_bi[O_NOUT], o_ph[O_NOUT], o_pw[O_NOUT];
+    bool o_ok[O_NOUT];
+#pragma unroll
+    for (int j = 0; j < O_NOUT; ++j) {
+      const int o = tid + 128 * j;
+      o_ok[j] = o < 2 * O_IH * OWT;
+      const int orow = o / OWT, ocol = o - orow * OWT;
+      o_ai[j] = 1 + (orow >> 1); o_bi[j] = 1 + (ocol >> 1);
+      o_ph[j] = orow & 1; o_pw[j] = ocol & 1;
+    }
     long i = 0;
     for (long t = blockIdx.x; t < ntl; t += gridDim.x, ++i) {
       const int buf = (int)(i & 1);
@@ -176,28 +189,29 @@ __global__ void __launch_bounds__(O_THREADS, 1) deconv_one_tc_kernel(const __gri
       for (int k = 0; k < KS * KS; ++k) tsm[buf][row][k] = __uint_as_float(v[k]);
       asm volatile("bar.sync 1, 128;" ::: "memory");   // T of this patch complete (the buffer of two
                                                       // patches ago was consumed before this point)
-      constexpr int OWT = 2 * O_IW;
-      for (int o = tid; o < 2 * O_IH * OWT; o += 128) {
-        const int orow = o / OWT, ocol = o - orow * OWT;
-        const int ai = 1 + (orow >> 1), bi = 1 + (ocol >> 1);
-        const int ph = orow & 1, pw = ocol & 1;
-        const int ar = a0 + ai, bc = b0 + bi;
-        const int oh = 2 * ar + ph, ow = 2 * bc + pw;
-        if (ar >= p.Hs || bc >= p.Ws || ow >= p.epi.Ws) continue;
-        // out[oh, ow] = sum over taps with (oh + 1 - kh) even of T[(oh + 1 - kh) / 2, ...][kh, kw] (pad 1, stride 2)
-        float acc = 0.f;
 #pragma unroll
-        for (int kh = 0; kh < KS; ++kh) {
-          if (((ph + 1 - kh) & 1) != 0) continue;
+      for (int j = 0; j < O_NOUT; ++j) {
+        if (!o_ok[j]) continue;
+        const int ar = a0 + o_ai[j], bc = b0 + o_bi[j];
+        const int ow = 2 * bc + o_pw[j];
+        if (ar >= p.Hs || bc >= p.Ws || ow >= p.epi.Ws) continue;
+        const int ph = o_ph[j], pw = o_pw[j], ai = o_ai[j], bi = o_bi[j];
+        float acc = 0.f;
+        const int kh0 = (ph + 1) & 1, kw0 = (pw + 1) & 1;   // taps of the right parity only
+#pragma unroll
+        for (int jh = 0; jh < (KS + 1) / 2; ++jh) {
+          const int kh = kh0 + 2 * jh;
+          if (kh >= KS) break;
           const int dr = (ph + 1 - kh) >> 1;          // -1, 0 or +1
 #pragma unroll
-          for (int kw = 0; kw < KS; ++kw) {
-            if (((pw + 1 - kw) & 1) != 0) continue;
+          for (int jw = 0; jw < (KS + 1) / 2; ++jw) {
+            const int kw = kw0 + 2 * jw;
+            if (kw >= KS) break;
             const int dc = (pw + 1 - kw) >> 1;
             acc += tsm[buf][(ai + dr) * O_PW + (bi + dc)][kh * KS + kw];
           }
         }
-        const size_t pix = ((size_t)img * p.epi.Hs + oh) * p.epi.Ws + ow;
+        const size_t pix = ((size_t)img * p.epi.Hs + (2 * ar + ph)) * p.epi.Ws + ow;
         epi_store(p.epi, pix, 0, acc);
       }
     }

@@ -70,7 +70,10 @@ __global__ void __launch_bounds__(128) desc_shift_probe(float* out, int shift, i
 //   mode 2: kind::f16 (same bytes per operand row)   mode 3: tf32 + tcgen05.commit after every 4 MMAs
 //   mode 4: tf32, A descriptor start shifted by 3 rows (un-aligned view)
 //   mode 5: tf32 issued from a warp-uniform loop under elect.sync (instead of `if (thread == 0)`)
-__global__ void __launch_bounds__(128) mma_rate_probe(unsigned long long* out, int n, int reps, int mode) {
+//   mode >= 16: bit flags, see the kernel (64 concurrent bulk copies into smem, 128 concurrent
+//   st.shared stream, 256 concurrent tcgen05.ld stream)
+__global__ void __launch_bounds__(128) mma_rate_probe(unsigned long long* out, int n, int reps, int mode,
+                                                      const float* gsrc) {
   extern __shared__ uint8_t raw[];
   __shared__ __align__(8) uint64_t bar, bar2;
   __shared__ uint32_t tmem_holder;
@@ -122,6 +125,61 @@ __global__ void __launch_bounds__(128) mma_rate_probe(unsigned long long* out, i
       }
     } else if (fl & 8) {
       while (!mbar_try_wait(&bar, 0u)) {}
+    } else if ((fl & 64) && threadIdx.x < 64) {
+      // warp 1: bulk copies global -> shared (16 KB each, like TMA operand fills) until the MMAs are done
+      if (threadIdx.x == 32) {
+        uint32_t ph = 0;
+        while (!mbar_try_wait(&bar, 0u)) {
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar2)), "r"(16384u) : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                           base + 96 * 1024),
+                       "l"(gsrc + (size_t)blockIdx.x * 4096), "r"(16384u), "r"(smem_u32(&bar2))
+                       : "memory");
+          while (!mbar_try_wait(&bar2, ph)) {}
+          ph ^= 1u;
+        }
+      }
+    } else if ((fl & 128) && threadIdx.x >= 64) {
+      // warps 2-3: st.shared.v4 stream (like the epilogue staging)
+      const uint32_t a = base + 112 * 1024 + (threadIdx.x - 64) * 16;
+      while (!mbar_try_wait(&bar, 0u)) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+          asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};" ::"r"(a + r * 1024), "f"(1.0f) : "memory");
+      }
+    } else if ((fl & 256) && threadIdx.x >= 64) {
+      // warps 2-3: tcgen05.ld stream from accumulator columns the MMAs do not touch
+      uint32_t v[32];
+      float sink = 0.f;
+      while (!mbar_try_wait(&bar, 0u)) {
+        tmem_ld32(tmem + ((uint32_t)((threadIdx.x >> 5) * 32) << 16) + 384u, v);
+        tmem_ld_wait();
+        sink += __uint_as_float(v[0]);
+      }
+      if (sink == 123.456f) out[0] = 1;
+    }
+  } else if (mode == 6) {
+    // the whole issue loop inside ONE elect.sync region (a single thread also does the waiting)
+    if (threadIdx.x < 32) {
+      if (elect_one()) {
+        const uint32_t idesc_tf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const long long t0 = clock64();
+        for (int i = 0; i < reps; i += 4) {
+          const int step = i >> 2;
+          const uint64_t da = make_smem_desc(base + (uint32_t)(1 + (step % 5) * 13) * 128u);
+          const uint64_t db = make_smem_desc(base + 64 * 1024 + (uint32_t)(step & 3) * 8192u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_tf32(tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_tf32, (i | k) ? 1u : 0u);
+          umma_commit(&bar2);
+          if ((step & 7) == 7) mbar_wait(&bar2, 0u, nullptr, 0u);   // a wait inside the region (already complete)
+        }
+        const long long t1 = clock64();
+        umma_commit(&bar);
+        mbar_wait(&bar, 0u, nullptr, 0u);
+        const long long t2 = clock64();
+        out[blockIdx.x * 2 + 0] = (unsigned long long)(t1 - t0);
+        out[blockIdx.x * 2 + 1] = (unsigned long long)(t2 - t0);
+      }
     }
   } else if (mode == 5) {
     if (threadIdx.x < 32) {
@@ -187,13 +245,17 @@ extern "C" __attribute__((visibility("default"))) int advoc_selftest_mma_rate(un
   ADVOC_REQUIRE(h_out && ctas > 0 && ctas <= 1024 && n >= 8 && n <= 256 && n % 8 == 0, ADVOC_BAD_ARG, "bad arguments");
   unsigned long long* d = nullptr;
   ADVOC_CHECK_CUDA(cudaMalloc(&d, ctas * 2 * sizeof(unsigned long long)));
-  const int smem = 64 * 1024 + 64 * 1024 + 1024;
+  const int smem = 64 * 1024 + 64 * 1024 + 64 * 1024 + 1024;
   ADVOC_CHECK_CUDA(cudaFuncSetAttribute(mma_rate_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  mma_rate_probe<<<ctas, 128, smem>>>(d, n, reps, mode);
+  float* gsrc = nullptr;
+  ADVOC_CHECK_CUDA(cudaMalloc(&gsrc, (size_t)ctas * 16384 + 65536));
+  ADVOC_CHECK_CUDA(cudaMemset(gsrc, 0, (size_t)ctas * 16384 + 65536));
+  mma_rate_probe<<<ctas, 128, smem>>>(d, n, reps, mode, gsrc);
   ADVOC_CHECK_CUDA(cudaGetLastError());
   ADVOC_CHECK_CUDA(cudaDeviceSynchronize());
   ADVOC_CHECK_CUDA(cudaMemcpy(h_out, d, ctas * 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   cudaFree(d);
+  cudaFree(gsrc);
   return ADVOC_OK;
 }
 

@@ -152,18 +152,16 @@ __global__ void __launch_bounds__(W_THREADS) wgrad_tc_kernel(const __grid_consta
       if (++stage == WSTAGES) { stage = 0; phase ^= 1u; }
     }
   } else if (warp == 1) {
-    // warp-uniform loop, MMAs issued by one elected lane (see tc::elect_one)
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int it = 0; it < iters; ++it) {
-      mbar_wait(&full_bar[stage], phase, p.dbg, 12u);
-      tc_fence_after();
-      const uint32_t a_addr = ring + stage * STAGE_BYTES;
-      const uint64_t da = make_mn_desc(a_addr, BLK_BYTES);
-      const uint64_t db0 = make_mn_desc(a_addr + A_BYTES, BLK_BYTES);
-      const uint64_t db1 = make_mn_desc(a_addr + A_BYTES + 8 * BLK_BYTES, BLK_BYTES);
-      __syncwarp();
-      if (elect_one()) {
+    // one thread waits and issues, inside a single elect.sync region (see tc::elect_one)
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < iters; ++it) {
+        mbar_wait(&full_bar[stage], phase, p.dbg, 12u);
+        const uint32_t a_addr = ring + stage * STAGE_BYTES;
+        const uint64_t da = make_mn_desc(a_addr, BLK_BYTES);
+        const uint64_t db0 = make_mn_desc(a_addr + A_BYTES, BLK_BYTES);
+        const uint64_t db1 = make_mn_desc(a_addr + A_BYTES + 8 * BLK_BYTES, BLK_BYTES);
 #pragma unroll
         for (int k = 0; k < WBK / 8; ++k) {
           // 8 pixels = 1024 bytes along K inside every box
@@ -172,11 +170,11 @@ __global__ void __launch_bounds__(W_THREADS) wgrad_tc_kernel(const __grid_consta
           umma_tf32(tmem_base + 256u, da + (uint64_t)(64 * k), db1 + (uint64_t)(64 * k), kIdescMN, acc);
         }
         umma_commit(&empty_bar[stage]);
-        if (it == iters - 1) umma_commit(&tmem_full_bar);
+        if (++stage == WSTAGES) { stage = 0; phase ^= 1u; }
       }
-      __syncwarp();
-      if (++stage == WSTAGES) { stage = 0; phase ^= 1u; }
+      umma_commit(&tmem_full_bar);
     }
+    __syncwarp();
   } else {
     const int q = warp & 3;
     const int cs = m0 + q * 32 + lane;

@@ -11,12 +11,12 @@ lib = N.lib()
 fn = lib.advoc_selftest_mma_rate
 fn.restype = C.c_int
 fn.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
-for mode, name in [(16, 'elect step4'), (20, '+commit/4'),
-                   (24, '+3 polling warps'), (48, '+B desc varies'), (16 + 1 + 2 + 4 + 8 + 32, 'all')]:
+for mode, name in [(6, 'one elect region, step4'), (16, 'elect step4'), (16 + 64, '+bulk copies into smem'), (16 + 128, '+st.shared stream'),
+                   (16 + 256, '+tcgen05.ld stream'), (16 + 64 + 128, '+copies +st.shared')]:
   for n in (32, 64, 128, 256):
     ctas, reps = 148, 2048
     out = np.zeros((ctas, 2), dtype=np.uint64)
     st = fn(out.ctypes.data, ctas, n, reps, mode)
     assert st == 0, st
-    print('%-18s N=%3d  issue %.1f cyc/MMA  complete %.1f cyc/MMA (ideal %d)'
+    print('%-26s N=%3d  issue %.1f cyc/MMA  complete %.1f cyc/MMA (ideal %d)'
           % (name, n, out[:, 0].mean() / reps, out[:, 1].mean() / reps, 128 * n // 256))
