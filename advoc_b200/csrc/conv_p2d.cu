@@ -251,9 +251,13 @@ __global__ void __launch_bounds__(Q_THREADS, 1) conv_p2d_kernel(const __grid_con
           mbar_wait_p(&a_empty[as], aph ^ 1u, p.dbg, 31u, p.prof, w_a);
           __syncwarp();
           if (elect_one()) {
-            mbar_expect_tx(&a_full[as], p.a_box_bytes);
-            tma_load_4d(&p.tmA[pl], &a_full[as], ring_ptr + (size_t)as * p.a_slot_bytes, kb * QK,
-                        tc_.w0 + p.plane_ow[pl], tc_.h0 + p.plane_oh[pl], tc_.img);
+            if (p.exp_flags & 4) {
+              mbar_arrive(&a_full[as]);
+            } else {
+              mbar_expect_tx(&a_full[as], p.a_box_bytes);
+              tma_load_4d(&p.tmA[pl], &a_full[as], ring_ptr + (size_t)as * p.a_slot_bytes, kb * QK,
+                          tc_.w0 + p.plane_ow[pl], tc_.h0 + p.plane_oh[pl], tc_.img);
+            }
           }
           __syncwarp();
           if (++as == p.a_stages) { as = 0; aph ^= 1u; }
@@ -291,11 +295,15 @@ __global__ void __launch_bounds__(Q_THREADS, 1) conv_p2d_kernel(const __grid_con
         for (int kb = 0; kb < p.kblocks; ++kb) {
           for (int t0 = 0; t0 < p.ntaps; t0 += G) {
             mbar_wait_p(&b_empty[bs], bph ^ 1u, p.dbg, 32u, p.prof, w_b);
-            if (lane == 0) mbar_expect_tx(&b_full[bs], slot_bytes);
-            __syncwarp();
-            if (lane < G)
-              tma_load_2d(&p.tmB, &b_full[bs], ring_ptr + b_off + (size_t)bs * slot_bytes + (size_t)lane * B_BYTES,
-                          kb * QK, (int)p.tap_wrow[t0 + lane] * p.Cn + n0);
+            if (p.exp_flags & 4) {
+              if (lane == 0) mbar_arrive(&b_full[bs]);
+            } else {
+              if (lane == 0) mbar_expect_tx(&b_full[bs], slot_bytes);
+              __syncwarp();
+              if (lane < G)
+                tma_load_2d(&p.tmB, &b_full[bs], ring_ptr + b_off + (size_t)bs * slot_bytes + (size_t)lane * B_BYTES,
+                            kb * QK, (int)p.tap_wrow[t0 + lane] * p.Cn + n0);
+            }
             __syncwarp();
             if (++bs == p.b_stages) { bs = 0; bph ^= 1u; }
           }
@@ -424,7 +432,7 @@ __global__ void __launch_bounds__(Q_THREADS, 1) conv_p2d_kernel(const __grid_con
       tc_fence_after();
       const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * acc_cols;
 #pragma unroll 1
-      for (int z = 0; z < p.ncls; ++z) {
+      for (int z = 0; z < ((p.exp_flags & 8) ? 0 : p.ncls); ++z) {
         const int oh = a * p.osh + p.cls_ph[z], ow = b * p.osw + p.cls_pw[z];
         const bool valid = row_ok && oh < e.Hs && ow < e.Ws;
         const size_t pix = valid ? ((size_t)tc_.img * e.Hs + oh) * e.Ws + ow : 0;
@@ -646,6 +654,8 @@ bool make_plan(const advoc_conv_desc* d, bool transposed, int Wstored, int n_out
   }
   p.plane_tap0[nplanes] = k;
   if (getenv("ADVOC_P2D_NOSHIFT"))   // timing experiment only (wrong results): every tap reads the aligned patch start
+    for (int t = 0; t < k; ++t) p.tap_shift[t] = 0;
+  if (getenv("ADVOC_P2D_EXP") && (atoi(getenv("ADVOC_P2D_EXP")) & 16))
     for (int t = 0; t < k; ++t) p.tap_shift[t] = 0;
   if (getenv("ADVOC_P2D_SHIFT8"))    // timing experiment only: shifts rounded down to whole 1 KB swizzle atoms
     for (int t = 0; t < k; ++t) p.tap_shift[t] &= ~7;

@@ -23,10 +23,12 @@ namespace {
 
 using namespace tc;
 
+unsigned long long* g_one_prof = nullptr;
+
 constexpr int O_PH = 8, O_PW = 16;            // patch (GEMM rows = O_PH * O_PW = 128)
 constexpr int O_IH = O_PH - 2, O_IW = O_PW - 2;
 constexpr int O_STAGES = 8;                   // 16 KB patch slots
-constexpr int O_THREADS = 192;
+constexpr int O_THREADS = 320;               // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
 constexpr int O_MAXKB = 8;                    // Cs <= 256
 
 struct alignas(64) OneParams {
@@ -36,7 +38,16 @@ struct alignas(64) OneParams {
   long total_tiles;
   EpiDev epi;
   unsigned int* dbg;
+  unsigned long long* prof;   // optional [grid][8] cycle counters (ADVOC_ONE_PROFILE)
 };
+
+__device__ __forceinline__ void wait_p(uint64_t* bar, uint32_t parity, unsigned int* dbg, unsigned code,
+                                       const unsigned long long* prof, unsigned long long& acc) {
+  if (prof == nullptr) { mbar_wait(bar, parity, dbg, code); return; }
+  const long long t0 = clock64();
+  mbar_wait(bar, parity, dbg, code);
+  acc += (unsigned long long)(clock64() - t0);
+}
 
 __device__ __forceinline__ void mbar_arrive1(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -49,6 +60,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
         "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr));
+}
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr));
 }
 
 // KS = filter size (4: AdVoc decoder_1; 5: MelspecGAN upconv_4, models/melspecgan/conv2d.py:139-141);
@@ -73,7 +90,7 @@ __global__ void __launch_bounds__(O_THREADS, 1) deconv_one_tc_kernel(const __gri
   if (threadIdx.x == 0) {
     for (int s = 0; s < O_STAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     mbar_init(&b_full, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     prefetch_tmap(&p.tmA);
     prefetch_tmap(&p.tmB);
@@ -103,91 +120,103 @@ __global__ void __launch_bounds__(O_THREADS, 1) deconv_one_tc_kernel(const __gri
       }
       __syncwarp();
     }
-    int as = 0;
-    uint32_t aph = 0;
-    for (long t = blockIdx.x; t < ntl; t += gridDim.x) {
-      const int img = (int)(t / per_img);
-      const int r = (int)(t - (long)img * per_img);
-      const int a0 = (r / p.tiles_w) * O_IH - 1, b0 = (r % p.tiles_w) * O_IW - 1;
-      for (int kb = 0; kb < p.kblocks; ++kb) {
-        mbar_wait(&a_empty[as], aph ^ 1u, p.dbg, 41u);
-        __syncwarp();
-        if (elect_one()) {
+    if (elect_one()) {
+      int as = 0;
+      uint32_t aph = 0;
+      unsigned long long w0 = 0;
+      const long long ts = clock64();
+      for (long t = blockIdx.x; t < ntl; t += gridDim.x) {
+        const int img = (int)(t / per_img);
+        const int r = (int)(t - (long)img * per_img);
+        const int a0 = (r / p.tiles_w) * O_IH - 1, b0 = (r % p.tiles_w) * O_IW - 1;
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          wait_p(&a_empty[as], aph ^ 1u, p.dbg, 41u, p.prof, w0);
           mbar_expect_tx(&a_full[as], A_BYTES);
           tma_load_4d(&p.tmA, &a_full[as], ring_ptr + (size_t)as * A_BYTES, kb * 32, b0, a0, img);
+          if (++as == O_STAGES) { as = 0; aph ^= 1u; }
         }
-        __syncwarp();
-        if (++as == O_STAGES) { as = 0; aph ^= 1u; }
       }
+      if (p.prof) { p.prof[blockIdx.x * 8 + 0] = (unsigned long long)(clock64() - ts); p.prof[blockIdx.x * 8 + 1] = w0; }
     }
+    __syncwarp();
   } else if (warp == 1) {
     // ===== MMA issuer: M = 128 positions, N = NP taps, K = Cs =====
     constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NP >> 3) << 17) |
                                ((uint32_t)(128 >> 4) << 24);
-    int as = 0;
-    uint32_t aph = 0;
-    long i = 0;
-    if ((long)blockIdx.x < ntl) mbar_wait(&b_full, 0u, p.dbg, 42u);
-    for (long t = blockIdx.x; t < ntl; t += gridDim.x, ++i) {
-      const int buf = (int)(i & 1);
-      const uint32_t use = (uint32_t)(i >> 1);
-      mbar_wait(&acc_empty[buf], (use & 1u) ^ 1u, p.dbg, 43u);
-      tc_fence_after();
-      for (int kb = 0; kb < p.kblocks; ++kb) {
-        mbar_wait(&a_full[as], aph, p.dbg, 44u);
+    if (elect_one()) {
+      int as = 0;
+      uint32_t aph = 0;
+      long i = 0;
+      unsigned long long w1 = 0, w2 = 0;
+      const long long ts = clock64();
+      if ((long)blockIdx.x < ntl) mbar_wait(&b_full, 0u, p.dbg, 42u);
+      for (long t = blockIdx.x; t < ntl; t += gridDim.x, ++i) {
+        const int buf = (int)(i & 1);
+        const uint32_t use = (uint32_t)(i >> 1);
+        wait_p(&acc_empty[buf], (use & 1u) ^ 1u, p.dbg, 43u, p.prof, w1);
         tc_fence_after();
-        const uint64_t da = make_smem_desc(ring + (uint32_t)as * A_BYTES);
-        const uint64_t db = make_smem_desc(ring + b_off + (uint32_t)kb * B_BYTES);
-        __syncwarp();
-        if (elect_one()) {
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          wait_p(&a_full[as], aph, p.dbg, 44u, p.prof, w2);
+          const uint64_t da = make_smem_desc(ring + (uint32_t)as * A_BYTES);
+          const uint64_t db = make_smem_desc(ring + b_off + (uint32_t)kb * B_BYTES);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             umma_tf32(tmem_base + (uint32_t)buf * NP, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
                       (kb | k) != 0 ? 1u : 0u);
           umma_commit(&a_empty[as]);
           if (kb == p.kblocks - 1) umma_commit(&acc_full[buf]);
+          if (++as == O_STAGES) { as = 0; aph ^= 1u; }
         }
-        __syncwarp();
-        if (++as == O_STAGES) { as = 0; aph ^= 1u; }
+      }
+      if (p.prof) {
+        p.prof[blockIdx.x * 8 + 2] = (unsigned long long)(clock64() - ts); p.prof[blockIdx.x * 8 + 3] = w1;
+        p.prof[blockIdx.x * 8 + 4] = w2; p.prof[blockIdx.x * 8 + 7] = (unsigned long long)i;
       }
     }
+    __syncwarp();
   } else {
     // ===== epilogue: TMEM -> T[pos][tap] in smem -> col2im -> output pixels =====
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const int tid = (warp - 2) * 32 + lane;    // 0..127
+    const int tid = (warp - 2) * 32 + lane;    // 0..255
+    const int half = (warp - 2) >> 2;          // which half of the tap columns this warp reads
     // the (up to O_NOUT) output pixels of this thread inside a patch are the same for every patch
     constexpr int OWT = 2 * O_IW;
-    constexpr int O_NOUT = (2 * O_IH * OWT + 127) / 128;
+    constexpr int O_NOUT = (2 * O_IH * OWT + 255) / 256;
     int o_ai[O_NOUT], o_bi[O_NOUT], o_ph[O_NOUT], o_pw[O_NOUT];
     bool o_ok[O_NOUT];
 #pragma unroll
     for (int j = 0; j < O_NOUT; ++j) {
-      const int o = tid + 128 * j;
+      const int o = tid + 256 * j;
       o_ok[j] = o < 2 * O_IH * OWT;
       const int orow = o / OWT, ocol = o - orow * OWT;
       o_ai[j] = 1 + (orow >> 1); o_bi[j] = 1 + (ocol >> 1);
       o_ph[j] = orow & 1; o_pw[j] = ocol & 1;
     }
     long i = 0;
+    unsigned long long w3 = 0;
+    const long long ts = clock64();
     for (long t = blockIdx.x; t < ntl; t += gridDim.x, ++i) {
       const int buf = (int)(i & 1);
       const uint32_t use = (uint32_t)(i >> 1);
       const int img = (int)(t / per_img);
       const int r = (int)(t - (long)img * per_img);
       const int a0 = (r / p.tiles_w) * O_IH - 1, b0 = (r % p.tiles_w) * O_IW - 1;
-      mbar_wait(&acc_full[buf], use & 1u, p.dbg, 45u);
+      wait_p(&acc_full[buf], use & 1u, p.dbg, 45u, p.prof, w3);
       tc_fence_after();
-      uint32_t v[NP];
-      if (NP == 16) tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * NP, v);
-      else tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * NP, v);
+      constexpr int HC = NP / 2;               // columns per warp
+      uint32_t v[HC];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * NP + half * HC);
+      if (HC == 8) tmem_ld8(taddr, v);
+      else tmem_ld16(taddr, v);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive1(&acc_empty[buf]);
 #pragma unroll
-      for (int k = 0; k < KS * KS; ++k) tsm[buf][row][k] = __uint_as_float(v[k]);
-      asm volatile("bar.sync 1, 128;" ::: "memory");   // T of this patch complete (the buffer of two
+      for (int k = 0; k < HC; ++k)
+        if (half * HC + k < KS * KS) tsm[buf][row][half * HC + k] = __uint_as_float(v[k]);
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // T of this patch complete (the buffer of two
                                                       // patches ago was consumed before this point)
 #pragma unroll
       for (int j = 0; j < O_NOUT; ++j) {
@@ -215,6 +244,7 @@ __global__ void __launch_bounds__(O_THREADS, 1) deconv_one_tc_kernel(const __gri
         epi_store(p.epi, pix, 0, acc);
       }
     }
+    if (p.prof && tid == 0) { p.prof[blockIdx.x * 8 + 5] = (unsigned long long)(clock64() - ts); p.prof[blockIdx.x * 8 + 6] = w3; }
   }
 
   tc_fence_before();
@@ -258,6 +288,15 @@ int deconv_one_tc(const advoc_conv_desc* d, const float* x, int ldx, const float
   st = encode_tiled2d(&p.tmB, w, d->Cout, d->kh * d->kw, (size_t)d->Cout * 4, 32, np);
   if (st) return st;
   p.dbg = debug_word();
+  static unsigned long long* prof = [] {
+    unsigned long long* b = nullptr;
+    if (getenv("ADVOC_ONE_PROFILE") == nullptr) return b;
+    if (cudaMalloc(&b, 256 * 8 * sizeof(unsigned long long)) != cudaSuccess) return (unsigned long long*)nullptr;
+    cudaMemset(b, 0, 256 * 8 * sizeof(unsigned long long));
+    return b;
+  }();
+  p.prof = prof;
+  if (prof) g_one_prof = prof;
   const int smem = O_STAGES * O_PH * O_PW * 128 + O_MAXKB * 32 * 128 + 1024;
   static bool configured = false;
   if (!configured) {
@@ -276,3 +315,12 @@ int deconv_one_tc(const advoc_conv_desc* d, const float* x, int ldx, const float
 }
 
 }  // namespace advoc
+
+// Developer hook (ADVOC_ONE_PROFILE=1): per-CTA cycle counters of the last deconv_one_tc launch, [256][8] u64.
+extern "C" __attribute__((visibility("default"))) int advoc_one_profile_read(unsigned long long* out) {
+  using namespace advoc;
+  ADVOC_REQUIRE(g_one_prof != nullptr && out != nullptr, ADVOC_UNSUPPORTED, "profiling is off (set ADVOC_ONE_PROFILE=1)");
+  ADVOC_CHECK_CUDA(cudaMemcpy(out, g_one_prof, 256 * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  ADVOC_CHECK_CUDA(cudaMemset(g_one_prof, 0, 256 * 8 * sizeof(unsigned long long)));
+  return ADVOC_OK;
+}

@@ -82,11 +82,14 @@ def test_train_step_gradients(math, gtol, loss):
   dn, gn = M.d_names(P), M.g_names(P)
   ref_d = dict(zip(dn, torch.autograd.grad(D_loss, [Pr[n] for n in dn], retain_graph=True)))
   ref_g = dict(zip(gn, torch.autograd.grad(G_loss, [Pr[n] for n in gn])))
+  # the wgan critic loss is a difference of two means: measure its error against the larger term
+  ltol = 2e-3 if math == 'fp32' else 5e-3
+  scale_d = max(abs(float(D_loss)), float(D_x.abs().mean()), float(D_G_z.abs().mean()), 1e-2)
   eng.d_step(x.cuda(), z.cuda(), apply=False)
-  assert abs(eng.loss_values()[0] - float(D_loss)) < 2e-3 * max(abs(float(D_loss)), 1e-2)
+  assert abs(eng.loss_values()[0] - float(D_loss)) < ltol * scale_d
   _check_grads(eng, ref_d, dn, gtol)
   eng.g_step(z.cuda(), apply=False)
-  assert abs(eng.loss_values()[1] - float(G_loss)) < 2e-3 * max(abs(float(G_loss)), 1e-2)
+  assert abs(eng.loss_values()[1] - float(G_loss)) < ltol * max(abs(float(G_loss)), 1e-2)
   _check_grads(eng, ref_g, gn, gtol)
 
 
