@@ -78,6 +78,8 @@ SIGNATURES = {
     'advoc_bn_backward': (_I, [_P, _I, _P, _I, _P, _I, _L, _I, _P, _P, _F, _I, _F, _P, _P, _I, _I, _P]),
     'advoc_tanh_backward': (_I, [_P, _P, _P, _L, _P]),
     'advoc_gan_logit_loss': (_I, [_P, _P, _I, _I, _P, _P, _P, _P]),
+    'advoc_gp_seed': (_I, [_P, _I, _L, _F, _P, _P, _I, _P]),
+    'advoc_bn_gp': (_I, [_P, _P, _P, _P, _L, _I, _P, _P, _F, _F, _P, _P, _P, _I, _P]),
     'advoc_conv2d_transpose_fwd': (_I, [C.POINTER(ConvDesc), _P, _I, _P, C.POINTER(Epilogue), _P]),
 }
 

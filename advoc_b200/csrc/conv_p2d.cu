@@ -184,13 +184,16 @@ struct TileCoord {
 };
 
 __device__ __forceinline__ TileCoord decode_tile(const P2dParams& p, long t) {
+  // total_tiles < 2^31 (checked on the host): 32-bit divisions
   TileCoord c;
-  c.n_tile = (int)(t % p.n_ntiles);
-  long s = t / p.n_ntiles;
-  c.w0 = (int)(s % p.tiles_w) * p.tw;
-  s /= p.tiles_w;
-  c.h0 = (int)(s % p.tiles_h) * p.th;
-  c.img = (int)(s / p.tiles_h);
+  unsigned s = (unsigned)t;
+  const unsigned nn = (unsigned)p.n_ntiles, tw = (unsigned)p.tiles_w, th = (unsigned)p.tiles_h;
+  c.n_tile = (int)(s % nn);
+  s /= nn;
+  c.w0 = (int)(s % tw) * p.tw;
+  s /= tw;
+  c.h0 = (int)(s % th) * p.th;
+  c.img = (int)(s / th);
   return c;
 }
 
@@ -722,7 +725,7 @@ bool make_plan(const advoc_conv_desc* d, bool transposed, int Wstored, int n_out
   p.use_gate = gate_bytes ? 1 : 0;
   pl->smem = (size_t)p.stage_off + staging + 1024;
   if (pl->smem < 120 * 1024) pl->smem = 120 * 1024;  // one CTA per SM: TMEM is not shared between CTAs here
-  return p.total_tiles > 0;
+  return p.total_tiles > 0 && p.total_tiles < 2147483647L;
 }
 
 template <int BN>

@@ -126,8 +126,8 @@ __global__ void __launch_bounds__(O_THREADS, 1) deconv_one_tc_kernel(const __gri
       unsigned long long w0 = 0;
       const long long ts = clock64();
       for (long t = blockIdx.x; t < ntl; t += gridDim.x) {
-        const int img = (int)(t / per_img);
-        const int r = (int)(t - (long)img * per_img);
+        const int img = (int)((unsigned)t / (unsigned)per_img);   // total_tiles < 2^31 (checked on the host)
+        const int r = (int)((unsigned)t - (unsigned)img * (unsigned)per_img);
         const int a0 = (r / p.tiles_w) * O_IH - 1, b0 = (r % p.tiles_w) * O_IW - 1;
         for (int kb = 0; kb < p.kblocks; ++kb) {
           wait_p(&a_empty[as], aph ^ 1u, p.dbg, 41u, p.prof, w0);
@@ -199,8 +199,8 @@ __global__ void __launch_bounds__(O_THREADS, 1) deconv_one_tc_kernel(const __gri
     for (long t = blockIdx.x; t < ntl; t += gridDim.x, ++i) {
       const int buf = (int)(i & 1);
       const uint32_t use = (uint32_t)(i >> 1);
-      const int img = (int)(t / per_img);
-      const int r = (int)(t - (long)img * per_img);
+      const int img = (int)((unsigned)t / (unsigned)per_img);   // total_tiles < 2^31 (checked on the host)
+      const int r = (int)((unsigned)t - (unsigned)img * (unsigned)per_img);
       const int a0 = (r / p.tiles_w) * O_IH - 1, b0 = (r % p.tiles_w) * O_IW - 1;
       wait_p(&acc_full[buf], use & 1u, p.dbg, 45u, p.prof, w3);
       tc_fence_after();
@@ -281,6 +281,7 @@ int deconv_one_tc(const advoc_conv_desc* d, const float* x, int ldx, const float
   p.tiles_w = (p.Ws + O_IW - 1) / O_IW;
   p.total_tiles = (long)p.N * p.tiles_h * p.tiles_w;
   if (p.total_tiles == 0) return ADVOC_OK;
+  ADVOC_REQUIRE(p.total_tiles < 2147483647L, ADVOC_BAD_SHAPE, "too many tiles");
   st = encode_tiled4d(&p.tmA, x, d->Cout, p.Ws, p.Hs, p.N, ldx, (long)p.Ws * ldx, (long)p.Hs * p.Ws * ldx, 32, O_PW,
                       O_PH);
   if (st) return st;

@@ -261,6 +261,103 @@ __global__ void __launch_bounds__(256) gan_logit_loss_kernel(const float* __rest
   if (threadIdx.x == 0) loss[0] = red[0] * inv;
 }
 
+// ---------------------------------------------------------------------------------------------
+// WGAN-GP (models/melspecgan/train.py:99-109): gradient penalty seed and the second-order terms
+// of batch normalisation that its parameter gradient needs (double backward).
+// ---------------------------------------------------------------------------------------------
+// One block per sample: s = ||g_b||_2, loss += lambda/B (s-1)^2, u_b = lambda * 2/B * (s-1)/s * g_b
+__global__ void __launch_bounds__(256) gp_seed_kernel(const float* __restrict__ g, int B, long n, float lambda,
+                                                      float* __restrict__ loss, float* __restrict__ u, int round) {
+  __shared__ float red[256];
+  const float* gb = g + (size_t)blockIdx.x * n;
+  float s = 0.f;
+  for (long i = threadIdx.x; i < n; i += blockDim.x) { const float v = __ldg(gb + i); s = fmaf(v, v, s); }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  const float norm = sqrtf(red[0]);
+  const float coef = lambda * 2.f / (float)B * (norm - 1.f) / fmaxf(norm, 1e-30f);
+  if (threadIdx.x == 0) atomicAdd(loss, lambda / (float)B * (norm - 1.f) * (norm - 1.f));
+  float* ub = u + (size_t)blockIdx.x * n;
+  for (long i = threadIdx.x; i < n; i += blockDim.x) {
+    float v = coef * __ldg(gb + i);
+    if (round) v = round_tf32(v);
+    ub[i] = v;
+  }
+}
+
+// Per channel, with a = dy * act'(y) (the first backward's gradient at the BN output) and
+// v = the adjoint of the first backward's BN input gradient:
+//   sums[0:C] = sum v, [C:2C] = sum a, [2C:3C] = sum v a, [3C:4C] = sum v xhat, [4C:5C] = sum a xhat
+__global__ void __launch_bounds__(256) bn_gp_reduce_kernel(const float* __restrict__ v, const float* __restrict__ dy,
+                                                           const float* __restrict__ y, const float* __restrict__ x,
+                                                           long pixels, int C, const float* __restrict__ stats,
+                                                           float eps, float alpha, float* __restrict__ sums) {
+  extern __shared__ float part[];  // [5C]
+  for (int i = threadIdx.x; i < 5 * C; i += blockDim.x) part[i] = 0.f;
+  __syncthreads();
+  const float inv_m = 1.f / (float)pixels;
+  const int lanes = C < 256 ? C : 256;
+  const int ppb = 256 / lanes;
+  const int c0 = threadIdx.x % lanes;
+  if ((int)(threadIdx.x / lanes) < ppb) {
+    for (int c = c0; c < C; c += lanes) {
+      float mean, invstd;
+      bn_moments(stats, C, c, inv_m, eps, &mean, &invstd);
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f;
+      for (long p = (long)blockIdx.x * ppb + threadIdx.x / lanes; p < pixels; p += (long)gridDim.x * ppb) {
+        const size_t o = (size_t)p * C + c;
+        const float vv = __ldg(v + o);
+        float a = __ldg(dy + o);
+        if (!(__ldg(y + o) > 0.f)) a *= alpha;
+        const float xh = (__ldg(x + o) - mean) * invstd;
+        s0 += vv; s1 += a; s2 = fmaf(vv, a, s2); s3 = fmaf(vv, xh, s3); s4 = fmaf(a, xh, s4);
+      }
+      atomicAdd(&part[c], s0); atomicAdd(&part[C + c], s1); atomicAdd(&part[2 * C + c], s2);
+      atomicAdd(&part[3 * C + c], s3); atomicAdd(&part[4 * C + c], s4);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 5 * C; i += blockDim.x) atomicAdd(sums + i, part[i]);
+}
+
+// vz   = act'(y) * gamma/sigma * (v - mean(v) - xhat mean(v xhat))     (adjoint of dy; feeds the next conv)
+// xbar = 1/sigma (G - mean(G) - xhat mean(G xhat)) + Gs xhat / M        (adjoint of the forward x)
+//   with G = -gamma/sigma (v A + a V), A = mean(a xhat), V = mean(v xhat), Gs = -S/sigma,
+//   S = gamma/sigma (sum v a - M mean(v) mean(a) - M V A)
+__global__ void __launch_bounds__(256) bn_gp_apply_kernel(const float* __restrict__ v, const float* __restrict__ dy,
+                                                          const float* __restrict__ y, const float* __restrict__ x,
+                                                          long pixels, int C, const float* __restrict__ stats,
+                                                          const float* __restrict__ gamma, float eps, float alpha,
+                                                          const float* __restrict__ sums, float* __restrict__ vz,
+                                                          float* __restrict__ xbar, int round) {
+  const long total = pixels * C;
+  const float M = (float)pixels, inv_m = 1.f / M;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    float mean, invstd;
+    bn_moments(stats, C, c, inv_m, eps, &mean, &invstd);
+    const float gs = __ldg(gamma + c) * invstd;
+    const float mv = __ldg(sums + c) * inv_m, ma = __ldg(sums + C + c) * inv_m, sva = __ldg(sums + 2 * C + c);
+    const float V = __ldg(sums + 3 * C + c) * inv_m, A = __ldg(sums + 4 * C + c) * inv_m;
+    const float vv = __ldg(v + i);
+    const bool pos = __ldg(y + i) > 0.f;
+    const float a = __ldg(dy + i) * (pos ? 1.f : alpha);
+    const float xh = (__ldg(x + i) - mean) * invstd;
+    float z = gs * (vv - mv - xh * V) * (pos ? 1.f : alpha);
+    if (round) z = round_tf32(z);
+    vz[i] = z;
+    const float S = gs * (sva - M * mv * ma - M * V * A);
+    const float G = -gs * (vv * A + a * V);
+    const float mG = -gs * (A * mv + V * ma), mGx = -2.f * gs * A * V;
+    float xb = invstd * (G - mG - xh * mGx) + (-S * invstd) * xh * inv_m;
+    xbar[i] = xb;
+  }
+}
+
 }  // namespace
 }  // namespace advoc
 
@@ -348,6 +445,34 @@ extern "C" int advoc_gan_logit_loss(const float* d_real, const float* d_fake, in
   gan_logit_loss_kernel<<<1, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d_real, d_fake, n, mode, d_loss,
                                                                               d_dreal, d_dfake);
   count_launch();
+  ADVOC_CHECK_CUDA(cudaGetLastError());
+  return ADVOC_OK;
+}
+
+extern "C" int advoc_gp_seed(const float* d_g, int batch, long n, float lambda, float* d_loss, float* d_u,
+                             int round_tf32, void* stream) {
+  ADVOC_REQUIRE(d_g && d_loss && d_u && batch > 0 && n > 0, ADVOC_BAD_ARG, "bad gp_seed arguments");
+  gp_seed_kernel<<<batch, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d_g, batch, n, lambda, d_loss, d_u, round_tf32);
+  count_launch();
+  ADVOC_CHECK_CUDA(cudaGetLastError());
+  return ADVOC_OK;
+}
+
+extern "C" int advoc_bn_gp(const float* d_v, const float* d_dy, const float* d_y, const float* d_x, long pixels, int C,
+                           const float* d_stats, const float* d_gamma, float eps, float alpha, float* d_sums,
+                           float* d_vz, float* d_xbar, int round_tf32, void* stream) {
+  ADVOC_REQUIRE(d_v && d_dy && d_y && d_x && d_stats && d_gamma && d_sums && d_vz && d_xbar && pixels > 0 && C > 0 &&
+                    C <= 2048,
+                ADVOC_BAD_ARG, "bad bn_gp arguments");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int ppb = 256 / (C < 256 ? C : 256);
+  int blocks = grid_for(pixels, ppb * 8);
+  if (blocks > sm_count() * 4) blocks = sm_count() * 4;
+  bn_gp_reduce_kernel<<<blocks, 256, 5 * C * sizeof(float), s>>>(d_v, d_dy, d_y, d_x, pixels, C, d_stats, eps, alpha,
+                                                                 d_sums);
+  bn_gp_apply_kernel<<<grid_for(pixels * C, 256 * 4), 256, 0, s>>>(d_v, d_dy, d_y, d_x, pixels, C, d_stats, d_gamma, eps,
+                                                                   alpha, d_sums, d_vz, d_xbar, round_tf32);
+  count_launch(2);
   ADVOC_CHECK_CUDA(cudaGetLastError());
   return ADVOC_OK;
 }

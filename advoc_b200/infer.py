@@ -70,6 +70,79 @@ class MelToMag(object):
     self._graph.replay()
     return self._out
 
+  # -- streaming host API: copies overlap the forward of the neighbouring batches ------------
+  def _stream_setup(self):
+    """Two input / output buffer sets, one captured graph per set, a copy stream and events."""
+    if getattr(self, '_sets', None) is not None:
+      return
+    dev = self.G.dev
+    self._copy_stream = torch.cuda.Stream(device=dev)
+    self._sets = []
+    for k in range(2):
+      s = dict(mel_d=torch.zeros_like(self.mel_d), out_d=torch.empty((self.B, self.T, 513, 1), dtype=torch.float32,
+                                                                     device=dev),
+               mel_h=torch.zeros((self.B, self.T, self.n_mels), dtype=torch.float32).pin_memory(),
+               out_h=torch.empty((self.B, self.T, 513), dtype=torch.float32).pin_memory(),
+               h2d=torch.cuda.Event(), done=torch.cuda.Event(), d2h=torch.cuda.Event(), graph=None)
+      self._sets.append(s)
+
+  def _launch_set(self, s, seed):
+    spectral_ptr = spectral._ptr
+    N.call('advoc_matmul_lastdim_f32', spectral_ptr(s['mel_d']), spectral_ptr(self.su.invmeltrans),
+           spectral_ptr(self.x_d), self.B * self.T, self.n_mels, 513,
+           1 if self.kind == 'dbnorm' else 0, spectral._stream())
+    return self.G.forward(self.x_d, out=s['out_d'], dropout=self.dropout, seed=seed)
+
+  def run_stream(self, batches):
+    """Generator over host batches [B, T, n_mels] (float32; pinned or not): yields one pinned host
+    tensor [B, T, 513] per input batch, in order, valid until the generator is advanced again.
+    The host->device copy of batch i+1 and the device->host copy of batch i-1 run on a copy stream
+    while batch i is in the generator (the reference's chunk loop, scripts/spectrogram_advoc.py:88-92,
+    pays both copies serially for every 256-frame chunk)."""
+    self._stream_setup()
+    main = torch.cuda.current_stream()
+    cs = self._copy_stream
+    pending = []
+    i = -1
+    for i, mel in enumerate(batches):
+      s = self._sets[i & 1]
+      if isinstance(mel, np.ndarray):
+        mel = torch.from_numpy(mel)
+      mel = mel.reshape(self.B, self.T, self.n_mels)
+      if mel.dtype != torch.float32:
+        raise ValueError()
+      if i >= 2:
+        s['d2h'].synchronize()          # the result that used this buffer set has reached the host
+        yield pending.pop(0)
+      if not mel.is_pinned():
+        s['mel_h'].copy_(mel)
+        mel = s['mel_h']
+      with torch.cuda.stream(cs):
+        s['mel_d'].copy_(mel, non_blocking=True)
+        s['h2d'].record(cs)
+      main.wait_event(s['h2d'])
+      if self.use_graph:
+        if s['graph'] is None:
+          self._launch_set(s, 1)        # warm-up outside capture
+          torch.cuda.synchronize()
+          g = torch.cuda.CUDAGraph()
+          with torch.cuda.graph(g):
+            self._launch_set(s, 1)
+          s['graph'] = g
+        s['graph'].replay()
+      else:
+        self._seed += 1
+        self._launch_set(s, self._seed)
+      s['done'].record(main)
+      with torch.cuda.stream(cs):
+        cs.wait_event(s['done'])
+        s['out_h'].copy_(s['out_d'].view(self.B, self.T, 513), non_blocking=True)
+        s['d2h'].record(cs)
+      pending.append(s['out_h'])
+    for k, out in enumerate(pending):
+      self._sets[(i - len(pending) + 1 + k) & 1]['d2h'].synchronize()
+      yield out
+
   # -- public host API ----------------------------------------------------
   def __call__(self, mel, n_valid=None):
     """mel: host float32 array/tensor [B, T, n_mels] (or [B, T, n_mels, 1]); frames at flat

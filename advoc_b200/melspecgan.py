@@ -16,10 +16,13 @@ Parameters are a dict keyed by the reference's variable names (`G/z_proj/{W,b}`,
 `G/upconv_{1..4}/{W,b}`, `G/batch_normalization{,_1,_2,_3}/{gamma,beta}`, `D/conv_{0..3}/{W,b}`,
 `D/batch_normalization{,_1,_2}/{gamma,beta}`, `D/out/{W,b}`), weights in the TF layouts.
 
-Not built: the gradient-penalty term of `TRAIN_LOSS = 'wgangp'` (train.py:99-109) needs the second
-derivative of the discriminator (double backward through conv + batch-norm + leaky-ReLU);
-`train_loss='wgangp'` raises NotImplementedError, 'dcgan' (train.py:76-94) is complete and
-'wgan' runs the critic losses of :96-97 without the penalty.
+All three losses of the reference are built: 'dcgan' (train.py:76-94), 'wgangp' (:96-111, the
+default: critic loss + 10 x gradient penalty on interpolates, 5 D steps per G step) and, for
+ablation, 'wgan' (the critic terms without the penalty).  The penalty's parameter gradient is the
+reference's `tf.gradients` inside the loss, i.e. a double backward through conv + batch-norm +
+leaky-ReLU; it is laid out explicitly in `_gp_backward`: an "up" sweep (the adjoint of the first
+backward pass: forward convs of the adjoint, the batch-norm second-order terms of
+`advoc_bn_gp`) and a "down" sweep (an ordinary backward pass seeded with those terms).
 """
 import ctypes as C
 
@@ -91,17 +94,24 @@ class _DBufs(object):
     self.logits = torch.empty(B, **f32)
     self.dlogits = torch.empty(B, **f32)
 
+  def alloc_gp(self):
+    """Extra buffers of the gradient-penalty double backward (interpolates pass only)."""
+    self.v, self.vy, self.xb, self.tmp, self.sums = {}, {}, {}, {}, {}
+    for i in range(4):
+      self.vy[i] = torch.empty_like(self.Y[i])      # adjoint of the first backward's dY_i (masked)
+      self.xb[i] = torch.empty_like(self.Y[i])      # adjoint of the forward X_i
+      if i > 0:
+        self.v[i] = torch.empty_like(self.Y[i])     # adjoint of the first backward's dX_i
+        self.tmp[i] = torch.empty_like(self.Y[i])
+        self.sums[i] = torch.zeros(5 * self.Y[i].shape[-1], dtype=torch.float32, device=self.Y[i].device)
+
 
 class MelspecGAN(object):
   """One replica of the MelspecGAN train step for a fixed per-GPU batch."""
 
   def __init__(self, params, batch, dim=64, train_loss='dcgan', math=N.MATH_AUTO, process_group=None,
                world_size=1):
-    if train_loss == 'wgangp':
-      raise NotImplementedError('the WGAN-GP gradient penalty (models/melspecgan/train.py:99-109) needs a '
-                                'double backward through the discriminator, which is not built; use '
-                                "train_loss='dcgan' (train.py:76-94) or 'wgan' (critic terms only)")
-    if train_loss not in ('dcgan', 'wgan'):
+    if train_loss not in ('dcgan', 'wgan', 'wgangp'):
       raise ValueError()
     self.loss_kind, self.B, self.dim, self.math = train_loss, batch, dim, math
     self.pg, self.world = process_group, world_size
@@ -151,6 +161,15 @@ class MelspecGAN(object):
       self.conv_t[i] = nets._Conv('D/conv_%d' % i, 'deconv', d)
       h, w = h // 2, w // 2
     self.real, self.fake = _DBufs(B, self.dch, dev), _DBufs(B, self.dch, dev)
+    self.gp_lambda = 10.0                      # LAMBDA, train.py:104
+    if train_loss == 'wgangp':
+      self.interp = _DBufs(B, self.dch, dev)
+      self.interp.alloc_gp()
+      self.x_hat = torch.zeros((B, 64, 80, 1), **f32)
+      self.g_hat = torch.zeros((B, 64, 80, 1), **f32)
+      self.u_hat = torch.zeros((B, 64, 80, 1), **f32)
+      self._alpha_gen = torch.Generator(device=dev)
+      self._alpha_gen.manual_seed(1234)
     self.x_real = torch.zeros((B, 64, 80, 1), **f32)
     self.losses = torch.zeros(2, **f32)     # D_loss, G_loss
     self.t_d = self.t_g = 0
@@ -275,8 +294,8 @@ class MelspecGAN(object):
     self._gemm(bufs.Y[3], k, P['D/out/W'], 1, bufs.logits, 1, B, 1, k, bias=P['D/out/b'])
     return bufs.logits
 
-  def _d_backward(self, x, bufs, param_grads, input_grad):
-    """bufs.dlogits holds d loss / d logits."""
+  def _d_backward(self, x, bufs, param_grads, input_grad, dst=None):
+    """bufs.dlogits holds d loss / d logits.  The input gradient goes to `dst` (default dG_z)."""
     P, B, G = self.P, self.B, self.flat.G
     k = 4 * 5 * self.dch[4]
     if param_grads:
@@ -304,8 +323,72 @@ class MelspecGAN(object):
       self._bgrad(bufs.dX[0], self.dch[1], L.name)
     if input_grad:
       Lt = self.conv_t[0]
-      ep = _epilogue(None, self.dG_z, 1, 0, N.ACT_NONE)
+      ep = _epilogue(None, self.dG_z if dst is None else dst, 1, 0, N.ACT_NONE)
       self._conv(Lt, bufs.dX[0], self.dch[1], self._w(self.Wb, Lt, Lt.name + '/W'), ep)
+
+  # -------------------------------------------------------------------------------------------
+  # gradient penalty (train.py:99-109): loss term and its gradient w.r.t. the critic's parameters
+  # -------------------------------------------------------------------------------------------
+  def _gp_backward(self, alpha=None):
+    """x_real and G_z are in place.  Adds LAMBDA * mean((||grad_xhat D(xhat)||_2 - 1)^2) to
+    losses[0] and its parameter gradient to the critic's slice of the flat gradient buffer."""
+    P, B, G, I = self.P, self.B, self.flat.G, self.interp
+    ch = self.dch
+    if alpha is None:
+      alpha = torch.rand((B, 1, 1, 1), generator=self._alpha_gen, device=self.x_hat.device)
+    torch.lerp(self.x_real, self.G_z, alpha.to(self.x_hat.device), out=self.x_hat)   # x + alpha (G_z - x)
+    # first order: D(xhat) and g = d sum_b D(xhat)_b / d xhat
+    self.discriminate(self.x_hat, I)
+    I.dlogits.fill_(1.0)
+    self._d_backward(self.x_hat, I, False, True, dst=self.g_hat)
+    n = self.g_hat.numel() // B
+    N.call('advoc_gp_seed', _ptr(self.g_hat), B, n, self.gp_lambda, _ptr(self.losses), _ptr(self.u_hat), self.rnd,
+           _stream())
+    # ---- up sweep: adjoint of the first backward pass (u = d penalty / d g)
+    L = self.conv[0]
+    ep = _epilogue(None, I.vy[0], ch[1], 0, N.ACT_NONE, gate=I.Y[0], ld_gate=ch[1], gate_act=N.ACT_LRELU,
+                   round_tf32=self.rnd)
+    self._conv(L, self.u_hat, 1, self._w(self.Wf, L, L.name + '/W'), ep)        # adjoint of dY_0 (masked)
+    self._wgrad(L.desc, self.u_hat, 1, I.dX[0], ch[1], L.name)
+    for i in range(1, 4):
+      L = self.conv[i]
+      Cc = ch[i + 1]
+      pixels = I.X[i].numel() // Cc
+      ep = _epilogue(None, I.v[i], Cc, 0, N.ACT_NONE)
+      self._conv(L, I.vy[i - 1], ch[i], self._w(self.Wf, L, L.name + '/W'), ep)   # adjoint of dX_i
+      self._wgrad(L.desc, I.vy[i - 1], ch[i], I.dX[i], Cc, L.name)
+      I.sums[i].zero_()
+      gamma = P[D_BN[i - 1] + '/gamma']
+      N.call('advoc_bn_gp', _ptr(I.v[i]), _ptr(I.dY[i]), _ptr(I.Y[i]), _ptr(I.X[i]), pixels, Cc, _ptr(I.stats[i]),
+             _ptr(gamma), BN_EPS, 0.2, _ptr(I.sums[i]), _ptr(I.vy[i]), _ptr(I.xb[i]), self.rnd, _stream())
+      # d penalty / d gamma = S / gamma = 1/sigma (sum v a - sum v sum a / M - sum v xhat sum a xhat / M)
+      st = I.stats[i]
+      mean = st[:Cc] / pixels
+      invstd = torch.rsqrt((st[Cc:] / pixels - mean * mean).clamp_min(0) + BN_EPS)
+      sv, sa, sva, svx, sax = I.sums[i].view(5, Cc)
+      G[D_BN[i - 1] + '/gamma'].add_(invstd * (sva - sv * sa / pixels - svx * sax / pixels))
+    k = 4 * 5 * ch[4]
+    self._gemm(self.ones, B, I.vy[3], k, G['D/out/W'], k, 1, k, B, acc=1)       # dY_3 = 1 (x) w_out
+    # ---- down sweep: ordinary backward pass seeded with the adjoints of the forward X_i
+    for i in range(3, 0, -1):
+      L = self.conv[i]
+      Cc = ch[i + 1]
+      self._wgrad(L.desc, I.Y[i - 1], ch[i], I.xb[i], Cc, L.name)
+      self._bgrad(I.xb[i], Cc, L.name)
+      Lt = self.conv_t[i]
+      if i > 1:
+        ep = _epilogue(None, I.tmp[i - 1], ch[i], 0, N.ACT_NONE)
+        self._conv(Lt, I.xb[i], Cc, self._w(self.Wb, Lt, Lt.name + '/W'), ep)
+        # through lrelu + batch norm of layer i-1; its input adjoint joins the second-order term
+        self._bn_bwd(I.tmp[i - 1], I.Y[i - 1], I.X[i - 1], I.stats[i - 1], P[D_BN[i - 2] + '/gamma'], N.ACT_LRELU,
+                     I.red[i - 1], I.v[i - 1], D_BN[i - 2], True)
+        I.xb[i - 1].add_(I.v[i - 1])
+      else:
+        ep = _epilogue(None, I.xb[0], ch[1], 0, N.ACT_NONE, gate=I.Y[0], ld_gate=ch[1], gate_act=N.ACT_LRELU)
+        self._conv(Lt, I.xb[1], Cc, self._w(self.Wb, Lt, Lt.name + '/W'), ep)
+    L = self.conv[0]
+    self._wgrad(L.desc, self.x_hat, 1, I.xb[0], ch[1], L.name)
+    self._bgrad(I.xb[0], ch[1], L.name)
 
   # -------------------------------------------------------------------------------------------
   # optimiser + collective
@@ -320,8 +403,9 @@ class MelspecGAN(object):
              t, 1.0 / self.world, _stream())
       self.refresh_weights()
 
-  def d_step(self, x, z, apply=True):
-    """`D_train_op` on one minibatch (train.py:139,151): x [B,64,80,1] in [-1,1], z [B,100]."""
+  def d_step(self, x, z, apply=True, alpha=None):
+    """`D_train_op` on one minibatch (train.py:139,151): x [B,64,80,1] in [-1,1], z [B,100];
+    `alpha` [B,1,1,1] fixes the interpolation draw of train.py:100 (tests)."""
     lo, hi = self.flat.dis_range()
     self.flat.g[lo:hi].zero_()
     self.x_real.copy_(x)
@@ -333,6 +417,8 @@ class MelspecGAN(object):
            _ptr(self.fake.dlogits), _stream())
     self._d_backward(self.x_real, self.real, True, False)
     self._d_backward(G_z, self.fake, True, False)
+    if self.loss_kind == 'wgangp':
+      self._gp_backward(alpha)
     if apply:
       self.t_d += 1
     self._finish(lo, hi, self.t_d, apply)
@@ -354,7 +440,7 @@ class MelspecGAN(object):
 
   def train_loop(self, batches, zs_d, z_g):
     """One outer iteration of train.py:149-153: `num_disc_updates_per_genr` D steps (1 for dcgan,
-    5 for the WGAN losses), each on a fresh minibatch and a fresh z, then one G step."""
+    5 for wgangp), each on a fresh minibatch and a fresh z, then one G step."""
     for x, z in zip(batches, zs_d):
       self.d_step(x, z)
     return self.g_step(z_g)

@@ -220,13 +220,31 @@ def run_gpu(args):
   eng.step_device()
   per_step = eng.launches_per_step or (N.launch_count() - n0)
 
+  def e2e_stream(steps, warmup):
+    """`steps` batches through the public streaming API (host buffers in, host buffers out; the
+    copies of neighbouring batches overlap the forward).  Every batch pays its own H2D and D2H
+    inside the timed region; timed on the device between the first copy and the last result."""
+    for _ in eng.run_stream([mel_h] * max(warmup, 2)):
+      pass
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    n = 0
+    for out in eng.run_stream([mel_h] * steps):
+      n += 1
+    b.record(stream)
+    barrier()
+    assert n == steps
+    return a.elapsed_time(b)
+
   with ClockSampler(local) as clk:
     total_ms = timed(eng.step_device, args.steps, args.warmup)
-    e2e_ms = timed(lambda: eng(mel_h), args.steps, args.warmup)
+    e2e_serial_ms = timed(lambda: eng(mel_h), args.steps, args.warmup)
+    e2e_ms = e2e_stream(args.steps, args.warmup)
   if world > 1:
-    t = torch.tensor([total_ms, e2e_ms], device='cuda', dtype=torch.float64)
+    t = torch.tensor([total_ms, e2e_ms, e2e_serial_ms], device='cuda', dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms = float(t[0]), float(t[1])
+    total_ms, e2e_ms, e2e_serial_ms = float(t[0]), float(t[1]), float(t[2])
 
   frames = world * args.batch * T * args.steps
   value = frames / (total_ms * 1e-3)
@@ -244,7 +262,11 @@ def run_gpu(args):
       'config': _config(args),
       'e2e': {'value': e2e, 'unit': 'mel-frames/s', 'ms_per_step': e2e_ms / args.steps,
               'h2d_bytes_per_step': int(mel_h.numel() * 4),
-              'd2h_bytes_per_step': int(eng.out_h.numel() * 4)},
+              'd2h_bytes_per_step': int(eng.out_h.numel() * 4),
+              'api': 'infer.MelToMag.run_stream (pinned host in / out, copies overlapped with the '
+                     'neighbouring batches)',
+              'serial_call_value': frames / (e2e_serial_ms * 1e-3),
+              'serial_call_api': 'infer.MelToMag.__call__ (H2D, forward, D2H back to back)'},
       'gpu_launches': int(per_step * args.steps * 2),
       'launches_per_step': int(per_step),
       'clocks': clk.summary(),
@@ -670,9 +692,10 @@ def run_gpu_melspecgan(args):
     total_ms, e2e_ms = float(t[0]), float(t[1])
   samples = world * B * args.steps
   value = samples / (total_ms * 1e-3)
-  # first-order passes only: D step = G_f + 2 D_f + 2 (2 D_f); G step = 3 G_f + 2 D_f (SURVEY 8(d) accounting)
+  # D step = G_f + 2 D_f + 2 (2 D_f) [+ 6 D_f for the penalty: forward, first backward (dgrad), the
+  # adjoint sweep (forward convs + wgrads) and the seeded backward (dgrad + wgrad)]; G step = 3 G_f + 2 D_f
   gf, df = MELSPECGAN_GFLOP['G_f'], MELSPECGAN_GFLOP['D_f']
-  gflop = n_d * (gf + 6 * df) + (3 * gf + 2 * df)
+  gflop = n_d * (gf + (12 if args.melspecgan_loss == 'wgangp' else 6) * df) + (3 * gf + 2 * df)
   tf32_peak = _tf32_peak()
   tflops = gflop * 1e9 * value / 1e12
   line = {
@@ -681,8 +704,7 @@ def run_gpu_melspecgan(args):
       'scaling': 'weak', 'vs_baseline': None, 'dtype': 'tf32 convs (fp32 accumulate), fp32 elsewhere',
       'data': 'synthetic',
       'config': {'workload': 'MelspecGAN 64x80 train iteration, train_loss=%s (%d D steps + 1 G step, '
-                             'models/melspecgan/train.py:149-153), batch %d per GPU; the WGAN-GP penalty term is '
-                             'not built' % (args.melspecgan_loss, n_d, B),
+                             'models/melspecgan/train.py:149-153), batch %d per GPU' % (args.melspecgan_loss, n_d, B),
                  'batch_per_gpu': B, 'global_batch': B * world, 'parallelism': 'dp%d' % world,
                  'l2': 'working set per iteration exceeds L2; no explicit flush'},
       'e2e': {'value': samples / (e2e_ms * 1e-3), 'unit': 'samples/s', 'ms_per_step': e2e_ms / args.steps,
@@ -707,7 +729,7 @@ def main():
   ap.add_argument('--model', default='small', choices=['small', 'regular'])
   ap.add_argument('--batch', type=int, default=32, help='samples per GPU')
   ap.add_argument('--workload', default='infer', choices=['infer', 'train', 'spectral', 'melspecgan'])
-  ap.add_argument('--melspecgan-loss', default='dcgan', choices=['dcgan', 'wgan'])
+  ap.add_argument('--melspecgan-loss', default='wgangp', choices=['dcgan', 'wgan', 'wgangp'])
   ap.add_argument('--no-graph', action='store_true')
   ap.add_argument('--no-cpu-baseline', action='store_true')
   args = ap.parse_args()

@@ -307,6 +307,21 @@ ADVOC_API int advoc_tanh_backward(const float* d_dy, const float* d_y, float* d_
 ADVOC_API int advoc_gan_logit_loss(const float* d_real, const float* d_fake, int n, int mode, float* d_loss,
                                    float* d_dreal, float* d_dfake, void* stream);
 
+/* WGAN-GP seed (models/melspecgan/train.py:105-109): per sample s = ||g_b||_2 over n values,
+ * d_loss[0] += lambda/B sum (s-1)^2, d_u = d penalty / d g.  d_g is the critic's input gradient. */
+ADVOC_API int advoc_gp_seed(const float* d_g, int batch, long n, float lambda, float* d_loss, float* d_u,
+                            int round_tf32, void* stream);
+
+/* Second-order terms of a batch-normalised leaky-ReLU layer for the penalty's parameter gradient
+ * (the double backward TF builds for tf.gradients inside the loss, train.py:106).  d_v = adjoint of
+ * the first backward's BN-input gradient, d_dy / d_y / d_x = the first backward's incoming gradient,
+ * the layer output and the BN input, all dense [pixels, C].  Outputs: d_sums [5C] (zeroed by the
+ * caller; sum v, sum a, sum v a, sum v xhat, sum a xhat with a = dy * act'(y)), d_vz = adjoint of
+ * d_dy (masked, feeds the next layer's forward conv), d_xbar = adjoint of d_x. */
+ADVOC_API int advoc_bn_gp(const float* d_v, const float* d_dy, const float* d_y, const float* d_x, long pixels,
+                          int C, const float* d_stats, const float* d_gamma, float eps, float alpha,
+                          float* d_sums, float* d_vz, float* d_xbar, int round_tf32, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -122,3 +122,22 @@ def test_data_parallel_gradient_equivalence():
       acc = eng.flat.g.clone() if acc is None else acc + eng.flat.g
     lo, hi = full.flat.dis_range() if step == 'd_step' else full.flat.gen_range()
     assert _rel(acc[lo:hi] * 0.5, full.flat.g[lo:hi]) < 1e-4
+
+
+def test_streaming_inference_matches_serial_calls():
+  """MelToMag.run_stream (copies overlapped with the neighbouring batches, two graph / buffer sets)
+  returns exactly what back-to-back __call__s return."""
+  import torch
+  from advoc_b200.infer import MelToMag
+  from advoc_b200.model import AdvocSmall, Modes
+  m = AdvocSmall(Modes.INFER)
+  m.init_params(seed=0)
+  eng = MelToMag(m, 2, 'linear', dropout=None, use_graph=True)
+  g = torch.Generator().manual_seed(9)
+  batches = [torch.randn(2, 256, 80, generator=g).abs() for _ in range(5)]
+  want = [eng(b).clone() for b in batches]
+  got = [o.clone() for o in eng.run_stream(batches)]
+  assert len(got) == 5
+  for a, b in zip(got, want):
+    assert torch.equal(a, b)
+  assert list(eng.run_stream([])) == []
