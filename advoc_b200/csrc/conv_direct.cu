@@ -124,11 +124,11 @@ __device__ __forceinline__ float act_slope(int act, float alpha) {
   return act == ADVOC_ACT_LRELU ? alpha : (act == ADVOC_ACT_RELU ? 0.f : 1.f);
 }
 
-template <int CIN, int COUT>
+template <int CIN, int COUT, int KS = 4>
 __global__ void __launch_bounds__(128) conv_thin_px_kernel(const ThinArgs<CIN> a) {
-  __shared__ float4 ws4[16 * CIN * COUT / 4];
+  __shared__ float4 ws4[KS * KS * CIN * COUT / 4];
   __shared__ float4 bs4[COUT / 4];
-  for (int i = threadIdx.x; i < 16 * CIN * COUT / 4; i += blockDim.x)
+  for (int i = threadIdx.x; i < KS * KS * CIN * COUT / 4; i += blockDim.x)
     ws4[i] = __ldg(reinterpret_cast<const float4*>(a.w) + i);
   const EpiDev& e = a.epi;
   if (threadIdx.x < COUT / 4)
@@ -148,18 +148,18 @@ __global__ void __launch_bounds__(128) conv_thin_px_kernel(const ThinArgs<CIN> a
 #pragma unroll
   for (int j = 0; j < COUT / 4; ++j) acc[j] = bs4[j];
 #pragma unroll
-  for (int kh = 0; kh < 4; ++kh) {
+  for (int kh = 0; kh < KS; ++kh) {
     const int ih = ih0 + kh;
     if (ih < 0 || ih >= a.H) continue;
     const float* row = xb + (size_t)ih * a.W * a.ldx;
 #pragma unroll
-    for (int kw = 0; kw < 4; ++kw) {
+    for (int kw = 0; kw < KS; ++kw) {
       const int iw = iw0 + kw;
       if (iw < 0 || iw >= a.W) continue;
 #pragma unroll
       for (int c = 0; c < CIN; ++c) {
         const float xv = __ldg(row + iw * a.ldx + c);
-        const float4* wp = ws4 + ((kh * 4 + kw) * CIN + c) * (COUT / 4);
+        const float4* wp = ws4 + ((kh * KS + kw) * CIN + c) * (COUT / 4);
 #pragma unroll
         for (int j = 0; j < COUT / 4; ++j) {
           const float4 w = wp[j];
@@ -296,9 +296,17 @@ __global__ void __launch_bounds__(256) deconv_to_one_kernel(const ToOneArgs a) {
 
 }  // namespace
 
+static bool thin_plain(const advoc_epilogue* ep) {
+  auto slope_act = [](int a) { return a == ADVOC_ACT_NONE || a == ADVOC_ACT_LRELU || a == ADVOC_ACT_RELU; };
+  return !ep->d_gate && !ep->accumulate && slope_act(ep->act0) && slope_act(ep->act1) &&
+         (!ep->d_bias || aligned16(ep->d_bias));
+}
+
 bool conv_thin_eligible(const advoc_conv_desc* d, const advoc_epilogue* ep) {
   auto ok = [](const float* p, int ld, int co) { return aligned16(p) && ld % 4 == 0 && co % 4 == 0; };
-  return (d->Cin == 1 || d->Cin == 2) && d->kh == 4 && d->kw == 4 && d->Cout % 4 == 0 && d->Cout <= 256 &&
+  // 5x5 (MelspecGAN conv_0, models/melspecgan/conv2d.py:182-184): the per-pixel fast path only
+  const bool k5 = d->kh == 5 && d->kw == 5 && d->Cin == 1 && d->Cout == 64 && thin_plain(ep);
+  return (d->Cin == 1 || d->Cin == 2) && ((d->kh == 4 && d->kw == 4) || k5) && d->Cout % 4 == 0 && d->Cout <= 256 &&
          256 % (d->Cout / 4) == 0 && (long)d->Ho * d->Wo < 2147483647L &&
          ep->keep_prob >= 1.f && ep->store_w == 0 && ok(ep->d_out0, ep->ld0, ep->c_off0) &&
          (!ep->d_out1 || ok(ep->d_out1, ep->ld1, ep->c_off1));
@@ -319,7 +327,8 @@ int conv_thin(const advoc_conv_desc* d, const float* x, int ldx, const float* w,
     const unsigned blocks = (unsigned)((npix + 127) / 128);
     if (d->Cin == 1) {
       ThinArgs<1> a = {x, w, d->N, d->H, d->W, ldx, d->Ho, d->Wo, d->Cout, d->sh, d->sw, d->pad_t, d->pad_l, e};
-      if (d->Cout == 32) conv_thin_px_kernel<1, 32><<<blocks, 128, 0, s>>>(a);
+      if (d->kh == 5) conv_thin_px_kernel<1, 64, 5><<<blocks, 128, 0, s>>>(a);
+      else if (d->Cout == 32) conv_thin_px_kernel<1, 32><<<blocks, 128, 0, s>>>(a);
       else conv_thin_px_kernel<1, 64><<<blocks, 128, 0, s>>>(a);
     } else {
       ThinArgs<2> a = {x, w, d->N, d->H, d->W, ldx, d->Ho, d->Wo, d->Cout, d->sh, d->sw, d->pad_t, d->pad_l, e};

@@ -205,14 +205,14 @@ __global__ void __launch_bounds__(256) wgrad_thin_kernel(const WgradThinArgs a) 
 // ---------------------------------------------------------------------------------------------
 constexpr int WT2_PX = 64;
 
-template <int CT, int C4>
+template <int CT, int C4, int KS = 4>
 __global__ void __launch_bounds__(256) wgrad_thin_tiled_kernel(const WgradThinArgs a) {
-  constexpr int ITEMS = 16 * CT * C4;                  // (tap, ct, channel quad) accumulators
-  constexpr int PER = ITEMS >= 256 ? ITEMS / 256 : 1;  // accumulators per thread
+  constexpr int ITEMS = KS * KS * CT * C4;             // (tap, ct, channel quad) accumulators
+  constexpr int PER = ITEMS >= 256 ? (ITEMS + 255) / 256 : 1;  // accumulators per thread
   constexpr int SPLIT = ITEMS >= 256 ? 1 : 256 / ITEMS;  // pixel splits when there are fewer items than threads
-  constexpr int TW = (WT2_PX - 1) * 2 + 4;             // thin columns per segment at stride <= 2
+  constexpr int TW = (WT2_PX - 1) * 2 + KS;            // thin columns per segment at stride <= 2
   __shared__ float4 wide_s[WT2_PX * C4];
-  __shared__ float thin_s[4][TW][CT];
+  __shared__ float thin_s[KS][TW][CT];
   const int segs = (a.Ww + WT2_PX - 1) / WT2_PX;
   const long units = (long)a.N * a.Hw * segs;
   float4 acc[PER];
@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(256) wgrad_thin_tiled_kernel(const WgradThinAr
     }
     // the 4 thin rows, zero outside the image
     const int tw0 = ow0 * a.sw - a.pl;
-    for (int i = threadIdx.x; i < 4 * TW * CT; i += 256) {
+    for (int i = threadIdx.x; i < KS * TW * CT; i += 256) {
       const int kh = i / (TW * CT);
       const int rem = i - kh * (TW * CT);
       const int col = rem / CT, ct = rem - col * CT;
@@ -251,10 +251,11 @@ __global__ void __launch_bounds__(256) wgrad_thin_tiled_kernel(const WgradThinAr
 #pragma unroll
     for (int k = 0; k < PER; ++k) {
       const int item = item0 + 256 * k;
+      if (item >= ITEMS) continue;
       const int q = item % C4;
       const int tc = item / C4;          // tap * CT + ct
       const int ct = tc % CT, tap = tc / CT;
-      const int kh = tap >> 2, kw = tap & 3;
+      const int kh = tap / KS, kw = tap - kh * KS;
       const int p0 = split * (WT2_PX / SPLIT), p1 = p0 + WT2_PX / SPLIT;
       float4 s = acc[k];
 #pragma unroll 8
@@ -272,6 +273,7 @@ __global__ void __launch_bounds__(256) wgrad_thin_tiled_kernel(const WgradThinAr
   // dW layout [tap][ct][C]: item index * 4 is the flat offset
 #pragma unroll
   for (int k = 0; k < PER; ++k) {
+    if (item0 + 256 * k >= ITEMS) continue;
     float* dst = a.dw + (size_t)(item0 + 256 * k) * 4;
     atomicAdd(dst, acc[k].x);
     atomicAdd(dst + 1, acc[k].y);
@@ -475,6 +477,17 @@ extern "C" int advoc_conv2d_wgrad(const advoc_conv_desc* d, const float* d_big, 
     return wgrad_tc(d, d_big, ld_big, d_small, ld_small, d_dw, stream);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const bool k4 = d->kh == 4 && d->kw == 4;
+  if (d->kh == 5 && d->kw == 5 && d->Cin == 1 && d->Cout == 64 && d->sw <= 2 && ld_small % 4 == 0 && aligned16(d_small)) {
+    // MelspecGAN conv_0 / upconv_4 filter gradients (one-channel side = conv input)
+    WgradThinArgs a = {d_big, d_small, d_dw, d->N, d->H, d->W, ld_big, d->Ho, d->Wo, ld_small, d->Cout,
+                       d->sh, d->sw, d->pad_t, d->pad_l};
+    const long units = (long)d->N * d->Ho * ((d->Wo + WT2_PX - 1) / WT2_PX);
+    const int blocks = (int)(units < (long)sm_count() * 4 ? units : (long)sm_count() * 4);
+    wgrad_thin_tiled_kernel<1, 16, 5><<<blocks, 256, 0, s>>>(a);
+    count_launch();
+    ADVOC_CHECK_CUDA(cudaGetLastError());
+    return ADVOC_OK;
+  }
   const bool vec_small = d->Cout % 4 == 0 && ld_small % 4 == 0 && aligned16(d_small) && d->Cout <= 256 &&
                          256 % (d->Cout / 4 > 0 ? d->Cout / 4 : 1) == 0;
   const bool vec_big = d->Cin % 4 == 0 && ld_big % 4 == 0 && aligned16(d_big) && d->Cin <= 512 &&

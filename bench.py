@@ -720,6 +720,91 @@ def run_gpu_melspecgan(args):
     dist.destroy_process_group()
 
 
+def run_reference_melspecgan(args):
+  """CPU restatement of one MelspecGAN outer iteration (oracle/melspecgan_torch.py, autograd incl. the
+  double backward of the gradient penalty) on a bounded sample of the batch."""
+  import torch
+  from oracle import melspecgan_torch as M
+  from oracle.nets_torch import TFAdam
+  if int(os.environ.get('RANK', '0')) != 0:
+    return
+  cores = os.cpu_count() or 1
+  torch.set_num_threads(cores)
+  loss = args.melspecgan_loss
+  n_d = 1 if loss == 'dcgan' else 5
+  sample = 8
+  P = M.init_params(seed=0)
+  g = torch.Generator().manual_seed(10)
+  dn, gn = M.d_names(P), M.g_names(P)
+  lr, b2 = (2e-4, 0.999) if loss == 'dcgan' else (1e-4, 0.9)
+  opt_d, opt_g = TFAdam(dn, P, lr=lr, beta2=b2), TFAdam(gn, P, lr=lr, beta2=b2)
+
+  def grads(names, which, z, x, alpha):
+    Pr = {n: (t.clone().requires_grad_(True) if n in names else t) for n, t in P.items()}
+    if loss == 'wgan':
+      G_z = M.generator(Pr, z)
+      D_x, D_G_z = M.discriminator(Pr, x), M.discriminator(Pr, G_z)
+      l = dict(D_loss=D_G_z.mean() - D_x.mean(), G_loss=-D_G_z.mean())
+    else:
+      l = M.losses(Pr, z, x, loss, alpha=alpha)
+    gs = torch.autograd.grad(l[which], [Pr[n] for n in names], allow_unused=True)
+    return {n: (gv if gv is not None else torch.zeros_like(P[n])) for n, gv in zip(names, gs)}
+
+  times = []
+  for it in range(max(args.warmup, 1) + max(args.steps, 1)):
+    t0 = time.perf_counter()
+    for _ in range(n_d):
+      x = torch.rand(sample, 64, 80, 1, generator=g) * 2 - 1
+      z = torch.randn(sample, M.Z_DIM, generator=g)
+      opt_d.step(P, grads(dn, 'D_loss', z, x, torch.rand(sample, 1, 1, 1, generator=g)))
+    z = torch.randn(sample, M.Z_DIM, generator=g)
+    opt_g.step(P, grads(gn, 'G_loss', z, torch.rand(sample, 64, 80, 1, generator=g) * 2 - 1,
+                        torch.rand(sample, 1, 1, 1, generator=g)))
+    if it >= max(args.warmup, 1):
+      times.append(time.perf_counter() - t0)
+  sps = sample / (sum(times) / len(times))
+  line = {'impl': 'reference', 'metric': 'MelspecGAN outer-iteration samples/sec', 'value': sps, 'unit': 'samples/s',
+          'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * args.batch / sps,
+          'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+          'config': {'workload': 'MelspecGAN 64x80 train iteration, train_loss=%s (%d D steps + 1 G step), batch %d'
+                                 % (loss, n_d, args.batch)},
+          'cpu_baseline': {'value': sps, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
+                           'sample': 'oracle/melspecgan_torch.py with torch autograd + TF1 Adam, %d of %d samples '
+                                     'per step' % (sample, args.batch)},
+          'e2e': {'value': sps, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+          'gpu_launches': 0}
+  print(json.dumps(line))
+
+
+def run_reference_spectral(args):
+  import numpy as np
+  from oracle import spectral_np as OS
+  if int(os.environ.get('RANK', '0')) != 0:
+    return
+  rng = np.random.RandomState(0)
+  x = rng.uniform(-1, 1, (4, 65536)).astype(np.float32)
+  times = []
+  for it in range(max(args.warmup, 1) + max(args.steps, 1)):
+    t0 = time.perf_counter()
+    frames = 0
+    for i in range(x.shape[0]):
+      frames += OS.waveform_to_r9y9_melspec(x[i].reshape(-1, 1, 1)).shape[0]
+    if it >= max(args.warmup, 1):
+      times.append(time.perf_counter() - t0)
+  fps = frames / (sum(times) / len(times))
+  line = {'impl': 'reference', 'metric': 'mel-frames/sec STFT+mel', 'value': fps, 'unit': 'mel-frames/s',
+          'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+          'ms_per_step': 1e3 * args.batch * 256 / fps, 'higher_is_better': True, 'scaling': 'weak',
+          'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+          'config': {'workload': 'advoc.spectral r9y9 mel on uniform noise [%d, 65536]' % args.batch},
+          'cpu_baseline': {'value': fps, 'unit': 'mel-frames/s', 'cores': 1, 'kind': 'port',
+                           'sample': 'oracle/spectral_np.py (numpy f64, single thread like lws), 4 of %d waveforms '
+                                     'per step' % args.batch},
+          'e2e': {'value': fps, 'unit': 'mel-frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+          'gpu_launches': 0}
+  print(json.dumps(line))
+
+
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument('--gpus', type=int, default=1)
@@ -735,11 +820,11 @@ def main():
   args = ap.parse_args()
   args.warmup = max(args.warmup, 3) if args.impl != 'reference' else args.warmup
   if args.workload == 'spectral':
-    run_gpu_spectral(args)
+    run_reference_spectral(args) if args.impl == 'reference' else run_gpu_spectral(args)
   elif args.workload == 'melspecgan':
     if args.batch == 32:
       args.batch = 64          # models/melspecgan/train.py:13
-    run_gpu_melspecgan(args)
+    run_reference_melspecgan(args) if args.impl == 'reference' else run_gpu_melspecgan(args)
   elif args.workload == 'train':
     if args.impl == 'reference':
       run_reference_train(args)
