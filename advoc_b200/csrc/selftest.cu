@@ -93,6 +93,17 @@ __global__ void __launch_bounds__(128) mma_rate_probe(unsigned long long* out, i
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_holder;
+  if (mode >= 16 && ((mode - 16) & 512)) {
+    // random operand data instead of whatever the shared memory held (zeros after a fresh launch)
+    uint32_t h = 0x9E3779B9u * (threadIdx.x + 1) + blockIdx.x;
+    float* sm = reinterpret_cast<float*>(raw + (base - smem_u32(raw)));
+    for (int i = threadIdx.x; i < (96 * 1024) / 4; i += blockDim.x) {
+      h = h * 1664525u + 1013904223u;
+      sm[i] = (float)((int)(h >> 8) - (1 << 23)) * (1.0f / (1 << 23));
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+  }
   if (mode >= 16) {
     // bit flags under elect.sync issue: 1 shifted A view, 2 four accumulators in rotation, 4 commit after
     // every 4 MMAs, 8 the other three warps poll an mbarrier meanwhile, 32 per-step descriptor rebuild

@@ -496,11 +496,12 @@ extern "C" int advoc_conv2d_wgrad(const advoc_conv_desc* d, const float* d_big, 
     // thin side = conv input (big), wide = conv output (small)
     WgradThinArgs a = {d_big, d_small, d_dw, d->N, d->H, d->W, ld_big, d->Ho, d->Wo, ld_small, d->Cout,
                        d->sh, d->sw, d->pad_t, d->pad_l};
-    if ((d->Cout == 32 || d->Cout == 64) && d->sw <= 2) {
+    if ((d->Cout == 32 || d->Cout == 64 || (d->Cout == 128 && d->Cin == 1)) && d->sw <= 2) {
       const long units = (long)d->N * d->Ho * ((d->Wo + WT2_PX - 1) / WT2_PX);
       const int blocks = (int)(units < (long)sm_count() * 4 ? units : (long)sm_count() * 4);
       if (d->Cin == 1 && d->Cout == 32) wgrad_thin_tiled_kernel<1, 8><<<blocks, 256, 0, s>>>(a);
-      else if (d->Cin == 1) wgrad_thin_tiled_kernel<1, 16><<<blocks, 256, 0, s>>>(a);
+      else if (d->Cin == 1 && d->Cout == 64) wgrad_thin_tiled_kernel<1, 16><<<blocks, 256, 0, s>>>(a);
+      else if (d->Cin == 1) wgrad_thin_tiled_kernel<1, 32><<<blocks, 256, 0, s>>>(a);   // regular decoder_1
       else if (d->Cout == 32) wgrad_thin_tiled_kernel<2, 8><<<blocks, 256, 0, s>>>(a);
       else wgrad_thin_tiled_kernel<2, 16><<<blocks, 256, 0, s>>>(a);
     } else {

@@ -11,7 +11,7 @@ lib = N.lib()
 fn = lib.advoc_selftest_mma_rate
 fn.restype = C.c_int
 fn.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
-for mode, name in [(6, 'one elect region, step4'), (16, 'elect step4'), (16 + 64, '+bulk copies into smem'), (16 + 128, '+st.shared stream'),
+for mode, name in [(16, 'elect step4 (zeros)'), (16 + 512, 'elect step4, random operands'), (6, 'one elect region, step4'), (16 + 64, '+bulk copies into smem'), (16 + 128, '+st.shared stream'),
                    (16 + 256, '+tcgen05.ld stream'), (16 + 64 + 128, '+copies +st.shared')]:
   for n in (32, 64, 128, 256):
     ctas, reps = 148, 2048

@@ -82,3 +82,29 @@ def test_train_loop_matches_oracle_adam():
     # the UPDATE (p - p0), not p
     upd, ref = eng.P[n].cpu() - P[n], Pref[n] - P[n]
     assert _rel(upd, ref) < 2e-2, n
+
+
+@pytest.mark.parametrize('cin,cout,k', [(1, 32, 4), (1, 64, 4), (1, 128, 4), (2, 32, 4), (2, 64, 4), (1, 64, 5),
+                                        (1, 16, 4)])
+def test_thin_filter_gradients(cin, cout, k):
+  """advoc_conv2d_wgrad on the one/two-channel-input layers (encoder_1, discriminator layer_1,
+  decoder_1, MelspecGAN conv_0 / upconv_4): shared-memory tiled kernels and their fallbacks against
+  torch's conv2d weight gradient (fp32, odd width, stride 2, SAME-style padding 1)."""
+  import ctypes as C
+  import torch.nn.functional as F
+  from advoc_b200 import _native as N
+  from advoc_b200.nets import _ptr, _stream
+  g = torch.Generator().manual_seed(cin * 100 + cout + k)
+  B, H, W = 3, 20, 37
+  ho, wo = (H + 1 + (2 if k == 5 else 1) - k) // 2 + 1, (W + 1 + 2 - k) // 2 + 1
+  x = torch.randn(B, H, W, cin, generator=g)
+  dy = torch.randn(B, ho, wo, cout, generator=g)
+  w = torch.zeros(k, k, cin, cout, requires_grad=True)
+  xt = F.pad(x.permute(0, 3, 1, 2), (1, 2, 1, 2))
+  y = F.conv2d(xt, w.permute(3, 2, 0, 1), stride=2)[:, :, :ho, :wo]
+  (ref,) = torch.autograd.grad(y, w, dy.permute(0, 3, 1, 2))
+  d = N.ConvDesc(B, H, W, cin, cout, k, k, 2, 2, 1, 1, ho, wo, N.MATH_FP32)
+  dw = torch.zeros(k, k, cin, cout, device='cuda')
+  xd, dyd = x.cuda().contiguous(), dy.cuda().contiguous()
+  N.call('advoc_conv2d_wgrad', C.byref(d), _ptr(xd), cin, _ptr(dyd), cout, _ptr(dw), _stream())
+  assert _rel(dw, ref) < 1e-4
