@@ -60,7 +60,8 @@ __global__ void __launch_bounds__(256) conv_thin_in_kernel(const ThinArgs<CIN> a
         ih = ih0 + kh;
       } else {
         const int q = oh + a.pt - kh;
-        ih = (q >= 0 && q % a.sh == 0) ? q / a.sh : -1;
+        if (a.sh == 1) ih = q;                                   // stride 1 (PatchGAN head): no division
+        else ih = (q >= 0 && q % a.sh == 0) ? q / a.sh : -1;
       }
       if (ih < 0 || ih >= a.H) continue;
 #pragma unroll
@@ -70,7 +71,8 @@ __global__ void __launch_bounds__(256) conv_thin_in_kernel(const ThinArgs<CIN> a
           iw = iw0 + kw;
         } else {
           const int q = ow + a.pl - kw;
-          iw = (q >= 0 && q % a.sw == 0) ? q / a.sw : -1;
+          if (a.sw == 1) iw = q;
+          else iw = (q >= 0 && q % a.sw == 0) ? q / a.sw : -1;
         }
         if (iw < 0 || iw >= a.W) continue;
         const float* xp = xb + ((size_t)ih * a.W + iw) * a.ldx;

@@ -147,7 +147,8 @@ __global__ void __launch_bounds__(256) wgrad_thin_kernel(const WgradThinArgs a) 
         th = ph * a.sh - a.pt + kh;
       } else {
         const int q = ph + a.pt - kh;
-        th = (q >= 0 && q % a.sh == 0) ? q / a.sh : -1;
+        if (a.sh == 1) th = q;                                   // stride 1 (PatchGAN head): no division
+        else th = (q >= 0 && q % a.sh == 0) ? q / a.sh : -1;
       }
       if (th < 0 || th >= a.Ht) continue;
 #pragma unroll
@@ -157,7 +158,8 @@ __global__ void __launch_bounds__(256) wgrad_thin_kernel(const WgradThinArgs a) 
           tw = pw * a.sw - a.pl + kw;
         } else {
           const int q = pw + a.pl - kw;
-          tw = (q >= 0 && q % a.sw == 0) ? q / a.sw : -1;
+          if (a.sw == 1) tw = q;
+          else tw = (q >= 0 && q % a.sw == 0) ? q / a.sw : -1;
         }
         if (tw < 0 || tw >= a.Wt) continue;
         const float* tp = tb + ((size_t)th * a.Wt + tw) * a.ldt;

@@ -16,6 +16,8 @@
 // fp32 atomics.
 #include "tc_ptx.cuh"
 
+#include <stdlib.h>
+
 namespace advoc {
 
 int check_conv_desc(const advoc_conv_desc* d);
@@ -239,7 +241,10 @@ int wgrad_tc(const advoc_conv_desc* d, const float* big, int ld_big, const float
   p.Ho = d->Ho; p.Wo = d->Wo; p.sh = d->sh; p.sw = d->sw; p.lower_h = lower_h; p.lower_w = lower_w;
   p.P = P;
   const long tiles = (long)p.mtiles * p.ntiles;
-  long splits = ((long)sm_count() * 2 + tiles - 1) / tiles;
+  // two CTAs' worth of pixel splits per SM (measured: 1 leaves a tail, 3-4 only add atomics; the
+  // 512-column accumulators of two CTAs cannot co-reside, so this is load balance, not overlap)
+  static const long waves = getenv("ADVOC_WGRAD_WAVES") ? atol(getenv("ADVOC_WGRAD_WAVES")) : 2;
+  long splits = ((long)sm_count() * waves + tiles - 1) / tiles;
   const long max_splits = (P + 8 * WBK - 1) / (8 * WBK);
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
