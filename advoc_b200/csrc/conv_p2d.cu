@@ -358,9 +358,10 @@ __global__ void __launch_bounds__(Q_THREADS, 1) conv_p2d_kernel(const __grid_con
               // no tcgen05.fence here: the operands were written by TMA (async proxy) and their
               // arrival is ordered by the mbarrier; the fence is only needed for the TMEM hand-off above
               for (int u = 0; u < G; ++u) {
-                const uint32_t info = s_tap[tp + u];
-                const uint32_t cls = info >> 24;
-                const uint64_t da = make_smem_desc(a_addr + (info & 0xFFFFFFu));
+                // tap tables come straight from the kernel parameters (constant bank, uniform index), so
+                // the whole descriptor chain stays on the uniform datapath: no LDS -> R2UR round trips
+                const uint32_t cls = p.tap_cls[tp + u];
+                const uint64_t da = make_smem_desc(a_addr + (uint32_t)p.tap_shift[tp + u] * 128u);
                 const uint64_t db = make_smem_desc(b_addr + (uint32_t)u * B_BYTES);
                 const uint32_t d_tmem = d_base + cls * BN;
                 const uint32_t acc0 = (started >> cls) & 1u;
