@@ -44,7 +44,7 @@ constexpr int Q_MAXC = 4;       // output parity classes
 constexpr int Q_MAXA = 8;       // patch ring depth
 constexpr int Q_MAXB = 32;      // filter-tile ring depth
 constexpr int Q_THREADS = 224;  // warp 0 patch producer, 1 MMA issuer, 2 filter producer, 3-6 epilogue
-constexpr size_t Q_SMEM_BUDGET = 216 * 1024;   // operand rings + output staging
+constexpr size_t Q_SMEM_MAX = 216 * 1024;      // operand rings + output staging, one CTA per SM
 constexpr uint32_t Q_STAGE_BYTES = QM * 128;   // one staged output chunk: <=128 pixels x 32 channels
 
 struct alignas(64) P2dParams {
@@ -198,7 +198,7 @@ __device__ __forceinline__ TileCoord decode_tile(const P2dParams& p, long t) {
 }
 
 template <int BN>
-__global__ void __launch_bounds__(Q_THREADS, 1) conv_p2d_kernel(const __grid_constant__ P2dParams p) {
+__global__ void __launch_bounds__(Q_THREADS, 2) conv_p2d_kernel(const __grid_constant__ P2dParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[Q_MAXA], a_empty[Q_MAXA];
   __shared__ __align__(8) uint64_t b_full[Q_MAXB], b_empty[Q_MAXB];
@@ -544,6 +544,7 @@ struct Plan {
   size_t smem;
   double efficiency;  // useful positions / GEMM rows
   size_t filter_bytes_per_tile;  // filter bytes one output tile streams through shared memory
+  int ctas_per_sm;
   // plane views of the contraction-side tensor
   int plane_ph[Q_MAXP], plane_pw[Q_MAXP];
   int plane_sh, plane_sw;
@@ -555,8 +556,30 @@ inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b
 
 // transposed == false: y[N,Ho,Wo,Cout] = conv(x[N,H,W,Cin]);  Cn = Cout, Ck = Cin
 // transposed == true : y[N,H,Wstored,Cin] = conv_transpose(x[N,Ho,Wo,Cout]);  Cn = Cin, Ck = Cout
+bool make_plan_budget(const advoc_conv_desc* d, bool transposed, int Wstored, int n_out, bool tma_store, bool gate,
+                      Plan* pl, size_t Q_SMEM_BUDGET, int max_tmem, size_t max_b_slot);
+
+// Two CTAs per SM when the rings fit in half the shared memory and the accumulators in half the
+// tensor memory: the second CTA's MMA stream fills the issue gaps of the first (measured: the
+// in-kernel MMA issue rate of one CTA is ~2x below the tensor pipe's).  Otherwise one CTA per SM.
 bool make_plan(const advoc_conv_desc* d, bool transposed, int Wstored, int n_out, bool tma_store, bool gate,
                Plan* pl) {
+  static const int ctas_per_sm = getenv("ADVOC_P2D_CTAS") ? atoi(getenv("ADVOC_P2D_CTAS")) : 2;
+  if (ctas_per_sm >= 2) {
+    Plan two = *pl;
+    if (make_plan_budget(d, transposed, Wstored, n_out, tma_store, gate, &two, 106 * 1024, 256, 8 * 1024) &&
+        two.p.total_tiles >= 2L * sm_count()) {
+      two.ctas_per_sm = 2;
+      *pl = two;
+      return true;
+    }
+  }
+  pl->ctas_per_sm = 1;
+  return make_plan_budget(d, transposed, Wstored, n_out, tma_store, gate, pl, 216 * 1024, 512, 32 * 1024);
+}
+
+bool make_plan_budget(const advoc_conv_desc* d, bool transposed, int Wstored, int n_out, bool tma_store, bool gate,
+                      Plan* pl, size_t Q_SMEM_BUDGET, int max_tmem, size_t max_b_slot) {
   P2dParams& p = pl->p;
   TapT taps[Q_MAXT];
   int nt = 0, ncls = 0, nplanes = 0;
@@ -667,12 +690,13 @@ bool make_plan(const advoc_conv_desc* d, bool transposed, int Wstored, int n_out
   const int Cn = transposed ? d->Cin : d->Cout, Ck = transposed ? d->Cout : d->Cin;
   if (Ck % QK != 0 || Cn % 32 != 0) return false;
   int bn = Cn % 256 == 0 ? 256 : (Cn % 128 == 0 ? 128 : (Cn % 64 == 0 ? 64 : 32));
-  while (ncls * bn > 512) bn >>= 1;
+  while (ncls * bn > max_tmem) bn >>= 1;
+  if (bn < 32) return false;
   pl->bn = bn;
   p.Cn = Cn; p.kblocks = Ck / QK;
   p.n_ntiles = Cn / bn;
   p.total_tiles = (long)d->N * best_tiles * p.n_ntiles;
-  p.acc_bufs = (2 * ncls * bn <= 512) ? 2 : 1;
+  p.acc_bufs = (2 * ncls * bn <= max_tmem) ? 2 : 1;
   uint32_t cols = (uint32_t)(p.acc_bufs * ncls * bn), pow2 = 32;
   while (pow2 < cols) pow2 <<= 1;
   p.tmem_cols = pow2;
@@ -684,7 +708,7 @@ bool make_plan(const advoc_conv_desc* d, bool transposed, int Wstored, int n_out
   p.a_slot_bytes = ((uint32_t)rows * 128u + 1023u) & ~1023u;
   // filter ring slot = G taps (<= 32 KB), G divides every plane's tap count
   int G = 1;
-  for (int g = 2; g <= 8 && g * bn * 128 <= 32 * 1024; g *= 2) {
+  for (int g = 2; g <= 8 && (size_t)g * bn * 128 <= max_b_slot; g *= 2) {
     bool ok = true;
     for (int q = 0; q < nplanes; ++q) ok = ok && ((p.plane_tap0[q + 1] - p.plane_tap0[q]) % g == 0);
     if (ok) G = g;
@@ -725,7 +749,7 @@ bool make_plan(const advoc_conv_desc* d, bool transposed, int Wstored, int n_out
   p.gate_off = p.stage_off + (uint32_t)(stage_only * p.stage_bufs);
   p.use_gate = gate_bytes ? 1 : 0;
   pl->smem = (size_t)p.stage_off + staging + 1024;
-  if (pl->smem < 120 * 1024) pl->smem = 120 * 1024;  // one CTA per SM: TMEM is not shared between CTAs here
+  if (max_tmem > 256 && pl->smem < 120 * 1024) pl->smem = 120 * 1024;  // one CTA per SM when it may own > half of TMEM
   return p.total_tiles > 0 && p.total_tiles < 2147483647L;
 }
 
@@ -734,10 +758,11 @@ int launch_p2d(const Plan& pl, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
     ADVOC_CHECK_CUDA(cudaFuncSetAttribute(conv_p2d_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)(Q_SMEM_BUDGET + 1024)));
+                                          (int)(Q_SMEM_MAX + 1024)));
     configured = true;
   }
-  long ctas = pl.p.total_tiles < (long)sm_count() ? pl.p.total_tiles : (long)sm_count();
+  const long slots = (long)sm_count() * pl.ctas_per_sm;
+  long ctas = pl.p.total_tiles < slots ? pl.p.total_tiles : slots;
   conv_p2d_kernel<BN><<<(unsigned)ctas, Q_THREADS, pl.smem, st>>>(pl.p);
   count_launch();
   ADVOC_CHECK_CUDA(cudaGetLastError());
@@ -841,10 +866,10 @@ int conv_p2d(const advoc_conv_desc* d, int transposed, const float* x, int ldx, 
   if (verbose)
     fprintf(stderr,
             "p2d %s N%d %dx%dx%d->%d k%d s%d | tile %dx%d patch %dx%d planes %d taps %d cls %d | bn %d ntiles %d "
-            "tiles %ld eff %.2f | A %d x %u B %d x %d %s stage %d x %d smem %zu tmem %u\n",
+            "tiles %ld eff %.2f | A %d x %u B %d x %d %s stage %d x %d smem %zu tmem %u ctas/sm %d\n",
             transposed ? "deconv" : "conv", d->N, Hin, Win, Ck, p.Cn, d->kh, d->sh, p.th, p.tw, p.PH, p.PW, p.nplanes,
             p.ntaps, p.ncls, pl.bn, p.n_ntiles, p.total_tiles, pl.efficiency, p.a_stages, p.a_slot_bytes, p.b_stages,
-            p.G * pl.bn * 128, p.b_resident ? "resident" : "ring", p.stage_bufs, p.n_out, pl.smem, p.tmem_cols);
+            p.G * pl.bn * 128, p.b_resident ? "resident" : "ring", p.stage_bufs, p.n_out, pl.smem, p.tmem_cols, pl.ctas_per_sm);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   switch (pl.bn) {
     case 256: return launch_p2d<256>(pl, s);
