@@ -239,8 +239,11 @@ __global__ void __launch_bounds__(Q_THREADS, 2) conv_p2d_kernel(const __grid_con
   const uint32_t tmem_base = tmem_base_holder;
   const bool aborted = p.dbg && *reinterpret_cast<volatile unsigned int*>(p.dbg) != 0;
 
-  if (aborted) {
-    // a previous launch timed out: do nothing
+  // timing experiments (ADVOC_P2D_EXP): 32 = bare MMA stream (no barriers, other roles idle),
+  // 32 + 512 = the same number of MMAs issued from a flat loop with loop-invariant descriptors
+  const bool mma_only = (p.exp_flags & 32) != 0;
+  if (aborted || (mma_only && warp != 1)) {
+    // a previous launch timed out (or the experiment idles this role): do nothing
   } else if (warp == 0) {
     // ===== patch producer: warp-uniform loop, TMA issued by one elected lane =====
     int as = 0;
@@ -332,27 +335,39 @@ __global__ void __launch_bounds__(Q_THREADS, 2) conv_p2d_kernel(const __grid_con
       long i = 0;
       unsigned long long w_acc = 0, w_a = 0, w_b = 0;
       const long long t_start = clock64();
-      for (long t = blockIdx.x; t < ntl; t += gridDim.x, ++i) {
+      const bool flat = mma_only && (p.exp_flags & 512);
+      if (flat) {
+        long my_tiles = ((long)blockIdx.x < ntl) ? (ntl - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+        const long total = my_tiles * p.kblocks * p.ntaps * 4;
+        const uint64_t da = make_smem_desc(ring), db = make_smem_desc(ring + b_off);
+        for (long q = 0; q < total; q += 4) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_tf32(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (q | k) ? 1u : 0u);
+        }
+        i = my_tiles;
+      }
+      for (long t = blockIdx.x; t < ntl && !flat; t += gridDim.x, ++i) {
         const int buf = (int)(i % p.acc_bufs);
         const uint32_t use = (uint32_t)(i / p.acc_bufs);
-        mbar_wait_p(&acc_empty[buf], (use & 1u) ^ 1u, p.dbg, 33u, p.prof, w_acc);
+        if (!mma_only) mbar_wait_p(&acc_empty[buf], (use & 1u) ^ 1u, p.dbg, 33u, p.prof, w_acc);
         tc_fence_after();
         const uint32_t d_base = tmem_base + (uint32_t)buf * acc_cols;
         uint32_t started = 0;
         for (int kb = 0; kb < p.kblocks; ++kb) {
           int tp = 0;
           for (int pl = 0; pl < p.nplanes; ++pl) {
-            mbar_wait_p(&a_full[as], aph, p.dbg, 34u, p.prof, w_a);
+            if (!mma_only) mbar_wait_p(&a_full[as], aph, p.dbg, 34u, p.prof, w_a);
             const uint32_t a_addr = ring + (uint32_t)as * p.a_slot_bytes;
             const int t_end = p.plane_tap0[pl + 1];
             for (; tp < t_end; tp += G) {
               uint32_t b_addr;
               if (p.b_resident) {
                 const int slot = kb * ngroups + tp / G;
-                if (i == 0) mbar_wait(&b_full[slot], 0u, p.dbg, 35u);
+                if (i == 0 && !mma_only) mbar_wait(&b_full[slot], 0u, p.dbg, 35u);
                 b_addr = ring + b_off + (uint32_t)slot * slot_bytes;
               } else {
-                mbar_wait_p(&b_full[bs], bph, p.dbg, 35u, p.prof, w_b);
+                if (!mma_only) mbar_wait_p(&b_full[bs], bph, p.dbg, 35u, p.prof, w_b);
                 b_addr = ring + b_off + (uint32_t)bs * slot_bytes;
               }
               // no tcgen05.fence here: the operands were written by TMA (async proxy) and their
@@ -371,15 +386,19 @@ __global__ void __launch_bounds__(Q_THREADS, 2) conv_p2d_kernel(const __grid_con
                   umma_tf32(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, acc0 | (uint32_t)(k != 0));
               }
               if (!p.b_resident) {
-                umma_commit(&b_empty[bs]);
+                if (!mma_only) umma_commit(&b_empty[bs]);
                 if (++bs == p.b_stages) { bs = 0; bph ^= 1u; }
               }
             }
-            umma_commit(&a_empty[as]);
+            if (!mma_only) umma_commit(&a_empty[as]);
             if (++as == p.a_stages) { as = 0; aph ^= 1u; }
           }
         }
-        umma_commit(&acc_full[buf]);
+        if (!mma_only) umma_commit(&acc_full[buf]);
+      }
+      if (mma_only) {   // wait for the stream to drain so that the cycle count covers execution
+        umma_commit(&acc_full[0]);
+        mbar_wait(&acc_full[0], 0u, p.dbg, 38u);
       }
       if (p.prof) {
         p.prof[blockIdx.x * 16 + 4] = (unsigned long long)(clock64() - t_start);

@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(128) desc_shift_probe(float* out, int shift, i
 //   mode 5: tf32 issued from a warp-uniform loop under elect.sync (instead of `if (thread == 0)`)
 //   mode >= 16: bit flags, see the kernel (64 concurrent bulk copies into smem, 128 concurrent
 //   st.shared stream, 256 concurrent tcgen05.ld stream)
-__global__ void __launch_bounds__(128) mma_rate_probe(unsigned long long* out, int n, int reps, int mode,
+__global__ void __launch_bounds__(256) mma_rate_probe(unsigned long long* out, int n, int reps, int mode,
                                                       const float* gsrc) {
   extern __shared__ uint8_t raw[];
   __shared__ __align__(8) uint64_t bar, bar2;
@@ -83,9 +83,10 @@ __global__ void __launch_bounds__(128) mma_rate_probe(unsigned long long* out, i
     mbar_init(&bar2, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  const uint32_t alloc_cols = (mode >= 16 && ((mode - 16) & 4096)) ? 128u : 512u;
   if (threadIdx.x < 32) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)),
-                 "r"(512u)
+                 "r"(alloc_cols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -108,7 +109,8 @@ __global__ void __launch_bounds__(128) mma_rate_probe(unsigned long long* out, i
     // bit flags under elect.sync issue: 1 shifted A view, 2 four accumulators in rotation, 4 commit after
     // every 4 MMAs, 8 the other three warps poll an mbarrier meanwhile, 32 per-step descriptor rebuild
     const int fl = mode - 16;
-    if (threadIdx.x < 32) {
+    const int issue_warp = (fl & 1024) ? 1 : ((fl & 2048) ? 3 : 0);
+    if ((int)(threadIdx.x >> 5) == issue_warp) {
       const uint32_t idesc_tf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const long long t0 = clock64();
       for (int i = 0; i < reps; i += 4) {
@@ -130,7 +132,7 @@ __global__ void __launch_bounds__(128) mma_rate_probe(unsigned long long* out, i
       __syncwarp();
       mbar_wait(&bar, 0u, nullptr, 0u);
       const long long t2 = clock64();
-      if (threadIdx.x == 0) {
+      if ((threadIdx.x & 31) == 0) {
         out[blockIdx.x * 2 + 0] = (unsigned long long)(t1 - t0);
         out[blockIdx.x * 2 + 1] = (unsigned long long)(t2 - t0);
       }
@@ -244,7 +246,7 @@ __global__ void __launch_bounds__(128) mma_rate_probe(unsigned long long* out, i
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x < 32)
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(alloc_cols) : "memory");
 }
 }  // namespace
 }  // namespace advoc
@@ -261,7 +263,12 @@ extern "C" __attribute__((visibility("default"))) int advoc_selftest_mma_rate(un
   float* gsrc = nullptr;
   ADVOC_CHECK_CUDA(cudaMalloc(&gsrc, (size_t)ctas * 16384 + 65536));
   ADVOC_CHECK_CUDA(cudaMemset(gsrc, 0, (size_t)ctas * 16384 + 65536));
-  mma_rate_probe<<<ctas, 128, smem>>>(d, n, reps, mode, gsrc);
+  const int fl = mode >= 16 ? mode - 16 : 0;
+  const int threads = (fl & 8192) ? 224 : 128;
+  const int smem_launch = (fl & 16384) ? 216 * 1024 : smem;
+  if (fl & 16384)
+    ADVOC_CHECK_CUDA(cudaFuncSetAttribute(mma_rate_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_launch));
+  mma_rate_probe<<<ctas, threads, smem_launch>>>(d, n, reps, mode, gsrc);
   ADVOC_CHECK_CUDA(cudaGetLastError());
   ADVOC_CHECK_CUDA(cudaDeviceSynchronize());
   ADVOC_CHECK_CUDA(cudaMemcpy(h_out, d, ctas * 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));

@@ -11,9 +11,9 @@ lib = N.lib()
 fn = lib.advoc_selftest_mma_rate
 fn.restype = C.c_int
 fn.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
-for mode, name in [(16, 'elect step4 (zeros)'), (16 + 512, 'elect step4, random operands'), (6, 'one elect region, step4'), (16 + 64, '+bulk copies into smem'), (16 + 128, '+st.shared stream'),
-                   (16 + 256, '+tcgen05.ld stream'), (16 + 64 + 128, '+copies +st.shared')]:
-  for n in (32, 64, 128, 256):
+for mode, name in [(16, '128 threads, 193 KB smem'), (16 + 8192, '224 threads'), (16 + 16384, '216 KB smem'),
+                   (16 + 8192 + 16384, '224 threads + 216 KB')]:
+  for n in (32, 64, 128):
     ctas, reps = 148, 2048
     out = np.zeros((ctas, 2), dtype=np.uint64)
     st = fn(out.ctypes.data, ctas, n, reps, mode)
