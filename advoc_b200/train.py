@@ -228,6 +228,23 @@ class TrainEngine(object):
   # -------------------------------------------------------------------------------------------
   # the two halves of `train_loop`
   # -------------------------------------------------------------------------------------------
+  def restore_adam(self, m, v, t_d, t_g=None):
+    """Resume the optimisers: `m` / `v` = {variable name: tensor} first / second moments (the
+    `/Adam`, `/Adam_1` slots of a TF training checkpoint, advoc_b200.checkpoint.load_adam_slots),
+    `t_d` / `t_g` = the number of D / G updates already applied (TF keeps them as beta powers;
+    the reference bumps global_step in the G op only, advoc_model.py:253-255, and runs one D and one
+    G update per loop, so both equal global_step)."""
+    for n in self.flat.names:
+      if n not in m or n not in v:
+        raise KeyError('no Adam slots for %s' % n)
+      o, k = self.flat.offsets[n], self.flat.P[n].numel()
+      if tuple(m[n].shape) != tuple(self.flat.P[n].shape) or tuple(v[n].shape) != tuple(self.flat.P[n].shape):
+        raise ValueError('Adam slot shape mismatch for %s' % n)
+      self.flat.m[o:o + k].copy_(m[n].reshape(-1))
+      self.flat.v[o:o + k].copy_(v[n].reshape(-1))
+    self.t_d = int(t_d)
+    self.t_g = int(t_d if t_g is None else t_g)
+
   def load_batch(self, x, target):
     """x, target f32 [B,T,513,1] on the device -> the discriminator input buffers."""
     self.cat_real[..., 0:1].copy_(x)

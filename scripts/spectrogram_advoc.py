@@ -2,8 +2,9 @@
 the adversarial vocoder on B200.
 
 Drop-in for the reference's scripts/spectrogram_advoc.py (same flags).  Differences, all forced
-by what exists here: `--model_ckpt` is an `.npz` written by advoc_b200.checkpoint (TF variable
-names; `--meta_fp` is accepted and ignored -- there is no TF graph), the reference's batch-1 chunk
+by what exists here: `--model_ckpt` is a TF-1 checkpoint prefix as in the reference (`model.ckpt-N`, read
+without TensorFlow by advoc_b200.tf_bundle) or an `.npz` written by advoc_b200.checkpoint (same variable
+names); `--meta_fp` is accepted and ignored -- there is no TF graph; the reference's batch-1 chunk
 loop (:80-95) is ONE batched forward, and the phase estimator is Griffin-Lim (--ngl, default 60)
 because the LWS reconstruction of the third-party `lws` package is not restated.
 """
@@ -23,7 +24,7 @@ if __name__ == '__main__':
   parser = ArgumentParser()
   parser.add_argument('--spec_dir', type=str, required=True, help='Directory of spectrograms')
   parser.add_argument('--out_dir', type=str, required=True, help='Directory for audio files')
-  parser.add_argument('--model_ckpt', type=str, help='Adversarial vocoder checkpoint (.npz)')
+  parser.add_argument('--model_ckpt', type=str, help='Adversarial vocoder checkpoint (TF prefix or .npz)')
   parser.add_argument('--meta_fp', type=str, help='Meta graph filepath (ignored)')
   parser.add_argument('--fs', type=int, help='Sample rate')
   parser.add_argument('--subseq_len', type=int, help='model subseq length')

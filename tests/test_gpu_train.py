@@ -84,6 +84,30 @@ def test_train_loop_matches_oracle_adam():
     assert _rel(upd, ref) < 2e-2, n
 
 
+def test_resume_from_adam_slots():
+  """Engine restarted from parameters + Adam slots (the `/Adam`, `/Adam_1` variables of a TF training
+  checkpoint, advoc_b200.checkpoint.load_adam_slots) continues like an uninterrupted run (to the
+  summation-order noise of the atomically accumulated filter gradients)."""
+  from advoc_b200 import _native as N
+  from advoc_b200 import nets
+  from advoc_b200.train import TrainEngine
+  O, P, eng, x, target, full, dmasks = _setup('fp32')
+  batch = (x.cuda(), target.cuda())
+  eng.train_loop(batch, batch, dropout=dmasks)
+  snap_p = {n: t.clone() for n, t in eng.P.items()}
+  fl = eng.flat
+  snap_m = {n: fl.m[fl.offsets[n]:fl.offsets[n] + fl.P[n].numel()].view(fl.P[n].shape).clone() for n in fl.names}
+  snap_v = {n: fl.v[fl.offsets[n]:fl.offsets[n] + fl.P[n].numel()].view(fl.P[n].shape).clone() for n in fl.names}
+  eng.train_loop(batch, batch, dropout=dmasks)
+  eng2 = TrainEngine(nets.GenSpec(32, 5, (5, 4)), 32, snap_p, 1, math=N.MATH_FP32)
+  eng2.restore_adam(snap_m, snap_v, 1)
+  assert eng2.train_loop(batch, batch, dropout=dmasks) == 2
+  for n in P:
+    assert float((eng2.P[n] - eng.P[n]).abs().max()) < 2e-6, n   # one Adam step moves a weight by ~2e-4
+  with pytest.raises(KeyError):
+    eng2.restore_adam({}, snap_v, 1)
+
+
 @pytest.mark.parametrize('cin,cout,k', [(1, 32, 4), (1, 64, 4), (1, 128, 4), (2, 32, 4), (2, 64, 4), (1, 64, 5),
                                         (1, 16, 4)])
 def test_thin_filter_gradients(cin, cout, k):
