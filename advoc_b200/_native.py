@@ -75,6 +75,8 @@ SIGNATURES = {
     'advoc_gemm_f32': (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     'advoc_bn_stats': (_I, [_P, _I, _L, _I, _P, _P]),
     'advoc_bn_apply': (_I, [_P, _I, _L, _I, _P, _P, _P, _F, _I, _F, _P, _I, _I, _P]),
+    'advoc_bn_inference': (_I, [_P, _I, _L, _I, _P, _P, _P, _P, _F, _I, _F, _P, _I, _I, _P]),
+    'advoc_bn_moving_update': (_I, [_P, _L, _I, _F, _P, _P, _P]),
     'advoc_bn_backward': (_I, [_P, _I, _P, _I, _P, _I, _L, _I, _P, _P, _F, _I, _F, _P, _P, _I, _I, _P]),
     'advoc_tanh_backward': (_I, [_P, _P, _P, _L, _P]),
     'advoc_gan_logit_loss': (_I, [_P, _P, _I, _I, _P, _P, _P, _P]),

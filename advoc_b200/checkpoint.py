@@ -68,6 +68,14 @@ def load_params(path, device='cuda'):
   return P, step
 
 
+def load_bn_moving(path, device='cuda'):
+  """-> {name: tensor} of the batch-norm moving statistics in the checkpoint (MelspecGAN's inference
+  graph restores them with the generator variables: models/melspecgan/infer.py:22-24)."""
+  A = load_arrays(path)
+  return {k: torch.from_numpy(np.ascontiguousarray(v, dtype=np.float32)).to(device)
+          for k, v in A.items() if k.startswith(_SCOPES) and k.endswith(_NON_TRAINABLE)}
+
+
 def load_adam_slots(path, device='cuda'):
   """-> (m, v, beta_powers): the first / second moment slots of a TF training checkpoint keyed by
   their variable's name, and {'beta1_power': .., 'beta2_power': ..} when stored (the step count of

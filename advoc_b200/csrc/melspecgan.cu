@@ -152,6 +152,41 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
   }
 }
 
+// inference-mode batch norm (training=False): per-channel mean / variance are given (the moving averages)
+__global__ void __launch_bounds__(256) bn_infer_kernel(const float* __restrict__ x, int ldx, long pixels, int C,
+                                                       const float* __restrict__ mean, const float* __restrict__ var,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       float eps, int act, float alpha, float* __restrict__ y, int ldy,
+                                                       int round) {
+  const long total = pixels * C;
+  const ActLin a = act_linear(act, alpha);
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long p = i / C;
+    const int c = (int)(i - p * C);
+    const float scale = rsqrtf(__ldg(var + c) + eps) * __ldg(gamma + c);
+    float v = (__ldg(x + (size_t)p * ldx + c) - __ldg(mean + c)) * scale + __ldg(beta + c);
+    v = apply_lin(v, a);
+    if (round) v = round_tf32(v);
+    y[(size_t)p * ldy + c] = v;
+  }
+}
+
+// moving <- moving - (moving - batch) * (1 - momentum); the batch variance carries Bessel's correction
+// M / (M - 1), as the fused batch-norm op reports it to the moving-average update
+__global__ void __launch_bounds__(256) bn_moving_update_kernel(const float* __restrict__ stats, long pixels, int C,
+                                                               float momentum, float* __restrict__ moving_mean,
+                                                               float* __restrict__ moving_var) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float inv_m = 1.f / (float)pixels;
+  const float m = stats[c] * inv_m;
+  float var = fmaxf(stats[C + c] * inv_m - m * m, 0.f);
+  if (pixels > 1) var *= (float)pixels / (float)(pixels - 1);
+  const float d = 1.f - momentum;
+  moving_mean[c] -= (moving_mean[c] - m) * d;
+  moving_var[c] -= (moving_var[c] - var) * d;
+}
+
 // g = dy * act'(y);  red[0:C] += sum g (= dbeta), red[C:2C] += sum g * xhat (= dgamma)
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restrict__ dy, int lddy,
                                                             const float* __restrict__ y, int ldy,
@@ -405,6 +440,31 @@ extern "C" int advoc_bn_apply(const float* d_x, int ldx, long pixels, int C, con
   bn_apply_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d_x, ldx, pixels, C, d_stats, d_gamma,
                                                                              d_beta, eps, act, alpha, d_y, ldy,
                                                                              round_tf32);
+  count_launch();
+  ADVOC_CHECK_CUDA(cudaGetLastError());
+  return ADVOC_OK;
+}
+
+extern "C" int advoc_bn_inference(const float* d_x, int ldx, long pixels, int C, const float* d_mean,
+                                  const float* d_var, const float* d_gamma, const float* d_beta, float eps, int act,
+                                  float alpha, float* d_y, int ldy, int round_tf32, void* stream) {
+  ADVOC_REQUIRE(d_x && d_mean && d_var && d_gamma && d_beta && d_y && pixels > 0 && C > 0, ADVOC_BAD_ARG,
+                "bad bn_inference arguments");
+  ADVOC_REQUIRE(act >= ADVOC_ACT_NONE && act <= ADVOC_ACT_RELU, ADVOC_BAD_ARG, "bn_inference fuses none / lrelu / relu only");
+  bn_infer_kernel<<<grid_for(pixels * C, 256 * 4), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      d_x, ldx, pixels, C, d_mean, d_var, d_gamma, d_beta, eps, act, alpha, d_y, ldy, round_tf32);
+  count_launch();
+  ADVOC_CHECK_CUDA(cudaGetLastError());
+  return ADVOC_OK;
+}
+
+extern "C" int advoc_bn_moving_update(const float* d_stats, long pixels, int C, float momentum, float* d_moving_mean,
+                                      float* d_moving_var, void* stream) {
+  ADVOC_REQUIRE(d_stats && d_moving_mean && d_moving_var && pixels > 0 && C > 0, ADVOC_BAD_ARG,
+                "bad bn_moving_update arguments");
+  ADVOC_REQUIRE(momentum >= 0.f && momentum <= 1.f, ADVOC_BAD_ARG, "momentum must lie in [0, 1]");
+  bn_moving_update_kernel<<<(C + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      d_stats, pixels, C, momentum, d_moving_mean, d_moving_var);
   count_launch();
   ADVOC_CHECK_CUDA(cudaGetLastError());
   return ADVOC_OK;

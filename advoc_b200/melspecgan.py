@@ -140,6 +140,10 @@ class MelspecGAN(object):
       self.gstats[i] = torch.zeros(2 * self.gch[i], **f32)
       self.gred[i] = torch.zeros(2 * self.gch[i], **f32)
       h, w = h * 2, w * 2
+    # moving averages of the generator's batch norms (UPDATE_OPS of conv2d.py:143-148, read by the
+    # training=False graph of models/melspecgan/infer.py:17); TF initialises them to 0 / 1
+    self.bn_momentum = 0.99
+    self.g_moving = {i: (torch.zeros(self.gch[i], **f32), torch.ones(self.gch[i], **f32)) for i in range(4)}
     self.G_z = torch.empty((B, 64, 80, 1), **f32)
     self.dG_z = torch.empty((B, 64, 80, 1), **f32)
     self.dX4 = torch.empty((B, 64, 80, 1), **f32)
@@ -209,6 +213,28 @@ class MelspecGAN(object):
     N.call('advoc_bn_apply', _ptr(x), Cc, pixels, Cc, _ptr(stats), _ptr(gamma), _ptr(beta), BN_EPS, act, 0.2,
            _ptr(y), Cc, self.rnd, _stream())
 
+  def _bn_track(self, x, stats, moving):
+    Cc = x.shape[-1]
+    N.call('advoc_bn_moving_update', _ptr(stats), x.numel() // Cc, Cc, self.bn_momentum, _ptr(moving[0]),
+           _ptr(moving[1]), _stream())
+
+  def _bn_infer(self, x, moving, gamma, beta, act, y):
+    Cc = x.shape[-1]
+    N.call('advoc_bn_inference', _ptr(x), Cc, x.numel() // Cc, Cc, _ptr(moving[0]), _ptr(moving[1]), _ptr(gamma),
+           _ptr(beta), BN_EPS, act, 0.2, _ptr(y), Cc, self.rnd, _stream())
+
+  def moving_averages(self):
+    """{TF variable name: tensor} of the generator's batch-norm moving statistics."""
+    out = {}
+    for i in range(4):
+      out[G_BN[i] + '/moving_mean'], out[G_BN[i] + '/moving_variance'] = self.g_moving[i]
+    return out
+
+  def load_moving_averages(self, moving):
+    for i in range(4):
+      self.g_moving[i][0].copy_(moving[G_BN[i] + '/moving_mean'])
+      self.g_moving[i][1].copy_(moving[G_BN[i] + '/moving_variance'])
+
   def _bn_bwd(self, dy, y, x, stats, gamma, act, red, dx, bn_name, param_grads):
     Cc = x.shape[-1]
     pixels = x.numel() // Cc
@@ -234,21 +260,31 @@ class MelspecGAN(object):
   # -------------------------------------------------------------------------------------------
   # generator  (conv2d.py:95-150)
   # -------------------------------------------------------------------------------------------
-  def generate(self, z):
-    """z [B, 100] on the device -> G_z [B, 64, 80, 1] in (-1, 1)."""
+  def generate(self, z, training=True):
+    """z [B, 100] on the device -> G_z [B, 64, 80, 1] in (-1, 1).  training=True normalises with batch
+    statistics and advances the moving averages (every evaluation of G_z in the reference's train graph
+    runs the update ops: conv2d.py:143-148); training=False normalises with the moving averages."""
     P, B = self.P, self.B
     self.z.copy_(z)
     n0 = 4 * 5 * self.gch[0]
     self._gemm(self.z, Z_DIM, P['G/z_proj/W'], n0, self.gX[0], n0, B, n0, Z_DIM, bias=P['G/z_proj/b'])
-    self._bn_fwd(self.gX[0], self.gstats[0], P[G_BN[0] + '/gamma'], P[G_BN[0] + '/beta'], N.ACT_RELU, self.gY[0])
+
+    def bn(i):
+      gamma, beta = P[G_BN[i] + '/gamma'], P[G_BN[i] + '/beta']
+      if training:
+        self._bn_fwd(self.gX[i], self.gstats[i], gamma, beta, N.ACT_RELU, self.gY[i])
+        self._bn_track(self.gX[i], self.gstats[i], self.g_moving[i])
+      else:
+        self._bn_infer(self.gX[i], self.g_moving[i], gamma, beta, N.ACT_RELU, self.gY[i])
+
+    bn(0)
     for i in range(1, 5):
       L = self.up[i]
       w = self._w(self.Wf, L, L.name + '/W')
       if i < 4:
         ep = _epilogue(P[L.name + '/b'], self.gX[i], self.gch[i], 0, N.ACT_NONE)
         self._conv(L, self.gY[i - 1], self.gch[i - 1], w, ep)
-        self._bn_fwd(self.gX[i], self.gstats[i], P[G_BN[i] + '/gamma'], P[G_BN[i] + '/beta'], N.ACT_RELU,
-                     self.gY[i])
+        bn(i)
       else:
         ep = _epilogue(P[L.name + '/b'], self.G_z, 1, 0, N.ACT_TANH)
         self._conv(L, self.gY[3], self.gch[3], w, ep)
@@ -453,8 +489,8 @@ class MelspecGAN(object):
 # ---------------------------------------------------------------------------------------------
 # Callable mirrors of the reference classes (models/melspecgan/conv2d.py:82-95,153-166): same
 # names, constructor arguments and call signature; tensors are CUDA float32 in the reference's
-# shapes.  `training=False` would need BatchNorm moving averages, which the reference only uses
-# in its `infer` / `incept` graphs (train.py:163,192); they are not tracked here.
+# shapes.  The generator's `training=False` graph (infer / incept, train.py:163,192) normalises with the
+# moving averages the engine tracks; the discriminator is never built with training=False by the reference.
 # ---------------------------------------------------------------------------------------------
 class _Net(object):
   def __init__(self, dim=64, kernel_len=5, batchnorm=True, params=None):
@@ -473,15 +509,23 @@ class _Net(object):
 
 
 class MelspecGANGenerator(_Net):
+  def __init__(self, dim=64, kernel_len=5, batchnorm=True, params=None, moving=None):
+    super(MelspecGANGenerator, self).__init__(dim, kernel_len, batchnorm, params)
+    self.moving = moving      # {'G/batch_normalization*/moving_{mean,variance}': tensor}, e.g. from a checkpoint
+
   def __call__(self, z, training=False):
-    if not training:
-      raise NotImplementedError('moving-average batch norm (inference graphs) is not tracked')
-    return self._engine(z.shape[0]).generate(z)
+    fresh = self._eng is None or self._eng.B != z.shape[0]
+    eng = self._engine(z.shape[0])
+    if fresh and self.moving is not None:
+      eng.load_moving_averages(self.moving)
+    out = eng.generate(z, training=training)
+    self.moving = eng.moving_averages()
+    return out
 
 
 class MelspecGANDiscriminator(_Net):
   def __call__(self, x, training=False):
     if not training:
-      raise NotImplementedError('moving-average batch norm (inference graphs) is not tracked')
+      raise NotImplementedError('the discriminator\'s moving-average batch norm is not tracked')
     eng = self._engine(x.shape[0])
     return eng.discriminate(x.contiguous(), eng.real)

@@ -289,6 +289,20 @@ ADVOC_API int advoc_bn_apply(const float* d_x, int ldx, long pixels, int C, cons
                              const float* d_gamma, const float* d_beta, float eps, int act, float alpha,
                              float* d_y, int ldy, int round_tf32, void* stream);
 
+/* Inference-mode batch norm (training=False): y = act(gamma * (x - mean) / sqrt(var + eps) + beta) with the
+ * given per-channel moving averages.  replaces: tf.layers.batch_normalization(training=False) + relu of
+ * the generator's inference graph, conv2d.py:108,116-137 as built by models/melspecgan/infer.py:14-17. */
+ADVOC_API int advoc_bn_inference(const float* d_x, int ldx, long pixels, int C, const float* d_mean,
+                                 const float* d_var, const float* d_gamma, const float* d_beta, float eps,
+                                 int act, float alpha, float* d_y, int ldy, int round_tf32, void* stream);
+
+/* moving_mean / moving_var <- moving - (moving - batch) * (1 - momentum) from the (sum, sum of squares) in
+ * d_stats; the batch variance carries Bessel's correction pixels / (pixels - 1) like TF's fused op.
+ * replaces: the UPDATE_OPS of tf.layers.batch_normalization run under control_dependencies,
+ * conv2d.py:143-148 (momentum 0.99). */
+ADVOC_API int advoc_bn_moving_update(const float* d_stats, long pixels, int C, float momentum,
+                                     float* d_moving_mean, float* d_moving_var, void* stream);
+
 /* Backward of advoc_bn_apply: g = dy * act'(y); d_red[0:C] += sum g (dbeta), d_red[C:2C] += sum g*xhat
  * (dgamma) (caller zeroes d_red); dx = gamma/sqrt(var+eps) * (g - dbeta/M - xhat*dgamma/M).
  * replaces: the autodiff of the same ops (opt.minimize, train.py:137-139). */

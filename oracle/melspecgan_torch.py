@@ -58,10 +58,35 @@ def init_params(seed=0, dim=DIM, dtype=torch.float32):
   return P
 
 
-def batchnorm(x, gamma, beta):
-  """Batch statistics over (N, H, W) per channel, biased variance (training=True)."""
+BN_MOMENTUM = 0.99   # tf.layers.batch_normalization default
+
+
+def init_moving(dim=DIM, dtype=torch.float32):
+  """moving_mean 0 / moving_variance 1 of the generator's four batch norms (infer.meta variable names)."""
+  M = {}
+  for name, c in zip(G_BN, [dim * 8, dim * 4, dim * 2, dim]):
+    M[name + '/moving_mean'] = torch.zeros(c, dtype=dtype)
+    M[name + '/moving_variance'] = torch.ones(c, dtype=dtype)
+  return M
+
+
+def batchnorm(x, gamma, beta, moving=None, name=None, training=True):
+  """training=True: batch statistics over (N, H, W) per channel, biased variance; when `moving` is given
+  its entries are updated in place the way the layer's UPDATE_OPS do (conv2d.py:143-148):
+  `moving -= (moving - batch) * (1 - 0.99)`, the batch variance with Bessel's correction n/(n-1) (what
+  TF's fused batch-norm op hands to the moving average for 4-D inputs).  training=False: normalise
+  with the moving statistics (models/melspecgan/infer.py:17)."""
+  if not training:
+    m, v = moving[name + '/moving_mean'], moving[name + '/moving_variance']
+    return (x - m) * torch.rsqrt(v + BN_EPS) * gamma + beta
   m = x.mean(dim=(0, 1, 2), keepdim=True)
   v = ((x - m) ** 2).mean(dim=(0, 1, 2), keepdim=True)
+  if moving is not None:
+    n = x.numel() // x.shape[-1]
+    with torch.no_grad():
+      mm, mv = moving[name + '/moving_mean'], moving[name + '/moving_variance']
+      mm -= (mm - m.reshape(-1)) * (1. - BN_MOMENTUM)
+      mv -= (mv - v.reshape(-1) * (n / (n - 1.))) * (1. - BN_MOMENTUM)
   return (x - m) * torch.rsqrt(v + BN_EPS) * gamma + beta
 
 
@@ -79,16 +104,16 @@ def deconv5(x, W, b):
   return y.permute(0, 2, 3, 1)
 
 
-def generator(P, z, dim=DIM, return_layers=False):
-  """z [b, 100] -> [b, 64, 80, 1] in (-1, 1)  (conv2d.py:95-150, training=True)."""
+def generator(P, z, dim=DIM, return_layers=False, moving=None, training=True):
+  """z [b, 100] -> [b, 64, 80, 1] in (-1, 1)  (conv2d.py:95-150).  `moving`: see batchnorm."""
   x = z @ P['G/z_proj/W'] + P['G/z_proj/b']
   x = x.reshape(-1, 4, 5, dim * 8)
-  x = torch.relu(batchnorm(x, P[G_BN[0] + '/gamma'], P[G_BN[0] + '/beta']))
+  x = torch.relu(batchnorm(x, P[G_BN[0] + '/gamma'], P[G_BN[0] + '/beta'], moving, G_BN[0], training))
   layers = [x]
   for i in range(1, 5):
     x = deconv5(x, P['G/upconv_%d/W' % i], P['G/upconv_%d/b' % i])
     if i < 4:
-      x = torch.relu(batchnorm(x, P[G_BN[i] + '/gamma'], P[G_BN[i] + '/beta']))
+      x = torch.relu(batchnorm(x, P[G_BN[i] + '/gamma'], P[G_BN[i] + '/beta'], moving, G_BN[i], training))
     else:
       x = torch.tanh(x)
     layers.append(x)

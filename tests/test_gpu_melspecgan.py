@@ -115,3 +115,74 @@ def test_wgangp_outer_iteration_runs():
   assert eng.t_d == 5 and eng.t_g == 1 and torch.isfinite(eng.flat.p).all()
   d_loss, g_loss = eng.loss_values()
   assert d_loss == d_loss and g_loss == g_loss
+
+
+@pytest.mark.parametrize('math,tol', [('fp32', 1e-4), ('auto', 1e-3)])
+def test_moving_averages_and_inference_graph(math, tol):
+  """Two training-mode evaluations advance the batch-norm moving averages like the layer's update ops;
+  the training=False graph (models/melspecgan/infer.py:17) then normalises with them."""
+  M, P, eng, z, x = _setup(math, 64, 8)
+  g = torch.Generator().manual_seed(9)
+  z2 = torch.randn(z.shape, generator=g)
+  z3 = torch.randn(z.shape, generator=g)
+  moving = M.init_moving(64)
+  for zi in (z, z2):
+    eng.generate(zi.cuda())
+    M.generator(P, zi, 64, moving=moving)
+  got = eng.moving_averages()
+  for n in moving:
+    # 0.99 of the value is still the initial 0 / 1: compare the part that moved
+    init = 1. if n.endswith('variance') else 0.
+    assert _rel(got[n] - init, moving[n] - init) < 10 * tol, n
+  # a trained net has moving statistics close to its batch statistics: install those, then infer
+  for n, v in moving.items():
+    v.copy_(torch.rand(v.shape, generator=g) * 0.05 + (0.02 if n.endswith('variance') else -0.02))
+  eng.load_moving_averages({n: v.cuda() for n, v in moving.items()})
+  before = {n: v.clone() for n, v in eng.moving_averages().items()}
+  G_z = eng.generate(z3.cuda(), training=False)
+  ref = M.generator(P, z3, 64, moving=moving, training=False)
+  assert _rel(G_z, ref) < tol
+  for n, v in eng.moving_averages().items():
+    assert torch.equal(v, before[n]), n       # inference leaves them alone
+
+
+def test_generate_spectrogram_cli_from_tf_checkpoint(tmp_path):
+  """scripts/generate_spectrogram.py restores generator weights + moving averages from a TF-1 checkpoint
+  prefix (written by the test-side bundle writer) and saves feats_denorm(G(z, training=False))."""
+  import os
+  import subprocess
+  import sys
+  import numpy as np
+  sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+  import tf_bundle_writer as W
+  from oracle import melspecgan_torch as M
+  P = M.init_params(seed=3, dim=64)
+  g = torch.Generator().manual_seed(4)
+  moving = M.init_moving(64)
+  momentum, M.BN_MOMENTUM = M.BN_MOMENTUM, 0.   # one evaluation installs that batch's statistics: a "trained" state
+  try:
+    M.generator(P, torch.randn(16, M.Z_DIM, generator=g), 64, moving=moving)
+  finally:
+    M.BN_MOMENTUM = momentum
+  T = {k: v.numpy() for k, v in P.items() if k.startswith('G/')}
+  T.update({k: v.numpy() for k, v in moving.items()})
+  T['global_step'] = np.int64(4321)
+  prefix = str(tmp_path / 'model.ckpt-4321')
+  W.write_bundle(prefix, T, block_size=4096)
+  out_dir = str(tmp_path / 'specs')
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  r = subprocess.run([sys.executable, os.path.join(root, 'scripts', 'generate_spectrogram.py'), '--out_dir', out_dir,
+                      '--ckpt_fp', prefix, '--n', '6', '--b', '3', '--seed', '7'], capture_output=True, text=True,
+                     timeout=600)
+  assert r.returncode == 0, r.stderr[-2000:]
+  assert 'Restored from step 4321' in r.stdout
+  files = sorted(os.listdir(out_dir))
+  assert files == ['%09d.npy' % i for i in range(6)]
+  gen = torch.Generator(device='cuda')
+  gen.manual_seed(7)
+  z = torch.randn((3, M.Z_DIM), dtype=torch.float32, device='cuda', generator=gen).cpu()
+  ref = (M.generator(P, z, 64, moving=moving, training=False) + 1.) * 0.5
+  for j in range(3):
+    s = np.load(os.path.join(out_dir, files[j]))
+    assert s.shape == (64, 80, 1) and s.dtype == np.float32
+    assert _rel(torch.from_numpy(s), ref[j]) < 1e-3

@@ -55,3 +55,22 @@ def test_losses_differentiate():
     gg = torch.autograd.grad(l['G_loss'], [P[n] for n in M.g_names(P)], allow_unused=True)
     assert all(t is not None and torch.isfinite(t).all() for t in gd)
     assert all(t is not None and torch.isfinite(t).all() for t in gg)
+
+
+def test_moving_average_update_rule():
+  """One training-mode evaluation from the TF initial values (0, 1): moving -= (moving - batch) * 0.01 with
+  the Bessel-corrected batch variance; training=False then reads them and a larger batch does not matter."""
+  import torch
+  from oracle import melspecgan_torch as M
+  P = M.init_params(seed=1, dim=8)
+  g = torch.Generator().manual_seed(2)
+  z = torch.randn(5, M.Z_DIM, generator=g)
+  moving = M.init_moving(8)
+  M.generator(P, z, 8, moving=moving)
+  x0 = (z @ P['G/z_proj/W'] + P['G/z_proj/b']).reshape(-1, 4, 5, 64).reshape(-1, 64)
+  assert torch.allclose(moving['G/batch_normalization/moving_mean'], 0.01 * x0.mean(0), atol=1e-7)
+  assert torch.allclose(moving['G/batch_normalization/moving_variance'], 0.99 + 0.01 * x0.var(0, unbiased=True),
+                        atol=1e-7)
+  one = M.generator(P, z[:1], 8, moving=moving, training=False)
+  many = M.generator(P, z, 8, moving=moving, training=False)
+  assert torch.allclose(one, many[:1], atol=1e-6)      # no batch coupling in the inference graph
