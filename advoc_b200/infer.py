@@ -72,11 +72,14 @@ class MelToMag(object):
 
   # -- streaming host API: copies overlap the forward of the neighbouring batches ------------
   def _stream_setup(self):
-    """Two input / output buffer sets, one captured graph per set, a copy stream and events."""
+    """Two input / output buffer sets, one captured graph per set, one stream per copy direction
+    (a shared copy stream would queue the next batch's input behind the previous batch's result and
+    with it serialise compute and device->host transfer) and events."""
     if getattr(self, '_sets', None) is not None:
       return
     dev = self.G.dev
-    self._copy_stream = torch.cuda.Stream(device=dev)
+    self._h2d_stream = torch.cuda.Stream(device=dev)
+    self._d2h_stream = torch.cuda.Stream(device=dev)
     self._sets = []
     for k in range(2):
       s = dict(mel_d=torch.zeros_like(self.mel_d), out_d=torch.empty((self.B, self.T, 513, 1), dtype=torch.float32,
@@ -96,12 +99,12 @@ class MelToMag(object):
   def run_stream(self, batches):
     """Generator over host batches [B, T, n_mels] (float32; pinned or not): yields one pinned host
     tensor [B, T, 513] per input batch, in order, valid until the generator is advanced again.
-    The host->device copy of batch i+1 and the device->host copy of batch i-1 run on a copy stream
-    while batch i is in the generator (the reference's chunk loop, scripts/spectrogram_advoc.py:88-92,
+    The host->device copy of batch i+1 and the device->host copy of batch i-1 run on their own
+    streams while batch i is in the generator (the reference's chunk loop, scripts/spectrogram_advoc.py:88-92,
     pays both copies serially for every 256-frame chunk)."""
     self._stream_setup()
     main = torch.cuda.current_stream()
-    cs = self._copy_stream
+    hs, ds = self._h2d_stream, self._d2h_stream
     pending = []
     i = -1
     for i, mel in enumerate(batches):
@@ -117,9 +120,11 @@ class MelToMag(object):
       if not mel.is_pinned():
         s['mel_h'].copy_(mel)
         mel = s['mel_h']
-      with torch.cuda.stream(cs):
+      # buffer set reuse is safe: the host waited above for the result of batch i-2, i.e. for everything
+      # that read this set's input or wrote its output
+      with torch.cuda.stream(hs):
         s['mel_d'].copy_(mel, non_blocking=True)
-        s['h2d'].record(cs)
+        s['h2d'].record(hs)
       main.wait_event(s['h2d'])
       if self.use_graph:
         if s['graph'] is None:
@@ -134,10 +139,10 @@ class MelToMag(object):
         self._seed += 1
         self._launch_set(s, self._seed)
       s['done'].record(main)
-      with torch.cuda.stream(cs):
-        cs.wait_event(s['done'])
+      with torch.cuda.stream(ds):
+        ds.wait_event(s['done'])
         s['out_h'].copy_(s['out_d'].view(self.B, self.T, 513), non_blocking=True)
-        s['d2h'].record(cs)
+        s['d2h'].record(ds)
       pending.append(s['out_h'])
     for k, out in enumerate(pending):
       self._sets[(i - len(pending) + 1 + k) & 1]['d2h'].synchronize()
