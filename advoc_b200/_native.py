@@ -70,6 +70,7 @@ SIGNATURES = {
     'advoc_gan_logloss': (_I, [_P, _P, _L, _I, _F, _P, _P, _P, _P]),
     'advoc_l1_loss': (_I, [_P, _I, _I, _P, _L, _F, _P, _P, _I, _P]),
     'advoc_adam_tf_step': (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _L, _F, _P]),
+    'advoc_adam_tf_step_dev': (_I, [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _P]),
     'advoc_conv2d_path': (_I, [C.POINTER(ConvDesc), _I, _I]),
     'advoc_conv2d_kernel': (_I, [C.POINTER(ConvDesc), _I, _I, _I]),
     'advoc_gemm_f32': (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),

@@ -432,6 +432,23 @@ __global__ void __launch_bounds__(256) adam_tf_kernel(float* __restrict__ p, con
   }
 }
 
+// same update with the bias-corrected step size read from device memory, so that a captured CUDA graph of
+// the optimiser step stays valid while t advances (the host refreshes the scalar before each replay)
+__global__ void __launch_bounds__(256) adam_tf_dev_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                          float* __restrict__ m, float* __restrict__ v, long n,
+                                                          const float* __restrict__ lr_t_ptr, float b1, float b2,
+                                                          float eps, float gscale) {
+  const float lr_t = __ldg(lr_t_ptr);
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * gscale;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= lr_t * mi / (sqrtf(vi) + eps);
+  }
+}
+
 int grid_for(long n, int per_block) {
   long b = (n + per_block - 1) / per_block;
   const long cap = (long)sm_count() * 16;
@@ -575,6 +592,18 @@ extern "C" int advoc_l1_loss(const float* d_gen, int ld_gen, int c_off_gen, cons
                 "bad l1 arguments");
   l1_loss_kernel<<<grid_for(n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       d_gen, ld_gen, c_off_gen, d_target, n, weight, d_loss, d_dgen, accumulate);
+  count_launch();
+  ADVOC_CHECK_CUDA(cudaGetLastError());
+  return ADVOC_OK;
+}
+
+extern "C" int advoc_adam_tf_step_dev(float* d_p, const float* d_g, float* d_m, float* d_v, long n,
+                                      const float* d_lr_t, float beta1, float beta2, float eps, float grad_scale,
+                                      void* stream) {
+  ADVOC_REQUIRE(d_p && d_g && d_m && d_v && d_lr_t && n >= 0, ADVOC_BAD_ARG, "bad adam arguments");
+  if (n == 0) return ADVOC_OK;
+  adam_tf_dev_kernel<<<grid_for(n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      d_p, d_g, d_m, d_v, n, d_lr_t, beta1, beta2, eps, grad_scale);
   count_launch();
   ADVOC_CHECK_CUDA(cudaGetLastError());
   return ADVOC_OK;

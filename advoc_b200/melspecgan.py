@@ -110,9 +110,14 @@ class MelspecGAN(object):
   """One replica of the MelspecGAN train step for a fixed per-GPU batch."""
 
   def __init__(self, params, batch, dim=64, train_loss='dcgan', math=N.MATH_AUTO, process_group=None,
-               world_size=1):
+               world_size=1, use_graphs=True):
+    """`use_graphs`: from the second call on, the gradient computation and the optimiser update of
+    `d_step` / `g_step` replay from captured CUDA graphs (the ~300 / ~250 launches of one step are
+    otherwise bound by the host's launch rate); the gradient all-reduce between the two stays eager."""
     if train_loss not in ('dcgan', 'wgan', 'wgangp'):
       raise ValueError()
+    self.use_graphs, self._graphs, self._graph_launches = use_graphs, {}, {}
+    self.capture_launches = self.replayed_launches = 0    # launch accounting for bench.py
     self.loss_kind, self.B, self.dim, self.math = train_loss, batch, dim, math
     self.pg, self.world = process_group, world_size
     # optimiser settings of train.py:117-135
@@ -176,23 +181,48 @@ class MelspecGAN(object):
       self._alpha_gen.manual_seed(1234)
     self.x_real = torch.zeros((B, 64, 80, 1), **f32)
     self.losses = torch.zeros(2, **f32)     # D_loss, G_loss
+    self.alpha_buf = torch.zeros((B, 1, 1, 1), **f32)
+    self.lr_t = torch.zeros(2, **f32)       # bias-corrected Adam step sizes of the D / G optimisers
     self.t_d = self.t_g = 0
+    self.Wf, self.Wb = {}, {}
     self.refresh_weights()
 
   # -------------------------------------------------------------------------------------------
-  def refresh_weights(self):
-    """Derived (packed / TF32-rounded) filter copies for the tcgen05 path, after every Adam step."""
+  def refresh_weights(self, which='GD'):
+    """Derived (packed / TF32-rounded) filter copies for the tcgen05 path, after every Adam step of the
+    named nets; refreshed in place so that captured graphs keep pointing at them."""
     P = self.P
-    self.Wf, self.Wb = {}, {}
-    for i in range(1, 5):
-      k = P['G/upconv_%d/W' % i]
-      self.Wf[self.up[i].name] = nets._pack_for_tc(self.up[i], k, self.gch[i - 1])
-      self.Wb[self.up_b[i].name] = nets._pack_for_tc(self.up_b[i], k, self.gch[i])
-    for i in range(4):
-      k = P['D/conv_%d/W' % i]
-      self.Wf[self.conv[i].name] = nets._pack_for_tc(self.conv[i], k, self.dch[i])
-      self.Wb[self.conv_t[i].name] = nets._pack_for_tc(self.conv_t[i], k, self.dch[i + 1])
-    self.WoutT = None
+    if 'G' in which:
+      for i in range(1, 5):
+        k = P['G/upconv_%d/W' % i]
+        n = self.up[i].name
+        self.Wf[n] = nets._pack_for_tc(self.up[i], k, self.gch[i - 1], self.Wf.get(n))
+        self.Wb[n] = nets._pack_for_tc(self.up_b[i], k, self.gch[i], self.Wb.get(n))
+    if 'D' in which:
+      for i in range(4):
+        k = P['D/conv_%d/W' % i]
+        n = self.conv[i].name
+        self.Wf[n] = nets._pack_for_tc(self.conv[i], k, self.dch[i], self.Wf.get(n))
+        self.Wb[n] = nets._pack_for_tc(self.conv_t[i], k, self.dch[i + 1], self.Wb.get(n))
+
+  def _replay(self, key, fn):
+    """Run `fn` (device work on static buffers only): eagerly the first time, then captured once and
+    replayed.  Host-side state (step counters, RNG draws, input staging) stays outside `fn`."""
+    if not self.use_graphs:
+      return fn()
+    g = self._graphs.get(key)
+    if g is not None:
+      self.replayed_launches += self._graph_launches[key]
+      return g.replay()
+    fn()
+    torch.cuda.synchronize()
+    n0 = N.launch_count()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+      fn()
+    self._graph_launches[key] = N.launch_count() - n0
+    self.capture_launches += self._graph_launches[key]    # counted by the library, but only recorded
+    self._graphs[key] = g
 
   def _w(self, table, L, key):
     w = table.get(L.name)
@@ -265,7 +295,8 @@ class MelspecGAN(object):
     statistics and advances the moving averages (every evaluation of G_z in the reference's train graph
     runs the update ops: conv2d.py:143-148); training=False normalises with the moving averages."""
     P, B = self.P, self.B
-    self.z.copy_(z)
+    if z is not self.z:
+      self.z.copy_(z)
     n0 = 4 * 5 * self.gch[0]
     self._gemm(self.z, Z_DIM, P['G/z_proj/W'], n0, self.gX[0], n0, B, n0, Z_DIM, bias=P['G/z_proj/b'])
 
@@ -371,8 +402,8 @@ class MelspecGAN(object):
     P, B, G, I = self.P, self.B, self.flat.G, self.interp
     ch = self.dch
     if alpha is None:
-      alpha = torch.rand((B, 1, 1, 1), generator=self._alpha_gen, device=self.x_hat.device)
-    torch.lerp(self.x_real, self.G_z, alpha.to(self.x_hat.device), out=self.x_hat)   # x + alpha (G_z - x)
+      alpha = self.alpha_buf.uniform_(0., 1., generator=self._alpha_gen)
+    torch.lerp(self.x_real, self.G_z, alpha, out=self.x_hat)   # x + alpha (G_z - x)
     # first order: D(xhat) and g = d sum_b D(xhat)_b / d xhat
     self.discriminate(self.x_hat, I)
     I.dlogits.fill_(1.0)
@@ -429,23 +460,28 @@ class MelspecGAN(object):
   # -------------------------------------------------------------------------------------------
   # optimiser + collective
   # -------------------------------------------------------------------------------------------
-  def _finish(self, lo, hi, t, apply):
+  def _finish(self, lo, hi, t, apply, which):
     from advoc_b200 import dist as D
     D.allreduce_sum_(self.flat.g, lo, hi, self.pg, self.world)
-    if apply:
+    if not apply:
+      return
+    # bias-corrected step size of tf.train.AdamOptimizer, kept on the device so that the captured update
+    # does not freeze t
+    slot = 0 if which == 'D' else 1
+    self.lr_t[slot:slot + 1].fill_(self.lr * (1.0 - self.b2 ** t) ** 0.5 / (1.0 - self.b1 ** t))
+
+    def update():
       f = self.flat
       o = lambda t_: C.c_void_p(t_.data_ptr() + 4 * lo)
-      N.call('advoc_adam_tf_step', o(f.p), o(f.g), o(f.m), o(f.v), hi - lo, self.lr, self.b1, self.b2, self.eps,
-             t, 1.0 / self.world, _stream())
-      self.refresh_weights()
+      N.call('advoc_adam_tf_step_dev', o(f.p), o(f.g), o(f.m), o(f.v), hi - lo,
+             C.c_void_p(self.lr_t.data_ptr() + 4 * slot), self.b1, self.b2, self.eps, 1.0 / self.world, _stream())
+      self.refresh_weights(which)
+    self._replay('adam_' + which, update)
 
-  def d_step(self, x, z, apply=True, alpha=None):
-    """`D_train_op` on one minibatch (train.py:139,151): x [B,64,80,1] in [-1,1], z [B,100];
-    `alpha` [B,1,1,1] fixes the interpolation draw of train.py:100 (tests)."""
+  def _d_compute(self):
     lo, hi = self.flat.dis_range()
     self.flat.g[lo:hi].zero_()
-    self.x_real.copy_(x)
-    G_z = self.generate(z)
+    G_z = self.generate(self.z)
     self.discriminate(self.x_real, self.real)
     self.discriminate(G_z, self.fake)
     N.call('advoc_gan_logit_loss', _ptr(self.real.logits), _ptr(self.fake.logits), self.B,
@@ -454,24 +490,42 @@ class MelspecGAN(object):
     self._d_backward(self.x_real, self.real, True, False)
     self._d_backward(G_z, self.fake, True, False)
     if self.loss_kind == 'wgangp':
-      self._gp_backward(alpha)
+      self._gp_backward(self.alpha_buf)
+
+  def d_step(self, x, z, apply=True, alpha=None):
+    """`D_train_op` on one minibatch (train.py:139,151): x [B,64,80,1] in [-1,1], z [B,100];
+    `alpha` [B,1,1,1] fixes the interpolation draw of train.py:100 (tests)."""
+    lo, hi = self.flat.dis_range()
+    self.x_real.copy_(x)
+    self.z.copy_(z)
+    if self.loss_kind == 'wgangp':
+      if alpha is None:
+        self.alpha_buf.uniform_(0., 1., generator=self._alpha_gen)
+      else:
+        self.alpha_buf.copy_(alpha.reshape(self.alpha_buf.shape))
+    self._replay('d', self._d_compute)
     if apply:
       self.t_d += 1
-    self._finish(lo, hi, self.t_d, apply)
+    self._finish(lo, hi, self.t_d, apply, 'D')
 
-  def g_step(self, z, apply=True):
-    """`G_train_op` on one draw of z (train.py:137-138,153)."""
+  def _g_compute(self):
     lo, hi = self.flat.gen_range()
     self.flat.g[lo:hi].zero_()
-    G_z = self.generate(z)
+    G_z = self.generate(self.z)
     self.discriminate(G_z, self.fake)
     N.call('advoc_gan_logit_loss', None, _ptr(self.fake.logits), self.B, 1 if self.loss_kind == 'dcgan' else 3,
            C.c_void_p(self.losses.data_ptr() + 4), None, _ptr(self.fake.dlogits), _stream())
     self._d_backward(G_z, self.fake, False, True)
     self._g_backward()
+
+  def g_step(self, z, apply=True):
+    """`G_train_op` on one draw of z (train.py:137-138,153)."""
+    lo, hi = self.flat.gen_range()
+    self.z.copy_(z)
+    self._replay('g', self._g_compute)
     if apply:
       self.t_g += 1
-    self._finish(lo, hi, self.t_g, apply)
+    self._finish(lo, hi, self.t_g, apply, 'G')
     return self.t_g
 
   def train_loop(self, batches, zs_d, z_g):

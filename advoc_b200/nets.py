@@ -129,15 +129,17 @@ def _epilogue(bias, out0, ld0, coff0, act0, out1=None, ld1=0, coff1=0, act1=N.AC
                     ld_gate, coff_gate, gate_act, gate_split, gate_scale0, gate_scale1)
 
 
-def _pack_for_tc(L, kernel, ldx):
+def _pack_for_tc(L, kernel, ldx, out=None):
   """Derived filter copy for the tcgen05 path (None if the layer runs on CUDA cores):
   conv HWIO -> K-major [tap][Cout][Cin]; conv_transpose HWOI is already K-major.  Values are
-  rounded to TF32 (round-to-nearest) because the tensor core would otherwise truncate."""
+  rounded to TF32 (round-to-nearest) because the tensor core would otherwise truncate.
+  `out`: an earlier result to refresh in place (fixed addresses for captured graphs)."""
   if not L.uses_tensor_cores(ldx):
     return None
   kh, kw, a, b = kernel.shape
-  out = torch.empty((kh * kw, b, a) if L.kind == 'conv' else (kh * kw, a, b),
-                    dtype=torch.float32, device=kernel.device)
+  if out is None:
+    out = torch.empty((kh * kw, b, a) if L.kind == 'conv' else (kh * kw, a, b),
+                      dtype=torch.float32, device=kernel.device)
   N.call('advoc_pack_filter', _ptr(kernel), _ptr(out), kh * kw, a, b, 1 if L.kind == 'conv' else 0,
          1, _stream())
   return out

@@ -255,6 +255,13 @@ ADVOC_API int advoc_adam_tf_step(float* d_p, const float* d_g, float* d_m, float
                                  float lr, float beta1, float beta2, float eps, long t,
                                  float grad_scale, void* stream);
 
+/* The same update with the bias-corrected step size lr*sqrt(1-b2^t)/(1-b1^t) read from device memory
+ * (one float at d_lr_t), so that a captured CUDA graph of the optimiser step stays valid while t advances.
+ * replaces: the AdamOptimizer train ops of models/melspecgan/train.py:117-139 when replayed from a graph. */
+ADVOC_API int advoc_adam_tf_step_dev(float* d_p, const float* d_g, float* d_m, float* d_v, long n,
+                                     const float* d_lr_t, float beta1, float beta2, float eps,
+                                     float grad_scale, void* stream);
+
 /* Which kernel family a call with this geometry takes: ADVOC_MATH_TF32 (tcgen05 implicit
  * GEMM) or ADVOC_MATH_FP32 (CUDA-core kernel).  transposed != 0 asks about
  * advoc_conv2d_transpose_fwd.  Pure host logic. */

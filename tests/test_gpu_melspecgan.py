@@ -117,6 +117,63 @@ def test_wgangp_outer_iteration_runs():
   assert d_loss == d_loss and g_loss == g_loss
 
 
+@pytest.mark.parametrize('loss', ['dcgan', 'wgangp'])
+def test_graph_replay_matches_eager_launches(loss):
+  """One outer iteration replayed from captured CUDA graphs against the same iteration launched kernel
+  by kernel, from identical state (TF32 path, so the in-place refresh of the packed filters is on the
+  replayed path too).  A GAN step at batch 4 amplifies the summation-order noise of the atomically
+  accumulated gradients ~50x per iteration (measured: two EAGER engines drift apart just as fast), so
+  the engines are re-synchronised after the capturing iteration and the yardstick is the drift
+  between two eager engines."""
+  from advoc_b200 import _native as N
+  from advoc_b200.melspecgan import MelspecGAN
+  M, P, eng, z, x = _setup('auto', 32, 4, loss)
+  assert eng.use_graphs
+  mk = lambda: MelspecGAN({k: v.cuda() for k, v in P.items()}, 4, dim=32, train_loss=loss, math=N.MATH_AUTO,
+                          use_graphs=False)
+  ref, ref2 = mk(), mk()
+  n_d = 5 if loss == 'wgangp' else 1
+  g = torch.Generator().manual_seed(6)
+
+  def iteration(it):
+    xs = [(torch.rand(4, 64, 80, 1, generator=g) * 2 - 1).cuda() for _ in range(n_d)]
+    zs = [torch.randn(4, M.Z_DIM, generator=g).cuda() for _ in range(n_d + 1)]
+    for e in (eng, ref, ref2):
+      for k in range(n_d):
+        alpha = torch.rand(4, 1, 1, 1, generator=torch.Generator().manual_seed(100 * it + k)).cuda()
+        e.d_step(xs[k], zs[k], alpha=alpha)
+      e.g_step(zs[n_d])
+
+  iteration(0)                                  # eager everywhere; `eng` records its graphs
+  assert set(eng._graphs) == {'d', 'g', 'adam_D', 'adam_G'} and not ref._graphs
+  for e in (eng, ref2):                         # identical state before the replayed iteration
+    for name in ('p', 'm', 'v'):
+      getattr(e.flat, name).copy_(getattr(ref.flat, name))
+    e.load_moving_averages(ref.moving_averages())
+    e.refresh_weights()
+  p1 = ref.flat.p.clone()
+  iteration(1)                                  # `eng` replays
+  assert eng.t_d == ref.t_d == 2 * n_d and eng.t_g == ref.t_g == 2
+  # the device-side Adam step sizes follow t although the update graph was captured at t = 1
+  for slot, t in ((0, eng.t_d), (1, eng.t_g)):
+    want = eng.lr * (1. - eng.b2 ** t) ** 0.5 / (1. - eng.b1 ** t)
+    assert abs(float(eng.lr_t[slot]) - want) < 1e-6 * want
+  # compare the UPDATE (like test_train_loop_matches_oracle_adam), leaving out the biases whose exact
+  # gradient is zero: Adam turns their rounding noise into steps of arbitrary sign
+  live = torch.ones_like(p1)
+  for n in _DEAD_BIAS:
+    o = eng.flat.offsets[n]
+    live[o:o + eng.flat.P[n].numel()] = 0
+  drift = lambda a, b, f: _rel(f(a) * live, f(b) * live)
+  for what, f in (('update', lambda e: e.flat.p - p1), ('m', lambda e: e.flat.m), ('v', lambda e: e.flat.v)):
+    noise = drift(ref2, ref, f)
+    assert drift(eng, ref, f) < max(5e-3, 5 * noise), (what, noise)
+  for n, v in eng.moving_averages().items():
+    assert _rel(v, ref.moving_averages()[n]) < 1e-3, n
+  a, b = eng.loss_values(), ref.loss_values()
+  assert abs(a[0] - b[0]) < 2e-2 * max(1., abs(b[0])) and abs(a[1] - b[1]) < 2e-2 * max(1., abs(b[1]))
+
+
 @pytest.mark.parametrize('math,tol', [('fp32', 1e-4), ('auto', 1e-3)])
 def test_moving_averages_and_inference_graph(math, tol):
   """Two training-mode evaluations advance the batch-norm moving averages like the layer's update ops;
