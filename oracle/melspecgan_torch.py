@@ -11,8 +11,14 @@ models/melspecgan/train.py (:74-111 losses, :117-135 optimisers) with TF's rules
   * tf.layers.batch_normalization defaults: eps 1e-3, batch statistics when training=True
     (biased variance), gamma 1 / beta 0 init.
 
-Parity status: **parity unpinned** -- the reference has no test, golden vector or checkpoint for
-these nets (models/melspecgan/infer.meta holds only the graph); fidelity rests on code reading.
+Parity status: **values unpinned, generator structure pinned** -- the reference has no test, golden vector
+or checkpoint for these nets; what it does hold is the exported inference graph
+models/melspecgan/infer.meta, whose variable names / layouts, op order, conv_transpose strides, padding and
+output sizes, FusedBatchNorm epsilon (1e-3) and decay (0.99; the FUSED op is what hands the
+Bessel-corrected batch variance to the moving average), latent size and feats_denorm tail are extracted
+into tests/golden/melspecgan_infer_graph.json (scripts/make_melspecgan_graph_fixture.py) and checked
+against this file by tests/test_oracle_melspecgan.py.  The discriminator and the losses rest on code
+reading.
 """
 import torch
 import torch.nn.functional as F

@@ -74,3 +74,68 @@ def test_moving_average_update_rule():
   one = M.generator(P, z[:1], 8, moving=moving, training=False)
   many = M.generator(P, z, 8, moving=moving, training=False)
   assert torch.allclose(one, many[:1], atol=1e-6)      # no batch coupling in the inference graph
+
+
+def _graph_fixture():
+  import json
+  import os
+  fp = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'melspecgan_infer_graph.json')
+  with open(fp) as f:
+    return json.load(f)
+
+
+def test_generator_matches_the_reference_metagraph():
+  """models/melspecgan/infer.meta (the reference's exported inference graph; facts extracted by
+  scripts/make_melspecgan_graph_fixture.py) pins the generator's variable names / layouts, op order,
+  conv_transpose strides + padding + output sizes, the fused batch norm's epsilon and decay, the latent
+  size and the feats_denorm tail.  The oracle and the product's host constants must agree with it."""
+  import numpy as np
+  import torch
+  from oracle import melspecgan_torch as M
+  fx = _graph_fixture()
+  # --- variables: names, shapes, dtype (DT_FLOAT = 1); global_step is the only non-G variable
+  ref_vars = {v['name']: tuple(v['shape']) for v in fx['variables']}
+  assert all(v['dtype'] == 1 for v in fx['variables'] if v['name'] != 'global_step')
+  assert ref_vars.pop('global_step') == ()
+  P = M.init_params(seed=0, dim=64)
+  mine = {k: tuple(v.shape) for k, v in P.items() if k.startswith('G/')}
+  mine.update({k: tuple(v.shape) for k, v in M.init_moving(64).items()})
+  assert mine == ref_vars
+  # --- op chain from the latent to G_z
+  ops = {o['name']: o for o in fx['ops']}
+  assert ops['G/z_proj/MatMul']['inputs'] == ['z', 'G/z_proj/W/read']
+  assert ops['G/z_proj/MatMul']['attr'] == {'transpose_a': False, 'transpose_b': False}
+  assert ops['G/Reshape']['inputs'][0] == 'G/z_proj/BiasAdd' and fx['consts']['G/Reshape/shape'] == [-1, 4, 5, 512]
+  prev, sizes = 'G/Reshape', []
+  for i in range(4):
+    bn = 'G/batch_normalization%s/FusedBatchNorm' % ('' if i == 0 else '_%d' % i)
+    stem = bn.rsplit('/', 1)[0]
+    assert stem == M.G_BN[i]
+    assert ops[bn]['inputs'] == [prev] + [stem + s for s in ('/gamma/read', '/beta/read', '/moving_mean/read',
+                                                             '/moving_variance/read')]
+    assert ops[bn]['attr']['is_training'] is False and ops[bn]['attr']['data_format'] == 'NHWC'
+    assert np.float32(ops[bn]['attr']['epsilon']) == np.float32(M.BN_EPS)
+    assert np.float32(fx['consts'][stem + '/Const'][0]) == np.float32(M.BN_MOMENTUM)
+    relu = 'G/Relu' + ('' if i == 0 else '_%d' % i)
+    assert ops[relu]['inputs'] == [bn]
+    up = 'G/upconv_%d' % (i + 1)
+    ct = ops[up + '/conv2d_transpose']
+    assert ct['op'] == 'Conv2DBackpropInput' and ct['inputs'][1:] == [up + '/W/read', relu]
+    assert ct['attr']['strides'] == [1, 2, 2, 1] and ct['attr']['padding'] == 'SAME'
+    assert ct['attr']['data_format'] == 'NHWC' and ct['attr']['dilations'] == [1, 1, 1, 1]
+    assert ops[up + '/BiasAdd']['inputs'] == [up + '/conv2d_transpose', up + '/b/read']
+    sizes.append(tuple(fx['consts'][up + '/conv2d_transpose/output_shape/%d' % k][0] for k in (1, 2, 3)))
+    prev = up + '/BiasAdd'
+  assert ops['G/Tanh']['inputs'] == ['G/upconv_4/BiasAdd']
+  tail = {t['name']: t for t in fx['tail']}
+  assert tail['add']['inputs'] == ['G/Tanh', 'add/y'] and tail['mul']['inputs'] == ['add', 'mul/y']
+  assert tail['G_z']['inputs'] == ['mul'] and fx['consts']['add/y'] == [1.0] and fx['consts']['mul/y'] == [0.5]
+  assert fx['consts']['samp_z/shape/1'] == [M.Z_DIM]
+  # --- the oracle's activations have the sizes the graph requests from conv2d_transpose
+  with torch.no_grad():
+    out, layers = M.generator(P, torch.zeros(2, M.Z_DIM), 64, return_layers=True, moving=M.init_moving(64),
+                              training=False)
+  assert [tuple(l.shape[1:]) for l in layers[1:]] == sizes and sizes[-1] == (64, 80, 1)
+  # --- the product's host-side constants (no device work at import)
+  from advoc_b200 import melspecgan as MG
+  assert MG.Z_DIM == M.Z_DIM and np.float32(MG.BN_EPS) == np.float32(M.BN_EPS) and list(MG.G_BN) == list(M.G_BN)
