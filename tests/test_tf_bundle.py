@@ -25,6 +25,13 @@ def test_crc32c_known_answers():
   assert tf_bundle.crc32c(b'world', c) == tf_bundle.crc32c(b'hello world')
   assert tf_bundle.mask_crc(c) != c
   assert tf_bundle.mask_crc(0) == 0xa282ead8
+  # the chunk-parallel path (buffers >= 64 KB) against the byte loop, with an odd tail and a running value
+  rng = np.random.default_rng(3)
+  for n in (65536, 300001, 1 << 20):
+    buf = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+    for start in (0, 0x1234abcd):
+      assert tf_bundle.crc32c(buf, start) == tf_bundle._crc32c_bytes(buf, start ^ 0xffffffff) ^ 0xffffffff
+  assert tf_bundle.crc32c(b'123456789' * 10000) == tf_bundle.crc32c(b'123456789' * 5000, tf_bundle.crc32c(b'123456789' * 5000))
 
 
 def _advoc_like(rng, with_slots=True):
@@ -158,6 +165,18 @@ def test_checkpoint_loader_accepts_tf_prefix(tmp_path):
   assert abs(powers['beta1_power'] - 0.5 ** 7) < 1e-9 and 'beta2_power_1' in powers
   with pytest.raises(FileNotFoundError):
     checkpoint.load_params(str(tmp_path / 'missing'), device='cpu')
+  # save_params with a non-.npz path writes a TF prefix + the state file; extras keep their own names
+  import torch
+  d2 = tmp_path / 'out'
+  d2.mkdir()
+  slots = {k + '/Adam': torch.from_numpy(np.asarray(T[k + '/Adam'])) for k in P}
+  checkpoint.save_params(str(d2 / 'model.ckpt-9'), P, step=9, extra=slots)
+  assert sorted(os.listdir(str(d2))) == ['checkpoint', 'model.ckpt-9.data-00000-of-00001', 'model.ckpt-9.index']
+  Q, step = checkpoint.load_params(str(d2), device='cpu')
+  assert step == 9 and sorted(Q) == sorted(P)
+  assert all(torch.equal(Q[k], P[k]) for k in P)
+  back = tf_bundle.read_bundle(str(d2 / 'model.ckpt-9'), verify_data=True)
+  np.testing.assert_array_equal(back['generator/encoder_1/conv2d/bias/Adam'], T['generator/encoder_1/conv2d/bias/Adam'])
   # the .npz container still loads through the same entry point
   npz = str(tmp_path / 'p.npz')
   import torch
