@@ -61,6 +61,11 @@ struct alignas(64) P2dParams {
   unsigned char tap_cls[Q_MAXT];
   unsigned short tap_wrow[Q_MAXT];   // row block of the filter matrix
   unsigned short tap_shift[Q_MAXT];  // rows from the patch start
+  // lean issue loop (lean_issue): per tap, bits 0-15 = descriptor-field offset of the tap's window into the
+  // patch (tap_shift * 128 >> 4), bits 16-30 = TMEM column offset of its class (cls * BN), bit 31 = first
+  // tap of its class in issue order (that MMA overwrites the accumulator in the first K block)
+  unsigned int tap_word[Q_MAXT + 1];   // + 1: the loop reads one entry ahead
+  int lean_issue;
   int cls_ph[Q_MAXC], cls_pw[Q_MAXC];
   int PW, PH, th, tw;          // patch box and useful tile extent (positions)
   int tiles_h, tiles_w, n_ntiles;
@@ -347,7 +352,64 @@ __global__ void __launch_bounds__(Q_THREADS, 2) conv_p2d_kernel(const __grid_con
         }
         i = my_tiles;
       }
-      for (long t = blockIdx.x; t < ntl && !flat; t += gridDim.x, ++i) {
+      // ---- lean issue loop (ADVOC_P2D_LEAN_ISSUE=1; default off until it has been through the GPU suite).
+      // ncu's per-instruction stall samples of the loop below show ~8 uniform-datapath instructions per
+      // MMA, all scheduled in front of a burst of 16 MMAs that then stalls on the tensor queue ('mio'): the
+      // queue (6-8 MMAs deep) drains during the scalar phase.  Here the descriptors are 64-bit adds onto a
+      // per-slot base descriptor (patch rows and filter tiles are 16-byte-granular offsets inside the 14-bit
+      // address field, which cannot carry: shared memory ends below 2^18), the per-tap constants come as one
+      // host-packed word, and the tap loop is kept rolled so that each tap's few scalar instructions sit
+      // between its four MMAs and the next tap's.
+      if (p.lean_issue && !mma_only) {
+        for (long t = blockIdx.x; t < ntl; t += gridDim.x, ++i) {
+          const int buf = (int)(i % p.acc_bufs);
+          const uint32_t use = (uint32_t)(i / p.acc_bufs);
+          mbar_wait_p(&acc_empty[buf], (use & 1u) ^ 1u, p.dbg, 33u, p.prof, w_acc);
+          tc_fence_after();
+          const uint32_t d_base = tmem_base + (uint32_t)buf * acc_cols;
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            const uint32_t later_kb = kb != 0 ? 1u : 0u;
+            int tp = 0;
+            for (int pl = 0; pl < p.nplanes; ++pl) {
+              mbar_wait_p(&a_full[as], aph, p.dbg, 34u, p.prof, w_a);
+              const uint64_t a_desc = make_smem_desc(ring + (uint32_t)as * p.a_slot_bytes);
+              const int t_end = p.plane_tap0[pl + 1];
+              for (; tp < t_end; tp += G) {
+                uint64_t db;
+                if (p.b_resident) {
+                  const int slot = kb * ngroups + tp / G;
+                  if (i == 0) mbar_wait(&b_full[slot], 0u, p.dbg, 35u);
+                  db = make_smem_desc(ring + b_off + (uint32_t)slot * slot_bytes);
+                } else {
+                  mbar_wait_p(&b_full[bs], bph, p.dbg, 35u, p.prof, w_b);
+                  db = make_smem_desc(ring + b_off + (uint32_t)bs * slot_bytes);
+                }
+                uint32_t w = p.tap_word[tp];
+#pragma unroll 1
+                for (int u = 0; u < G; ++u) {
+                  const uint32_t w_next = p.tap_word[tp + u + 1];   // constant-bank latency off the critical path
+                  const uint64_t da = a_desc + (uint64_t)(w & 0xffffu);
+                  const uint32_t d_tmem = d_base + ((w >> 16) & 0x7fffu);
+                  const uint32_t acc0 = later_kb | ((w >> 31) ^ 1u);
+#pragma unroll
+                  for (int k = 0; k < QK / 8; ++k)
+                    umma_tf32(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, acc0 | (uint32_t)(k != 0));
+                  db += (uint64_t)(B_BYTES >> 4);
+                  w = w_next;
+                }
+                if (!p.b_resident) {
+                  umma_commit(&b_empty[bs]);
+                  if (++bs == p.b_stages) { bs = 0; bph ^= 1u; }
+                }
+              }
+              umma_commit(&a_empty[as]);
+              if (++as == p.a_stages) { as = 0; aph ^= 1u; }
+            }
+          }
+          umma_commit(&acc_full[buf]);
+        }
+      }
+      for (long t = blockIdx.x; t < ntl && !flat && !(p.lean_issue && !mma_only); t += gridDim.x, ++i) {
         const int buf = (int)(i % p.acc_bufs);
         const uint32_t use = (uint32_t)(i / p.acc_bufs);
         if (!mma_only) mbar_wait_p(&acc_empty[buf], (use & 1u) ^ 1u, p.dbg, 33u, p.prof, w_acc);
@@ -706,12 +768,23 @@ bool make_plan_budget(const advoc_conv_desc* d, bool transposed, int Wstored, in
   if (getenv("ADVOC_P2D_SHIFT8"))    // timing experiment only: shifts rounded down to whole 1 KB swizzle atoms
     for (int t = 0; t < k; ++t) p.tap_shift[t] &= ~7;
   p.nplanes = nplanes; p.ntaps = nt; p.ncls = ncls;
+  p.lean_issue = (getenv("ADVOC_P2D_LEAN_ISSUE") && atoi(getenv("ADVOC_P2D_LEAN_ISSUE"))) ? 1 : 0;
   const int Cn = transposed ? d->Cin : d->Cout, Ck = transposed ? d->Cout : d->Cin;
   if (Ck % QK != 0 || Cn % 32 != 0) return false;
   int bn = Cn % 256 == 0 ? 256 : (Cn % 128 == 0 ? 128 : (Cn % 64 == 0 ? 64 : 32));
   while (ncls * bn > max_tmem) bn >>= 1;
   if (bn < 32) return false;
   pl->bn = bn;
+  {
+    unsigned seen = 0;
+    for (int t = 0; t < nt; ++t) {
+      const unsigned cls = p.tap_cls[t];
+      const unsigned first = (seen >> cls) & 1u ? 0u : 1u;
+      seen |= 1u << cls;
+      p.tap_word[t] = ((unsigned)p.tap_shift[t] * 8u) | ((cls * (unsigned)bn) << 16) | (first << 31);
+    }
+    p.tap_word[nt] = 0;
+  }
   p.Cn = Cn; p.kblocks = Ck / QK;
   p.n_ntiles = Cn / bn;
   p.total_tiles = (long)d->N * best_tiles * p.n_ntiles;
