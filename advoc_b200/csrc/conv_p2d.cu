@@ -202,7 +202,9 @@ __device__ __forceinline__ TileCoord decode_tile(const P2dParams& p, long t) {
   return c;
 }
 
-template <int BN>
+// LEAN selects the issue loop of the MMA warp (see the comment there); it is a template parameter so that the
+// default instantiation's code is exactly the one that went through the GPU parity suite
+template <int BN, bool LEAN = false>
 __global__ void __launch_bounds__(Q_THREADS, 2) conv_p2d_kernel(const __grid_constant__ P2dParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[Q_MAXA], a_empty[Q_MAXA];
@@ -360,7 +362,7 @@ __global__ void __launch_bounds__(Q_THREADS, 2) conv_p2d_kernel(const __grid_con
       // address field, which cannot carry: shared memory ends below 2^18), the per-tap constants come as one
       // host-packed word, and the tap loop is kept rolled so that each tap's few scalar instructions sit
       // between its four MMAs and the next tap's.
-      if (p.lean_issue && !mma_only) {
+      if (LEAN && !mma_only) {
         for (long t = blockIdx.x; t < ntl; t += gridDim.x, ++i) {
           const int buf = (int)(i % p.acc_bufs);
           const uint32_t use = (uint32_t)(i / p.acc_bufs);
@@ -409,7 +411,7 @@ __global__ void __launch_bounds__(Q_THREADS, 2) conv_p2d_kernel(const __grid_con
           umma_commit(&acc_full[buf]);
         }
       }
-      for (long t = blockIdx.x; t < ntl && !flat && !(p.lean_issue && !mma_only); t += gridDim.x, ++i) {
+      for (long t = blockIdx.x; t < ntl && !flat && !(LEAN && !mma_only); t += gridDim.x, ++i) {
         const int buf = (int)(i % p.acc_bufs);
         const uint32_t use = (uint32_t)(i / p.acc_bufs);
         if (!mma_only) mbar_wait_p(&acc_empty[buf], (use & 1u) ^ 1u, p.dbg, 33u, p.prof, w_acc);
@@ -849,13 +851,18 @@ template <int BN>
 int launch_p2d(const Plan& pl, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    ADVOC_CHECK_CUDA(cudaFuncSetAttribute(conv_p2d_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    ADVOC_CHECK_CUDA(cudaFuncSetAttribute(conv_p2d_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)(Q_SMEM_MAX + 1024)));
+    ADVOC_CHECK_CUDA(cudaFuncSetAttribute(conv_p2d_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)(Q_SMEM_MAX + 1024)));
     configured = true;
   }
   const long slots = (long)sm_count() * pl.ctas_per_sm;
   long ctas = pl.p.total_tiles < slots ? pl.p.total_tiles : slots;
-  conv_p2d_kernel<BN><<<(unsigned)ctas, Q_THREADS, pl.smem, st>>>(pl.p);
+  if (pl.p.lean_issue)
+    conv_p2d_kernel<BN, true><<<(unsigned)ctas, Q_THREADS, pl.smem, st>>>(pl.p);
+  else
+    conv_p2d_kernel<BN, false><<<(unsigned)ctas, Q_THREADS, pl.smem, st>>>(pl.p);
   count_launch();
   ADVOC_CHECK_CUDA(cudaGetLastError());
   return ADVOC_OK;
