@@ -139,3 +139,26 @@ def test_generator_matches_the_reference_metagraph():
   # --- the product's host-side constants (no device work at import)
   from advoc_b200 import melspecgan as MG
   assert MG.Z_DIM == M.Z_DIM and np.float32(MG.BN_EPS) == np.float32(M.BN_EPS) and list(MG.G_BN) == list(M.G_BN)
+
+
+def test_graph_fixture_is_reproducible_from_the_reference():
+  """In the authoring container (reference checkout present) the committed fixture must be exactly what
+  scripts/make_melspecgan_graph_fixture.py extracts; on the GPU box there is no reference: skipped."""
+  import importlib.util
+  import json
+  import os
+  import pytest
+  src = '/root/reference/models/melspecgan/infer.meta'
+  if not os.path.isfile(src):
+    pytest.skip('reference checkout not present')
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  spec = importlib.util.spec_from_file_location('mkfix', os.path.join(root, 'scripts', 'make_melspecgan_graph_fixture.py'))
+  mod = importlib.util.module_from_spec(spec)
+  spec.loader.exec_module(mod)
+  import tempfile
+  with tempfile.TemporaryDirectory() as d:
+    mod.DST = os.path.join(d, 'out.json')
+    mod.main()
+    with open(mod.DST) as f:
+      fresh = json.load(f)
+  assert fresh == _graph_fixture()
