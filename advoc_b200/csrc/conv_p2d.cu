@@ -900,7 +900,12 @@ bool conv_p2d_eligible(const advoc_conv_desc* d, int ldx, int transposed, int st
   // 128-position tile); deep, filter-heavy layers stay on the per-tap kernel of conv_tc.cu.
   static const bool force = getenv("ADVOC_P2D_FORCE") != nullptr;
   if (force) return true;
-  return pl.p.total_tiles >= 3L * sm_count() && pl.filter_bytes_per_tile <= 512 * 1024;
+  // both thresholds can be swept without a rebuild (defaults = the measured rule above)
+  static const long max_filter_kb = getenv("ADVOC_P2D_MAX_FILTER_KB") ? atol(getenv("ADVOC_P2D_MAX_FILTER_KB")) : 512;
+  static const long min_tiles_per_sm =
+      getenv("ADVOC_P2D_MIN_TILES_PER_SM") ? atol(getenv("ADVOC_P2D_MIN_TILES_PER_SM")) : 3;
+  return pl.p.total_tiles >= min_tiles_per_sm * sm_count() &&
+         (long)pl.filter_bytes_per_tile <= max_filter_kb * 1024;
 }
 
 int conv_p2d(const advoc_conv_desc* d, int transposed, const float* x, int ldx, const float* w,

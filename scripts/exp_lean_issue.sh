@@ -28,3 +28,12 @@ except Exception as e:
 PY
   done
 done | tee gpurun_out/lean_summary.txt
+# 4. finer than FORCE: sweep the filter-bytes threshold of the routing rule with the lean loop on
+export ADVOC_P2D_LEAN_ISSUE=1
+unset ADVOC_P2D_FORCE
+for kb in 1024 2048 4096; do
+  ADVOC_P2D_MAX_FILTER_KB=$kb timeout 200 python bench.py --no-cpu-baseline > gpurun_out/lean_infer_kb$kb.json 2> gpurun_out/lean_infer_kb$kb.err
+  python -c "
+import json
+d=json.loads(open('gpurun_out/lean_infer_kb$kb.json').read().strip().splitlines()[-1]); print('max_filter_kb=$kb', d['value'], d['ms_per_step'])" | tee -a gpurun_out/lean_summary.txt
+done
