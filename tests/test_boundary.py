@@ -64,3 +64,43 @@ def test_struct_layouts_match_the_header():
   assert N.Epilogue.d_dropout_mask.offset == 64 and N.Epilogue.seed.offset == 80
   assert N.Epilogue.d_gate.offset == 96 and N.Epilogue.gate_scale1.offset == 124
   assert C.sizeof(N.Epilogue) == 128
+
+
+def _prototypes():
+  """{name: [C parameter type strings]} parsed from the header (comments stripped)."""
+  src = open(os.path.join(ROOT, 'include', 'advoc_b200.h')).read()
+  src = re.sub(r'/\*.*?\*/', ' ', src, flags=re.S)
+  out = {}
+  for name, args in re.findall(r'ADVOC_API\s+[\w\s\*]+?\b(advoc_\w+)\s*\(([^;]*?)\)\s*;', src, flags=re.S):
+    args = ' '.join(args.split())
+    params = [] if args in ('', 'void') else [a.strip() for a in args.split(',')]
+    out[name] = [re.sub(r'\s*\b\w+$', '', p).strip() if not p.endswith('*') else p for p in params]
+  return out
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+  """Every entry of _native.SIGNATURES has the header's parameter count, and each ctypes type is of the
+  header parameter's kind (pointer / long / int / float / size_t): a silent mismatch here would shift
+  every later argument of a call."""
+  protos = _prototypes()
+  assert sorted(protos) == sorted(N.SIGNATURES)
+  def kind_of_ctype(ct):
+    if ct in (C.c_void_p, C.c_char_p) or (isinstance(ct, type) and issubclass(ct, C._Pointer)):
+      return 'ptr'
+    if ct in (C.c_float, C.c_double):
+      return 'f%d' % (8 * C.sizeof(ct))
+    signed = ct(-1).value < 0
+    return '%s%d' % ('i' if signed else 'u', 8 * C.sizeof(ct))
+
+  def kind_of_c(t):
+    if '*' in t:
+      return 'ptr'
+    t = t.replace('const', '').strip()
+    return {'int': 'i32', 'long': 'i64', 'long long': 'i64', 'float': 'f32', 'double': 'f64', 'size_t': 'u64',
+            'unsigned int': 'u32', 'unsigned': 'u32', 'unsigned long long': 'u64', 'unsigned long': 'u64'}.get(t, t)
+
+  for name, (restype, argtypes) in N.SIGNATURES.items():
+    want = protos[name]
+    assert len(argtypes) == len(want), (name, len(argtypes), want)
+    for i, (ct, c_decl) in enumerate(zip(argtypes, want)):
+      assert kind_of_ctype(ct) == kind_of_c(c_decl), (name, i, ct, c_decl)
