@@ -775,6 +775,10 @@ bool make_plan_budget(const advoc_conv_desc* d, bool transposed, int Wstored, in
   if (Ck % QK != 0 || Cn % 32 != 0) return false;
   int bn = Cn % 256 == 0 ? 256 : (Cn % 128 == 0 ? 128 : (Cn % 64 == 0 ? 64 : 32));
   while (ncls * bn > max_tmem) bn >>= 1;
+  {  // experiment knob: narrower N tiles = more tiles and room for a second accumulator (default: no cap)
+    static const int max_bn = getenv("ADVOC_P2D_MAX_BN") ? atoi(getenv("ADVOC_P2D_MAX_BN")) : 256;
+    while (bn > max_bn && bn > 32) bn >>= 1;
+  }
   if (bn < 32) return false;
   pl->bn = bn;
   {

@@ -37,3 +37,11 @@ for kb in 1024 2048 4096; do
 import json
 d=json.loads(open('gpurun_out/lean_infer_kb$kb.json').read().strip().splitlines()[-1]); print('max_filter_kb=$kb', d['value'], d['ms_per_step'])" | tee -a gpurun_out/lean_summary.txt
 done
+
+# 5. deep layers on the patch kernel with narrower N tiles (more tiles, double-buffered accumulators)
+for bn in 64 128; do
+  ADVOC_P2D_FORCE=1 ADVOC_P2D_MAX_BN=$bn timeout 200 python bench.py --no-cpu-baseline > gpurun_out/lean_infer_bn$bn.json 2> gpurun_out/lean_infer_bn$bn.err
+  python -c "
+import json
+d=json.loads(open('gpurun_out/lean_infer_bn$bn.json').read().strip().splitlines()[-1]); print('force, max_bn=$bn', d['value'], d['ms_per_step'], {k: round(v['us']) for k, v in d['roofline']['by_layer'].items()})" | tee -a gpurun_out/lean_summary.txt
+done
