@@ -354,7 +354,8 @@ __global__ void __launch_bounds__(Q_THREADS, 2) conv_p2d_kernel(const __grid_con
         }
         i = my_tiles;
       }
-      // ---- lean issue loop (ADVOC_P2D_LEAN_ISSUE=1; default off until it has been through the GPU suite).
+      // ---- lean issue loop (ADVOC_P2D_LEAN_ISSUE=1; default off: forward parity verified on the GPU, backward
+      // suites and timing pending -- scripts/exp_lean_issue.sh).
       // ncu's per-instruction stall samples of the loop below show ~8 uniform-datapath instructions per
       // MMA, all scheduled in front of a burst of 16 MMAs that then stalls on the tensor queue ('mio'): the
       // queue (6-8 MMAs deep) drains during the scalar phase.  Here the descriptors are 64-bit adds onto a
