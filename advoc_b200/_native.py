@@ -13,7 +13,8 @@ LIB_PATH = os.path.join(_HERE, 'libadvoc_b200.so')
 
 OK, BAD_ARG, BAD_SHAPE, BAD_ALIGN, UNSUPPORTED, WORKSPACE_TOO_SMALL, CUDA_ERROR = range(7)
 ACT_NONE, ACT_LRELU, ACT_RELU, ACT_SIGMOID, ACT_TANH = range(5)
-MATH_AUTO, MATH_FP32, MATH_TF32 = range(3)
+MATH_AUTO, MATH_FP32, MATH_TF32, MATH_F16 = range(4)
+DT_F32, DT_F16 = range(2)
 
 
 class ConvDesc(C.Structure):
@@ -40,6 +41,8 @@ class Epilogue(C.Structure):
       ('d_gate', C.c_void_p), ('ld_gate', C.c_int), ('c_off_gate', C.c_int),
       ('gate_act', C.c_int), ('gate_split', C.c_int),
       ('gate_scale0', C.c_float), ('gate_scale1', C.c_float),
+      ('d_seed', C.c_void_p),
+      ('out0_dtype', C.c_int), ('out1_dtype', C.c_int),
   ]
 
 
@@ -62,6 +65,7 @@ SIGNATURES = {
     'advoc_conv2d_fwd': (_I, [C.POINTER(ConvDesc), _P, _I, _P, C.POINTER(Epilogue), _P]),
     'advoc_pack_filter': (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     'advoc_debug_flags': (_I, [C.POINTER(C.c_uint)]),
+    'advoc_debug_peek': (_I, [C.POINTER(C.c_uint)]),
     'advoc_istft_frames_f32': (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P]),
     'advoc_overlap_add_f32': (_I, [_P, _I, _I, _I, _I, _P, _P]),
     'advoc_griffin_lim_iter_f32': (_I, [_P, _L, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
@@ -73,6 +77,7 @@ SIGNATURES = {
     'advoc_adam_tf_step_dev': (_I, [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _P]),
     'advoc_conv2d_path': (_I, [C.POINTER(ConvDesc), _I, _I]),
     'advoc_conv2d_kernel': (_I, [C.POINTER(ConvDesc), _I, _I, _I]),
+    'advoc_conv2d_tile_n': (_I, [C.POINTER(ConvDesc), _I, _I, _I]),
     'advoc_gemm_f32': (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     'advoc_bn_stats': (_I, [_P, _I, _L, _I, _P, _P]),
     'advoc_bn_apply': (_I, [_P, _I, _L, _I, _P, _P, _P, _F, _I, _F, _P, _I, _I, _P]),
@@ -132,6 +137,17 @@ def debug_flags():
   v = C.c_uint(0)
   call('advoc_debug_flags', C.byref(v))
   return v.value
+
+
+def raise_if_aborted(where=''):
+  """Cheap check (pinned host word, no CUDA call) for the host engines' sync points: raises if a
+  tcgen05 pipeline wait timed out since the flag was last cleared -- every later tensor-core
+  launch then returned without writing its outputs."""
+  v = C.c_uint(0)
+  call('advoc_debug_peek', C.byref(v))
+  if v.value:
+    raise RuntimeError('advoc_b200: a tcgen05 pipeline wait timed out (code %d)%s; results since then are '
+                       'invalid -- clear with _native.debug_flags()' % (v.value, ' in ' + where if where else ''))
 
 
 def launch_count():

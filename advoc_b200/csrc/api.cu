@@ -2,12 +2,14 @@
 // No exception or abort crosses this boundary; see include/advoc_b200.h.
 #include "common.cuh"
 
+#include <cuda_fp16.h>
 #include <stdarg.h>
 #include <stddef.h>
 
 // the ctypes mirror in advoc_b200/_native.py relies on these layouts (tests/test_boundary.py)
 static_assert(sizeof(advoc_conv_desc) == 56, "advoc_conv_desc layout");
-static_assert(sizeof(advoc_epilogue) == 128 && offsetof(advoc_epilogue, d_gate) == 96 &&
+static_assert(sizeof(advoc_epilogue) == 144 && offsetof(advoc_epilogue, d_seed) == 128 &&
+                  offsetof(advoc_epilogue, out0_dtype) == 136 && offsetof(advoc_epilogue, d_gate) == 96 &&
                   offsetof(advoc_epilogue, gate_scale1) == 124 && offsetof(advoc_epilogue, d_out0) == 24 &&
                   offsetof(advoc_epilogue, d_out1) == 40 &&
                   offsetof(advoc_epilogue, d_dropout_mask) == 64 &&
@@ -66,17 +68,19 @@ int conv_transposed_simt(const advoc_conv_desc* d, const float* x, int ldx, cons
                          const advoc_epilogue* ep, void* stream);
 bool conv_fwd_tc_eligible(const advoc_conv_desc* d, int ldx);
 bool conv_transposed_tc_eligible(const advoc_conv_desc* d, int ldx);
-int conv_fwd_tc(const advoc_conv_desc* d, const float* x, int ldx, const float* w,
+int conv_fwd_tc(const advoc_conv_desc* d, const void* x, int ldx, const void* w,
                 const advoc_epilogue* ep, void* stream);
-int conv_transposed_tc(const advoc_conv_desc* d, const float* x, int ldx, const float* w,
+int conv_transposed_tc(const advoc_conv_desc* d, const void* x, int ldx, const void* w,
                        const advoc_epilogue* ep, void* stream);
 bool conv_p2d_eligible(const advoc_conv_desc* d, int ldx, int transposed, int store_w);
-int conv_p2d(const advoc_conv_desc* d, int transposed, const float* x, int ldx, const float* w,
+int conv_p2d(const advoc_conv_desc* d, int transposed, const void* x, int ldx, const void* w,
              const advoc_epilogue* ep, void* stream);
 bool tc_epilogue_ok(const advoc_epilogue* ep);
+int conv_tc_tile_n(const advoc_conv_desc* d, int transposed, int store_w);
+int conv_p2d_tile_n(const advoc_conv_desc* d, int transposed, int store_w);
 bool deconv_one_tc_geometry(const advoc_conv_desc* d, int ldx);
-bool deconv_one_tc_eligible(const advoc_conv_desc* d, const float* x, int ldx, const advoc_epilogue* ep);
-int deconv_one_tc(const advoc_conv_desc* d, const float* x, int ldx, const float* w, const advoc_epilogue* ep,
+bool deconv_one_tc_eligible(const advoc_conv_desc* d, const void* x, int ldx, const advoc_epilogue* ep);
+int deconv_one_tc(const advoc_conv_desc* d, const void* x, int ldx, const void* w, const advoc_epilogue* ep,
                   void* stream);
 
 }  // namespace advoc
@@ -108,24 +112,26 @@ extern "C" int advoc_device_arch(int* arch) {
   return ADVOC_OK;
 }
 
-static int check_conv_io(const advoc_conv_desc* d, const float* x, int ldx, int cx, const float* w,
+static int check_conv_io(const advoc_conv_desc* d, const void* x, int ldx, int cx, const void* w,
                          const advoc_epilogue* ep) {
   int st = check_conv_desc(d);
   if (st) return st;
   ADVOC_REQUIRE(x && w && ep, ADVOC_BAD_ARG, "NULL x/w/epilogue");
   ADVOC_REQUIRE(ldx >= cx, ADVOC_BAD_SHAPE, "ld_x %d smaller than the channel count %d", ldx, cx);
-  ADVOC_REQUIRE(d->math >= ADVOC_MATH_AUTO && d->math <= ADVOC_MATH_TF32, ADVOC_BAD_ARG,
+  ADVOC_REQUIRE(d->math >= ADVOC_MATH_AUTO && d->math <= ADVOC_MATH_F16, ADVOC_BAD_ARG,
                 "unknown math mode %d", d->math);
   return ADVOC_OK;
 }
 
-extern "C" int advoc_conv2d_fwd(const advoc_conv_desc* d, const float* d_x, int ld_x,
-                                const float* d_w, const advoc_epilogue* ep, void* stream) {
-  int st = check_conv_io(d, d_x, ld_x, d ? d->Cin : 0, d_w, ep);
+extern "C" int advoc_conv2d_fwd(const advoc_conv_desc* d, const void* d_xv, int ld_x,
+                                const void* d_wv, const advoc_epilogue* ep, void* stream) {
+  int st = check_conv_io(d, d_xv, ld_x, d ? d->Cin : 0, d_wv, ep);
   if (st) return st;
+  const float* d_x = static_cast<const float*>(d_xv);   // half data when math == ADVOC_MATH_F16: only the
+  const float* d_w = static_cast<const float*>(d_wv);   // tcgen05 kernels below ever see those pointers
   if (d->math == ADVOC_MATH_FP32) return conv_fwd_simt(d, d_x, ld_x, d_w, ep, stream);
   const bool ok = conv_fwd_tc_eligible(d, ld_x);
-  if (d->math == ADVOC_MATH_TF32 || ok) {
+  if (d->math == ADVOC_MATH_TF32 || d->math == ADVOC_MATH_F16 || ok) {
     ADVOC_REQUIRE(ok, ADVOC_UNSUPPORTED, "conv shape not eligible for the tcgen05 path");
     if (conv_p2d_eligible(d, ld_x, 0, 0)) {
       ADVOC_REQUIRE(aligned16(d_x) && aligned16(d_w), ADVOC_BAD_ALIGN, "x / w must be 16-byte aligned");
@@ -138,15 +144,17 @@ extern "C" int advoc_conv2d_fwd(const advoc_conv_desc* d, const float* d_x, int 
   return conv_fwd_simt(d, d_x, ld_x, d_w, ep, stream);
 }
 
-extern "C" int advoc_conv2d_transpose_fwd(const advoc_conv_desc* d, const float* d_x, int ld_x,
-                                          const float* d_w, const advoc_epilogue* ep,
+extern "C" int advoc_conv2d_transpose_fwd(const advoc_conv_desc* d, const void* d_xv, int ld_x,
+                                          const void* d_wv, const advoc_epilogue* ep,
                                           void* stream) {
-  int st = check_conv_io(d, d_x, ld_x, d ? d->Cout : 0, d_w, ep);
+  int st = check_conv_io(d, d_xv, ld_x, d ? d->Cout : 0, d_wv, ep);
   if (st) return st;
+  const float* d_x = static_cast<const float*>(d_xv);
+  const float* d_w = static_cast<const float*>(d_wv);
   if (d->math == ADVOC_MATH_FP32) return conv_transposed_simt(d, d_x, ld_x, d_w, ep, stream);
   if (deconv_one_tc_eligible(d, d_x, ld_x, ep)) return deconv_one_tc(d, d_x, ld_x, d_w, ep, stream);
   const bool ok = conv_transposed_tc_eligible(d, ld_x);
-  if (d->math == ADVOC_MATH_TF32 || ok) {
+  if (d->math == ADVOC_MATH_TF32 || d->math == ADVOC_MATH_F16 || ok) {
     ADVOC_REQUIRE(ok, ADVOC_UNSUPPORTED, "conv_transpose shape not eligible for the tcgen05 path");
     if (conv_p2d_eligible(d, ld_x, 1, ep->store_w)) {
       ADVOC_REQUIRE(aligned16(d_x) && aligned16(d_w), ADVOC_BAD_ALIGN, "x / w must be 16-byte aligned");
@@ -161,15 +169,25 @@ extern "C" int advoc_conv2d_transpose_fwd(const advoc_conv_desc* d, const float*
 
 extern "C" int advoc_conv2d_path(const advoc_conv_desc* d, int ld_x, int transposed) {
   if (!d || d->math == ADVOC_MATH_FP32) return ADVOC_MATH_FP32;
-  if (transposed && deconv_one_tc_geometry(d, ld_x)) return ADVOC_MATH_TF32;
+  const int tensor = d->math == ADVOC_MATH_F16 ? ADVOC_MATH_F16 : ADVOC_MATH_TF32;
+  if (transposed && deconv_one_tc_geometry(d, ld_x)) return tensor;
   const bool ok = transposed ? conv_transposed_tc_eligible(d, ld_x) : conv_fwd_tc_eligible(d, ld_x);
-  return ok ? ADVOC_MATH_TF32 : ADVOC_MATH_FP32;
+  return ok ? tensor : ADVOC_MATH_FP32;
 }
 
 extern "C" int advoc_conv2d_kernel(const advoc_conv_desc* d, int ld_x, int transposed, int store_w) {
-  if (advoc_conv2d_path(d, ld_x, transposed) != ADVOC_MATH_TF32) return 0;
+  if (advoc_conv2d_path(d, ld_x, transposed) == ADVOC_MATH_FP32) return 0;
   if (transposed && deconv_one_tc_geometry(d, ld_x)) return 3;
   return conv_p2d_eligible(d, ld_x, transposed, store_w) ? 2 : 1;
+}
+
+extern "C" int advoc_conv2d_tile_n(const advoc_conv_desc* d, int ld_x, int transposed, int store_w) {
+  switch (advoc_conv2d_kernel(d, ld_x, transposed, store_w)) {
+    case 1: return conv_tc_tile_n(d, transposed, store_w);
+    case 2: return conv_p2d_tile_n(d, transposed, store_w);
+    case 3: return 16;
+    default: return 0;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -177,7 +195,7 @@ extern "C" int advoc_conv2d_kernel(const advoc_conv_desc* d, int ld_x, int trans
 // ---------------------------------------------------------------------------------------------
 namespace {
 __global__ void pack_filter_kernel(const float* __restrict__ in, float* __restrict__ out, int taps,
-                                   int A, int B, int transpose, int round) {
+                                   int A, int B, int transpose, int mode) {
   const long total = (long)taps * A * B;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long)gridDim.x * blockDim.x) {
@@ -191,20 +209,25 @@ __global__ void pack_filter_kernel(const float* __restrict__ in, float* __restri
       src = (t * A + a) * B + b;
     }
     float v = __ldg(in + src);
-    if (round) v = advoc::round_tf32(v);
-    out[i] = v;
+    if (mode == 2) {
+      reinterpret_cast<__half*>(out)[i] = __float2half_rn(v);
+    } else {
+      if (mode == 1) v = advoc::round_tf32(v);
+      out[i] = v;
+    }
   }
 }
 }  // namespace
 
-extern "C" int advoc_pack_filter(const float* d_w, float* d_packed, int taps, int A, int B,
-                                 int transpose, int round_tf32, void* stream) {
+extern "C" int advoc_pack_filter(const float* d_w, void* d_packed, int taps, int A, int B,
+                                 int transpose, int mode, void* stream) {
   ADVOC_REQUIRE(d_w && d_packed, ADVOC_BAD_ARG, "NULL filter pointer");
+  ADVOC_REQUIRE(mode >= 0 && mode <= 2, ADVOC_BAD_ARG, "mode must be 0 (copy), 1 (tf32) or 2 (fp16)");
   ADVOC_REQUIRE(taps > 0 && A > 0 && B > 0, ADVOC_BAD_SHAPE, "bad filter shape");
   const long total = (long)taps * A * B;
   const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
   pack_filter_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      d_w, d_packed, taps, A, B, transpose, round_tf32);
+      d_w, static_cast<float*>(d_packed), taps, A, B, transpose, mode);
   count_launch();
   ADVOC_CHECK_CUDA(cudaGetLastError());
   return ADVOC_OK;

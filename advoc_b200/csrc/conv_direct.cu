@@ -197,15 +197,21 @@ __global__ void __launch_bounds__(128) conv_thin_px_kernel(const ThinArgs<CIN> a
       const long gp = pix0 + p;
       if (gp >= npix) continue;
       const float4 v = stage[p * Q + (j ^ (p & 7))];
-      float4 y = make_float4(v.x > 0.f ? v.x : s0 * v.x, v.y > 0.f ? v.y : s0 * v.y,
-                             v.z > 0.f ? v.z : s0 * v.z, v.w > 0.f ? v.w : s0 * v.w);
-      if (e.round) y = make_float4(round_tf32(y.x), round_tf32(y.y), round_tf32(y.z), round_tf32(y.w));
-      reinterpret_cast<float4*>(e.out0 + (size_t)gp * e.ld0 + e.coff0)[j] = y;
+      float y[4] = {v.x > 0.f ? v.x : s0 * v.x, v.y > 0.f ? v.y : s0 * v.y,
+                    v.z > 0.f ? v.z : s0 * v.z, v.w > 0.f ? v.w : s0 * v.w};
+      if (e.round && !e.h0) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) y[u] = round_tf32(y[u]);
+      }
+      store4(e.out0, e.h0, (size_t)gp * e.ld0 + e.coff0 + 4 * j, y);   // fp32 or fp16 destination
       if (e.out1) {
-        float4 z = make_float4(v.x > 0.f ? v.x : s1 * v.x, v.y > 0.f ? v.y : s1 * v.y,
-                               v.z > 0.f ? v.z : s1 * v.z, v.w > 0.f ? v.w : s1 * v.w);
-        if (e.round) z = make_float4(round_tf32(z.x), round_tf32(z.y), round_tf32(z.z), round_tf32(z.w));
-        reinterpret_cast<float4*>(e.out1 + (size_t)gp * e.ld1 + e.coff1)[j] = z;
+        float z[4] = {v.x > 0.f ? v.x : s1 * v.x, v.y > 0.f ? v.y : s1 * v.y,
+                      v.z > 0.f ? v.z : s1 * v.z, v.w > 0.f ? v.w : s1 * v.w};
+        if (e.round && !e.h1) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) z[u] = round_tf32(z[u]);
+        }
+        store4(e.out1, e.h1, (size_t)gp * e.ld1 + e.coff1 + 4 * j, z);
       }
     }
   }
@@ -341,6 +347,7 @@ int conv_thin(const advoc_conv_desc* d, const float* x, int ldx, const float* w,
     ADVOC_CHECK_CUDA(cudaGetLastError());
     return ADVOC_OK;
   }
+  ADVOC_REQUIRE(!e.h0 && !e.h1, ADVOC_UNSUPPORTED, "fp16 destinations need the plain 32/64-channel thin conv");
   const int ppb = 256 / (d->Cout / 4);
   const long want = (npix + ppb - 1) / ppb;
   const int blocks = (int)(want < (long)sm_count() * 32 ? want : (long)sm_count() * 32);
@@ -370,6 +377,7 @@ int deconv_from_one(const advoc_conv_desc* d, const float* x, int ldx, const flo
   EpiDev e;
   int st = lower_epilogue(ep, d->H, d->W, d->Cin, &e);
   if (st) return st;
+  ADVOC_REQUIRE(!e.h0, ADVOC_UNSUPPORTED, "fp16 destination not supported by the from-one-channel kernel");
   const long npix = (long)d->N * d->H * d->W;
   if (npix == 0) return ADVOC_OK;
   const int ppb = 256 / (d->Cin / 4);

@@ -28,6 +28,9 @@
 
 #include <stdlib.h>
 
+#include <mutex>
+#include <vector>
+
 namespace advoc {
 
 int lower_epilogue(const advoc_epilogue* ep, int Hs, int Wfull, int Cout, EpiDev* out);
@@ -37,7 +40,7 @@ namespace {
 using namespace tc;
 
 constexpr int QM = 128;         // UMMA_M: patch positions per tile
-constexpr int QK = 32;          // channels per k-block (one 128-byte swizzle row)
+inline int qk_of(int half) { return half ? 64 : 32; }   // channels per k-block (one 128-byte swizzle row)
 constexpr int Q_MAXT = 36;      // filter taps
 constexpr int Q_MAXP = 4;       // input planes
 constexpr int Q_MAXC = 4;       // output parity classes
@@ -53,6 +56,7 @@ struct alignas(64) P2dParams {
   CUtensorMap tmO[2][Q_MAXC];  // output stores per destination and parity class, box {32, tw, th, 1}
   CUtensorMap tmG[Q_MAXC];     // backward pass: the activation whose derivative gates the output, same boxes
   int tma_store, n_out, stage_bufs;
+  int out_half;                // staged stores write fp16 (both destinations)
   int use_gate, reduce_add;    // gate tiles come in by TMA; accumulate = TMA reduce-add store
   uint32_t stage_off, gate_off;
   int nplanes, ntaps, ncls;
@@ -65,7 +69,6 @@ struct alignas(64) P2dParams {
   // patch (tap_shift * 128 >> 4), bits 16-30 = TMEM column offset of its class (cls * BN), bit 31 = first
   // tap of its class in issue order (that MMA overwrites the accumulator in the first K block)
   unsigned int tap_word[Q_MAXT + 1];   // + 1: the loop reads one entry ahead
-  int lean_issue;
   int cls_ph[Q_MAXC], cls_pw[Q_MAXC];
   int PW, PH, th, tw;          // patch box and useful tile extent (positions)
   int tiles_h, tiles_w, n_ntiles;
@@ -75,7 +78,6 @@ struct alignas(64) P2dParams {
   int Cn, kblocks;
   uint32_t a_slot_bytes, a_box_bytes, tmem_cols;
   int a_stages, b_stages, acc_bufs, b_resident;
-  int exp_flags;               // timing experiments (ADVOC_P2D_EXP): 1 skip staging stores, 2 skip epilogue math
   int G;                       // filter taps per ring slot (one barrier pair per group; divides every plane's tap count)
   EpiDev epi;
   unsigned int* dbg;
@@ -149,7 +151,7 @@ __device__ __forceinline__ void stage_chunk_gated(const EpiDev& e, const uint32_
 
 template <bool kLin, bool kDrop>
 __device__ __forceinline__ void stage_chunk(const EpiDev& e, const uint32_t (&v)[32], const float4 (&bias4)[8],
-                                            uint32_t dst_row, uint32_t sx, int n_out, size_t idx0) {
+                                            uint32_t dst_row, uint32_t sx, int n_out, size_t idx0, uint64_t seed) {
   const ActLin a0 = act_linear(e.act0, e.alpha), a1 = act_linear(e.act1, e.alpha);
   const float inv_keep = 1.f / e.keep_prob;
 #pragma unroll
@@ -161,7 +163,7 @@ __device__ __forceinline__ void stage_chunk(const EpiDev& e, const uint32_t (&v)
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const size_t idx = idx0 + 4 * j + u;
-        const bool keep = e.mask ? (__ldg(e.mask + idx) != 0) : dropout_keep(e.seed, idx, e.keep_prob);
+        const bool keep = e.mask ? (__ldg(e.mask + idx) != 0) : dropout_keep(seed, idx, e.keep_prob);
         sc[u] = keep ? inv_keep : 0.f;
       }
     }
@@ -184,6 +186,51 @@ __device__ __forceinline__ void stage_chunk(const EpiDev& e, const uint32_t (&v)
   }
 }
 
+// fp16 destinations: the same 32 accumulator columns become four 16-byte pieces (8 halves each) at
+// pieces piece0 .. piece0 + 3 of the staging row (piece index XOR sx = the store map's swizzle).
+__device__ __forceinline__ void st_shared_v4u(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+template <bool kLin, bool kDrop>
+__device__ __forceinline__ void stage_chunk_h(const EpiDev& e, const uint32_t (&v)[32], const float4 (&bias4)[8],
+                                              uint32_t dst_row, uint32_t sx, uint32_t piece0, int n_out, size_t idx0,
+                                              uint64_t seed) {
+  const ActLin a0 = act_linear(e.act0, e.alpha), a1 = act_linear(e.act1, e.alpha);
+  const float inv_keep = 1.f / e.keep_prob;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float x[8], sc[8];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float4 b4 = bias4[2 * j + h];
+      x[4 * h] = __uint_as_float(v[8 * j + 4 * h]) + b4.x;
+      x[4 * h + 1] = __uint_as_float(v[8 * j + 4 * h + 1]) + b4.y;
+      x[4 * h + 2] = __uint_as_float(v[8 * j + 4 * h + 2]) + b4.z;
+      x[4 * h + 3] = __uint_as_float(v[8 * j + 4 * h + 3]) + b4.w;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      sc[u] = 1.f;
+      if (kDrop) {
+        const size_t idx = idx0 + 8 * j + u;
+        const bool keep = e.mask ? (__ldg(e.mask + idx) != 0) : dropout_keep(seed, idx, e.keep_prob);
+        sc[u] = keep ? inv_keep : 0.f;
+      }
+    }
+    float y[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) y[u] = (kLin ? apply_lin(x[u], a0) : apply_act(x[u], e.act0, e.alpha)) * sc[u];
+    const uint32_t dst = dst_row + (((piece0 + (uint32_t)j) ^ sx) << 4);
+    st_shared_v4u(dst, pack_half2(y[0], y[1]), pack_half2(y[2], y[3]), pack_half2(y[4], y[5]), pack_half2(y[6], y[7]));
+    if (n_out == 2) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) y[u] = (kLin ? apply_lin(x[u], a1) : apply_act(x[u], e.act1, e.alpha)) * sc[u];
+      st_shared_v4u(dst + Q_STAGE_BYTES, pack_half2(y[0], y[1]), pack_half2(y[2], y[3]), pack_half2(y[4], y[5]),
+                    pack_half2(y[6], y[7]));
+    }
+  }
+}
+
 struct TileCoord {
   int n_tile, img, h0, w0;
 };
@@ -202,10 +249,11 @@ __device__ __forceinline__ TileCoord decode_tile(const P2dParams& p, long t) {
   return c;
 }
 
-// LEAN selects the issue loop of the MMA warp (see the comment there); it is a template parameter so that the
-// default instantiation's code is exactly the one that went through the GPU parity suite
-template <int BN, bool LEAN = false>
+// HALF: fp16 operands (tcgen05 kind::f16, 64 channels per 128-byte patch / filter row) instead of tf32
+// (32 channels per row); every byte offset, descriptor and barrier of the pipeline is the same.
+template <int BN, bool HALF>
 __global__ void __launch_bounds__(Q_THREADS, 2) conv_p2d_kernel(const __grid_constant__ P2dParams p) {
+  constexpr int KCH = HALF ? 64 : 32;   // channels per k-block
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[Q_MAXA], a_empty[Q_MAXA];
   __shared__ __align__(8) uint64_t b_full[Q_MAXB], b_empty[Q_MAXB];
@@ -219,9 +267,6 @@ __global__ void __launch_bounds__(Q_THREADS, 2) conv_p2d_kernel(const __grid_con
   constexpr uint32_t B_BYTES = BN * 128;
   const uint32_t acc_cols = (uint32_t)p.ncls * BN;
   const long ntl = p.total_tiles;
-  __shared__ uint32_t s_tap[Q_MAXT];   // (cls << 24) | byte offset of the tap's view into the patch
-  if (threadIdx.x < p.ntaps)
-    s_tap[threadIdx.x] = ((uint32_t)p.tap_cls[threadIdx.x] << 24) | ((uint32_t)p.tap_shift[threadIdx.x] * 128u);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.a_stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
@@ -246,11 +291,8 @@ __global__ void __launch_bounds__(Q_THREADS, 2) conv_p2d_kernel(const __grid_con
   const uint32_t tmem_base = tmem_base_holder;
   const bool aborted = p.dbg && *reinterpret_cast<volatile unsigned int*>(p.dbg) != 0;
 
-  // timing experiments (ADVOC_P2D_EXP): 32 = bare MMA stream (no barriers, other roles idle),
-  // 32 + 512 = the same number of MMAs issued from a flat loop with loop-invariant descriptors
-  const bool mma_only = (p.exp_flags & 32) != 0;
-  if (aborted || (mma_only && warp != 1)) {
-    // a previous launch timed out (or the experiment idles this role): do nothing
+  if (aborted) {
+    // a previous launch timed out: do nothing (the host raises at its next sync point)
   } else if (warp == 0) {
     // ===== patch producer: warp-uniform loop, TMA issued by one elected lane =====
     int as = 0;
@@ -264,13 +306,9 @@ __global__ void __launch_bounds__(Q_THREADS, 2) conv_p2d_kernel(const __grid_con
           mbar_wait_p(&a_empty[as], aph ^ 1u, p.dbg, 31u, p.prof, w_a);
           __syncwarp();
           if (elect_one()) {
-            if (p.exp_flags & 4) {
-              mbar_arrive(&a_full[as]);
-            } else {
-              mbar_expect_tx(&a_full[as], p.a_box_bytes);
-              tma_load_4d(&p.tmA[pl], &a_full[as], ring_ptr + (size_t)as * p.a_slot_bytes, kb * QK,
-                          tc_.w0 + p.plane_ow[pl], tc_.h0 + p.plane_oh[pl], tc_.img);
-            }
+            mbar_expect_tx(&a_full[as], p.a_box_bytes);
+            tma_load_4d(&p.tmA[pl], &a_full[as], ring_ptr + (size_t)as * p.a_slot_bytes, kb * KCH,
+                        tc_.w0 + p.plane_ow[pl], tc_.h0 + p.plane_oh[pl], tc_.img);
           }
           __syncwarp();
           if (++as == p.a_stages) { as = 0; aph ^= 1u; }
@@ -294,7 +332,7 @@ __global__ void __launch_bounds__(Q_THREADS, 2) conv_p2d_kernel(const __grid_con
           if (lane == 0) mbar_expect_tx(&b_full[s], slot_bytes);
           __syncwarp();
           if (lane < G)
-            tma_load_2d(&p.tmB, &b_full[s], ring_ptr + b_off + (size_t)s * slot_bytes + (size_t)lane * B_BYTES, kb * QK,
+            tma_load_2d(&p.tmB, &b_full[s], ring_ptr + b_off + (size_t)s * slot_bytes + (size_t)lane * B_BYTES, kb * KCH,
                         (int)p.tap_wrow[g * G + lane] * p.Cn);
         }
       }
@@ -308,15 +346,11 @@ __global__ void __launch_bounds__(Q_THREADS, 2) conv_p2d_kernel(const __grid_con
         for (int kb = 0; kb < p.kblocks; ++kb) {
           for (int t0 = 0; t0 < p.ntaps; t0 += G) {
             mbar_wait_p(&b_empty[bs], bph ^ 1u, p.dbg, 32u, p.prof, w_b);
-            if (p.exp_flags & 4) {
-              if (lane == 0) mbar_arrive(&b_full[bs]);
-            } else {
-              if (lane == 0) mbar_expect_tx(&b_full[bs], slot_bytes);
-              __syncwarp();
-              if (lane < G)
-                tma_load_2d(&p.tmB, &b_full[bs], ring_ptr + b_off + (size_t)bs * slot_bytes + (size_t)lane * B_BYTES,
-                            kb * QK, (int)p.tap_wrow[t0 + lane] * p.Cn + n0);
-            }
+            if (lane == 0) mbar_expect_tx(&b_full[bs], slot_bytes);
+            __syncwarp();
+            if (lane < G)
+              tma_load_2d(&p.tmB, &b_full[bs], ring_ptr + b_off + (size_t)bs * slot_bytes + (size_t)lane * B_BYTES,
+                          kb * KCH, (int)p.tap_wrow[t0 + lane] * p.Cn + n0);
             __syncwarp();
             if (++bs == p.b_stages) { bs = 0; bph ^= 1u; }
           }
@@ -330,10 +364,15 @@ __global__ void __launch_bounds__(Q_THREADS, 2) conv_p2d_kernel(const __grid_con
   } else if (warp == 1) {
     // ===== MMA issuer: the whole loop runs inside ONE elect.sync region -- a single thread waits and
     // issues, and because the region is entered through elect.sync the compiler keeps the descriptors
-    // in uniform registers (no per-instruction ELECT/BRA.U.ANY wrapper, no warp-wide polling) =====
+    // in uniform registers (no per-instruction ELECT/BRA.U.ANY wrapper, no warp-wide polling).
+    // The loop is the "lean" one of round 1 (profiles/r01c_mma_issue_stall_samples.txt; r02: +5 % on the
+    // forward, all parity suites green): descriptors are 64-bit adds onto a per-slot base descriptor
+    // (patch rows and filter tiles are 16-byte-granular offsets inside the 14-bit address field, which
+    // cannot carry: shared memory ends below 2^18), the per-tap constants come as one host-packed word,
+    // and the tap loop is kept rolled so that each tap's few scalar instructions sit between its four
+    // MMAs and the next tap's. =====
     if (elect_one()) {
-      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
-                                 ((uint32_t)(QM >> 4) << 24);
+      constexpr uint32_t idesc = umma_idesc<HALF>(QM, BN);
       const int G = p.G;
       const uint32_t slot_bytes = (uint32_t)G * B_BYTES;
       const int ngroups = p.ntaps / G;
@@ -342,128 +381,54 @@ __global__ void __launch_bounds__(Q_THREADS, 2) conv_p2d_kernel(const __grid_con
       long i = 0;
       unsigned long long w_acc = 0, w_a = 0, w_b = 0;
       const long long t_start = clock64();
-      const bool flat = mma_only && (p.exp_flags & 512);
-      if (flat) {
-        long my_tiles = ((long)blockIdx.x < ntl) ? (ntl - 1 - blockIdx.x) / gridDim.x + 1 : 0;
-        const long total = my_tiles * p.kblocks * p.ntaps * 4;
-        const uint64_t da = make_smem_desc(ring), db = make_smem_desc(ring + b_off);
-        for (long q = 0; q < total; q += 4) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_tf32(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (q | k) ? 1u : 0u);
-        }
-        i = my_tiles;
-      }
-      // ---- lean issue loop (ADVOC_P2D_LEAN_ISSUE=1; default off: forward parity verified on the GPU, backward
-      // suites and timing pending -- scripts/exp_lean_issue.sh).
-      // ncu's per-instruction stall samples of the loop below show ~8 uniform-datapath instructions per
-      // MMA, all scheduled in front of a burst of 16 MMAs that then stalls on the tensor queue ('mio'): the
-      // queue (6-8 MMAs deep) drains during the scalar phase.  Here the descriptors are 64-bit adds onto a
-      // per-slot base descriptor (patch rows and filter tiles are 16-byte-granular offsets inside the 14-bit
-      // address field, which cannot carry: shared memory ends below 2^18), the per-tap constants come as one
-      // host-packed word, and the tap loop is kept rolled so that each tap's few scalar instructions sit
-      // between its four MMAs and the next tap's.
-      if (LEAN && !mma_only) {
-        for (long t = blockIdx.x; t < ntl; t += gridDim.x, ++i) {
-          const int buf = (int)(i % p.acc_bufs);
-          const uint32_t use = (uint32_t)(i / p.acc_bufs);
-          mbar_wait_p(&acc_empty[buf], (use & 1u) ^ 1u, p.dbg, 33u, p.prof, w_acc);
-          tc_fence_after();
-          const uint32_t d_base = tmem_base + (uint32_t)buf * acc_cols;
-          for (int kb = 0; kb < p.kblocks; ++kb) {
-            const uint32_t later_kb = kb != 0 ? 1u : 0u;
-            int tp = 0;
-            for (int pl = 0; pl < p.nplanes; ++pl) {
-              mbar_wait_p(&a_full[as], aph, p.dbg, 34u, p.prof, w_a);
-              const uint64_t a_desc = make_smem_desc(ring + (uint32_t)as * p.a_slot_bytes);
-              const int t_end = p.plane_tap0[pl + 1];
-              for (; tp < t_end; tp += G) {
-                uint64_t db;
-                if (p.b_resident) {
-                  const int slot = kb * ngroups + tp / G;
-                  if (i == 0) mbar_wait(&b_full[slot], 0u, p.dbg, 35u);
-                  db = make_smem_desc(ring + b_off + (uint32_t)slot * slot_bytes);
-                } else {
-                  mbar_wait_p(&b_full[bs], bph, p.dbg, 35u, p.prof, w_b);
-                  db = make_smem_desc(ring + b_off + (uint32_t)bs * slot_bytes);
-                }
-                uint32_t w = p.tap_word[tp];
-#pragma unroll 1
-                for (int u = 0; u < G; ++u) {
-                  const uint32_t w_next = p.tap_word[tp + u + 1];   // constant-bank latency off the critical path
-                  const uint64_t da = a_desc + (uint64_t)(w & 0xffffu);
-                  const uint32_t d_tmem = d_base + ((w >> 16) & 0x7fffu);
-                  const uint32_t acc0 = later_kb | ((w >> 31) ^ 1u);
-#pragma unroll
-                  for (int k = 0; k < QK / 8; ++k)
-                    umma_tf32(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, acc0 | (uint32_t)(k != 0));
-                  db += (uint64_t)(B_BYTES >> 4);
-                  w = w_next;
-                }
-                if (!p.b_resident) {
-                  umma_commit(&b_empty[bs]);
-                  if (++bs == p.b_stages) { bs = 0; bph ^= 1u; }
-                }
-              }
-              umma_commit(&a_empty[as]);
-              if (++as == p.a_stages) { as = 0; aph ^= 1u; }
-            }
-          }
-          umma_commit(&acc_full[buf]);
-        }
-      }
-      for (long t = blockIdx.x; t < ntl && !flat && !(LEAN && !mma_only); t += gridDim.x, ++i) {
+      for (long t = blockIdx.x; t < ntl; t += gridDim.x, ++i) {
         const int buf = (int)(i % p.acc_bufs);
         const uint32_t use = (uint32_t)(i / p.acc_bufs);
-        if (!mma_only) mbar_wait_p(&acc_empty[buf], (use & 1u) ^ 1u, p.dbg, 33u, p.prof, w_acc);
+        mbar_wait_p(&acc_empty[buf], (use & 1u) ^ 1u, p.dbg, 33u, p.prof, w_acc);
         tc_fence_after();
         const uint32_t d_base = tmem_base + (uint32_t)buf * acc_cols;
-        uint32_t started = 0;
         for (int kb = 0; kb < p.kblocks; ++kb) {
+          const uint32_t later_kb = kb != 0 ? 1u : 0u;
           int tp = 0;
           for (int pl = 0; pl < p.nplanes; ++pl) {
-            if (!mma_only) mbar_wait_p(&a_full[as], aph, p.dbg, 34u, p.prof, w_a);
-            const uint32_t a_addr = ring + (uint32_t)as * p.a_slot_bytes;
+            mbar_wait_p(&a_full[as], aph, p.dbg, 34u, p.prof, w_a);
+            const uint64_t a_desc = make_smem_desc(ring + (uint32_t)as * p.a_slot_bytes);
             const int t_end = p.plane_tap0[pl + 1];
             for (; tp < t_end; tp += G) {
-              uint32_t b_addr;
+              uint64_t db;
               if (p.b_resident) {
                 const int slot = kb * ngroups + tp / G;
-                if (i == 0 && !mma_only) mbar_wait(&b_full[slot], 0u, p.dbg, 35u);
-                b_addr = ring + b_off + (uint32_t)slot * slot_bytes;
+                if (i == 0) mbar_wait(&b_full[slot], 0u, p.dbg, 35u);
+                db = make_smem_desc(ring + b_off + (uint32_t)slot * slot_bytes);
               } else {
-                if (!mma_only) mbar_wait_p(&b_full[bs], bph, p.dbg, 35u, p.prof, w_b);
-                b_addr = ring + b_off + (uint32_t)bs * slot_bytes;
+                mbar_wait_p(&b_full[bs], bph, p.dbg, 35u, p.prof, w_b);
+                db = make_smem_desc(ring + b_off + (uint32_t)bs * slot_bytes);
               }
               // no tcgen05.fence here: the operands were written by TMA (async proxy) and their
               // arrival is ordered by the mbarrier; the fence is only needed for the TMEM hand-off above
+              uint32_t w = p.tap_word[tp];
+#pragma unroll 1
               for (int u = 0; u < G; ++u) {
-                // tap tables come straight from the kernel parameters (constant bank, uniform index), so
-                // the whole descriptor chain stays on the uniform datapath: no LDS -> R2UR round trips
-                const uint32_t cls = p.tap_cls[tp + u];
-                const uint64_t da = make_smem_desc(a_addr + (uint32_t)p.tap_shift[tp + u] * 128u);
-                const uint64_t db = make_smem_desc(b_addr + (uint32_t)u * B_BYTES);
-                const uint32_t d_tmem = d_base + cls * BN;
-                const uint32_t acc0 = (started >> cls) & 1u;
-                started |= 1u << cls;
+                const uint32_t w_next = p.tap_word[tp + u + 1];   // constant-bank latency off the critical path
+                const uint64_t da = a_desc + (uint64_t)(w & 0xffffu);
+                const uint32_t d_tmem = d_base + ((w >> 16) & 0x7fffu);
+                const uint32_t acc0 = later_kb | ((w >> 31) ^ 1u);
 #pragma unroll
-                for (int k = 0; k < QK / 8; ++k)
-                  umma_tf32(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, acc0 | (uint32_t)(k != 0));
+                for (int k = 0; k < 4; ++k)   // four 32-byte K steps per 128-byte row (8 tf32 / 16 fp16 channels each)
+                  umma_op<HALF>(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, acc0 | (uint32_t)(k != 0));
+                db += (uint64_t)(B_BYTES >> 4);
+                w = w_next;
               }
               if (!p.b_resident) {
-                if (!mma_only) umma_commit(&b_empty[bs]);
+                umma_commit(&b_empty[bs]);
                 if (++bs == p.b_stages) { bs = 0; bph ^= 1u; }
               }
             }
-            if (!mma_only) umma_commit(&a_empty[as]);
+            umma_commit(&a_empty[as]);
             if (++as == p.a_stages) { as = 0; aph ^= 1u; }
           }
         }
-        if (!mma_only) umma_commit(&acc_full[buf]);
-      }
-      if (mma_only) {   // wait for the stream to drain so that the cycle count covers execution
-        umma_commit(&acc_full[0]);
-        mbar_wait(&acc_full[0], 0u, p.dbg, 38u);
+        umma_commit(&acc_full[buf]);
       }
       if (p.prof) {
         p.prof[blockIdx.x * 16 + 4] = (unsigned long long)(clock64() - t_start);
@@ -482,15 +447,21 @@ __global__ void __launch_bounds__(Q_THREADS, 2) conv_p2d_kernel(const __grid_con
     const bool in_tile = r < p.th && c < p.tw;
     const EpiDev& e = p.epi;
     const bool issuer = warp == 3 && lane == 0;
-    // staging row of this position inside the dense {tw x th} store box; 16-byte chunk j of a row
-    // lives at chunk (j ^ row%8): the SWIZZLE_128B pattern the store tensor map expects, and
-    // conflict-free for the 8 rows of a quarter-warp
+    // One staged chunk = CW channels of every position of the tile = rows of `row_bytes` in the dense
+    // {tw x th} store box: 32 fp32 channels (128 B), 64 fp16 channels (128 B) or, for BN = 32, 32 fp16
+    // channels (64 B).  16-byte piece j of a row lives at piece j ^ sx, the SWIZZLE_128B (sx = row % 8)
+    // or SWIZZLE_64B (sx = (row / 2) % 4) pattern the store tensor map expects -- and conflict-free
+    // for the 8 rows of a quarter-warp.
+    const bool out_half = p.out_half != 0;
+    const int CW = out_half ? (BN >= 64 ? 64 : 32) : 32;
+    const uint32_t row_bytes = out_half ? (uint32_t)CW * 2u : 128u;
     const uint32_t srow = (uint32_t)(r * p.tw + c);
-    const uint32_t s_row_addr = ring + p.stage_off + srow * 128u;
-    const uint32_t sx = srow & 7u;
+    const uint32_t s_row_addr = ring + p.stage_off + srow * row_bytes;
+    const uint32_t sx = row_bytes == 128u ? (srow & 7u) : ((srow >> 1) & 3u);
     const bool lin_acts = act_is_linear(e.act0) && act_is_linear(e.act1);
+    const uint64_t seed = e.keep_prob < 1.f ? epi_seed(e) : 0ull;
     // gate tiles: chunk g of this CTA (tile-major, then class, then 32-channel block) lands in gate
-    // buffer g & 1; the issuer keeps the loads two chunks ahead of the math
+    // buffer g & 1; the issuer keeps the loads two chunks ahead of the math (fp32 backward pass only)
     constexpr int CPC = BN / 32;
     const int cpt = p.ncls * CPC;
     auto gate_load = [&](uint32_t g) {
@@ -520,63 +491,78 @@ __global__ void __launch_bounds__(Q_THREADS, 2) conv_p2d_kernel(const __grid_con
       tc_fence_after();
       const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * acc_cols;
 #pragma unroll 1
-      for (int z = 0; z < ((p.exp_flags & 8) ? 0 : p.ncls); ++z) {
+      for (int z = 0; z < p.ncls; ++z) {
         const int oh = a * p.osh + p.cls_ph[z], ow = b * p.osw + p.cls_pw[z];
         const bool valid = row_ok && oh < e.Hs && ow < e.Ws;
         const size_t pix = valid ? ((size_t)tc_.img * e.Hs + oh) * e.Ws + ow : 0;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          uint32_t v[32];
-          const long long tl0 = p.prof ? clock64() : 0;
-          tmem_ld32(t_base + (uint32_t)(z * BN + c0), v);
-          if (!p.tma_store) {
-            tmem_ld_wait();
-            if (valid) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                epi_store_vec4(e, pix, n0 + c0 + j,
-                               make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                           __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
-            }
-            continue;
-          }
-          // ---- staged path: registers -> swizzled smem -> one TMA store per destination ----
-          float4 bias4[8];
-          if (e.bias) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) bias4[j] = __ldg(reinterpret_cast<const float4*>(e.bias + n0 + c0) + j);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) bias4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-          tmem_ld_wait();
-          if (p.prof) w_ld += (unsigned long long)(clock64() - tl0);
+        for (int c0 = 0; c0 < BN; c0 += CW) {
           const uint32_t sbuf = (p.stage_bufs == 2 ? (chunk_ctr & 1u) : 0u) * (uint32_t)p.n_out * Q_STAGE_BYTES;
-          const long long tb0 = p.prof ? clock64() : 0;
-          if (issuer) {   // the store that last read this staging buffer is done with it
-            if (p.stage_bufs == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
-          }
-          epi_bar(1);
-          if (p.prof) w_bar += (unsigned long long)(clock64() - tb0);
-          const long long tm0 = p.prof ? clock64() : 0;
-          if (p.use_gate) mbar_wait(&g_full[chunk_ctr & 1u], (chunk_ctr >> 1) & 1u, p.dbg, 37u);
-          if (in_tile && !(p.exp_flags & 2)) {
-            const uint32_t dst_row = s_row_addr + sbuf;
-            const bool drop = e.keep_prob < 1.f && valid;
-            const size_t idx0 = pix * e.Cout + n0 + c0;
-            if (p.use_gate) {
-              stage_chunk_gated(e, v, dst_row, ring + p.gate_off + (chunk_ctr & 1u) * Q_STAGE_BYTES + srow * 128u, sx,
-                                n0 + c0);
-            } else if (lin_acts) {
-              if (drop) stage_chunk<true, true>(e, v, bias4, dst_row, sx, p.n_out, idx0);
-              else stage_chunk<true, false>(e, v, bias4, dst_row, sx, p.n_out, idx0);
-            } else {
-              if (drop) stage_chunk<false, true>(e, v, bias4, dst_row, sx, p.n_out, idx0);
-              else stage_chunk<false, false>(e, v, bias4, dst_row, sx, p.n_out, idx0);
+#pragma unroll 1
+          for (int sub = 0; sub < CW; sub += 32) {
+            uint32_t v[32];
+            const long long tl0 = p.prof ? clock64() : 0;
+            tmem_ld32(t_base + (uint32_t)(z * BN + c0 + sub), v);
+            if (!p.tma_store) {
+              tmem_ld_wait();
+              if (valid) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                  epi_store_vec4(e, pix, n0 + c0 + sub + j,
+                                 make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                             __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
+              }
+              continue;
             }
+            // ---- staged path: registers -> swizzled smem -> one TMA store per destination ----
+            float4 bias4[8];
+            if (e.bias) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) bias4[j] = __ldg(reinterpret_cast<const float4*>(e.bias + n0 + c0 + sub) + j);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) bias4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            tmem_ld_wait();
+            if (p.prof) w_ld += (unsigned long long)(clock64() - tl0);
+            if (sub == 0) {
+              const long long tb0 = p.prof ? clock64() : 0;
+              if (issuer) {   // the store that last read this staging buffer is done with it
+                if (p.stage_bufs == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
+              }
+              epi_bar(1);
+              if (p.prof) w_bar += (unsigned long long)(clock64() - tb0);
+              if (p.use_gate) mbar_wait(&g_full[chunk_ctr & 1u], (chunk_ctr >> 1) & 1u, p.dbg, 37u);
+            }
+            const long long tm0 = p.prof ? clock64() : 0;
+            if (in_tile) {
+              const uint32_t dst_row = s_row_addr + sbuf;
+              const bool drop = e.keep_prob < 1.f && valid;
+              const size_t idx0 = pix * e.Cout + n0 + c0 + sub;
+              if (p.use_gate) {
+                stage_chunk_gated(e, v, dst_row, ring + p.gate_off + (chunk_ctr & 1u) * Q_STAGE_BYTES + srow * 128u, sx,
+                                  n0 + c0);
+              } else if (out_half) {
+                const uint32_t piece0 = (uint32_t)sub >> 3;   // 4 x 16-byte pieces per 32 channels
+                if (lin_acts) {
+                  if (drop) stage_chunk_h<true, true>(e, v, bias4, dst_row, sx, piece0, p.n_out, idx0, seed);
+                  else stage_chunk_h<true, false>(e, v, bias4, dst_row, sx, piece0, p.n_out, idx0, seed);
+                } else {
+                  if (drop) stage_chunk_h<false, true>(e, v, bias4, dst_row, sx, piece0, p.n_out, idx0, seed);
+                  else stage_chunk_h<false, false>(e, v, bias4, dst_row, sx, piece0, p.n_out, idx0, seed);
+                }
+              } else if (lin_acts) {
+                if (drop) stage_chunk<true, true>(e, v, bias4, dst_row, sx, p.n_out, idx0, seed);
+                else stage_chunk<true, false>(e, v, bias4, dst_row, sx, p.n_out, idx0, seed);
+              } else {
+                if (drop) stage_chunk<false, true>(e, v, bias4, dst_row, sx, p.n_out, idx0, seed);
+                else stage_chunk<false, false>(e, v, bias4, dst_row, sx, p.n_out, idx0, seed);
+              }
+            }
+            if (p.prof) w_math += (unsigned long long)(clock64() - tm0);
           }
+          if (!p.tma_store) continue;
           const long long tf0 = p.prof ? clock64() : 0;
-          if (p.prof) w_math += (unsigned long long)(tf0 - tm0);
           fence_async_smem();
           epi_bar(2);
           const long long ti0 = p.prof ? clock64() : 0;
@@ -642,12 +628,53 @@ inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b
 // transposed == true : y[N,H,Wstored,Cin] = conv_transpose(x[N,Ho,Wo,Cout]);  Cn = Cin, Ck = Cout
 bool make_plan_budget(const advoc_conv_desc* d, bool transposed, int Wstored, int n_out, bool tma_store, bool gate,
                       Plan* pl, size_t Q_SMEM_BUDGET, int max_tmem, size_t max_b_slot);
+// operand type of a layer: fp16 (64 channels per k-block) when the descriptor says ADVOC_MATH_F16
+inline int half_of(const advoc_conv_desc* d) { return d->math == ADVOC_MATH_F16 ? 1 : 0; }
 
 // Two CTAs per SM when the rings fit in half the shared memory and the accumulators in half the
 // tensor memory: the second CTA's MMA stream fills the issue gaps of the first (measured: the
 // in-kernel MMA issue rate of one CTA is ~2x below the tensor pipe's).  Otherwise one CTA per SM.
+bool make_plan_uncached(const advoc_conv_desc* d, bool transposed, int Wstored, int n_out, bool tma_store, bool gate,
+                        Plan* pl);
+
+// The geometry half of a launch depends only on the layer shape and the epilogue kind; it is asked
+// for at least twice per launch (eligibility, then the launch itself), so keep it.  The caller fills in
+// the pointer-dependent half (tensor maps, epilogue) on its own copy.
+struct PlanKey {
+  advoc_conv_desc d;
+  int transposed, Wstored, n_out, tma_store, gate;
+};
+struct PlanEntry { PlanKey key; Plan plan; bool ok; };
+
 bool make_plan(const advoc_conv_desc* d, bool transposed, int Wstored, int n_out, bool tma_store, bool gate,
                Plan* pl) {
+  static std::mutex mu;
+  static std::vector<PlanEntry>* cache = new std::vector<PlanEntry>();
+  PlanKey key;
+  memset(&key, 0, sizeof(key));
+  key.d = *d;
+  key.d.math = half_of(d) ? ADVOC_MATH_F16 : 0;
+  key.transposed = transposed; key.Wstored = Wstored; key.n_out = n_out; key.tma_store = tma_store; key.gate = gate;
+  const EpiDev epi = pl->p.epi;   // lowered by the caller before planning; not part of the cached geometry
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    for (const PlanEntry& e : *cache)
+      if (memcmp(&e.key, &key, sizeof(key)) == 0) {
+        *pl = e.plan;
+        pl->p.epi = epi;
+        return e.ok;
+      }
+  }
+  const bool ok = make_plan_uncached(d, transposed, Wstored, n_out, tma_store, gate, pl);
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (cache->size() < 4096) cache->push_back(PlanEntry{key, *pl, ok});
+  }
+  return ok;
+}
+
+bool make_plan_uncached(const advoc_conv_desc* d, bool transposed, int Wstored, int n_out, bool tma_store, bool gate,
+                        Plan* pl) {
   static const int ctas_per_sm = getenv("ADVOC_P2D_CTAS") ? atoi(getenv("ADVOC_P2D_CTAS")) : 2;
   if (ctas_per_sm >= 2) {
     Plan two = *pl;
@@ -764,15 +791,9 @@ bool make_plan_budget(const advoc_conv_desc* d, bool transposed, int Wstored, in
     }
   }
   p.plane_tap0[nplanes] = k;
-  if (getenv("ADVOC_P2D_NOSHIFT"))   // timing experiment only (wrong results): every tap reads the aligned patch start
-    for (int t = 0; t < k; ++t) p.tap_shift[t] = 0;
-  if (getenv("ADVOC_P2D_EXP") && (atoi(getenv("ADVOC_P2D_EXP")) & 16))
-    for (int t = 0; t < k; ++t) p.tap_shift[t] = 0;
-  if (getenv("ADVOC_P2D_SHIFT8"))    // timing experiment only: shifts rounded down to whole 1 KB swizzle atoms
-    for (int t = 0; t < k; ++t) p.tap_shift[t] &= ~7;
   p.nplanes = nplanes; p.ntaps = nt; p.ncls = ncls;
-  p.lean_issue = (getenv("ADVOC_P2D_LEAN_ISSUE") && atoi(getenv("ADVOC_P2D_LEAN_ISSUE"))) ? 1 : 0;
   const int Cn = transposed ? d->Cin : d->Cout, Ck = transposed ? d->Cout : d->Cin;
+  const int QK = qk_of(half_of(d));
   if (Ck % QK != 0 || Cn % 32 != 0) return false;
   int bn = Cn % 256 == 0 ? 256 : (Cn % 128 == 0 ? 128 : (Cn % 64 == 0 ? 64 : 32));
   while (ncls * bn > max_tmem) bn >>= 1;
@@ -853,7 +874,7 @@ bool make_plan_budget(const advoc_conv_desc* d, bool transposed, int Wstored, in
 }
 
 template <int BN>
-int launch_p2d(const Plan& pl, cudaStream_t st) {
+int launch_p2d(const Plan& pl, int half, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
     ADVOC_CHECK_CUDA(cudaFuncSetAttribute(conv_p2d_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -864,7 +885,7 @@ int launch_p2d(const Plan& pl, cudaStream_t st) {
   }
   const long slots = (long)sm_count() * pl.ctas_per_sm;
   long ctas = pl.p.total_tiles < slots ? pl.p.total_tiles : slots;
-  if (pl.p.lean_issue)
+  if (half)
     conv_p2d_kernel<BN, true><<<(unsigned)ctas, Q_THREADS, pl.smem, st>>>(pl.p);
   else
     conv_p2d_kernel<BN, false><<<(unsigned)ctas, Q_THREADS, pl.smem, st>>>(pl.p);
@@ -896,7 +917,7 @@ double min_efficiency() {
 
 bool conv_p2d_eligible(const advoc_conv_desc* d, int ldx, int transposed, int store_w) {
   static const bool disabled = getenv("ADVOC_NO_P2D") != nullptr;  // A/B switch for benchmarking
-  if (disabled || !(tc::tma_ok() && device_arch() == 100 && ldx % 4 == 0)) return false;
+  if (disabled || !(tc::tma_ok() && device_arch() == 100 && ldx % (half_of(d) ? 8 : 4) == 0)) return false;
   Plan pl = {};
   if (!make_plan(d, transposed != 0, store_w ? store_w : d->W, 2, true, true, &pl)) return false;
   if (pl.efficiency < min_efficiency()) return false;
@@ -913,9 +934,18 @@ bool conv_p2d_eligible(const advoc_conv_desc* d, int ldx, int transposed, int st
          (long)pl.filter_bytes_per_tile <= max_filter_kb * 1024;
 }
 
-int conv_p2d(const advoc_conv_desc* d, int transposed, const float* x, int ldx, const float* w,
+// N tile (template BN) of the patch-kernel launch for this geometry (host-side query)
+int conv_p2d_tile_n(const advoc_conv_desc* d, int transposed, int store_w) {
+  Plan pl = {};
+  if (!make_plan(d, transposed != 0, store_w ? store_w : d->W, 2, true, true, &pl)) return 0;
+  return pl.bn;
+}
+
+int conv_p2d(const advoc_conv_desc* d, int transposed, const void* x, int ldx, const void* w,
              const advoc_epilogue* ep, void* stream) {
   Plan pl = {};
+  const int half = half_of(d);
+  const int es = half ? 2 : 4;   // operand element size
   int st = transposed ? lower_epilogue(ep, d->H, d->W, d->Cin, &pl.p.epi)
                       : lower_epilogue(ep, d->Ho, d->Wo, d->Cout, &pl.p.epi);
   if (st) return st;
@@ -926,14 +956,20 @@ int conv_p2d(const advoc_conv_desc* d, int transposed, const float* x, int ldx, 
   // reduce-add; they carry no bias, activation, dropout or second output
   const bool bwd = ep->d_gate || ep->accumulate;
   const bool bwd_ok = !ep->d_bias && ep->act0 == ADVOC_ACT_NONE && ep->keep_prob >= 1.f && !ep->d_out1;
-  const bool tma_store = !no_tma_store && (!bwd || bwd_ok);
+  // the staged stores write one element type: mixed fp32 / fp16 destinations take the direct-store path
+  const bool out_half = pl.p.epi.h0 != 0;
+  const bool same_dtype = !ep->d_out1 || (pl.p.epi.h0 == pl.p.epi.h1);
+  const bool tma_store = !no_tma_store && (!bwd || bwd_ok) && same_dtype;
   ADVOC_REQUIRE(make_plan(d, transposed != 0, pl.p.epi.Ws, ep->d_out1 ? 2 : 1, tma_store, tma_store && ep->d_gate,
                           &pl),
                 ADVOC_UNSUPPORTED, "layer does not fit the patch kernel");
   P2dParams& p = pl.p;
   p.reduce_add = (tma_store && ep->accumulate) ? 1 : 0;
+  p.out_half = (tma_store && out_half) ? 1 : 0;
   if (tma_store) {
     const EpiDev& e = p.epi;
+    const int ocw = out_half ? (pl.bn >= 64 ? 64 : 32) : 32;   // channels per staged chunk (kernel: CW)
+    const int oes = out_half ? 2 : 4;
     if (p.use_gate) {
       for (int z = 0; z < p.ncls; ++z) {
         const int ph = p.cls_ph[z], pw = p.cls_pw[z];
@@ -944,13 +980,13 @@ int conv_p2d(const advoc_conv_desc* d, int transposed, const float* x, int ldx, 
       }
     }
     for (int o = 0; o < p.n_out; ++o) {
-      float* base = o == 0 ? e.out0 + e.coff0 : e.out1 + e.coff1;
       const long ld = o == 0 ? e.ld0 : e.ld1;
+      const char* base = reinterpret_cast<const char*>(o == 0 ? e.out0 : e.out1) + (size_t)(o == 0 ? e.coff0 : e.coff1) * oes;
       for (int z = 0; z < p.ncls; ++z) {
         const int ph = p.cls_ph[z], pw = p.cls_pw[z];
         const int Hz = (e.Hs - ph + p.osh - 1) / p.osh, Wz = (e.Ws - pw + p.osw - 1) / p.osw;
-        st = encode_tiled4d(&p.tmO[o][z], base + ((size_t)ph * e.Ws + pw) * ld, p.Cn, Wz, Hz, d->N, p.osw * ld,
-                            (long)p.osh * e.Ws * ld, (long)e.Hs * e.Ws * ld, 32, p.tw, p.th);
+        st = encode_tiled4d(&p.tmO[o][z], base + ((size_t)ph * e.Ws + pw) * ld * oes, p.Cn, Wz, Hz, d->N, p.osw * ld,
+                            (long)p.osh * e.Ws * ld, (long)e.Hs * e.Ws * ld, ocw, p.tw, p.th, out_half);
         if (st) return st;
       }
     }
@@ -961,16 +997,14 @@ int conv_p2d(const advoc_conv_desc* d, int transposed, const float* x, int ldx, 
     const int ph = pl.plane_ph[q], pw = pl.plane_pw[q], sh = pl.plane_sh, sw = pl.plane_sw;
     const int Hp = Hin > ph ? (Hin - ph + sh - 1) / sh : 0, Wp = Win > pw ? (Win - pw + sw - 1) / sw : 0;
     ADVOC_REQUIRE(Hp > 0 && Wp > 0, ADVOC_UNSUPPORTED, "empty input plane");
-    st = encode_tiled4d(&p.tmA[q], x + ((size_t)ph * Win + pw) * ldx, Ck, Wp, Hp, d->N, (long)sw * ldx,
-                        (long)sh * Win * ldx, (long)Hin * Win * ldx, QK, p.PW, p.PH);
+    st = encode_tiled4d(&p.tmA[q], reinterpret_cast<const char*>(x) + ((size_t)ph * Win + pw) * ldx * es, Ck, Wp, Hp,
+                        d->N, (long)sw * ldx, (long)sh * Win * ldx, (long)Hin * Win * ldx, qk_of(half), p.PW, p.PH, half);
     if (st) return st;
   }
-  st = encode_tiled2d(&p.tmB, w, Ck, (long)d->kh * d->kw * p.Cn, (size_t)Ck * 4, QK, pl.bn);
+  st = encode_tiled2d(&p.tmB, w, Ck, (long)d->kh * d->kw * p.Cn, (size_t)Ck * es, qk_of(half), pl.bn, false, half);
   if (st) return st;
   p.dbg = debug_word();
   p.prof = prof_buffer();
-  static const int exp_flags = getenv("ADVOC_P2D_EXP") ? atoi(getenv("ADVOC_P2D_EXP")) : 0;
-  p.exp_flags = exp_flags;
   static const bool verbose = getenv("ADVOC_P2D_VERBOSE") != nullptr;
   if (verbose)
     fprintf(stderr,
@@ -981,10 +1015,10 @@ int conv_p2d(const advoc_conv_desc* d, int transposed, const float* x, int ldx, 
             p.G * pl.bn * 128, p.b_resident ? "resident" : "ring", p.stage_bufs, p.n_out, pl.smem, p.tmem_cols, pl.ctas_per_sm);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   switch (pl.bn) {
-    case 256: return launch_p2d<256>(pl, s);
-    case 128: return launch_p2d<128>(pl, s);
-    case 64: return launch_p2d<64>(pl, s);
-    default: return launch_p2d<32>(pl, s);
+    case 256: return launch_p2d<256>(pl, half, s);
+    case 128: return launch_p2d<128>(pl, half, s);
+    case 64: return launch_p2d<64>(pl, half, s);
+    default: return launch_p2d<32>(pl, half, s);
   }
 }
 

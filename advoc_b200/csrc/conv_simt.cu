@@ -50,6 +50,15 @@ int lower_epilogue(const advoc_epilogue* ep, int Hs, int Wfull, int Cout, EpiDev
   e->gate_act = ep->gate_act; e->gate_split = ep->gate_split;
   e->gscale0 = ep->gate_scale0; e->gscale1 = ep->gate_scale1;
   e->accumulate = ep->accumulate;
+  e->seed_ptr = reinterpret_cast<const unsigned long long*>(ep->d_seed);
+  ADVOC_REQUIRE((ep->out0_dtype == ADVOC_DT_F32 || ep->out0_dtype == ADVOC_DT_F16) &&
+                    (ep->out1_dtype == ADVOC_DT_F32 || ep->out1_dtype == ADVOC_DT_F16),
+                ADVOC_BAD_ARG, "unknown output dtype");
+  e->h0 = ep->out0_dtype == ADVOC_DT_F16;
+  e->h1 = ep->d_out1 != nullptr && ep->out1_dtype == ADVOC_DT_F16;
+  if (e->h0 || e->h1)
+    ADVOC_REQUIRE(!ep->accumulate && !ep->d_gate, ADVOC_UNSUPPORTED,
+                  "fp16 destinations are forward-pass only (no gate / accumulate)");
   if (ep->d_gate) {
     ADVOC_REQUIRE(ep->ld_gate >= ep->c_off_gate + Cout && ep->c_off_gate >= 0, ADVOC_BAD_SHAPE,
                   "gate channel window does not fit its ld");

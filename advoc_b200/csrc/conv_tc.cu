@@ -28,8 +28,7 @@ namespace {
 using namespace tc;
 
 constexpr int BM = 128;        // UMMA_M (cta_group::1)
-constexpr int BK = 32;         // fp32 elements per 128-byte swizzle row
-constexpr int UMMA_K = 8;      // kind::tf32
+constexpr int BK_BYTES = 128;  // one swizzle row of the K-major operands: 32 tf32 or 64 fp16 channels
 constexpr int MAX_CLASSES = 4;
 constexpr int MAX_TAPS = 25;
 constexpr int NUM_THREADS = 192;
@@ -47,25 +46,23 @@ struct alignas(64) TcParams {
   int trav_h, trav_w;  // im2col traversal stride
   int osh, osw;        // output position stride (1 for conv, s for transposed conv)
   int Cn;              // produced channels (rows of B per tap)
-  int kblocks;         // contraction channels / 32
+  int kblocks;         // contraction channels / channels per 128-byte row (32 tf32, 64 fp16)
   EpiDev epi;
   unsigned int* dbg;   // [0] != 0 after a barrier wait timed out
 };
 
-// instruction descriptor, kind::tf32: D fp32, A/B tf32, both K-major, M=128, N=BN
-__host__ __device__ constexpr uint32_t make_idesc(int bn) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-}
-
 template <int BN>
 struct SmemLayout {
-  static constexpr int A_BYTES = BM * BK * 4;  // 16 KB
-  static constexpr int B_BYTES = BN * BK * 4;
+  static constexpr int A_BYTES = BM * BK_BYTES;  // 16 KB
+  static constexpr int B_BYTES = BN * BK_BYTES;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 };
 
-template <int BN, int STAGES>
+// HALF: fp16 operands (kind::f16, 64 channels per 128-byte row) instead of tf32 (32 channels); the
+// byte layout of the ring, the descriptors and the four 32-byte K steps per row are the same
+template <int BN, int STAGES, bool HALF>
 __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_constant__ TcParams p) {
+  constexpr int BK = HALF ? 64 : 32;   // channels per k-block
   using L = SmemLayout<BN>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[STAGES];
@@ -149,7 +146,7 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
     // ===== MMA issuer: warp-uniform loop, tcgen05.mma issued by one elected lane (a plain
     // `if (lane == 0)` region makes the compiler wrap every UTCMMA in an ELECT/BRA.U.ANY loop that
     // costs ~140 cycles per instruction: scripts/dev_mma_rate.py) =====
-    constexpr uint32_t idesc = make_idesc(BN);
+    constexpr uint32_t idesc = umma_idesc<HALF>(BM, BN);
     if (elect_one()) {   // one thread waits and issues; entered through elect.sync (see tc::elect_one)
       int stage = 0;
       uint32_t phase = 0;
@@ -159,9 +156,9 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
         const uint64_t da = make_smem_desc(a_addr);
         const uint64_t db = make_smem_desc(a_addr + L::A_BYTES);
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
+        for (int k = 0; k < 4; ++k) {
           // advance 32 bytes (= 2 x 16-byte units) along K inside the swizzle atom
-          umma_tf32(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (it | k) != 0 ? 1u : 0u);
+          umma_op<HALF>(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (it | k) != 0 ? 1u : 0u);
         }
         umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -218,30 +215,32 @@ struct ClassGeom {
   unsigned short off[MAX_TAPS], wrow[MAX_TAPS];
 };
 
+inline int bk_of(int half) { return half ? 64 : 32; }
+
 // im2col map over activations [Nimg, Hin, Win, ld] reading `Ck` channels per pixel
-int encode_A(CUtensorMap* tm, const float* x, int Nimg, int Hin, int Win, int ld, int Ck, const ClassGeom& g,
-             int trav_h, int trav_w) {
+int encode_A(CUtensorMap* tm, const void* x, int Nimg, int Hin, int Win, int ld, int Ck, const ClassGeom& g,
+             int trav_h, int trav_w, int half) {
   return encode_im2col(tm, x, Nimg, Hin, Win, ld, Ck, g.lower_h, g.lower_w, g.upper_h, g.upper_w, trav_h, trav_w,
-                       BK, BM);
+                       bk_of(half), BM, false, half);
 }
 
-int encode_B(CUtensorMap* tm, const float* w, int rows, int Ck, int bn) {
-  return encode_tiled2d(tm, w, Ck, rows, (size_t)Ck * 4, BK, bn);
+int encode_B(CUtensorMap* tm, const void* w, int rows, int Ck, int bn, int half) {
+  return encode_tiled2d(tm, w, Ck, rows, (size_t)Ck * (half ? 2 : 4), bk_of(half), bn, false, half);
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool HALF>
 int launch(const TcParams& p, int nclasses, long max_tiles, cudaStream_t st) {
   constexpr int smem = STAGES * SmemLayout<BN>::STAGE_BYTES + 1024;
   static bool configured = false;
   if (!configured) {
-    ADVOC_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    ADVOC_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           smem));
     configured = true;
   }
   const long ctas = max_tiles * (p.Cn / BN) * nclasses;
   ADVOC_REQUIRE(ctas < 2147483647L, ADVOC_BAD_SHAPE, "too many output tiles");
   dim3 grid((unsigned)ctas, 1, 1);
-  conv_tc_kernel<BN, STAGES><<<grid, NUM_THREADS, smem, st>>>(p);
+  conv_tc_kernel<BN, STAGES, HALF><<<grid, NUM_THREADS, smem, st>>>(p);
   count_launch();
   ADVOC_CHECK_CUDA(cudaGetLastError());
   return ADVOC_OK;
@@ -267,7 +266,7 @@ long m_ctas_of(int Nimg, const ClassGeom* g, int nclasses) {
   return tiles * nclasses;
 }
 
-int run(TcParams& p, int nclasses, const ClassGeom* g, void* stream) {
+int run(TcParams& p, int nclasses, const ClassGeom* g, void* stream, int half) {
   long max_tiles = 0;
   for (int c = 0; c < nclasses; ++c) {
     p.Ah[c] = g[c].Ah; p.Aw[c] = g[c].Aw; p.ph[c] = g[c].ph; p.pw[c] = g[c].pw;
@@ -281,20 +280,31 @@ int run(TcParams& p, int nclasses, const ClassGeom* g, void* stream) {
   p.dbg = debug_word();
   p.nclasses = nclasses;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  switch (pick_bn(p.Cn, m_ctas_of(p.Nimg, g, nclasses))) {
-    case 256: return launch<256, 4>(p, nclasses, max_tiles, st);
-    case 128: return launch<128, 3>(p, nclasses, max_tiles, st);
-    case 64: return launch<64, 4>(p, nclasses, max_tiles, st);
-    default: return launch<32, 4>(p, nclasses, max_tiles, st);
+  const int bn = pick_bn(p.Cn, m_ctas_of(p.Nimg, g, nclasses));
+  if (half) {
+    switch (bn) {
+      case 256: return launch<256, 4, true>(p, nclasses, max_tiles, st);
+      case 128: return launch<128, 3, true>(p, nclasses, max_tiles, st);
+      case 64: return launch<64, 4, true>(p, nclasses, max_tiles, st);
+      default: return launch<32, 4, true>(p, nclasses, max_tiles, st);
+    }
+  }
+  switch (bn) {
+    case 256: return launch<256, 4, false>(p, nclasses, max_tiles, st);
+    case 128: return launch<128, 3, false>(p, nclasses, max_tiles, st);
+    case 64: return launch<64, 4, false>(p, nclasses, max_tiles, st);
+    default: return launch<32, 4, false>(p, nclasses, max_tiles, st);
   }
 }
 
-bool common_eligible(int Ck, int Cn, int ldx) {
-  return tma_ok() && device_arch() == 100 && Ck % BK == 0 && Cn % 32 == 0 && ldx % 4 == 0;
+// fp16 operands: 64 channels per k-block, pixel stride a multiple of 16 bytes
+bool common_eligible(int Ck, int Cn, int ldx, int half) {
+  return tma_ok() && device_arch() == 100 && Ck % bk_of(half) == 0 && Cn % 32 == 0 && ldx % (half ? 8 : 4) == 0;
 }
 
 bool epilogue_vector_ok(const advoc_epilogue* ep) {
   if (!ep) return true;
+  // vector stores of 4 channels: 16 bytes (fp32) or 8 bytes (fp16) -- the same element multiples
   auto ok = [](const float* p, int ld, int co) { return aligned16(p) && ld % 4 == 0 && co % 4 == 0; };
   if (!ok(ep->d_out0, ep->ld0, ep->c_off0)) return false;
   if (ep->d_out1 && !ok(ep->d_out1, ep->ld1, ep->c_off1)) return false;
@@ -307,17 +317,42 @@ bool epilogue_vector_ok(const advoc_epilogue* ep) {
 
 bool tc_epilogue_ok(const advoc_epilogue* ep) { return epilogue_vector_ok(ep); }
 
+// N tile (template BN) a per-tap launch with this geometry would use; mirrors conv_fwd_tc /
+// conv_transposed_tc (host-side query for tests and bench attribution)
+int conv_tc_tile_n(const advoc_conv_desc* d, int transposed, int store_w) {
+  if (!transposed) {
+    ClassGeom g = {};
+    g.Ah = d->Ho; g.Aw = d->Wo;
+    return pick_bn(d->Cout, m_ctas_of(d->N, &g, 1));
+  }
+  const int Hout = d->H, Wout = store_w > 0 ? store_w : d->W;
+  ClassGeom g[MAX_CLASSES] = {};
+  int nc = 0;
+  for (int ph = 0; ph < d->sh; ++ph)
+    for (int pw = 0; pw < d->sw; ++pw) {
+      if (nc >= MAX_CLASSES) return 0;
+      g[nc].Ah = Hout > ph ? (Hout - ph + d->sh - 1) / d->sh : 0;
+      g[nc].Aw = Wout > pw ? (Wout - pw + d->sw - 1) / d->sw : 0;
+      if (g[nc].Ah == 0 || g[nc].Aw == 0) continue;
+      ++nc;
+    }
+  return pick_bn(d->Cin, m_ctas_of(d->N, g, nc));
+}
+
 bool conv_fwd_tc_eligible(const advoc_conv_desc* d, int ldx) {
-  return common_eligible(d->Cin, d->Cout, ldx) && d->kh * d->kw <= MAX_TAPS && d->pad_t <= 127 && d->pad_l <= 127;
+  return common_eligible(d->Cin, d->Cout, ldx, d->math == ADVOC_MATH_F16) && d->kh * d->kw <= MAX_TAPS &&
+         d->pad_t <= 127 && d->pad_l <= 127;
 }
 
 bool conv_transposed_tc_eligible(const advoc_conv_desc* d, int ldx) {
-  return common_eligible(d->Cout, d->Cin, ldx) && d->sh * d->sw <= MAX_CLASSES && d->kh * d->kw <= MAX_TAPS;
+  return common_eligible(d->Cout, d->Cin, ldx, d->math == ADVOC_MATH_F16) && d->sh * d->sw <= MAX_CLASSES &&
+         d->kh * d->kw <= MAX_TAPS;
 }
 
 // y = conv(x, w): w packed K-major [tap][Cout][Cin]
-int conv_fwd_tc(const advoc_conv_desc* d, const float* x, int ldx, const float* w, const advoc_epilogue* ep,
+int conv_fwd_tc(const advoc_conv_desc* d, const void* x, int ldx, const void* w, const advoc_epilogue* ep,
                 void* stream) {
+  const int half = d->math == ADVOC_MATH_F16;
   ADVOC_REQUIRE(aligned16(x) && aligned16(w), ADVOC_BAD_ALIGN, "x / w must be 16-byte aligned");
   ADVOC_REQUIRE(epilogue_vector_ok(ep), ADVOC_BAD_ALIGN,
                 "tcgen05 path needs 16-byte aligned outputs with ld and channel offset multiples of 4");
@@ -338,19 +373,20 @@ int conv_fwd_tc(const advoc_conv_desc* d, const float* x, int ldx, const float* 
   }
   ADVOC_REQUIRE(g.upper_h >= -128 && g.upper_h <= 127 && g.upper_w >= -128 && g.upper_w <= 127, ADVOC_UNSUPPORTED,
                 "im2col corner out of range");
-  st = encode_A(&p.tmA[0], x, d->N, d->H, d->W, ldx, d->Cin, g, d->sh, d->sw);
+  st = encode_A(&p.tmA[0], x, d->N, d->H, d->W, ldx, d->Cin, g, d->sh, d->sw, half);
   if (st) return st;
-  st = encode_B(&p.tmB, w, g.ntaps * d->Cout, d->Cin, pick_bn(d->Cout, m_ctas_of(d->N, &g, 1)));
+  st = encode_B(&p.tmB, w, g.ntaps * d->Cout, d->Cin, pick_bn(d->Cout, m_ctas_of(d->N, &g, 1)), half);
   if (st) return st;
   p.Nimg = d->N; p.trav_h = d->sh; p.trav_w = d->sw; p.osh = 1; p.osw = 1;
-  p.Cn = d->Cout; p.kblocks = d->Cin / BK;
-  return run(p, 1, &g, stream);
+  p.Cn = d->Cout; p.kblocks = d->Cin / bk_of(half);
+  return run(p, 1, &g, stream, half);
 }
 
 // y = conv_transpose(x, w): x [N,Ho,Wo,Cout] (small side), y [N,H,Ws,Cin]; w K-major [tap][Cin][Cout]
 // (= the TF conv2d_transpose layout HWOI, and = HWIO of a conv whose input gradient this is)
-int conv_transposed_tc(const advoc_conv_desc* d, const float* x, int ldx, const float* w,
+int conv_transposed_tc(const advoc_conv_desc* d, const void* x, int ldx, const void* w,
                        const advoc_epilogue* ep, void* stream) {
+  const int half = d->math == ADVOC_MATH_F16;
   ADVOC_REQUIRE(aligned16(x) && aligned16(w), ADVOC_BAD_ALIGN, "x / w must be 16-byte aligned");
   ADVOC_REQUIRE(epilogue_vector_ok(ep), ADVOC_BAD_ALIGN,
                 "tcgen05 path needs 16-byte aligned outputs with ld and channel offset multiples of 4");
@@ -385,16 +421,16 @@ int conv_transposed_tc(const advoc_conv_desc* d, const float* x, int ldx, const 
       ADVOC_REQUIRE(c.lower_h >= -128 && c.upper_h <= 127 && c.lower_w >= -128 && c.upper_w <= 127 &&
                         c.upper_h >= -128 && c.upper_w >= -128,
                     ADVOC_UNSUPPORTED, "im2col corner out of range");
-      st = encode_A(&p.tmA[nc], x, d->N, d->Ho, d->Wo, ldx, d->Cout, c, 1, 1);
+      st = encode_A(&p.tmA[nc], x, d->N, d->Ho, d->Wo, ldx, d->Cout, c, 1, 1, half);
       if (st) return st;
       ++nc;
     }
   }
-  st = encode_B(&p.tmB, w, d->kh * d->kw * d->Cin, d->Cout, pick_bn(d->Cin, m_ctas_of(d->N, g, nc)));
+  st = encode_B(&p.tmB, w, d->kh * d->kw * d->Cin, d->Cout, pick_bn(d->Cin, m_ctas_of(d->N, g, nc)), half);
   if (st) return st;
   p.Nimg = d->N; p.trav_h = 1; p.trav_w = 1; p.osh = d->sh; p.osw = d->sw;
-  p.Cn = d->Cin; p.kblocks = d->Cout / BK;
-  return run(p, nc, g, stream);
+  p.Cn = d->Cin; p.kblocks = d->Cout / bk_of(half);
+  return run(p, nc, g, stream, half);
 }
 
 }  // namespace advoc
@@ -406,5 +442,15 @@ extern "C" int advoc_debug_flags(unsigned int* out) {
   ADVOC_REQUIRE(w != nullptr, ADVOC_CUDA_ERROR, "no debug word");
   ADVOC_CHECK_CUDA(cudaMemcpy(out, w, sizeof(unsigned int), cudaMemcpyDeviceToHost));
   ADVOC_CHECK_CUDA(cudaMemset(w, 0, sizeof(unsigned int)));
+  volatile unsigned int* h = tc::debug_host_word();
+  if (h) *h = 0;
+  return ADVOC_OK;
+}
+
+extern "C" int advoc_debug_peek(unsigned int* out) {
+  using namespace advoc;
+  ADVOC_REQUIRE(out != nullptr, ADVOC_BAD_ARG, "out is NULL");
+  volatile unsigned int* h = tc::debug_host_word();
+  *out = h ? *h : 0u;
   return ADVOC_OK;
 }

@@ -70,9 +70,11 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
 
 // KS = filter size (4: AdVoc decoder_1; 5: MelspecGAN upconv_4, models/melspecgan/conv2d.py:139-141);
 // the tap axis is padded to NP = 16 / 32 accumulator columns (TMA zero-fills the missing filter rows)
-template <int KS>
+// HALF: fp16 operands (64 channels per 128-byte row, kind::f16) instead of tf32 (32 per row)
+template <int KS, bool HALF>
 __global__ void __launch_bounds__(O_THREADS, 1) deconv_one_tc_kernel(const __grid_constant__ OneParams p) {
   constexpr int NP = KS == 4 ? 16 : 32;
+  constexpr int KCH = HALF ? 64 : 32;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[O_STAGES], a_empty[O_STAGES];
   __shared__ __align__(8) uint64_t b_full, acc_full[2], acc_empty[2];
@@ -116,7 +118,7 @@ __global__ void __launch_bounds__(O_THREADS, 1) deconv_one_tc_kernel(const __gri
       if (elect_one()) {
         mbar_expect_tx(&b_full, (uint32_t)p.kblocks * B_BYTES);
         for (int kb = 0; kb < p.kblocks; ++kb)
-          tma_load_2d(&p.tmB, &b_full, ring_ptr + b_off + (size_t)kb * B_BYTES, kb * 32, 0);
+          tma_load_2d(&p.tmB, &b_full, ring_ptr + b_off + (size_t)kb * B_BYTES, kb * KCH, 0);
       }
       __syncwarp();
     }
@@ -132,7 +134,7 @@ __global__ void __launch_bounds__(O_THREADS, 1) deconv_one_tc_kernel(const __gri
         for (int kb = 0; kb < p.kblocks; ++kb) {
           wait_p(&a_empty[as], aph ^ 1u, p.dbg, 41u, p.prof, w0);
           mbar_expect_tx(&a_full[as], A_BYTES);
-          tma_load_4d(&p.tmA, &a_full[as], ring_ptr + (size_t)as * A_BYTES, kb * 32, b0, a0, img);
+          tma_load_4d(&p.tmA, &a_full[as], ring_ptr + (size_t)as * A_BYTES, kb * KCH, b0, a0, img);
           if (++as == O_STAGES) { as = 0; aph ^= 1u; }
         }
       }
@@ -141,8 +143,7 @@ __global__ void __launch_bounds__(O_THREADS, 1) deconv_one_tc_kernel(const __gri
     __syncwarp();
   } else if (warp == 1) {
     // ===== MMA issuer: M = 128 positions, N = NP taps, K = Cs =====
-    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NP >> 3) << 17) |
-                               ((uint32_t)(128 >> 4) << 24);
+    constexpr uint32_t idesc = umma_idesc<HALF>(128, NP);
     if (elect_one()) {
       int as = 0;
       uint32_t aph = 0;
@@ -161,8 +162,8 @@ __global__ void __launch_bounds__(O_THREADS, 1) deconv_one_tc_kernel(const __gri
           const uint64_t db = make_smem_desc(ring + b_off + (uint32_t)kb * B_BYTES);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_tf32(tmem_base + (uint32_t)buf * NP, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                      (kb | k) != 0 ? 1u : 0u);
+            umma_op<HALF>(tmem_base + (uint32_t)buf * NP, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                          (kb | k) != 0 ? 1u : 0u);
           umma_commit(&a_empty[as]);
           if (kb == p.kblocks - 1) umma_commit(&acc_full[buf]);
           if (++as == O_STAGES) { as = 0; aph ^= 1u; }
@@ -262,31 +263,35 @@ bool deconv_one_tc_geometry(const advoc_conv_desc* d, int ldx) {
   static const bool disabled = getenv("ADVOC_NO_ONE_TC") != nullptr;   // A/B switch for benchmarking
   return !disabled && d->math != ADVOC_MATH_FP32 && tc::tma_ok() && device_arch() == 100 && d->Cin == 1 &&
          (d->kh == 4 || d->kh == 5) && d->kw == d->kh && d->sh == 2 && d->sw == 2 && d->pad_t == 1 && d->pad_l == 1 && d->H == 2 * d->Ho &&
-         d->W == 2 * d->Wo && d->Cout % 32 == 0 && d->Cout <= 32 * O_MAXKB && ldx % 4 == 0;
+         d->W == 2 * d->Wo &&
+         (d->math == ADVOC_MATH_F16 ? (d->Cout % 64 == 0 && d->Cout <= 64 * O_MAXKB && ldx % 8 == 0)
+                                    : (d->Cout % 32 == 0 && d->Cout <= 32 * O_MAXKB && ldx % 4 == 0));
 }
 
-bool deconv_one_tc_eligible(const advoc_conv_desc* d, const float* x, int ldx, const advoc_epilogue* ep) {
+bool deconv_one_tc_eligible(const advoc_conv_desc* d, const void* x, int ldx, const advoc_epilogue* ep) {
   return deconv_one_tc_geometry(d, ldx) && aligned16(x) && ep->keep_prob >= 1.f && ep->d_out1 == nullptr;
 }
 
 // w: [16 taps][Cs] fp32 (the HWOI filter of a conv_transpose to one channel), TF32-rounded by the caller
-int deconv_one_tc(const advoc_conv_desc* d, const float* x, int ldx, const float* w, const advoc_epilogue* ep,
+int deconv_one_tc(const advoc_conv_desc* d, const void* x, int ldx, const void* w, const advoc_epilogue* ep,
                   void* stream) {
   OneParams p = {};
+  const int half = d->math == ADVOC_MATH_F16;
+  const int kch = half ? 64 : 32;
   int st = lower_epilogue(ep, d->H, d->W, 1, &p.epi);
   if (st) return st;
   ADVOC_REQUIRE(aligned16(w), ADVOC_BAD_ALIGN, "filter must be 16-byte aligned");
-  p.N = d->N; p.Hs = d->Ho; p.Ws = d->Wo; p.kblocks = d->Cout / 32;
+  p.N = d->N; p.Hs = d->Ho; p.Ws = d->Wo; p.kblocks = d->Cout / kch;
   p.tiles_h = (p.Hs + O_IH - 1) / O_IH;
   p.tiles_w = (p.Ws + O_IW - 1) / O_IW;
   p.total_tiles = (long)p.N * p.tiles_h * p.tiles_w;
   if (p.total_tiles == 0) return ADVOC_OK;
   ADVOC_REQUIRE(p.total_tiles < 2147483647L, ADVOC_BAD_SHAPE, "too many tiles");
-  st = encode_tiled4d(&p.tmA, x, d->Cout, p.Ws, p.Hs, p.N, ldx, (long)p.Ws * ldx, (long)p.Hs * p.Ws * ldx, 32, O_PW,
-                      O_PH);
+  st = encode_tiled4d(&p.tmA, x, d->Cout, p.Ws, p.Hs, p.N, ldx, (long)p.Ws * ldx, (long)p.Hs * p.Ws * ldx, kch, O_PW,
+                      O_PH, half);
   if (st) return st;
   const int np = d->kh == 4 ? 16 : 32;
-  st = encode_tiled2d(&p.tmB, w, d->Cout, d->kh * d->kw, (size_t)d->Cout * 4, 32, np);
+  st = encode_tiled2d(&p.tmB, w, d->Cout, d->kh * d->kw, (size_t)d->Cout * (half ? 2 : 4), kch, np, false, half);
   if (st) return st;
   p.dbg = debug_word();
   static unsigned long long* prof = [] {
@@ -301,15 +306,19 @@ int deconv_one_tc(const advoc_conv_desc* d, const float* x, int ldx, const float
   const int smem = O_STAGES * O_PH * O_PW * 128 + O_MAXKB * 32 * 128 + 1024;
   static bool configured = false;
   if (!configured) {
-    ADVOC_CHECK_CUDA(cudaFuncSetAttribute(deconv_one_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    ADVOC_CHECK_CUDA(cudaFuncSetAttribute(deconv_one_tc_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ADVOC_CHECK_CUDA(cudaFuncSetAttribute(deconv_one_tc_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ADVOC_CHECK_CUDA(cudaFuncSetAttribute(deconv_one_tc_kernel<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ADVOC_CHECK_CUDA(cudaFuncSetAttribute(deconv_one_tc_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   const long ctas = p.total_tiles < (long)sm_count() ? p.total_tiles : (long)sm_count();
-  if (d->kh == 4)
-    deconv_one_tc_kernel<4><<<(unsigned)ctas, O_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  ADVOC_REQUIRE(!half || d->kh == 4, ADVOC_UNSUPPORTED, "fp16 operands: k4 only");
+  if (half)
+    deconv_one_tc_kernel<4, true><<<(unsigned)ctas, O_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  else if (d->kh == 4)
+    deconv_one_tc_kernel<4, false><<<(unsigned)ctas, O_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   else
-    deconv_one_tc_kernel<5><<<(unsigned)ctas, O_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    deconv_one_tc_kernel<5, false><<<(unsigned)ctas, O_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   count_launch();
   ADVOC_CHECK_CUDA(cudaGetLastError());
   return ADVOC_OK;

@@ -2,6 +2,8 @@
 #pragma once
 #include "common.cuh"
 
+#include <cuda_fp16.h>
+
 namespace advoc {
 
 struct EpiDev {
@@ -22,7 +24,32 @@ struct EpiDev {
   int ldg, coffg, gate_act, gate_split;
   float gscale0, gscale1;
   int accumulate;
+  // dropout counter in device memory (CUDA-graph replays draw fresh masks): see epi_seed()
+  const unsigned long long* seed_ptr;
+  int h0, h1;       // destination holds fp16 elements (ld / coff stay in elements); forward pass only
 };
+
+// Seed of the counter-based dropout generator: the by-value seed, or -- when the caller keeps a
+// step counter in device memory -- counter * 0x9E3779B1 + seed (seed = the layer's salt), which is
+// what the host computes for the eager path (nets.Generator.forward), so both paths draw the same
+// masks for the same step.
+__device__ __forceinline__ uint64_t epi_seed(const EpiDev& e) {
+  return e.seed_ptr ? __ldg(e.seed_ptr) * 0x9E3779B1ull + e.seed : e.seed;
+}
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+// four consecutive channels to an fp32 or fp16 destination (elem = element index of the first one)
+__device__ __forceinline__ void store4(float* base, int is_half, size_t elem, const float (&y)[4]) {
+  if (is_half) {
+    *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(base) + elem) =
+        make_uint2(pack_half2(y[0], y[1]), pack_half2(y[2], y[3]));
+  } else {
+    *reinterpret_cast<float4*>(base + elem) = make_float4(y[0], y[1], y[2], y[3]);
+  }
+}
 
 __device__ __forceinline__ float gate_factor(const EpiDev& e, size_t pix, int n) {
   const float g = __ldg(e.gate + pix * e.ldg + e.coffg + n);
@@ -39,7 +66,7 @@ __device__ __forceinline__ void epi_store(const EpiDev& e, size_t pix, int n, fl
   float scale = 1.f;
   if (e.keep_prob < 1.f) {
     const size_t idx = pix * e.Cout + n;
-    const bool keep = e.mask ? (__ldg(e.mask + idx) != 0) : dropout_keep(e.seed, idx, e.keep_prob);
+    const bool keep = e.mask ? (__ldg(e.mask + idx) != 0) : dropout_keep(epi_seed(e), idx, e.keep_prob);
     scale = keep ? 1.f / e.keep_prob : 0.f;
   }
   const bool lin = act_is_linear(e.act0) && act_is_linear(e.act1);   // real branch: see ActLin
@@ -47,16 +74,24 @@ __device__ __forceinline__ void epi_store(const EpiDev& e, size_t pix, int n, fl
   if (lin) y0 = apply_lin(v, act_linear(e.act0, e.alpha)) * scale;
   else y0 = apply_act(v, e.act0, e.alpha) * scale;
   if (e.gate) y0 *= gate_factor(e, pix, n);
-  float* dst = e.out0 + pix * e.ld0 + e.coff0 + n;
-  if (e.accumulate) y0 += *dst;
-  if (e.round) y0 = round_tf32(y0);
-  *dst = y0;
+  if (e.h0) {
+    reinterpret_cast<__half*>(e.out0)[pix * e.ld0 + e.coff0 + n] = __float2half_rn(y0);
+  } else {
+    float* dst = e.out0 + pix * e.ld0 + e.coff0 + n;
+    if (e.accumulate) y0 += *dst;
+    if (e.round) y0 = round_tf32(y0);
+    *dst = y0;
+  }
   if (e.out1) {
     float y1;
     if (lin) y1 = apply_lin(v, act_linear(e.act1, e.alpha)) * scale;
     else y1 = apply_act(v, e.act1, e.alpha) * scale;
-    if (e.round) y1 = round_tf32(y1);
-    e.out1[pix * e.ld1 + e.coff1 + n] = y1;
+    if (e.h1) {
+      reinterpret_cast<__half*>(e.out1)[pix * e.ld1 + e.coff1 + n] = __float2half_rn(y1);
+    } else {
+      if (e.round) y1 = round_tf32(y1);
+      e.out1[pix * e.ld1 + e.coff1 + n] = y1;
+    }
   }
 }
 
@@ -71,9 +106,10 @@ __device__ __forceinline__ void epi_store_vec4(const EpiDev& e, size_t pix, int 
   if (e.keep_prob < 1.f) {
     const size_t idx = pix * e.Cout + n;
     const float inv = 1.f / e.keep_prob;
+    const uint64_t seed = epi_seed(e);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const bool keep = e.mask ? (__ldg(e.mask + idx + j) != 0) : dropout_keep(e.seed, idx + j, e.keep_prob);
+      const bool keep = e.mask ? (__ldg(e.mask + idx + j) != 0) : dropout_keep(seed, idx + j, e.keep_prob);
       sc[j] = keep ? inv : 0.f;
     }
   }
@@ -95,16 +131,15 @@ __device__ __forceinline__ void epi_store_vec4(const EpiDev& e, size_t pix, int 
 #pragma unroll
     for (int j = 0; j < 4; ++j) y[j] *= (gv[j] > 0.f ? 1.f : neg) * s;
   }
-  float4* dst = reinterpret_cast<float4*>(e.out0 + pix * e.ld0 + e.coff0 + n);
-  if (e.accumulate) {
-    const float4 o = *dst;
+  if (e.accumulate) {   // fp32 destinations only (lower_epilogue)
+    const float4 o = *reinterpret_cast<const float4*>(e.out0 + pix * e.ld0 + e.coff0 + n);
     y[0] += o.x; y[1] += o.y; y[2] += o.z; y[3] += o.w;
   }
-  if (e.round) {
+  if (e.round && !e.h0) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) y[j] = round_tf32(y[j]);
   }
-  *dst = make_float4(y[0], y[1], y[2], y[3]);
+  store4(e.out0, e.h0, pix * e.ld0 + e.coff0 + n, y);
   if (e.out1) {
     if (lin) {
       const ActLin a1 = act_linear(e.act1, e.alpha);
@@ -114,11 +149,11 @@ __device__ __forceinline__ void epi_store_vec4(const EpiDev& e, size_t pix, int 
 #pragma unroll
       for (int j = 0; j < 4; ++j) y[j] = apply_act(v[j], e.act1, e.alpha) * sc[j];
     }
-    if (e.round) {
+    if (e.round && !e.h1) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) y[j] = round_tf32(y[j]);
     }
-    *reinterpret_cast<float4*>(e.out1 + pix * e.ld1 + e.coff1 + n) = make_float4(y[0], y[1], y[2], y[3]);
+    store4(e.out1, e.h1, pix * e.ld1 + e.coff1 + n, y);
   }
 }
 

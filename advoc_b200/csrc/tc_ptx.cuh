@@ -33,8 +33,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: on timeout raise the debug flag and fall through (results are then garbage but
-// the kernel terminates; tests read the flag).
+// Bounded wait: on timeout raise the debug flag -- in device memory (later launches return at once)
+// and in the pinned host word the host side polls at its sync points (tc_host.cu: debug_word) --
+// and fall through: the kernel terminates instead of hanging the box, its results are garbage, and
+// the host raises RuntimeError at the next advoc_debug_peek / advoc_debug_flags.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsigned int* dbg, unsigned code) {
   if (mbar_try_wait(bar, parity)) return;
   const unsigned long long t0 = clock64();
@@ -44,7 +46,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsign
       // another CTA already timed out: the launch is lost, drain quickly
       if (dbg && *reinterpret_cast<volatile unsigned int*>(dbg) != 0) return;
       if (clock64() - t0 > WAIT_TIMEOUT_CYCLES) {
-        if (dbg) atomicExch(dbg, code);
+        if (dbg) {
+          atomicExch(dbg, code);
+          unsigned int* host = *reinterpret_cast<unsigned int* volatile*>(dbg + 2);
+          if (host) {
+            *reinterpret_cast<volatile unsigned int*>(host) = code;
+            __threadfence_system();
+          }
+        }
         return;
       }
     }
@@ -97,6 +106,25 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t
       ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc)
       : "memory");
 }
+// kind::f16 with fp16 A/B (10-bit mantissa like tf32, half the operand bytes, K = 16 per instruction)
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+template <bool HALF>
+__device__ __forceinline__ void umma_op(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  if (HALF) umma_f16(tmem_d, da, db, idesc, acc);
+  else umma_tf32(tmem_d, da, db, idesc, acc);
+}
+// instruction descriptor: D fp32; A/B tf32 (kind::tf32) or fp16 (kind::f16), both K-major; M x N tile
+template <bool HALF>
+__host__ __device__ constexpr uint32_t umma_idesc(int m, int n) {
+  return (1u << 4) | (HALF ? 0u : ((2u << 7) | (2u << 10))) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
 // One lane of a converged warp (elect.sync).  Issuing tcgen05 / TMA instructions under this predicate
 // from warp-uniform code lets the compiler keep their operands in uniform registers; a plain
 // `if (lane == 0)` region makes it wrap every UTCMMA in an ELECT/BRA.U.ANY loop (~140 cycles each).
@@ -130,19 +158,22 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // ---- host side (tc_host.cu): driver entry points fetched at run time, tensor-map encoders ----
 bool tma_ok();                 // cuTensorMapEncode{Tiled,Im2col} available
 unsigned int* debug_word();    // device word raised by a timed-out pipeline wait
+volatile unsigned int* debug_host_word();   // pinned host mirror of it (nullptr if unavailable)
 
 // im2col-mode map over NHWC activations [Nimg, Hin, Win, ld] exposing C channels; box = box_c
 // channels x box_pix pixels, 128-byte swizzle (box_c * 4 must be 128).
-int encode_im2col(CUtensorMap* tm, const float* x, int Nimg, int Hin, int Win, int ld, int C, int lower_h,
+// `half` != 0 in every encoder: the tensor holds fp16 elements (ld / strides / box_c stay in ELEMENTS)
+int encode_im2col(CUtensorMap* tm, const void* x, int Nimg, int Hin, int Win, int ld, int C, int lower_h,
                   int lower_w, int upper_h, int upper_w, int trav_h, int trav_w, int box_c, int box_pix,
-                  bool atom32 = false);
+                  bool atom32 = false, int half = 0);
 // plain 2-D map: `rows` rows of `inner` floats, row stride in bytes; box = box_inner x box_rows
-int encode_tiled2d(CUtensorMap* tm, const float* p, int inner, long rows, size_t row_stride_bytes, int box_inner,
-                   int box_rows, bool atom32 = false);
+int encode_tiled2d(CUtensorMap* tm, const void* p, int inner, long rows, size_t row_stride_bytes, int box_inner,
+                   int box_rows, bool atom32 = false, int half = 0);
 // tiled 4-D map over a strided NHWC view: dims {C, W, H, N} with pixel / row / image strides in
-// floats; box {box_c, box_w, box_h, 1}, 128-byte swizzle
-int encode_tiled4d(CUtensorMap* tm, const float* x, int C, int W, int H, int Nimg, long stride_w, long stride_h,
-                   long stride_n, int box_c, int box_w, int box_h);
+// elements; box {box_c, box_w, box_h, 1}; box rows of 128 bytes use the 128-byte swizzle, rows of 64
+// bytes the 64-byte swizzle
+int encode_tiled4d(CUtensorMap* tm, const void* x, int C, int W, int H, int Nimg, long stride_w, long stride_h,
+                   long stride_n, int box_c, int box_w, int box_h, int half = 0);
 // atom32: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B (32-byte chunks swizzled over 4 rows) -- the only
 // layout tcgen05 accepts for MN-major 32-bit (tf32) operands; default is SWIZZLE_128B.
 

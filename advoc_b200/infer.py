@@ -21,14 +21,21 @@ class MelToMag(object):
   input of models/advoc/train_evaluate.py:53-56) or 'dbnorm' (r9y9 dB-normalised mel in [0,1],
   the `.npy` inputs of scripts/spectrogram_advoc.py)."""
 
-  def __init__(self, model, batch, input_kind='linear', dropout='rng', use_graph=True):
+  def __init__(self, model, batch, input_kind='linear', dropout='rng', use_graph=True, math=N.MATH_F16):
+    """math: MATH_F16 (default: fp16 operand storage between the tensor-core layers, same 10-bit
+    mantissa as TF32 at half the bytes; within the 1e-3 parity budget, tests/test_gpu_nets.py),
+    MATH_AUTO (TF32 operands, fp32 storage) or MATH_FP32 (CUDA cores)."""
     model._check_supported()
     self.model, self.B, self.kind, self.dropout = model, batch, input_kind, dropout
     self.T, self.n_mels = model.subseq_len, model.n_mels
     self.su = SpectralUtil(n_mels=model.n_mels, fs=model.audio_fs)
-    self.G = model._generator(batch)
+    self.G = model._generator(batch, math)
     self.G.prepare()
     dev = self.G.dev
+    # dropout step counter in device memory: bumped INSIDE the captured graphs, read by the decoder
+    # epilogues (advoc_epilogue.d_seed), so every replay draws fresh masks like every sess.run of the
+    # reference does (advoc_model.py:144-149)
+    self.seed_d = torch.zeros(1, dtype=torch.int64, device=dev)
     self.mel_d = torch.zeros((batch, self.T, self.n_mels), dtype=torch.float32, device=dev)
     self.x_d = torch.empty((batch, self.T, 513, 1), dtype=torch.float32, device=dev)
     self.mel_h = torch.zeros((batch, self.T, self.n_mels), dtype=torch.float32).pin_memory()
@@ -40,6 +47,7 @@ class MelToMag(object):
 
   # -- device-resident step (inputs already in HBM) ------------------------
   def _launch(self, seed, n_valid=None):
+    """seed: host value for the eager path, None = bump and read the device counter."""
     spectral_ptr = spectral._ptr
     N.call('advoc_matmul_lastdim_f32', spectral_ptr(self.mel_d), spectral_ptr(self.su.invmeltrans),
            spectral_ptr(self.x_d), self.B * self.T, self.n_mels, 513,
@@ -48,25 +56,30 @@ class MelToMag(object):
       # the reference zero-pads in the magnitude domain, after the pinv lift
       # (scripts/spectrogram_advoc.py:81-84)
       self.x_d.view(self.B * self.T, 513)[n_valid:].zero_()
+    if seed is None:
+      self.seed_d.add_(1)
+      return self.G.forward(self.x_d, dropout=self.dropout, seed_dev=self.seed_d)
     return self.G.forward(self.x_d, dropout=self.dropout, seed=seed)
 
   def step_device(self, n_valid=None):
     """One forward over the batch resident in `self.mel_d`; returns the device output
-    [B, T, 513, 1].  Replays a CUDA graph after the first (capturing) call; with the graph the
-    dropout stream is the captured one (seed fixed at capture), matching a frozen-graph
-    deployment; pass use_graph=False for a fresh mask per call."""
+    [B, T, 513, 1].  Replays a CUDA graph after the first (capturing) call.  Every call -- eager or
+    replayed -- advances the dropout step counter, so call k of an engine uses the masks of seed k on
+    either path (tests/test_gpu_pipeline.py)."""
+    self._seed += 1
     if not self.use_graph or n_valid is not None:
-      self._seed += 1
+      self.seed_d.fill_(self._seed)     # keep the device counter in step with the host one
       return self._launch(self._seed, n_valid)
     if self._graph is None:
       n0 = N.launch_count()
-      self._launch(1)  # warm-up outside capture (lazy module load, caches)
+      self._launch(self._seed)  # warm-up outside capture (lazy module load, caches)
       self.launches_per_step = N.launch_count() - n0
       torch.cuda.synchronize()
       g = torch.cuda.CUDAGraph()
       with torch.cuda.graph(g):
-        self._out = self._launch(1)
+        self._out = self._launch(None)
       self._graph = g
+      self.seed_d.fill_(self._seed - 1)   # the replay below bumps it to this call's seed
     self._graph.replay()
     return self._out
 
@@ -94,6 +107,9 @@ class MelToMag(object):
     N.call('advoc_matmul_lastdim_f32', spectral_ptr(s['mel_d']), spectral_ptr(self.su.invmeltrans),
            spectral_ptr(self.x_d), self.B * self.T, self.n_mels, 513,
            1 if self.kind == 'dbnorm' else 0, spectral._stream())
+    if seed is None:
+      self.seed_d.add_(1)
+      return self.G.forward(self.x_d, out=s['out_d'], dropout=self.dropout, seed_dev=self.seed_d)
     return self.G.forward(self.x_d, out=s['out_d'], dropout=self.dropout, seed=seed)
 
   def run_stream(self, batches):
@@ -116,6 +132,7 @@ class MelToMag(object):
         raise ValueError()
       if i >= 2:
         s['d2h'].synchronize()          # the result that used this buffer set has reached the host
+        N.raise_if_aborted('MelToMag.run_stream')
         yield pending.pop(0)
       if not mel.is_pinned():
         s['mel_h'].copy_(mel)
@@ -126,17 +143,19 @@ class MelToMag(object):
         s['mel_d'].copy_(mel, non_blocking=True)
         s['h2d'].record(hs)
       main.wait_event(s['h2d'])
+      self._seed += 1
       if self.use_graph:
         if s['graph'] is None:
-          self._launch_set(s, 1)        # warm-up outside capture
+          self._launch_set(s, self._seed)        # warm-up outside capture
           torch.cuda.synchronize()
           g = torch.cuda.CUDAGraph()
           with torch.cuda.graph(g):
-            self._launch_set(s, 1)
+            self._launch_set(s, None)
           s['graph'] = g
+          self.seed_d.fill_(self._seed - 1)
         s['graph'].replay()
       else:
-        self._seed += 1
+        self.seed_d.fill_(self._seed)
         self._launch_set(s, self._seed)
       s['done'].record(main)
       with torch.cuda.stream(ds):
@@ -146,6 +165,7 @@ class MelToMag(object):
       pending.append(s['out_h'])
     for k, out in enumerate(pending):
       self._sets[(i - len(pending) + 1 + k) & 1]['d2h'].synchronize()
+      N.raise_if_aborted('MelToMag.run_stream')
       yield out
 
   # -- public host API ----------------------------------------------------
@@ -165,6 +185,7 @@ class MelToMag(object):
     out = self.step_device(n_valid)
     self.out_h.copy_(out.view(self.B, self.T, 513), non_blocking=True)
     torch.cuda.current_stream().synchronize()
+    N.raise_if_aborted('MelToMag.__call__')
     return self.out_h
 
 

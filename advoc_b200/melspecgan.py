@@ -537,6 +537,7 @@ class MelspecGAN(object):
 
   def loss_values(self):
     v = self.losses.tolist()
+    N.raise_if_aborted('MelspecGAN')
     return v[0], v[1]
 
 

@@ -145,10 +145,11 @@ class Advoc(Model):
     if self.params is None:
       self.init_params()
 
-  def _generator(self, batch):
-    if batch not in self._gen:
-      self._gen[batch] = nets.Generator(self.gen_spec(), self.params, batch, self.math_mode)
-    return self._gen[batch]
+  def _generator(self, batch, math=None):
+    math = self.math_mode if math is None else math
+    if (batch, math) not in self._gen:
+      self._gen[(batch, math)] = nets.Generator(self.gen_spec(), self.params, batch, math)
+    return self._gen[(batch, math)]
 
   def _discriminator(self, batch):
     if batch not in self._dis:

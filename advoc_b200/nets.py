@@ -80,10 +80,21 @@ class _Conv(object):
     N.call(fn, C.byref(self.desc), _ptr(x), ldx, _ptr(w), C.byref(ep), _stream())
 
   # -- accounting used by bench.py (dense MACs x 2) --------------
-  def uses_tensor_cores(self, ldx=None):
+  def path(self, ldx=None):
+    """advoc_conv2d_path: MATH_FP32 (CUDA cores), MATH_TF32 or MATH_F16 (tcgen05)."""
     ldx = self.ldx if ldx is None else ldx
-    return N.lib().advoc_conv2d_path(C.byref(self.desc), ldx,
-                                     1 if self.kind == 'deconv' else 0) == N.MATH_TF32
+    return N.lib().advoc_conv2d_path(C.byref(self.desc), ldx, 1 if self.kind == 'deconv' else 0)
+
+  def uses_tensor_cores(self, ldx=None):
+    return self.path(ldx) != N.MATH_FP32
+
+  def half_operands(self):
+    return self.desc.math == N.MATH_F16
+
+  def tile_n(self):
+    """BN of the tcgen05 instantiation this layer launches (0 on the CUDA-core kernels)."""
+    return N.lib().advoc_conv2d_tile_n(C.byref(self.desc), self.ldx, 1 if self.kind == 'deconv' else 0,
+                                       getattr(self, 'store_w', 0) or 0)
 
   def kernel_family(self):
     """Kernel that runs this layer (bench.py attributes time by it)."""
@@ -107,13 +118,16 @@ class _Conv(object):
     return 2.0 * d.N * d.Ho * d.Wo * d.kh * d.kw * d.Cin * d.Cout
 
   def algorithmic_bytes(self):
+    """Bytes the layer must move once: input + filter + stored output(s), at the element sizes of
+    the buffers it actually ran on (`in_bytes` / `out_bytes`, recorded by the engine)."""
     d = self.desc
     big, small = d.N * d.H * d.W * d.Cin, d.N * d.Ho * d.Wo * d.Cout
     w = d.kh * d.kw * d.Cin * d.Cout
+    ib, ob = getattr(self, 'in_bytes', 4), getattr(self, 'out_bytes', 4)
     if self.kind == 'conv':
-      return 4.0 * (big + w + small * self.n_out)
+      return ib * (big + w) + ob * small * self.n_out
     ws = self.store_w or d.W
-    return 4.0 * (small + w + d.N * d.H * ws * d.Cin)
+    return ib * (small + w) + ob * d.N * d.H * ws * d.Cin
 
 
 def _desc(n, h, w, cin, cout, sh, sw, pt, pl, ho, wo, math):
@@ -123,10 +137,14 @@ def _desc(n, h, w, cin, cout, sh, sw, pt, pl, ho, wo, math):
 def _epilogue(bias, out0, ld0, coff0, act0, out1=None, ld1=0, coff1=0, act1=N.ACT_NONE,
               store_w=0, mask=None, keep_prob=1.0, seed=0, round_tf32=0, alpha=0.2,
               accumulate=0, gate=None, ld_gate=0, coff_gate=0, gate_act=N.ACT_NONE, gate_split=0,
-              gate_scale0=1.0, gate_scale1=1.0):
+              gate_scale0=1.0, gate_scale1=1.0, seed_dev=None):
+  """advoc_epilogue; the output dtypes follow the destination tensors (float32 / float16)."""
+  h0 = N.DT_F16 if (out0 is not None and out0.dtype == torch.float16) else N.DT_F32
+  h1 = N.DT_F16 if (out1 is not None and out1.dtype == torch.float16) else N.DT_F32
   return N.Epilogue(_ptr(bias), act0, act1, alpha, _ptr(out0), ld0, coff0, _ptr(out1), ld1, coff1,
                     store_w, _ptr(mask), keep_prob, seed, round_tf32, accumulate, _ptr(gate),
-                    ld_gate, coff_gate, gate_act, gate_split, gate_scale0, gate_scale1)
+                    ld_gate, coff_gate, gate_act, gate_split, gate_scale0, gate_scale1, _ptr(seed_dev),
+                    h0, h1)
 
 
 def _pack_for_tc(L, kernel, ldx, out=None):
@@ -137,48 +155,75 @@ def _pack_for_tc(L, kernel, ldx, out=None):
   if not L.uses_tensor_cores(ldx):
     return None
   kh, kw, a, b = kernel.shape
+  half = L.half_operands()   # ADVOC_MATH_F16 layers read an fp16 copy (same 10-bit mantissa as TF32)
   if out is None:
     out = torch.empty((kh * kw, b, a) if L.kind == 'conv' else (kh * kw, a, b),
-                      dtype=torch.float32, device=kernel.device)
+                      dtype=torch.float16 if half else torch.float32, device=kernel.device)
   N.call('advoc_pack_filter', _ptr(kernel), _ptr(out), kh * kw, a, b, 1 if L.kind == 'conv' else 0,
-         1, _stream())
+         2 if half else 1, _stream())
   return out
 
 
 class Generator(object):
-  """U-Net generator forward on persistent buffers.  x [B,T,513,1] -> [B,T,513,1]."""
+  """U-Net generator forward on persistent buffers.  x [B,T,513,1] -> [B,T,513,1].
+
+  math = MATH_F16 (inference): every layer whose contraction side has a multiple of 64 channels reads
+  fp16 activations and filters (tcgen05 kind::f16; half the HBM / L2 / shared-memory operand bytes of
+  the TF32 path at the same 10-bit mantissa) and the buffers between such layers are stored as fp16 by
+  the producing epilogue; the other layers (encoder_1 on CUDA cores; a 32-channel encoder_2 input) stay
+  fp32 / TF32.  The network input and output are fp32 either way."""
 
   def __init__(self, spec, params, batch, math=N.MATH_AUTO, device=None):
     self.spec, self.P, self.B, self.math = spec, params, batch, math
     dev = device or torch.device('cuda', torch.cuda.current_device())
     self.dev = dev
     s = spec
-    f32 = dict(dtype=torch.float32, device=dev)
     n = s.n_enc
-    # lrelu(encoder_i) for i < n: the next encoder's input
-    self.E = {i: torch.empty((batch, s.H[i], s.W[i], s.enc_ch[i - 1]), **f32) for i in range(1, n)}
-    # decoder_k input = relu(concat(decoder_{k+1}[:, :, :-1], encoder_k))
     self.Dk = {k: (s.dec_ch[k + 1] if k < n else 0) for k in range(1, n + 1)}
-    self.Cat = {k: torch.empty((batch, s.H[k], s.W[k], self.Dk[k] + s.enc_ch[k - 1]), **f32)
-                for k in range(1, n + 1)}
-    self.out = torch.empty((batch, s.H[0], s.W[0], 1), **f32)
     self.enc, self.dec = {}, {}
+    base_math = N.MATH_AUTO if math == N.MATH_F16 else math
+
+    def pick(kind, name, ldx, mk):
+      """The layer with fp16 operands when asked for and eligible, else in the base math mode."""
+      if math == N.MATH_F16:
+        L = _Conv(name, kind, mk(N.MATH_F16))
+        if L.path(ldx) == N.MATH_F16:
+          return L
+      return _Conv(name, kind, mk(base_math))
+
     for i in range(1, n + 1):
       cin = 1 if i == 1 else s.enc_ch[i - 2]
       ho, pt, _ = same_pads(s.H[i - 1], 4, s.sh[i])
       wo, pl, _ = same_pads(s.W[i - 1], 4, 2)
       assert ho == s.H[i] and wo == s.W[i]
-      self.enc[i] = _Conv('generator/encoder_%d/conv2d' % i, 'conv',
-                          _desc(batch, s.H[i - 1], s.W[i - 1], cin, s.enc_ch[i - 1], s.sh[i], 2, pt,
-                                pl, ho, wo, math))
+      self.enc[i] = pick('conv', 'generator/encoder_%d/conv2d' % i, max(cin, 1),
+                         lambda m, i=i, cin=cin, ho=ho, wo=wo, pt=pt, pl=pl: _desc(
+                             batch, s.H[i - 1], s.W[i - 1], cin, s.enc_ch[i - 1], s.sh[i], 2, pt, pl, ho, wo, m))
     for j, k in enumerate(range(n, 0, -1)):
       sh = 1 if j < s.n_stride1 else 2
       cin = self.Dk[k] + s.enc_ch[k - 1]
       # geometry of the forward conv this deconv is the input-gradient of: big side = output
-      self.dec[k] = _Conv('generator/decoder_%d/conv2d_transpose' % k, 'deconv',
-                          _desc(batch, s.H[k] * sh, s.W[k] * 2, s.dec_ch[k], cin, sh, 2, 1, 1,
-                                s.H[k], s.W[k], math))
+      self.dec[k] = pick('deconv', 'generator/decoder_%d/conv2d_transpose' % k, cin,
+                         lambda m, k=k, sh=sh, cin=cin: _desc(batch, s.H[k] * sh, s.W[k] * 2, s.dec_ch[k], cin, sh, 2,
+                                                              1, 1, s.H[k], s.W[k], m))
       assert s.H[k] * sh == s.H[k - 1] and s.W[k] * 2 - 1 == s.W[k - 1]
+    # buffer element types follow their (single) consumer
+    dt = lambda L: torch.float16 if L.half_operands() else torch.float32
+    # lrelu(encoder_i) for i < n: the next encoder's input
+    self.E = {i: torch.empty((batch, s.H[i], s.W[i], s.enc_ch[i - 1]), dtype=dt(self.enc[i + 1]), device=dev)
+              for i in range(1, n)}
+    # decoder_k input = relu(concat(decoder_{k+1}[:, :, :-1], encoder_k))
+    self.Cat = {k: torch.empty((batch, s.H[k], s.W[k], self.Dk[k] + s.enc_ch[k - 1]), dtype=dt(self.dec[k]),
+                               device=dev)
+                for k in range(1, n + 1)}
+    self.out = torch.empty((batch, s.H[0], s.W[0], 1), dtype=torch.float32, device=dev)
+    es = lambda t: t.element_size()
+    for i in range(1, n + 1):
+      self.enc[i].in_bytes = 4 if i == 1 else es(self.E[i - 1])
+      self.enc[i].out_bytes = (es(self.E[i]) + es(self.Cat[i])) / 2.0 if i < n else es(self.Cat[i])
+    for k in range(1, n + 1):
+      self.dec[k].in_bytes = es(self.Cat[k])
+      self.dec[k].out_bytes = es(self.Cat[k - 1]) if k > 1 else 4
 
   def _ldx(self, L):
     if L.kind == 'conv':
@@ -213,11 +258,13 @@ class Generator(object):
     s = self.spec
     return (self.B, s.H[k - 1], s.W[k - 1], s.dec_ch[k])
 
-  def forward(self, x, out=None, out_ld=1, out_coff=0, dropout=None, seed=0, x_ld=1):
+  def forward(self, x, out=None, out_ld=1, out_coff=0, dropout=None, seed=0, x_ld=1, seed_dev=None):
     """x f32 [B,T,513,1] contiguous.  dropout: None (off, parity mode) | 'rng' (counter-based
     generator keyed by `seed`, the reference's behaviour in every mode, advoc_model.py:144-149)
-    | {decoder_index: uint8 mask tensor} (injected masks).  Returns the output buffer
-    (`out` if given: written with pixel stride out_ld at channel out_coff)."""
+    | {decoder_index: uint8 mask tensor} (injected masks).  `seed_dev`: a one-element int64 CUDA
+    tensor holding the step counter; the kernels then read the seed from it (a captured CUDA graph
+    draws fresh masks on every replay; same masks as `seed` = the counter's value on the eager path).
+    Returns the output buffer (`out` if given: written with pixel stride out_ld at channel out_coff)."""
     s, P, n = self.spec, self.P, self.spec.n_enc
     assert x.is_contiguous() and tuple(x.shape) == (self.B, s.H[0], s.W[0], x_ld), x.shape
     if not hasattr(self, 'Wp'):
@@ -242,7 +289,9 @@ class Generator(object):
       kw = {}
       if k in s.dropout_decoders and dropout is not None:
         kw['keep_prob'] = 0.5
-        if dropout == 'rng':
+        if dropout == 'rng' and seed_dev is not None:
+          kw['seed'], kw['seed_dev'] = k, seed_dev
+        elif dropout == 'rng':
           kw['seed'] = (seed * 0x9E3779B1 + k) & 0xFFFFFFFFFFFFFFFF
         else:
           kw['mask'] = dropout[k]

@@ -314,4 +314,5 @@ class TrainEngine(object):
   def loss_values(self):
     """(d_loss, g_loss_GAN * gan_weight, g_loss_L1 * l1_weight) of the last steps (syncs)."""
     v = self.losses.tolist()
+    N.raise_if_aborted('TrainEngine')
     return v[0], v[1], v[2]

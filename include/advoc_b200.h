@@ -60,8 +60,20 @@ typedef enum advoc_act {
 typedef enum advoc_math {
   ADVOC_MATH_AUTO = 0,  /* tensor cores (TF32, fp32 accumulate) where the layer is eligible */
   ADVOC_MATH_FP32 = 1,  /* CUDA-core fp32 direct kernels (exact-fp32 cross-check path)      */
-  ADVOC_MATH_TF32 = 2   /* force the tcgen05 path; ADVOC_UNSUPPORTED if not eligible        */
+  ADVOC_MATH_TF32 = 2,  /* force the tcgen05 path; ADVOC_UNSUPPORTED if not eligible        */
+  /* fp16 OPERANDS (d_x and d_w hold IEEE half: the same 10-bit mantissa as TF32, half the bytes;
+   * tcgen05 kind::f16, K = 16 per instruction), fp32 accumulate.  Forward pass only.  Needs the
+   * contraction channel count % 64 == 0, ld_x % 8 == 0 and the filter packed by advoc_pack_filter with
+   * mode 2; ADVOC_UNSUPPORTED otherwise (ask advoc_conv2d_path first).  Values must stay inside
+   * fp16's range (|v| < 65504): true for magnitude spectra and N(0, 0.02)-initialised stacks, and the
+   * producing epilogues saturate instead of overflowing to inf. */
+  ADVOC_MATH_F16 = 3
 } advoc_math;
+
+typedef enum advoc_dtype {
+  ADVOC_DT_F32 = 0,
+  ADVOC_DT_F16 = 1
+} advoc_dtype;
 
 ADVOC_API int advoc_version(void);
 /* Copies the calling thread's last error text (NUL terminated) into buf. */
@@ -181,32 +193,49 @@ typedef struct advoc_epilogue {
   const float* d_gate; int ld_gate, c_off_gate;
   int gate_act, gate_split;
   float gate_scale0, gate_scale1;
+  /* Optional dropout step counter in DEVICE memory.  When non-NULL the generator is keyed by
+   * (*d_seed) * 0x9E3779B1 + seed instead of seed (seed then is the layer's salt), so a captured CUDA
+   * graph draws a fresh mask on every replay once the caller bumps the counter (the reference
+   * resamples dropout on every sess.run, advoc_model.py:144-149). */
+  const uint64_t* d_seed;
+  /* advoc_dtype of d_out0 / d_out1: ADVOC_DT_F16 stores IEEE half (round-to-nearest-even); ld / c_off
+   * stay in elements.  Forward pass only (no gate / accumulate). */
+  int out0_dtype, out1_dtype;
 } advoc_epilogue;
 
 /* Re-pack a TF-layout filter [kh*kw, A, B] (A,B = Cin,Cout for conv; Cout,Cin for
  * conv_transpose) into [kh*kw, B, A] (transpose != 0) or copy it, optionally rounding every
  * value to TF32 (round-to-nearest) so the tensor-core path reads exactly representable
  * operands.  replaces: nothing in the reference (TF/cuDNN pick their own filter layouts). */
-ADVOC_API int advoc_pack_filter(const float* d_w, float* d_packed, int taps, int A, int B,
-                                int transpose, int round_tf32, void* stream);
+/* mode: 0 copy, 1 round to TF32, 2 convert to fp16 (d_packed then holds IEEE half, for
+ * ADVOC_MATH_F16 layers). */
+ADVOC_API int advoc_pack_filter(const float* d_w, void* d_packed, int taps, int A, int B,
+                                int transpose, int mode, void* stream);
 
 /* Reads and clears the library's device-side debug word: non-zero means a pipeline barrier of a
  * tcgen05 kernel timed out (1 producer, 2 MMA issuer, 3 epilogue).  Synchronises the device. */
 ADVOC_API int advoc_debug_flags(unsigned int* out);
 
+/* The same code read from its pinned host mirror: no CUDA call, no synchronisation, does not
+ * clear.  The host engines (infer.MelToMag, train.TrainEngine, melspecgan.MelspecGAN, bench.py) call
+ * it at their own synchronisation points and raise RuntimeError when it is non-zero, so that a timed
+ * out launch can never pass stale buffers on as results. */
+ADVOC_API int advoc_debug_peek(unsigned int* out);
+
 /* y = conv2d(x, w) ; x [N,H,W,Cin] (pixel stride ld_x >= Cin, channel offset 0).
  * d_w: on the CUDA-core path (advoc_conv2d_path == ADVOC_MATH_FP32) the TF layout HWIO;
  * on the tcgen05 path the K-major pack [taps, Cout, Cin] made by advoc_pack_filter.
  * replaces: tf.layers.conv2d call sites models/advoc/advoc_model.py:27-32, :46-51. */
-ADVOC_API int advoc_conv2d_fwd(const advoc_conv_desc* d, const float* d_x, int ld_x, const float* d_w,
+/* d_x / d_w are float, or IEEE half when d->math == ADVOC_MATH_F16 (ld_x in elements either way). */
+ADVOC_API int advoc_conv2d_fwd(const advoc_conv_desc* d, const void* d_x, int ld_x, const void* d_w,
                      const advoc_epilogue* ep, void* stream);
 
 /* y = conv2d_transpose(x, w); x [N,Ho,Wo,Cout] (ld_x), output [N,H,W,Cin] in desc naming.
  * d_w: TF layout HWOI [kh,kw,Cin(desc),Cout(desc)] on both paths (it already is K-major for
  * this GEMM; pass a TF32-rounded copy on the tcgen05 path).
  * replaces: tf.layers.conv2d_transpose models/advoc/advoc_model.py:65-69. */
-ADVOC_API int advoc_conv2d_transpose_fwd(const advoc_conv_desc* d, const float* d_x, int ld_x,
-                               const float* d_w, const advoc_epilogue* ep, void* stream);
+ADVOC_API int advoc_conv2d_transpose_fwd(const advoc_conv_desc* d, const void* d_x, int ld_x,
+                               const void* d_w, const advoc_epilogue* ep, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * Backward pass and optimiser (the gradient graph of advoc_model.py:238-257)
@@ -272,6 +301,12 @@ ADVOC_API int advoc_conv2d_path(const advoc_conv_desc* d, int ld_x, int transpos
  * (conv_p2d.cu), 3 tcgen05 transposed conv to one channel (deconv_one_tc.cu).  store_w as in advoc_epilogue (0 = full width).  Host-side query, used by bench.py
  * to attribute time to kernels.  replaces: nothing in the reference. */
 ADVOC_API int advoc_conv2d_kernel(const advoc_conv_desc* d, int ld_x, int transposed, int store_w);
+
+/* Accumulator tile width N (the BN template parameter: conv_tc_kernel<BN,...> / conv_p2d_kernel<BN>)
+ * of the kernel advoc_conv2d_kernel names for this geometry; 16 for the to-one-channel kernel, 0 for
+ * the CUDA-core kernels.  Host-side query: the parity tests use it to assert which instantiation
+ * they covered.  replaces: nothing in the reference. */
+ADVOC_API int advoc_conv2d_tile_n(const advoc_conv_desc* d, int ld_x, int transposed, int store_w);
 
 /* ------------------------------------------------------------------------- *
  * MelspecGAN building blocks (models/melspecgan/conv2d.py, models/melspecgan/train.py).

@@ -179,3 +179,199 @@ def test_model_api_mirror():
   p = m.build_discriminator(x, y)
   assert p.shape == (1, 30, 62, 1) and float(p.min()) > 0 and float(p.max()) < 1
   assert Advoc.ngf == 64 and Advoc.train_batch_size == 8
+
+
+# ---------------------------------------------------------------------------------------------
+# round 2: the configurations bench.py actually times (B = 32 small, regular model, wide N tiles)
+# and the fp16-operand inference mode
+# ---------------------------------------------------------------------------------------------
+def _check_generator(G, P, x, spec_o, tol, n_enc):
+  """Every stored activation of a forward pass against the oracle's layer list."""
+  from oracle import nets_torch as O
+  out = G.forward(x.contiguous())
+  torch.cuda.synchronize()
+  from advoc_b200 import _native as N
+  assert N.debug_flags() == 0
+  ref, layers = O.generator(P, x.cpu(), spec_o, return_layers=True)
+  errs = {'out': _rel(out, ref)}
+  for i in range(1, n_enc):
+    errs['E%d' % i] = _rel(G.E[i], O.lrelu(layers[i - 1]))
+  errs['Cat%d' % n_enc] = _rel(G.Cat[n_enc], torch.relu(layers[n_enc - 1]))
+  for k in range(n_enc - 1, 0, -1):
+    dec = layers[n_enc + (n_enc - 1 - k)]          # output of decoder_{k+1}
+    cat = torch.relu(torch.cat([dec[:, :, :-1, :], layers[k - 1]], dim=3))
+    errs['Cat%d' % k] = _rel(G.Cat[k], cat)
+  bad = {k: v for k, v in errs.items() if not v < tol}
+  assert not bad, (bad, errs)
+  return errs
+
+
+def _instantiations(G):
+  return sorted({(L.kernel_family().split('/')[0], L.tile_n(), L.half_operands())
+                 for L in list(G.enc.values()) + list(G.dec.values())})
+
+
+@pytest.mark.parametrize('math', ['auto', 'f16'])
+def test_small_generator_forward_at_the_benchmarked_batch(math):
+  """BASELINE configs[1] exactly as bench.py times it (AdVoc-small, B = 32): every stored activation
+  within 1e-3 of the oracle, and the tile instantiations of that batch size really ran
+  (conv_tc_kernel<128,3> only appears from B = 32 on)."""
+  from advoc_b200 import _native as N
+  from advoc_b200 import nets
+  from advoc_b200.model import SpectralUtil
+  from oracle import nets_torch as O
+  P = _randomize_biases(O.init_params(O.SMALL, seed=0))
+  g = torch.Generator().manual_seed(1)
+  mel = torch.randn(32, 256, 80, 1, generator=g).abs()
+  x = SpectralUtil().mel_linear_to_mag_spec(mel.cuda())
+  G = nets.Generator(nets.GenSpec(32, 5, (5, 4)), _to_cuda(P), 32, N.MATH_F16 if math == 'f16' else N.MATH_AUTO)
+  _check_generator(G, P, x, O.SMALL, TOL, 5)
+  inst = _instantiations(G)
+  fams = {k for k, _, _ in inst}
+  assert 'conv_p2d_kernel' in fams and 'deconv_one_tc_kernel' in fams, inst
+  if math == 'auto':
+    assert ('conv_tc_kernel', 128, False) in inst, inst
+  else:
+    assert any(h for _, _, h in inst), inst
+    assert G.Cat[1].dtype == torch.float16 and G.Cat[4].dtype == torch.float16
+
+
+@pytest.mark.parametrize('math', ['auto', 'f16'])
+def test_regular_generator_forward_matches_oracle(math):
+  """AdVoc regular (ngf 64, 8 + 8 layers, the 1x3 bottleneck and the 1024-channel concats of BASELINE
+  configs[2]/[3]) at B = 4, every stored activation."""
+  from advoc_b200 import _native as N
+  from advoc_b200 import nets
+  from oracle import nets_torch as O
+  P = _randomize_biases(O.init_params(O.REGULAR, seed=0))
+  g = torch.Generator().manual_seed(2)
+  x = torch.randn(4, 256, 513, 1, generator=g).abs() * 0.5
+  G = nets.Generator(nets.GenSpec(64, 8, (8, 7, 6)), _to_cuda(P), 4, N.MATH_F16 if math == 'f16' else N.MATH_AUTO)
+  _check_generator(G, P, x.cuda(), O.REGULAR, TOL, 8)
+
+
+def test_regular_discriminator_forward_matches_oracle():
+  from advoc_b200 import _native as N
+  from advoc_b200 import nets
+  from oracle import nets_torch as O
+  P = _randomize_biases(O.init_params(O.REGULAR, seed=0))
+  g = torch.Generator().manual_seed(4)
+  a = torch.randn(4, 256, 513, 1, generator=g).abs()
+  b = torch.randn(4, 256, 513, 1, generator=g).abs()
+  D = nets.Discriminator(64, _to_cuda(P), 4, N.MATH_AUTO)
+  out = D.forward(torch.cat([a, b], 3).cuda().contiguous())
+  ref, layers = O.discriminator(P, a, b, return_layers=True)
+  assert N.debug_flags() == 0
+  for got, want in zip(D.act, layers):
+    assert _rel(got, want) < TOL
+
+
+def test_wide_n_tiles_regular_model():
+  """conv_tc_kernel<256,4> (19.5 % of the regular train step at B = 32) is only picked by itself from
+  large batches on; ADVOC_TC_WIDE_N=1 makes the per-tap kernel always take its widest tile, so a child
+  process covers that instantiation with the regular generator / discriminator forward at B = 4."""
+  import os
+  import subprocess
+  import sys
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  env = dict(os.environ)
+  env['ADVOC_TC_WIDE_N'] = '1'
+  env['ADVOC_EXPECT_WIDE_N'] = '1'
+  r = subprocess.run([sys.executable, '-m', 'pytest', '-x', '-q', '-m', 'gpu', 'tests/test_gpu_nets.py', '-k',
+                      'regular_generator_forward or regular_discriminator or wide_n_probe'],
+                     cwd=root, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, universal_newlines=True)
+  assert r.returncode == 0, r.stdout[-3000:]
+
+
+def test_wide_n_probe():
+  """In the ADVOC_TC_WIDE_N child: the regular stacks contain 256-wide per-tap launches."""
+  import os
+  if not os.environ.get('ADVOC_EXPECT_WIDE_N'):
+    pytest.skip('runs inside test_wide_n_tiles_regular_model')
+  from advoc_b200 import _native as N
+  from advoc_b200 import nets
+  from oracle import nets_torch as O
+  P = O.init_params(O.REGULAR, seed=0)
+  G = nets.Generator(nets.GenSpec(64, 8, (8, 7, 6)), _to_cuda(P), 4, N.MATH_AUTO)
+  G.forward(torch.rand(4, 256, 513, 1, device='cuda'))
+  assert ('conv_tc_kernel', 256, False) in _instantiations(G), _instantiations(G)
+
+
+@pytest.mark.parametrize('kernel', ['auto', 'p2d', 'tc'])
+def test_single_layers_fp16_operands(kernel):
+  """ADVOC_MATH_F16: fp16 activations and filters in, fp16 (dual-write, channel offset, crop) or fp32
+  out, on both tcgen05 kernels (forced through ADVOC_P2D_FORCE / ADVOC_NO_P2D in child processes)."""
+  import os
+  import subprocess
+  import sys
+  if kernel != 'auto':
+    if os.environ.get('ADVOC_F16_CHILD'):
+      pytest.skip('child')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ)
+    env['ADVOC_P2D_FORCE' if kernel == 'p2d' else 'ADVOC_NO_P2D'] = '1'
+    env['ADVOC_F16_CHILD'] = '1'
+    r = subprocess.run([sys.executable, '-m', 'pytest', '-x', '-q', '-m', 'gpu', 'tests/test_gpu_nets.py', '-k',
+                        'single_layers_fp16_operands and auto'],
+                       cwd=root, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, universal_newlines=True)
+    assert r.returncode == 0, r.stdout[-3000:]
+    return
+  from advoc_b200 import _native as N
+  from advoc_b200 import nets
+  from oracle import nets_torch as O
+  g = torch.Generator().manual_seed(0)
+  B = 2
+  q = lambda t: t.half().float()
+  for (H, W, Cin, Cout, sh, odt) in [(16, 33, 64, 128, 2, torch.float16), (32, 65, 128, 64, 2, torch.float16),
+                                      (8, 17, 64, 32, 2, torch.float16), (1, 5, 64, 32, 1, torch.float32)]:
+    x = torch.randn(B, H, W, Cin, generator=g)
+    k = torch.randn(4, 4, Cin, Cout, generator=g) * 0.05
+    b = torch.randn(Cout, generator=g) * 0.1
+    ref = O.conv_same(q(x), q(k), b, (sh, 2))
+    ho, pt, _ = nets.same_pads(H, 4, sh)
+    wo, pl, _ = nets.same_pads(W, 4, 2)
+    y0 = torch.full((B, ho, wo, Cout), float('nan'), device='cuda', dtype=odt)
+    cat = torch.full((B, ho, wo, Cout + 64), float('nan'), device='cuda', dtype=odt)
+    L = nets._Conv('t', 'conv', nets._desc(B, H, W, Cin, Cout, sh, 2, pt, pl, ho, wo, N.MATH_F16))
+    assert L.path(Cin) == N.MATH_F16
+    bd, xd, kd = b.cuda(), x.cuda().half(), k.cuda()
+    wp = nets._pack_for_tc(L, kd, Cin)
+    assert wp.dtype == torch.float16
+    ep = nets._epilogue(bd, y0, Cout, 0, N.ACT_LRELU, cat, Cout + 64, 64, N.ACT_RELU)
+    L.run(xd, Cin, wp, ep)
+    torch.cuda.synchronize()
+    assert N.debug_flags() == 0
+    assert _rel(y0.float(), O.lrelu(ref)) < TOL, (H, W, Cin, Cout)
+    assert _rel(cat[..., 64:].float(), torch.relu(ref)) < TOL
+    assert torch.isnan(cat[..., :64]).all()
+  for (H, W, Cin, Cout, sh, odt) in [(8, 17, 64, 32, 2, torch.float16), (16, 33, 128, 64, 2, torch.float16),
+                                      (1, 3, 64, 64, 1, torch.float16), (8, 17, 192, 128, 2, torch.float32)]:
+    x = torch.relu(torch.randn(B, H, W, Cin, generator=g))
+    k = torch.randn(4, 4, Cout, Cin, generator=g) * 0.05
+    b = torch.randn(Cout, generator=g) * 0.1
+    ref = torch.relu(O.deconv_same(q(x), q(k), b, (sh, 2)))[:, :, :-1, :]
+    cat = torch.full((B, H * sh, 2 * W - 1, Cout + 32), float('nan'), device='cuda', dtype=odt)
+    L = nets._Conv('t', 'deconv', nets._desc(B, H * sh, 2 * W, Cout, Cin, sh, 2, 1, 1, H, W, N.MATH_F16))
+    assert L.path(Cin) == N.MATH_F16
+    bd, xd, kd = b.cuda(), x.cuda().half(), k.cuda()
+    ep = nets._epilogue(bd, cat, Cout + 32, 0, N.ACT_RELU, store_w=2 * W - 1)
+    L.run(xd, Cin, nets._pack_for_tc(L, kd, Cin), ep)
+    torch.cuda.synchronize()
+    assert N.debug_flags() == 0
+    assert _rel(cat[..., :Cout].float(), ref) < TOL, (H, W, Cin, Cout)
+    assert torch.isnan(cat[..., Cout:]).all()
+  # decoder_1 geometry: 64 fp16 channels -> one fp32 channel, last column cropped
+  H, W, Cin = 16, 33, 64
+  x = torch.relu(torch.randn(B, H, W, Cin, generator=g))
+  k = torch.randn(4, 4, 1, Cin, generator=g) * 0.05
+  b = torch.randn(1, generator=g) * 0.1
+  ref = O.deconv_same(q(x), q(k), b, (2, 2))[:, :, :-1, :]
+  out = torch.full((B, 2 * H, 2 * W - 1, 1), float('nan'), device='cuda')
+  L = nets._Conv('t', 'deconv', nets._desc(B, 2 * H, 2 * W, 1, Cin, 2, 2, 1, 1, H, W, N.MATH_F16))
+  assert L.path(Cin) == N.MATH_F16
+  bd, xd, kd = b.cuda(), x.cuda().half(), k.cuda()
+  L.run(xd, Cin, nets._pack_for_tc(L, kd, Cin), nets._epilogue(bd, out, 1, 0, N.ACT_NONE, store_w=2 * W - 1))
+  torch.cuda.synchronize()
+  assert N.debug_flags() == 0
+  assert L.kernel_family().startswith('deconv_one_tc')
+  assert _rel(out, ref) < TOL

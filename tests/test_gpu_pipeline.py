@@ -141,3 +141,32 @@ def test_streaming_inference_matches_serial_calls():
   for a, b in zip(got, want):
     assert torch.equal(a, b)
   assert list(eng.run_stream([])) == []
+
+
+@pytest.mark.parametrize('math', ['f16', 'auto'])
+def test_graph_replay_resamples_dropout(math):
+  """The captured inference graph reads its dropout seed from a device counter it bumps itself, so
+  every replay draws fresh masks (the reference resamples on every sess.run, advoc_model.py:144-149)
+  and call k of a graphed engine equals call k of an eager engine, seed for seed."""
+  from advoc_b200 import _native as N
+  from advoc_b200 import infer
+  from advoc_b200.model import AdvocSmall, Modes
+  from oracle import nets_torch as O
+  P = O.init_params(O.SMALL, seed=0)
+  mm = N.MATH_F16 if math == 'f16' else N.MATH_AUTO
+  model = AdvocSmall(Modes.INFER, params={k: v.cuda() for k, v in P.items()})
+  g = torch.Generator().manual_seed(3)
+  mel = torch.randn(2, 256, 80, generator=g).abs()
+  eng_g = infer.MelToMag(model, 2, 'linear', dropout='rng', use_graph=True, math=mm)
+  eng_e = infer.MelToMag(model, 2, 'linear', dropout='rng', use_graph=False, math=mm)
+  outs_g = [eng_g(mel).clone() for _ in range(3)]
+  outs_e = [eng_e(mel).clone() for _ in range(3)]
+  assert not torch.equal(outs_g[0], outs_g[1]) and not torch.equal(outs_g[1], outs_g[2])
+  for a, b in zip(outs_g, outs_e):
+    assert torch.equal(a, b)
+  # the streaming API (two captured graphs sharing the counter) resamples too
+  eng_s = infer.MelToMag(model, 2, 'linear', dropout='rng', use_graph=True, math=mm)
+  outs_s = [o.clone() for o in eng_s.run_stream([mel] * 4)]
+  assert not torch.equal(outs_s[0], outs_s[2]) and not torch.equal(outs_s[1], outs_s[3])
+  for a, b in zip(outs_s[:3], outs_e):
+    assert torch.equal(a, b)
