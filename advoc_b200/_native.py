@@ -61,7 +61,7 @@ SIGNATURES = {
     'advoc_stft_f32': (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     'advoc_melspec_f32': (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _F, _F, _P, _P]),
     'advoc_mel_ranges': (_I, [_P, _I, _I, _P, _P]),
-    'advoc_matmul_lastdim_f32': (_I, [_P, _P, _P, _L, _I, _I, _I, _P]),
+    'advoc_matmul_lastdim_f32': (_I, [_P, _P, _P, _L, _I, _I, _I, _F, _F, _P]),
     'advoc_conv2d_fwd': (_I, [C.POINTER(ConvDesc), _P, _I, _P, C.POINTER(Epilogue), _P]),
     'advoc_pack_filter': (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     'advoc_debug_flags': (_I, [C.POINTER(C.c_uint)]),

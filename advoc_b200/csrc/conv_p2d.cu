@@ -898,8 +898,8 @@ unsigned long long* prof_buffer() {
   static unsigned long long* buf = [] {
     unsigned long long* b = nullptr;
     if (getenv("ADVOC_P2D_PROFILE") == nullptr) return b;
-    if (cudaMalloc(&b, 256 * 16 * sizeof(unsigned long long)) != cudaSuccess) return (unsigned long long*)nullptr;
-    cudaMemset(b, 0, 256 * 16 * sizeof(unsigned long long));
+    if (cudaMalloc(&b, 512 * 16 * sizeof(unsigned long long)) != cudaSuccess) return (unsigned long long*)nullptr;
+    cudaMemset(b, 0, 512 * 16 * sizeof(unsigned long long));
     return b;
   }();
   return buf;
@@ -1025,12 +1025,12 @@ int conv_p2d(const advoc_conv_desc* d, int transposed, const void* x, int ldx, c
 }  // namespace advoc
 
 // Developer hook (ADVOC_P2D_PROFILE=1): copies the per-CTA cycle counters of the last patch-kernel
-// launches to the host ([256][16] u64) and clears them.  Synchronises the device.
+// launches to the host ([512][16] u64: up to 3 CTAs on each of 148 SMs) and clears them.  Synchronises the device.
 extern "C" __attribute__((visibility("default"))) int advoc_p2d_profile_read(unsigned long long* out) {
   using namespace advoc;
   unsigned long long* b = prof_buffer();
   ADVOC_REQUIRE(b != nullptr && out != nullptr, ADVOC_UNSUPPORTED, "profiling is off (set ADVOC_P2D_PROFILE=1)");
-  ADVOC_CHECK_CUDA(cudaMemcpy(out, b, 256 * 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-  ADVOC_CHECK_CUDA(cudaMemset(b, 0, 256 * 16 * sizeof(unsigned long long)));
+  ADVOC_CHECK_CUDA(cudaMemcpy(out, b, 512 * 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  ADVOC_CHECK_CUDA(cudaMemset(b, 0, 512 * 16 * sizeof(unsigned long long)));
   return ADVOC_OK;
 }

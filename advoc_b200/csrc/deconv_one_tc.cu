@@ -27,7 +27,7 @@ unsigned long long* g_one_prof = nullptr;
 
 constexpr int O_PH = 8, O_PW = 16;            // patch (GEMM rows = O_PH * O_PW = 128)
 constexpr int O_IH = O_PH - 2, O_IW = O_PW - 2;
-constexpr int O_STAGES = 8;                   // 16 KB patch slots
+constexpr int O_STAGES = 8;                   // most 16 KB patch slots a CTA may own (OneParams::stages are used)
 constexpr int O_THREADS = 320;               // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
 constexpr int O_MAXKB = 8;                    // Cs <= 256
 
@@ -35,6 +35,7 @@ struct alignas(64) OneParams {
   CUtensorMap tmA;   // tiled 4-D {c, w, h, n}, box {32, 16, 8, 1}
   CUtensorMap tmB;   // taps [16][Cs], box {32, 16}
   int N, Hs, Ws, kblocks, tiles_h, tiles_w;
+  int stages;        // patch ring depth of this launch (<= O_STAGES): fewer slots = more CTAs per SM
   long total_tiles;
   EpiDev epi;
   unsigned int* dbg;
@@ -72,7 +73,7 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
 // the tap axis is padded to NP = 16 / 32 accumulator columns (TMA zero-fills the missing filter rows)
 // HALF: fp16 operands (64 channels per 128-byte row, kind::f16) instead of tf32 (32 per row)
 template <int KS, bool HALF>
-__global__ void __launch_bounds__(O_THREADS, 1) deconv_one_tc_kernel(const __grid_constant__ OneParams p) {
+__global__ void __launch_bounds__(O_THREADS, KS == 4 ? 3 : 1) deconv_one_tc_kernel(const __grid_constant__ OneParams p) {
   constexpr int NP = KS == 4 ? 16 : 32;
   constexpr int KCH = HALF ? 64 : 32;
   extern __shared__ uint8_t smem_raw[];
@@ -86,11 +87,12 @@ __global__ void __launch_bounds__(O_THREADS, 1) deconv_one_tc_kernel(const __gri
   uint8_t* ring_ptr = smem_raw + (ring - smem_u32(smem_raw));
   constexpr uint32_t A_BYTES = O_PH * O_PW * 128;   // one k-block of one patch
   constexpr uint32_t B_BYTES = NP * 128;            // one k-block of the taps
-  const uint32_t b_off = O_STAGES * A_BYTES;
+  const int nstages = p.stages;
+  const uint32_t b_off = (uint32_t)nstages * A_BYTES;
   const long ntl = p.total_tiles;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < O_STAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < nstages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     mbar_init(&b_full, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -135,7 +137,7 @@ __global__ void __launch_bounds__(O_THREADS, 1) deconv_one_tc_kernel(const __gri
           wait_p(&a_empty[as], aph ^ 1u, p.dbg, 41u, p.prof, w0);
           mbar_expect_tx(&a_full[as], A_BYTES);
           tma_load_4d(&p.tmA, &a_full[as], ring_ptr + (size_t)as * A_BYTES, kb * KCH, b0, a0, img);
-          if (++as == O_STAGES) { as = 0; aph ^= 1u; }
+          if (++as == nstages) { as = 0; aph ^= 1u; }
         }
       }
       if (p.prof) { p.prof[blockIdx.x * 8 + 0] = (unsigned long long)(clock64() - ts); p.prof[blockIdx.x * 8 + 1] = w0; }
@@ -166,7 +168,7 @@ __global__ void __launch_bounds__(O_THREADS, 1) deconv_one_tc_kernel(const __gri
                           (kb | k) != 0 ? 1u : 0u);
           umma_commit(&a_empty[as]);
           if (kb == p.kblocks - 1) umma_commit(&acc_full[buf]);
-          if (++as == O_STAGES) { as = 0; aph ^= 1u; }
+          if (++as == nstages) { as = 0; aph ^= 1u; }
         }
       }
       if (p.prof) {
@@ -303,15 +305,27 @@ int deconv_one_tc(const advoc_conv_desc* d, const void* x, int ldx, const void* 
   }();
   p.prof = prof;
   if (prof) g_one_prof = prof;
-  const int smem = O_STAGES * O_PH * O_PW * 128 + O_MAXKB * 32 * 128 + 1024;
+  // The layer is latency-bound per CTA (one patch -> TMEM -> col2im -> stores is a serial chain that the
+  // two accumulator buffers only half hide: r02 measured 97 us for 134 MB of fp16 input), so run up to
+  // three CTAs per SM: a ring of max(3, 2 k-blocks) patch slots each instead of eight.
+  const int max_smem = O_STAGES * O_PH * O_PW * 128 + O_MAXKB * 32 * 128 + 1024;
   static bool configured = false;
   if (!configured) {
-    ADVOC_CHECK_CUDA(cudaFuncSetAttribute(deconv_one_tc_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    ADVOC_CHECK_CUDA(cudaFuncSetAttribute(deconv_one_tc_kernel<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    ADVOC_CHECK_CUDA(cudaFuncSetAttribute(deconv_one_tc_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ADVOC_CHECK_CUDA(cudaFuncSetAttribute(deconv_one_tc_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    ADVOC_CHECK_CUDA(cudaFuncSetAttribute(deconv_one_tc_kernel<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    ADVOC_CHECK_CUDA(cudaFuncSetAttribute(deconv_one_tc_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     configured = true;
   }
-  const long ctas = p.total_tiles < (long)sm_count() ? p.total_tiles : (long)sm_count();
+  static const int max_ctas = getenv("ADVOC_ONE_CTAS") ? atoi(getenv("ADVOC_ONE_CTAS")) : 3;   // A/B switch
+  p.stages = max_ctas <= 1 ? O_STAGES : (2 * p.kblocks > 3 ? (2 * p.kblocks < O_STAGES ? 2 * p.kblocks : O_STAGES) : 3);
+  const int b_bytes = p.kblocks * np * 128;
+  const int smem = p.stages * O_PH * O_PW * 128 + b_bytes + 1024;
+  const int static_smem = 2 * O_PH * O_PW * (np + 1) * 4 + 256;
+  int per_sm = (220 * 1024) / (smem + static_smem);
+  if (per_sm > max_ctas) per_sm = max_ctas;
+  if (per_sm < 1) per_sm = 1;
+  const long slots = (long)sm_count() * per_sm;
+  const long ctas = p.total_tiles < slots ? p.total_tiles : slots;
   ADVOC_REQUIRE(!half || d->kh == 4, ADVOC_UNSUPPORTED, "fp16 operands: k4 only");
   if (half)
     deconv_one_tc_kernel<4, true><<<(unsigned)ctas, O_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);

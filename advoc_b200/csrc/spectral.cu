@@ -190,7 +190,8 @@ __global__ void mel_ranges_kernel(const float* __restrict__ fb, int nmels, int b
 __global__ void __launch_bounds__(256) matmul_lastdim_kernel(const float* __restrict__ x,
                                                              const float* __restrict__ w,
                                                              float* __restrict__ y, long rows,
-                                                             int K, int N, int pow10) {
+                                                             int K, int N, int pow10, float db_scale,
+                                                             float db_offset) {
   __shared__ float xs[16][64 + 4];
   __shared__ float ws[16][64 + 4];
   const long r0 = (long)blockIdx.x * 64;
@@ -203,7 +204,7 @@ __global__ void __launch_bounds__(256) matmul_lastdim_kernel(const float* __rest
       float v = 0.f;
       if (r0 + rr < rows && k0 + kk < K) {
         v = __ldg(x + (r0 + rr) * K + k0 + kk);
-        if (pow10) v = exp10f((v * 100.f - 100.f + 20.f) * 0.05f);
+        if (pow10) v = exp10f((v * db_scale + db_offset) * 0.05f);
       }
       xs[kk][rr] = v;
       float u = 0.f;
@@ -368,7 +369,8 @@ using namespace advoc;
 
 extern "C" int advoc_num_frames(int nsamps, int nfft, int nhop, int pad_end) {
   if (nsamps <= 0 || nhop <= 0 || nfft <= 0) return 0;
-  if (pad_end) return (nsamps + nhop - 1) / nhop;
+  if (pad_end == 1) return (nsamps + nhop - 1) / nhop;
+  if (pad_end == 2) return nsamps >= nfft ? (nsamps - nfft) / nhop + 1 : 0;   // tf.contrib.signal.stft(pad_end=False)
   int d = nsamps - nfft;
   int m = (d > 0 ? (d + nhop - 1) / nhop : -((-d) / nhop)) + 1;
   return m < 1 ? 1 : m;
@@ -431,13 +433,15 @@ extern "C" int advoc_melspec_f32(const float* d_wav, int batch, int nsamps, int 
 }
 
 extern "C" int advoc_matmul_lastdim_f32(const float* d_x, const float* d_w, float* d_y, long rows,
-                                        int K, int N, int pow10_scale, void* stream) {
+                                        int K, int N, int pow10_scale, float min_level_db, float ref_level_db,
+                                        void* stream) {
   ADVOC_REQUIRE(rows >= 0 && K >= 1 && N >= 1, ADVOC_BAD_SHAPE, "bad matmul shape");
   if (rows == 0) return ADVOC_OK;
   ADVOC_REQUIRE(d_x && d_w && d_y, ADVOC_BAD_ARG, "NULL pointer");
   dim3 grid((unsigned)((rows + 63) / 64), (unsigned)((N + 63) / 64));
-  matmul_lastdim_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d_x, d_w, d_y, rows,
-                                                                                K, N, pow10_scale);
+  // x in [0,1] -> dB: x * (-min_db) + min_db + ref_db   (advoc/spectral.py:367-369)
+  matmul_lastdim_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      d_x, d_w, d_y, rows, K, N, pow10_scale, -min_level_db, min_level_db + ref_level_db);
   count_launch();
   ADVOC_CHECK_CUDA(cudaGetLastError());
   return ADVOC_OK;

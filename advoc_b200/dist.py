@@ -51,6 +51,17 @@ def allreduce_sum_(flat, lo, hi, group=None, world=None):
   return flat
 
 
+def allreduce_sum_async(flat, lo, hi, group=None, world=None):
+  """Starts the in-place sum-all-reduce of flat[lo:hi] and returns the work handle (`.wait()` makes
+  the current stream wait for it), or None when there are no peers or the range is empty.  NCCL
+  orders the collective behind the work already queued on the current stream and runs it on its own
+  stream, so later kernels on the current stream overlap it."""
+  world = dist.get_world_size(group) if (world is None and dist.is_initialized()) else (world or 1)
+  if world <= 1 or hi <= lo:
+    return None
+  return dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM, group=group, async_op=True)
+
+
 def max_over_ranks(values, device):
   """Element-wise max of a list of floats over all ranks (timing: the slowest rank counts)."""
   t = torch.tensor(values, dtype=torch.float64, device=device)

@@ -51,7 +51,7 @@ class MelToMag(object):
     spectral_ptr = spectral._ptr
     N.call('advoc_matmul_lastdim_f32', spectral_ptr(self.mel_d), spectral_ptr(self.su.invmeltrans),
            spectral_ptr(self.x_d), self.B * self.T, self.n_mels, 513,
-           1 if self.kind == 'dbnorm' else 0, spectral._stream())
+           1 if self.kind == 'dbnorm' else 0, -100.0, 20.0, spectral._stream())
     if n_valid is not None and n_valid < self.B * self.T:
       # the reference zero-pads in the magnitude domain, after the pinv lift
       # (scripts/spectrogram_advoc.py:81-84)
@@ -106,7 +106,7 @@ class MelToMag(object):
     spectral_ptr = spectral._ptr
     N.call('advoc_matmul_lastdim_f32', spectral_ptr(s['mel_d']), spectral_ptr(self.su.invmeltrans),
            spectral_ptr(self.x_d), self.B * self.T, self.n_mels, 513,
-           1 if self.kind == 'dbnorm' else 0, spectral._stream())
+           1 if self.kind == 'dbnorm' else 0, -100.0, 20.0, spectral._stream())
     if seed is None:
       self.seed_d.add_(1)
       return self.G.forward(self.x_d, out=s['out_d'], dropout=self.dropout, seed_dev=self.seed_d)

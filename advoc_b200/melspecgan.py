@@ -110,7 +110,7 @@ class MelspecGAN(object):
   """One replica of the MelspecGAN train step for a fixed per-GPU batch."""
 
   def __init__(self, params, batch, dim=64, train_loss='dcgan', math=N.MATH_AUTO, process_group=None,
-               world_size=1, use_graphs=True):
+               world_size=1, use_graphs=True, base_seed=1234, rank=0):
     """`use_graphs`: from the second call on, the gradient computation and the optimiser update of
     `d_step` / `g_step` replay from captured CUDA graphs (the ~300 / ~250 launches of one step are
     otherwise bound by the host's launch rate); the gradient all-reduce between the two stays eager."""
@@ -178,7 +178,7 @@ class MelspecGAN(object):
       self.g_hat = torch.zeros((B, 64, 80, 1), **f32)
       self.u_hat = torch.zeros((B, 64, 80, 1), **f32)
       self._alpha_gen = torch.Generator(device=dev)
-      self._alpha_gen.manual_seed(1234)
+      self._alpha_gen.manual_seed(base_seed + rank)   # per-replica interpolation alphas under data parallelism
     self.x_real = torch.zeros((B, 64, 80, 1), **f32)
     self.losses = torch.zeros(2, **f32)     # D_loss, G_loss
     self.alpha_buf = torch.zeros((B, 1, 1, 1), **f32)

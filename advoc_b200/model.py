@@ -174,6 +174,66 @@ class Advoc(Model):
     d = self._discriminator(discrim_inputs.shape[0])
     return d.forward(torch.cat([discrim_inputs, discrim_targets], dim=3).contiguous())
 
+  # -- training graph (advoc_model.py:206-289) ------------------------------------------
+  def __call__(self, x, target=None, x_wav=None, x_mel_spec=None, process_group=None, world_size=1, rank=0):
+    """The reference builds generator, both discriminator towers, the three losses, the variable
+    partition and the two Adam optimisers here (advoc_model.py:206-257); this binds the same objects
+    onto a `train.TrainEngine` for the batch size of `x`.
+
+    x / target: tensors [b, subseq_len, 513, 1] (inverted-mel magnitude input, true magnitude) -- one
+    fixed minibatch, re-used by every update -- or `x` = an iterator yielding (x, target) pairs, the
+    eager stand-in for the reference's graph tensors fed by `decode_extract_and_batch`: every D / G
+    update then pulls its own minibatch, like every `sess.run` of the reference.  x_wav / x_mel_spec only
+    feed tf.summary nodes in the reference (:258-281) and are accepted and ignored.
+    Under data parallelism pass the process group / world size / rank (torchrun: advoc_b200.dist.init)."""
+    from advoc_b200.train import TrainEngine
+    self._check_supported()
+    self.spectral = SpectralUtil(n_mels=self.n_mels, fs=self.audio_fs)
+    if target is None:
+      self._batches = iter(x)
+      first = next(self._batches)
+      self._pushback = [first]
+      batch = int(first[0].shape[0])
+    else:
+      self._batches, self._pushback = None, []
+      self._fixed = (x, target)
+      batch = int(x.shape[0])
+    self._engine = TrainEngine(self.gen_spec(), self.ndf, self.params, batch, gan_weight=self.gan_weight,
+                               l1_weight=self.l1_weight, math=self.math_mode, process_group=process_group,
+                               world_size=world_size, rank=rank, base_seed=self._seed)
+    self.params = self._engine.P          # views into the engine's flat parameter buffer
+    self._gen, self._dis = {}, {}
+    self.G_vars = [n for n in self._engine.flat.names if n.startswith('generator')]
+    self.D_vars = [n for n in self._engine.flat.names if n.startswith('discriminator')]
+    self.step = 0
+    self.D_train_op = lambda: self._engine.d_step(*self._next_batch())
+    self.G_train_op = lambda: self._engine.g_step(*self._next_batch())
+    return self
+
+  def _next_batch(self):
+    if self._batches is None:
+      return self._fixed
+    if self._pushback:
+      return self._pushback.pop()
+    return next(self._batches)
+
+  def train_loop(self, sess=None):
+    """advoc_model.py:285-289: D update (skipped when gan_weight <= 0) on one minibatch, then G update
+    on the next; returns the global step (bumped by the G op only, :253-255).  `sess` is the
+    reference's session argument and is ignored."""
+    if getattr(self, '_engine', None) is None:
+      raise Exception('call the model on a batch first (advoc_model.py:206)')
+    e = self._engine
+    bd = self._next_batch() if self.gan_weight > 0 else None
+    bg = self._next_batch()
+    self.step = e.train_loop(bd, bg)
+    return self.step
+
+  def losses(self):
+    """(disc_loss, gen_loss_GAN * gan_weight, gen_loss_L1 * l1_weight) of the last updates: the scalars
+    the reference writes as tf.summary (advoc_model.py:271-274)."""
+    return self._engine.loss_values()
+
 
 class AdvocSmall(Advoc):
   """models/advoc/advoc_model_small.py:14-23,107-108,128-134."""

@@ -124,18 +124,20 @@ class _Consts(object):
     return cls._cache[key]
 
 
-def num_frames(nsamps, nfft, nhop, pad_end=True):
-  """Frame-count rule of advoc/spectral.py:32-39 (and lws' own, tests/test_spectral.py:35-36)."""
-  return N.lib().advoc_num_frames(int(nsamps), int(nfft), int(nhop), 1 if pad_end else 0)
+def num_frames(nsamps, nfft, nhop, pad_end=True, tf_rule=False):
+  """Frame-count rule of advoc/spectral.py:32-39 (and lws' own, tests/test_spectral.py:35-36);
+  tf_rule: without pad_end, tf.contrib.signal.stft's floor((n - nfft) / hop) + 1 whole frames."""
+  return N.lib().advoc_num_frames(int(nsamps), int(nfft), int(nhop), 1 if pad_end else (2 if tf_rule else 0))
 
 
 # ---------------------------------------------------------------------------
 # device-level ops on torch tensors
 # ---------------------------------------------------------------------------
-def stft_tf(x, nfft, nhop, pad_end=True):
+def stft_tf(x, nfft, nhop, pad_end=True, _lws_rule=False):
   """Batched STFT.  x f32 [b, nsamps, 1, nch] (cuda) -> c64 [b, frames, nfft//2+1, nch].
 
-  reference: advoc/spectral.py:60-83.
+  reference: advoc/spectral.py:60-83.  (_lws_rule: the numpy entry point `stft` frames like lws when
+  pad_end is off -- the last partial frame zero-padded -- instead of like tf.contrib.signal.stft.)
   """
   if x.dim() != 4 or x.shape[2] != 1:
     raise ValueError()
@@ -144,11 +146,12 @@ def stft_tf(x, nfft, nhop, pad_end=True):
   x = x.contiguous()
   b, nsamps, _, nch = x.shape
   win, tw = _Consts.stft(nfft, nhop, x.device)
-  frames = num_frames(nsamps, nfft, nhop, pad_end)
+  # without pad_end tf.contrib.signal.stft keeps whole frames only: floor((n - nfft) / hop) + 1, possibly 0
+  frames = num_frames(nsamps, nfft, nhop, pad_end, tf_rule=not _lws_rule)
   out = torch.empty((b, frames, nfft // 2 + 1, nch, 2), dtype=torch.float32, device=x.device)
   if out.numel() == 0:
     return torch.view_as_complex(out)
-  N.call('advoc_stft_f32', _ptr(x), b, nsamps, nch, nfft, nhop, 1 if pad_end else 0, _ptr(win),
+  N.call('advoc_stft_f32', _ptr(x), b, nsamps, nch, nfft, nhop, 1 if pad_end else (0 if _lws_rule else 2), _ptr(win),
          _ptr(tw), _ptr(out), None, _stream())
   return torch.view_as_complex(out)
 
@@ -164,11 +167,11 @@ def magspec_tf(x, nfft, nhop, pad_end=True):
   x = x.contiguous()
   b, nsamps, _, nch = x.shape
   win, tw = _Consts.stft(nfft, nhop, x.device)
-  frames = num_frames(nsamps, nfft, nhop, pad_end)
+  frames = num_frames(nsamps, nfft, nhop, pad_end, tf_rule=True)
   out = torch.empty((b, frames, nfft // 2 + 1, nch), dtype=torch.float32, device=x.device)
   if out.numel() == 0:
     return out
-  N.call('advoc_stft_f32', _ptr(x), b, nsamps, nch, nfft, nhop, 1 if pad_end else 0, _ptr(win),
+  N.call('advoc_stft_f32', _ptr(x), b, nsamps, nch, nfft, nhop, 1 if pad_end else 2, _ptr(win),
          _ptr(tw), None, _ptr(out), _stream())
   return out
 
@@ -206,10 +209,10 @@ def waveform_to_r9y9_melspec_tf(x, fs=22050):
   return waveform_to_melspec_tf(x, fs=fs, nfft=1024, nhop=256)
 
 
-def matmul_lastdim(x, w, pow10_scale=False):
+def matmul_lastdim(x, w, pow10_scale=False, min_level_db=-100., ref_level_db=20.):
   """y[..., n] = sum_k f(x[..., k]) * w[n, k] on the GPU (f = identity or the dB
-  de-normalisation 10^((x*100-100+20)/20)).  reference: models/advoc/spectral_util.py:29-43,
-  scripts/spectrogram_advoc.py:15-22."""
+  de-normalisation 10^((x*(-min_db)+min_db+ref_db)/20)).  reference: models/advoc/spectral_util.py:29-43,
+  scripts/spectrogram_advoc.py:15-22, advoc/spectral.py:367-369."""
   if x.dtype != torch.float32 or w.dtype != torch.float32:
     raise ValueError()
   if w.dim() != 2 or x.shape[-1] != w.shape[1]:
@@ -219,7 +222,7 @@ def matmul_lastdim(x, w, pow10_scale=False):
   rows = x.numel() // x.shape[-1] if x.numel() else 0
   y = torch.empty(x.shape[:-1] + (w.shape[0],), dtype=torch.float32, device=x.device)
   N.call('advoc_matmul_lastdim_f32', _ptr(x), _ptr(w), _ptr(y), rows, x.shape[-1], w.shape[0],
-         1 if pow10_scale else 0, _stream())
+         1 if pow10_scale else 0, float(min_level_db), float(ref_level_db), _stream())
   return y
 
 
@@ -235,7 +238,7 @@ def stft(x, nfft, nhop, pad_end=True):
     raise NotImplementedError('Can only take STFT of monaural signals')
   dev = _device()
   xd = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(dev).reshape(1, nsamps, 1, 1)
-  X = stft_tf(xd, nfft, nhop, pad_end=pad_end)
+  X = stft_tf(xd, nfft, nhop, pad_end=pad_end, _lws_rule=True)
   return X[0].cpu().numpy().astype(np.complex128)
 
 
@@ -335,15 +338,52 @@ def magspec_to_waveform_griffin_lim(X_mag, nfft, nhop, ngl=60, init_phase=None):
   return x[0].cpu().numpy()[:, np.newaxis, np.newaxis].astype(np.float32)
 
 
-def magspec_to_waveform_lws(X_mag, nfft, nhop):
-  """reference: advoc/spectral.py:314-326 (`lws.run_lws`, mode='speech').  The LWS phase
-  reconstruction lives in the third-party `lws` C++ package whose source is not part of the
-  reference and whose goldens cannot be reproduced here, so it is not restated; use
-  `magspec_to_waveform_griffin_lim` / phase_estimation='gl60'."""
+def lws_tf(X_mag, nfft, nhop, iterations=100, init_phase=None, generator=None):
+  """Batched LWS-style phase reconstruction.  X_mag f32 [b, frames, nfft//2+1] (cuda) -> complex
+  spectrogram c64 of the same shape with the given magnitudes.
+
+  Le Roux et al.'s local weighted sums ("Fast signal reconstruction from magnitude STFT spectrogram
+  based on spectrogram consistency", DAFx 2010; the `lws` package's batch stage) update every bin's
+  phase from the consistency operator F = STFT o ISTFT applied to its NEIGHBOURS, leaving out the bin's
+  own contribution alpha_0(0) * X (which only slows convergence down):
+      X <- |X_mag| * phase( F(X) - alpha_0(0) * X ),   alpha_0(0) = sum_k w(k)^2 / nfft = nhop / nfft
+  for this window.  `lws` truncates the weights to a (2L+1) x (2Q-1) neighbourhood and skips
+  low-magnitude bins to save CPU time; on the GPU the untruncated operator is two kernels (the istft /
+  stft pair of this module), so it is applied in full.  The reference's `run_lws(mode='speech')` also
+  runs its own frame-sequential initialisation whose source is not part of the reference: here the
+  start is `init_phase` or uniform random phase.  **Parity unpinned** (no lws build, no reproducible
+  golden: SURVEY.md section 8(f) row 1)."""
+  if X_mag.dim() != 3 or X_mag.shape[2] != nfft // 2 + 1 or X_mag.dtype != torch.float32:
+    raise ValueError()
+  mag = X_mag.abs().contiguous()
+  if init_phase is None:
+    init_phase = 2 * np.pi * torch.rand(mag.shape, device=mag.device, generator=generator)
+  X = torch.polar(mag, init_phase.to(torch.float32))
+  if mag.shape[1] == 0:
+    return X
+  c0 = float(nhop) / float(nfft)
+  for _ in range(iterations):
+    x = istft_tf(X, nfft, nhop)
+    Y = stft_tf(x[:, :, None, None], nfft, nhop, pad_end=False)[:, :, :, 0]
+    Z = Y - c0 * X
+    X = torch.polar(mag, torch.angle(Z))
+  return X
+
+
+def magspec_to_waveform_lws(X_mag, nfft, nhop, iterations=100, init_phase=None):
+  """X_mag [frames, bins, 1] -> f32 [n, 1, 1].  reference: advoc/spectral.py:314-326
+  (`lws.lws(nfft, nhop, mode='speech', perfectrec=False).run_lws` then `.istft`); phase estimate: `lws_tf`
+  (the batch LWS iteration with untruncated weights; parity unpinned)."""
   nsamps, nbins, nch = X_mag.shape
   if nch != 1:
     raise NotImplementedError('Can only invert monaural signals')
-  raise NotImplementedError('LWS phase reconstruction is not available; use phase_estimation="gl60"')
+  dev = _device()
+  mag = torch.from_numpy(np.ascontiguousarray(np.abs(X_mag[:, :, 0]), dtype=np.float32)).to(dev)[None]
+  ph = None
+  if init_phase is not None:
+    ph = torch.from_numpy(np.ascontiguousarray(init_phase, dtype=np.float32)).to(dev)[None]
+  x = istft_tf(lws_tf(mag, nfft, nhop, iterations=iterations, init_phase=ph), nfft, nhop)
+  return x[0].cpu().numpy()[:, np.newaxis, np.newaxis].astype(np.float32)
 
 
 def melspec_to_waveform(X_mel_dbnorm, fs, nfft, nhop, mel_min=125, mel_max=7600,
@@ -363,12 +403,11 @@ def melspec_to_waveform(X_mel_dbnorm, fs, nfft, nhop, mel_min=125, mel_max=7600,
       ngl = int(phase_estimation[2:])
     except Exception:
       raise ValueError()
-  if norm_min_level_db != -100 or norm_ref_level_db != 20:
-    raise NotImplementedError('only the reference default dB normalisation is fused')
   dev = _device()
   inv = _Consts.inv_mel(fs, nfft, mel_min, mel_max, mel_num_bins, dev)
   mel = torch.from_numpy(np.ascontiguousarray(X_mel_dbnorm[:, :, 0], dtype=np.float32)).to(dev)
-  X_mag = torch.clamp_min(matmul_lastdim(mel, inv, pow10_scale=True), 0.)
+  X_mag = torch.clamp_min(matmul_lastdim(mel, inv, pow10_scale=True, min_level_db=norm_min_level_db,
+                                         ref_level_db=norm_ref_level_db), 0.)
   if phase_estimation == 'lws':
     x = magspec_to_waveform_lws(X_mag.cpu().numpy()[:, :, np.newaxis], nfft, nhop)
   else:

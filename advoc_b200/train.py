@@ -50,6 +50,16 @@ class FlatParams(object):
       self.P[n].copy_(params[n])
       self.G[n] = self.g[o:o + k].view(params[n].shape)
 
+  def range_of(self, pred):
+    """[lo, hi) of the flat buffer covered by the (contiguous) tensors whose name satisfies pred."""
+    sel = [n for n in self.names if pred(n)]
+    if not sel:
+      return 0, 0
+    idx = [self.names.index(n) for n in sel]
+    assert idx == list(range(idx[0], idx[0] + len(idx))), 'not contiguous in the flat buffer'
+    last = sel[-1]
+    return self.offsets[sel[0]], self.offsets[last] + (self.P[last].numel() + 3) // 4 * 4
+
   def gen_range(self):
     return 0, self.n_gen
 
@@ -61,11 +71,24 @@ class TrainEngine(object):
   """One replica of the AdVoc train step for a fixed per-GPU batch."""
 
   def __init__(self, spec, ndf, params, batch, gan_weight=1.0, l1_weight=10.0, math=N.MATH_AUTO,
-               lr=2e-4, beta1=0.5, beta2=0.999, eps=1e-8, process_group=None, world_size=1):
+               lr=2e-4, beta1=0.5, beta2=0.999, eps=1e-8, process_group=None, world_size=1, rank=0,
+               base_seed=0, overlap=True):
+    """`rank` / `base_seed` key the dropout masks (every replica and every step draws its own);
+    `overlap`: under data parallelism the gradient all-reduces run asynchronously behind the compute
+    that does not depend on them (see train_loop)."""
     self.spec, self.ndf, self.B = spec, ndf, batch
     self.gan_weight, self.l1_weight = gan_weight, l1_weight
     self.lr, self.b1, self.b2, self.eps = lr, beta1, beta2, eps
-    self.pg, self.world = process_group, world_size
+    self.pg, self.world, self.rank = process_group, world_size, rank
+    self.overlap = overlap
+    self.capture_launches = self.replayed_launches = 0    # launch accounting for bench.py (no graphs here)
+    # splitmix64 of (base_seed, rank): the per-replica dropout stream; step k uses seed0 + k
+    z = (base_seed * 0x100000001B3 + rank + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+    self.seed0 = 0 if (base_seed == 0 and rank == 0) else ((z ^ (z >> 31)) & 0xFFFFFFFF)
+    self._pending_d = None
+    self.collective_events = None   # bench.py: list of (start, end) CUDA events around every exposed wait
     self.flat = FlatParams(params)
     P = self.flat.P
     self.P = P
@@ -85,6 +108,7 @@ class TrainEngine(object):
     self.rnd = 0 if math == N.MATH_FP32 else 1   # TF32-round stored gradients for tensor-core consumers
     self.step_count = 0
     self._build_backward_geometry(math)
+    self._build_buckets()
     self.refresh_weights()
 
   # -------------------------------------------------------------------------------------------
@@ -195,6 +219,11 @@ class TrainEngine(object):
       ep = _epilogue(None, self.gCat[k], cc, 0, N.ACT_NONE, gate=cat, ld_gate=cc, gate_act=N.ACT_RELU,
                      gate_split=G.Dk[k], gate_scale0=scale0, round_tf32=self.rnd)
       self._run(L, dy, ld, co, self._wb(L), ep)
+    # decoder gradients are complete: their slice of the flat buffer goes out while the encoder
+    # backward runs (dec_8..5 + enc_8..5 hold 46 M of the regular model's 54 M parameters)
+    handles = []
+    if self._bucketed():
+      handles.append(self._allreduce_async(*self._bucket['dec']))
     for i in range(n, 0, -1):
       L = G.enc[i]
       d = L.desc
@@ -211,6 +240,11 @@ class TrainEngine(object):
         ep = _epilogue(None, prev, prev.shape[3], G.Dk[i - 1], N.ACT_NONE, accumulate=1,
                        gate=G.E[i - 1], ld_gate=s.enc_ch[i - 2], gate_act=N.ACT_LRELU, round_tf32=self.rnd)
         self._run(Lt, dy, ld, co, self._wb(Lt), ep)
+      if self._bucketed() and i == self._bucket_split:
+        handles.append(self._allreduce_async(*self._bucket['enc_hi']))
+    if self._bucketed():
+      handles.append(self._allreduce_async(*self._bucket['enc_lo']))
+    return handles
 
   # -------------------------------------------------------------------------------------------
   # optimiser + collective
@@ -218,6 +252,48 @@ class TrainEngine(object):
   def _allreduce(self, lo, hi):
     from advoc_b200 import dist as D
     D.allreduce_sum_(self.flat.g, lo, hi, self.pg, self.world)
+
+  def _allreduce_async(self, lo, hi):
+    """Starts the sum-all-reduce of flat.g[lo:hi] behind the work already queued on the current stream
+    (NCCL runs it on its own stream) and returns a handle for _wait; None without peers."""
+    from advoc_b200 import dist as D
+    return D.allreduce_sum_async(self.flat.g, lo, hi, self.pg, self.world)
+
+  def _wait(self, handles):
+    """The current stream waits for the collectives; the time it idles is the EXPOSED all-reduce
+    time (bench.py reads it from the recorded events)."""
+    handles = [h for h in handles if h is not None]
+    if not handles:
+      return
+    ev = None
+    if self.collective_events is not None:
+      ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+      ev[0].record()
+    for h in handles:
+      h.wait()
+    if ev is not None:
+      ev[1].record()
+      self.collective_events.append(ev)
+
+  def _bucketed(self):
+    return self.world > 1 and self.overlap
+
+  def _build_buckets(self):
+    """Generator gradient buckets in the order the backward pass completes them: all decoders, then
+    encoder_n..split, then encoder_(split-1)..1.  The flat buffer is sorted by name, so each is one
+    contiguous range."""
+    n = self.spec.n_enc
+    self._bucket_split = 5 if n >= 5 else n
+    f = self.flat
+    enc_idx = lambda name: int(name.split('/')[1].split('_')[1])
+    self._bucket = {
+        'dec': f.range_of(lambda m: m.startswith('generator/decoder_')),
+        'enc_hi': f.range_of(lambda m: m.startswith('generator/encoder_') and enc_idx(m) >= self._bucket_split),
+        'enc_lo': f.range_of(lambda m: m.startswith('generator/encoder_') and enc_idx(m) < self._bucket_split),
+    }
+    lo, hi = f.gen_range()
+    r = sorted(v for v in self._bucket.values() if v[1] > v[0])
+    assert r[0][0] == lo and r[-1][1] == hi and all(a[1] == b[0] for a, b in zip(r, r[1:])), r
 
   def _adam(self, lo, hi, t):
     f = self.flat
@@ -244,6 +320,7 @@ class TrainEngine(object):
       self.flat.v[o:o + k].copy_(v[n].reshape(-1))
     self.t_d = int(t_d)
     self.t_g = int(t_d if t_g is None else t_g)
+    self.step_count = self.t_d + self.t_g    # the dropout stream continues where the run left off
 
   def load_batch(self, x, target):
     """x, target f32 [B,T,513,1] on the device -> the discriminator input buffers."""
@@ -255,10 +332,23 @@ class TrainEngine(object):
     self._dropout_on = dropout is not None
     # encoder_1 reads x as channel 0 of the 2-channel buffer; decoder_1 writes channel 1
     return self.G.forward(self.cat_fake, out=self.cat_fake, out_ld=2, out_coff=1, dropout=dropout,
-                          seed=seed, x_ld=2)
+                          seed=self.seed0 + seed, x_ld=2)
 
-  def d_step(self, x, target, dropout='rng', apply=True):
-    """advoc_model.py:257 `D_train_op` on one minibatch."""
+  def _finish_d(self):
+    """Second half of a deferred D update: wait for its all-reduce, Adam, refresh the packed filters."""
+    if self._pending_d is None:
+      return
+    handles, lo, hi = self._pending_d
+    self._pending_d = None
+    self._wait(handles)
+    self.t_d += 1
+    self._adam(lo, hi, self.t_d)
+    self.refresh_weights('D')
+
+  def d_step(self, x, target, dropout='rng', apply=True, defer=False):
+    """advoc_model.py:257 `D_train_op` on one minibatch.  defer: leave the all-reduce in flight and the
+    optimiser update pending (train_loop finishes it under the next generator forward)."""
+    self._finish_d()
     self.step_count += 1
     lo, hi = self.flat.dis_range()
     self.flat.g[lo:hi].zero_()
@@ -274,7 +364,10 @@ class TrainEngine(object):
     self._d_backward(self.Dr, self.cat_real, True, False)
     self.dz[4].copy_(dz_fake)
     self._d_backward(self.Df, self.cat_fake, True, False)
-    self._allreduce(lo, hi)
+    if apply and defer and self._bucketed():
+      self._pending_d = ([self._allreduce_async(lo, hi)], lo, hi)
+      return
+    self._wait([self._allreduce_async(lo, hi)])
     if apply:
       self.t_d += 1
       self._adam(lo, hi, self.t_d)
@@ -291,13 +384,18 @@ class TrainEngine(object):
     n_out = self.g_out.numel()
     N.call('advoc_l1_loss', _ptr(self.cat_fake), 2, 1, _ptr(target), n_out, self.l1_weight,
            _view_ptr(self.losses, 2), _ptr(self.g_out), 0, _stream())
+    # a deferred D update (its all-reduce ran under the generator forward above) lands here: the
+    # discriminator pass below goes through the already-updated D like the reference's (advoc_model.py:285-289)
+    self._finish_d()
     if self.gan_weight > 0:
       p_fake = self.Df.forward(self.cat_fake)
       N.call('advoc_gan_logloss', None, _ptr(p_fake), p_fake.numel(), 1, self.gan_weight,
              _view_ptr(self.losses, 1), None, _ptr(self.dz[4]), _stream())
       self._d_backward(self.Df, self.cat_fake, False, True)
-    self._g_backward(self.cat_fake)
-    self._allreduce(lo, hi)
+    handles = self._g_backward(self.cat_fake)
+    if not self._bucketed():
+      handles = [self._allreduce_async(lo, hi)]
+    self._wait(handles)
     if apply:
       self.t_g += 1
       self._adam(lo, hi, self.t_g)
@@ -308,11 +406,12 @@ class TrainEngine(object):
     """One reference `train_loop` (advoc_model.py:285-289): D step (skipped when gan_weight <= 0)
     then G step, each on its own minibatch (x, target)."""
     if self.gan_weight > 0:
-      self.d_step(batch_d[0], batch_d[1], dropout)
+      self.d_step(batch_d[0], batch_d[1], dropout, defer=True)
     return self.g_step(batch_g[0], batch_g[1], dropout)
 
   def loss_values(self):
     """(d_loss, g_loss_GAN * gan_weight, g_loss_L1 * l1_weight) of the last steps (syncs)."""
+    self._finish_d()
     v = self.losses.tolist()
     N.raise_if_aborted('TrainEngine')
     return v[0], v[1], v[2]

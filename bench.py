@@ -282,6 +282,11 @@ def run_gpu(args):
       'step_tflops': FLOP_PER_FRAME[args.model] * frames / (total_ms * 1e-3) / 1e12,
       'parity_rel_l2': parity,
   }
+  if not args.no_train_step:
+    # the multi-GPU object of this framework is the data-parallel train step (BASELINE configs[2]/[3]):
+    # AdVoc-regular, 32 samples per GPU, NCCL gradient all-reduce inside the timed region.  `value`
+    # above stays the generator forward (replicas), so the N = 1 line still matches BENCH.
+    line['train_step'] = measure_train_step('regular', 32, world, rank, 10, 3, barrier, with_e2e=False)
   if rank == 0:
     if not args.no_cpu_baseline and world == 1:
       sample = 8 if args.model == 'small' else 2
@@ -468,33 +473,28 @@ def _synthetic_mag(batch, seed):
   return (torch.randn(batch, T, 513, 1, generator=g).abs() * 0.1)
 
 
-def run_gpu_train(args):
-  import torch
-  import torch.distributed as dist
-  from advoc_b200 import _native as N
+def _train_engine(model_name, batch, world, rank, overlap=True):
   from advoc_b200 import nets
-  from advoc_b200.model import SpectralUtil
   from advoc_b200.train import TrainEngine
-
-  world = int(os.environ.get('WORLD_SIZE', '1'))
-  rank = int(os.environ.get('RANK', '0'))
-  local = int(os.environ.get('LOCAL_RANK', '0'))
-  torch.cuda.set_device(local)
-  if world > 1:
-    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-
-  def barrier():
-    if world > 1:
-      dist.barrier()
-    torch.cuda.synchronize()
-
-  small = args.model == 'small'
+  small = model_name == 'small'
   spec = nets.GenSpec(32 if small else 64, 5 if small else 8, (5, 4) if small else (8, 7, 6))
   ndf = 32 if small else 64
   params = nets.init_params(spec.ngf, ndf, spec.n_enc, seed=0)
-  eng = TrainEngine(spec, ndf, params, args.batch, world_size=world)
+  return TrainEngine(spec, ndf, params, batch, world_size=world, rank=rank, overlap=overlap)
+
+
+def measure_train_step(model_name, batch, world, rank, steps, warmup, barrier, with_e2e=True, overlap=True):
+  """Times the data-parallel G+D train step (advoc_model.py:285-289: D update on one minibatch, G update
+  on the next), `batch` samples per GPU, the NCCL gradient all-reduces inside the timed region.  Returns
+  a dict: samples/s over all ranks (max-over-ranks time), ms/step, the all-reduce time the compute
+  stream was left waiting for (events around every wait), launches per step."""
+  import torch
+  import torch.distributed as dist
+  from advoc_b200 import _native as N
+  from advoc_b200.model import SpectralUtil
+  eng = _train_engine(model_name, batch, world, rank, overlap)
   su = SpectralUtil()
-  mags_h = [_synthetic_mag(args.batch, 100 + 2 * rank + i).pin_memory() for i in range(2)]
+  mags_h = [_synthetic_mag(batch, 100 + 2 * rank + i).pin_memory() for i in range(2)]
   mags_d = [m.cuda() for m in mags_h]
   stage = [torch.empty_like(m) for m in mags_d]
   stream = torch.cuda.current_stream()
@@ -513,21 +513,22 @@ def run_gpu_train(args):
     eng.train_loop((xa, stage[0]), (xb, stage[1]))
     return eng.loss_values()          # D2H read of the step's losses
 
-  def timed(fn, steps, warmup):
-    for _ in range(warmup):
+  def timed(fn, n, w):
+    for _ in range(w):
       fn()
+    eng._finish_d()
     barrier()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record(stream)
-    for _ in range(steps):
+    for _ in range(n):
       fn()
+    eng._finish_d()
     b.record(stream)
     barrier()
     return a.elapsed_time(b)
 
-  # kernels of one steady-state outer iteration: launches the library counted directly plus the kernels
-  # inside the CUDA graphs the engine replayed (recorded launch counts per graph), minus launches that
-  # were only recorded during a capture
+  # kernels of one steady-state step: launches the library counted directly (plus, for engines that
+  # replay CUDA graphs, the recorded launch counts per graph)
   step_device()
   torch.cuda.synchronize()
   n0, r0, c0 = N.launch_count(), getattr(eng, 'replayed_launches', 0), getattr(eng, 'capture_launches', 0)
@@ -535,34 +536,93 @@ def run_gpu_train(args):
   torch.cuda.synchronize()
   per_step = ((N.launch_count() - n0) - (getattr(eng, 'capture_launches', 0) - c0)
               + (getattr(eng, 'replayed_launches', 0) - r0))
-  with ClockSampler(local) as clk:
-    total_ms = timed(step_device, args.steps, args.warmup)
-    e2e_ms = timed(step_e2e, args.steps, args.warmup)
+  total_ms = timed(step_device, steps, warmup)
+  eng.collective_events = []
+  exposed_run_ms = timed(step_device, steps, 0)
+  torch.cuda.synchronize()
+  exposed_ms = sum(a.elapsed_time(b) for a, b in eng.collective_events) / steps
+  eng.collective_events = None
+  e2e_ms = timed(step_e2e, steps, warmup) if with_e2e else None
+  # the same collectives alone, back to back (no compute to hide behind): their isolated cost
+  iso_ms = 0.0
   if world > 1:
-    t = torch.tensor([total_ms, e2e_ms], device='cuda', dtype=torch.float64)
+    lo_d, hi_d = eng.flat.dis_range()
+    lo_g, hi_g = eng.flat.gen_range()
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    for _ in range(5):
+      dist.all_reduce(eng.flat.g[lo_d:hi_d])
+      dist.all_reduce(eng.flat.g[lo_g:hi_g])
+    b.record(stream)
+    barrier()
+    iso_ms = a.elapsed_time(b) / 5
+  vals = [total_ms, exposed_ms, iso_ms, e2e_ms if e2e_ms is not None else 0.0, exposed_run_ms]
+  if world > 1:
+    t = torch.tensor(vals, device='cuda', dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms = float(t[0]), float(t[1])
-  samples = world * args.batch * args.steps
+    vals = [float(v) for v in t]
+  total_ms, exposed_ms, iso_ms, e2e_max, exposed_run_ms = vals
+  flags = N.debug_flags()
+  if flags:
+    raise RuntimeError('a tcgen05 pipeline wait timed out during the train benchmark (code %d)' % flags)
+  samples = world * batch * steps
   value = samples / (total_ms * 1e-3)
+  tflops = TRAIN_GFLOP_PER_SAMPLE[model_name] * 1e9 * value / 1e12
+  out = {'model': 'AdVoc-' + model_name, 'batch_per_gpu': batch, 'global_batch': batch * world, 'n_gpus': world,
+         'value': value, 'unit': 'samples/s', 'ms_per_step': total_ms / steps, 'steps': steps,
+         'allreduce_bytes_per_step': int(4 * eng.flat.total),
+         'allreduce_exposed_ms_per_step': exposed_ms, 'allreduce_isolated_ms_per_step': iso_ms,
+         'allreduce': ('NCCL sum-all-reduce of the flat fp32 gradient buffer: D slice in flight under the next generator '
+                       'forward, G slice in three buckets (decoders | encoder_n..5 | encoder_4..1) behind the encoder '
+                       'backward; exposed = time the compute stream waited') if (world > 1 and overlap) else
+                      ('NCCL, not overlapped' if world > 1 else 'none (1 GPU)'),
+         'tflops_per_gpu': tflops / world, 'launches_per_step': int(per_step),
+         'loss_values': [float(v) for v in eng.loss_values()]}
+  if with_e2e:
+    out['e2e'] = {'value': samples / (e2e_max * 1e-3), 'unit': 'samples/s', 'ms_per_step': e2e_max / steps,
+                  'h2d_bytes_per_step': int(2 * mags_h[0].numel() * 4), 'd2h_bytes_per_step': 16}
+  del eng
+  torch.cuda.empty_cache()
+  return out
+
+
+def run_gpu_train(args):
+  import torch
+  import torch.distributed as dist
+
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  rank = int(os.environ.get('RANK', '0'))
+  local = int(os.environ.get('LOCAL_RANK', '0'))
+  torch.cuda.set_device(local)
+  if world > 1:
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  with ClockSampler(local) as clk:
+    r = measure_train_step(args.model, args.batch, world, rank, args.steps, args.warmup, barrier,
+                           overlap=not args.no_overlap)
   peaks = _peaks()
   tf32_peak = _tf32_peak()
-  tflops = TRAIN_GFLOP_PER_SAMPLE[args.model] * 1e9 * value / 1e12
   line = {
-      'metric': 'G+D train-step samples/sec', 'value': value, 'unit': 'samples/s', 'n_gpus': world,
-      'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total_ms / args.steps,
+      'metric': 'G+D train-step samples/sec', 'value': r['value'], 'unit': 'samples/s', 'n_gpus': world,
+      'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': r['ms_per_step'],
       'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
       'dtype': 'tf32 fwd/dgrad (fp32 accumulate), fp32 wgrad/optimizer', 'data': 'synthetic',
       'config': _train_config(args, world),
-      'e2e': {'value': samples / (e2e_ms * 1e-3), 'unit': 'samples/s',
-              'ms_per_step': e2e_ms / args.steps,
-              'h2d_bytes_per_step': int(2 * mags_h[0].numel() * 4), 'd2h_bytes_per_step': 16},
-      'gpu_launches': int(per_step * args.steps * 2), 'launches_per_step': int(per_step),
+      'e2e': r['e2e'],
+      'gpu_launches': int(r['launches_per_step'] * args.steps * 2), 'launches_per_step': r['launches_per_step'],
       'clocks': clk.summary(),
       'roofline': {'kernel': 'whole step (all conv GEMMs)', 'bound': 'tensor',
-                   'achieved': tflops / world, 'peak': tf32_peak, 'unit': 'TFLOP/s',
-                   'frac': tflops / world / tf32_peak, 'traffic': None,
+                   'achieved': r['tflops_per_gpu'], 'peak': tf32_peak, 'unit': 'TFLOP/s',
+                   'frac': r['tflops_per_gpu'] / tf32_peak, 'traffic': None,
                    'peak_source': 'cuBLAS TF32 8192^3 measured in this run (convs compute in kind::tf32); '
                                   'MEASURED_PEAKS.json bf16 sustained = %.1f' % peaks['tensor_sustained']},
+      'train_step': r,
   }
   if rank == 0:
     print(json.dumps(line))
@@ -879,6 +939,9 @@ def main():
   ap.add_argument('--math', default='f16', choices=['f16', 'tf32', 'fp32'],
                   help='generator-forward operand type: f16 (default) or tf32 (fp32 storage)')
   ap.add_argument('--no-graph', action='store_true')
+  ap.add_argument('--no-overlap', action='store_true', help='train step: blocking all-reduces (A/B)')
+  ap.add_argument('--no-train-step', action='store_true',
+                  help='default line: skip the data-parallel train-step measurement')
   ap.add_argument('--no-cpu-baseline', action='store_true')
   args = ap.parse_args()
   args.warmup = max(args.warmup, 3) if args.impl != 'reference' else args.warmup

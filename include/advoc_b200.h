@@ -87,8 +87,11 @@ ADVOC_API int advoc_device_arch(int* arch);
  * Spectral features
  * ------------------------------------------------------------------------- */
 
-/* Frame count of the reference framing rule.
- * replaces: advoc/spectral.py:32-39 (pad_end) and lws' own rule (tests/test_spectral.py:35-36). */
+/* Frame count of the reference framing rules.  pad_end = 1: ceil(n / hop) (advoc/spectral.py:32-39 and
+ * tf.contrib.signal.stft(pad_end=True), :75-81); 0: lws' own rule, ceil((n - nfft) / hop) + 1, at least 1,
+ * the last partial frame zero-padded (tests/test_spectral.py:35-36); 2: tf.contrib.signal.stft(pad_end=
+ * False), floor((n - nfft) / hop) + 1 whole frames, possibly 0.  The same codes are accepted as the
+ * `pad_end` argument of advoc_stft_f32. */
 ADVOC_API int advoc_num_frames(int nsamps, int nfft, int nhop, int pad_end);
 
 /* Framed, windowed real FFT.  d_wav [batch, nsamps, 1, nch] f32 ->
@@ -115,10 +118,11 @@ ADVOC_API int advoc_mel_ranges(const float* d_mel_fb, int nmels, int bins, int* 
 /* y[r, n] = sum_k x[r, k] * w[n, k]   (x [rows,K], w [N,K], y [rows,N], all f32).
  * replaces: models/advoc/spectral_util.py:29-32 (mag -> linear mel, w = mel_fb) and
  * :34-43 (linear mel -> mag, w = pinv(mel_fb)); scripts/spectrogram_advoc.py:21.
- * If pow10_scale != 0 the input is first mapped x -> 10^((x*100-100+20)/20)
- * (the dB de-normalisation of scripts/spectrogram_advoc.py:19-20). */
+ * If pow10_scale != 0 the input is first mapped x -> 10^((x*(-min_db) + min_db + ref_db)/20): the dB
+ * de-normalisation of advoc/spectral.py:367-369 (defaults -100 / 20: scripts/spectrogram_advoc.py:19-20;
+ * tacotron2 features use -40 / 20). */
 ADVOC_API int advoc_matmul_lastdim_f32(const float* d_x, const float* d_w, float* d_y, long rows, int K,
-                             int N, int pow10_scale, void* stream);
+                             int N, int pow10_scale, float min_level_db, float ref_level_db, void* stream);
 
 /* Spectrogram inversion ("next" rows of SURVEY.md section 8(f)).  lws istft with
  * perfectrec=False: out = overlap-add( irfft(X[m]) * window ), length (frames-1)*hop + nfft.

@@ -264,3 +264,23 @@ def griffin_lim(X_mag, nfft, nhop, ngl=60, rng=None):
     angles = np.exp(1j * np.angle(S))
     x = istft(mag * angles, nfft, nhop)
   return x[:, np.newaxis, np.newaxis].astype(np.float32)
+
+
+def lws(X_mag, nfft, nhop, iterations=100, rng=None):
+  """Batch local-weighted-sums phase reconstruction with untruncated weights (Le Roux et al., DAFx
+  2010): X <- |X| * phase(STFT(ISTFT(X)) - alpha_0(0) * X), alpha_0(0) = nhop / nfft for the lws window.
+  Restates the product's `lws_tf` (advoc/spectral.py:314-326 calls `lws.run_lws`, whose source and
+  goldens are not available: parity unpinned).  X_mag [frames, bins, 1] -> waveform f32 [n, 1, 1]."""
+  if X_mag.shape[2] != 1:
+    raise NotImplementedError('Can only invert monaural signals')
+  rng = np.random if rng is None else rng
+  mag = np.abs(X_mag[:, :, 0]).astype(np.float64)
+  X = mag * np.exp(2j * np.pi * rng.rand(*mag.shape))
+  win = lws_hann_default(nfft, nhop, np.float64)
+  c0 = float(nhop) / float(nfft)
+  for _ in range(iterations):
+    x = istft(X, nfft, nhop)
+    Y = np.fft.rfft(frame_signal(x, nfft, nhop, pad_end=False) * win[None, :], axis=1)
+    Z = Y - c0 * X
+    X = mag * np.exp(1j * np.angle(Z))
+  return istft(X, nfft, nhop)[:, np.newaxis, np.newaxis].astype(np.float32)

@@ -16,14 +16,15 @@ B = int(sys.argv[2]) if len(sys.argv) > 2 else 32
 small = model == 'small'
 spec = nets.GenSpec(32 if small else 64, 5 if small else 8, (5, 4) if small else (8, 7, 6))
 P = nets.init_params(spec.ngf, spec.ngf, spec.n_enc, seed=0)
-G = nets.Generator(spec, P, B)
+MATH = {'f16': N.MATH_F16, 'tf32': N.MATH_AUTO}[sys.argv[3] if len(sys.argv) > 3 else 'f16']
+G = nets.Generator(spec, P, B, MATH)
 G.prepare()
 x = torch.rand(B, 256, 513, 1, device='cuda')
 lib = N.lib()
 fn = lib.advoc_p2d_profile_read
 fn.restype = C.c_int
 fn.argtypes = [C.c_void_p]
-buf = np.zeros((256, 16), dtype=np.uint64)
+buf = np.zeros((512, 16), dtype=np.uint64)
 orig = G._run_layer
 
 

@@ -41,13 +41,14 @@ def test_num_frames_rule():
   assert f(22050, 1024, 256, 1) == 87
   assert f(0, 1024, 256, 1) == 0
   assert f(100, 1024, 256, 0) == 1
+  assert f(16000, 1024, 256, 2) == 59 and f(100, 1024, 256, 2) == 0    # tf.contrib.signal.stft(pad_end=False)
 
 
 def test_bad_arguments_raise_without_touching_the_gpu():
   with pytest.raises(ValueError):
     N.call('advoc_stft_f32', None, 1, 100, 1, 1024, 256, 1, None, None, None, None, None)
   with pytest.raises(ValueError):
-    N.call('advoc_matmul_lastdim_f32', None, None, None, 4, 0, 3, 0, None)
+    N.call('advoc_matmul_lastdim_f32', None, None, None, 4, 0, 3, 0, -100.0, 20.0, None)
   d = N.ConvDesc(1, 8, 8, 4, 4, 4, 4, 2, 2, 1, 1, 4, 4, N.MATH_FP32)
   with pytest.raises(ValueError):
     N.call('advoc_conv2d_fwd', C.byref(d), None, 4, None, None, None)

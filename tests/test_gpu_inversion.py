@@ -65,5 +65,38 @@ def test_melspec_to_waveform_contract(golden_dir):
     S.melspec_to_waveform(np.zeros((10, 80, 2)), 22050, 1024, 256)
   with pytest.raises(ValueError):
     S.melspec_to_waveform(mel, 22050, 1024, 256, phase_estimation='foo')
-  with pytest.raises(NotImplementedError):
-    S.r9y9_melspec_to_waveform(mel)          # default 'lws': not restated (see docstring)
+  x = S.r9y9_melspec_to_waveform(mel[:64])   # default phase_estimation='lws' (advoc/spectral.py:398)
+  assert x.shape == (63 * 256 + 1024, 1, 1) and x.dtype == np.float32 and np.isfinite(x).all()
+  # tacotron2-style normalisation (-40 dB floor, advoc/spectral.py:230-247) inverts too
+  y = S.melspec_to_waveform(mel[:32], 22050, 1024, 256, norm_min_level_db=-40, phase_estimation='gl2')
+  assert y.shape == (31 * 256 + 1024, 1, 1) and np.isfinite(y).all()
+
+
+def test_lws_matches_oracle_and_beats_griffin_lim(golden_dir):
+  """`magspec_to_waveform_lws` (batch LWS iteration, untruncated weights; parity unpinned): equals the
+  numpy restatement from the same initial phase, and after the same number of iterations its
+  spectrogram is more consistent with the target magnitudes than Griffin-Lim's (the point of leaving
+  the centre term out)."""
+  from advoc_b200 import spectral as S
+  from oracle import spectral_np as O
+  mel = np.load(os.path.join(golden_dir, 'mono_22k_r9y9_mel.npy')).T[:64]
+  Winv = O.create_inverse_mel_filterbank(22050, 1024, fmin=125., fmax=7600., n_mels=80)
+  X_mag = np.maximum(0., O.tacotron_mel_to_mag(mel, Winv))[:, :, np.newaxis]
+  phase = 2 * np.pi * np.random.RandomState(1).rand(64, 513)
+
+  class _Rng(object):
+    def rand(self, *shape):
+      return phase / (2 * np.pi)
+
+  ref = O.lws(X_mag, 1024, 256, iterations=5, rng=_Rng())
+  got = S.magspec_to_waveform_lws(X_mag, 1024, 256, iterations=5, init_phase=phase)
+  assert got.shape == ref.shape == (63 * 256 + 1024, 1, 1) and got.dtype == np.float32
+  assert _rel(got, ref) < 2e-3
+
+  def inconsistency(x):
+    mag = np.abs(O.stft(x[:, 0, 0][:, None, None], 1024, 256, pad_end=False)[:, :, 0])
+    return float(np.linalg.norm(mag[:64] - X_mag[:, :, 0]) / np.linalg.norm(X_mag))
+
+  x_lws = S.magspec_to_waveform_lws(X_mag, 1024, 256, iterations=30, init_phase=phase)
+  x_gl = S.magspec_to_waveform_griffin_lim(X_mag, 1024, 256, ngl=30, init_phase=phase)
+  assert inconsistency(x_lws) < inconsistency(x_gl)

@@ -170,3 +170,47 @@ def test_graph_replay_resamples_dropout(math):
   assert not torch.equal(outs_s[0], outs_s[2]) and not torch.equal(outs_s[1], outs_s[3])
   for a, b in zip(outs_s[:3], outs_e):
     assert torch.equal(a, b)
+
+
+def test_loader_melspec_extract_and_paired_audio_slices(tmp_path):
+  """advoc/loader.py:103-115 (extract_type='melspec': what models/melspecgan/train.py:20-42 trains on)
+  and :133-186 (feature and audio slices cut in parallel, the audio slice slice_len * nhop samples long)
+  through the reference's own entry point `decode_extract_and_batch`."""
+  from advoc_b200 import audioio, loader
+  from oracle import spectral_np as O
+  rng = np.random.RandomState(0)
+  wav = rng.uniform(-0.5, 0.5, (40000, 1, 1)).astype(np.float32)
+  f, a = loader.extract_slices(wav, 'melspec', 64, slice_pad_end=True)
+  mel = O.waveform_to_r9y9_melspec(wav).astype(np.float32)           # [157, 80, 1]
+  n = -(-mel.shape[0] // 64)
+  assert f.shape == (n, 64, 80, 1) and a.shape == (n, 64 * 256, 1, 1)
+  ref = np.zeros((n * 64, 80, 1), np.float32)
+  ref[:mel.shape[0]] = mel
+  assert _rel(f.reshape(-1, 80, 1), ref) < 1e-4
+  flat = np.zeros(n * 64 * 256, np.float32)
+  flat[:40000] = wav[:, 0, 0]
+  assert np.array_equal(a.cpu().numpy().reshape(-1), flat)
+  # no padding: whole slices only, both streams the same count
+  f2, a2 = loader.extract_slices(wav, 'magspec', 64, slice_pad_end=False)
+  assert f2.shape == (2, 64, 513, 1) and a2.shape == (2, 64 * 256, 1, 1)
+  # random offset: the audio offset follows the feature offset (loader.py:160-165)
+  class _R(object):
+    def randint(self, n):
+      return 5
+  f3, a3 = loader.extract_slices(wav, 'magspec', 64, slice_pad_end=False, slice_randomize_offset=True, rng=_R())
+  assert np.array_equal(a3[0, :, 0, 0].cpu().numpy(), wav[5 * 256:5 * 256 + 64 * 256, 0, 0])
+  assert _rel(f3[0], f2.reshape(-1, 513, 1)[5:69]) < 1e-5
+  # the reference's entry point over files on disk
+  fps = []
+  for i in range(3):
+    fp = str(tmp_path / ('f%d.wav' % i))
+    audioio.save_as_wav(fp, 22050, rng.uniform(-0.5, 0.5, (30000 + 4000 * i, 1, 1)).astype(np.float32))
+    fps.append(fp)
+  got = list(loader.decode_extract_and_batch(fps, batch_size=2, slice_len=64, decode_fastwav=True,
+                                             extract_type='melspec', slice_pad_end=True))
+  n_slices = sum(-(-(-(-(30000 + 4000 * i) // 256)) // 64) for i in range(3))
+  assert len(got) == n_slices // 2
+  for xf, xa in got:
+    assert xf.shape == (2, 64, 80, 1) and xa.shape == (2, 64 * 256, 1, 1) and xf.is_cuda
+  with pytest.raises(ValueError):
+    list(loader.decode_extract_and_batch(fps, 2, 64, extract_type='bogus'))

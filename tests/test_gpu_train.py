@@ -132,3 +132,118 @@ def test_thin_filter_gradients(cin, cout, k):
   xd, dyd = x.cuda().contiguous(), dy.cuda().contiguous()
   N.call('advoc_conv2d_wgrad', C.byref(d), _ptr(xd), cin, _ptr(dyd), cout, _ptr(dw), _stream())
   assert _rel(dw, ref) < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------
+# round 2: the benchmarked configurations (regular model, TF32 trajectory) and real NCCL
+# ---------------------------------------------------------------------------------------------
+def _setup_regular(math, batch=1):
+  from advoc_b200 import _native as N
+  from advoc_b200 import nets
+  from advoc_b200.train import TrainEngine
+  from oracle import nets_torch as O
+  P = O.init_params(O.REGULAR, seed=0)
+  g = torch.Generator().manual_seed(12)
+  for k in P:
+    if k.endswith('/bias'):
+      P[k] = torch.randn(P[k].shape, generator=g) * 0.05
+  spec = nets.GenSpec(64, 8, (8, 7, 6))
+  eng = TrainEngine(spec, 64, {k: v.cuda() for k, v in P.items()}, batch,
+                    math=N.MATH_FP32 if math == 'fp32' else N.MATH_AUTO)
+  target = torch.randn(batch, 256, 513, 1, generator=g).abs() * 0.1
+  x = (target + torch.randn(batch, 256, 513, 1, generator=g) * 0.02)
+  return O, P, eng, x, target
+
+
+@pytest.mark.parametrize('math,gtol', [('fp32', 5e-4), ('auto', 1e-2)])
+def test_regular_model_step_gradients(math, gtol):
+  """BASELINE configs[2] net (AdVoc regular: ngf = ndf = 64, 8 + 8 layers, 1x3 bottleneck, 1024-channel
+  concats): D-step and G-step gradients against autograd on the oracle, on the exact-fp32 path (checks
+  the backward construction for the stride-(1,2) bottleneck layers) and on the production TF32 path."""
+  O, P, eng, x, target = _setup_regular(math)
+  eng.d_step(x.cuda(), target.cuda(), dropout=None, apply=False)
+  Pd = {n: t.clone().requires_grad_(n.startswith('discriminator')) for n, t in P.items()}
+  l = O.losses(Pd, x, target, O.REGULAR)
+  ref = O.grads_of(l['d_loss'], Pd, O.d_names(P))
+  assert abs(eng.loss_values()[0] - float(l['d_loss'])) < 1e-3 * abs(float(l['d_loss']))
+  for n in O.d_names(P):
+    assert _rel(eng.flat.G[n], ref[n]) < gtol, n
+  eng.g_step(x.cuda(), target.cuda(), dropout=None, apply=False)
+  Pg = {n: t.clone().requires_grad_(n.startswith('generator')) for n, t in P.items()}
+  l = O.losses(Pg, x, target, O.REGULAR)
+  ref = O.grads_of(l['g_loss'], Pg, O.g_names(P))
+  _, g_gan, g_l1 = eng.loss_values()
+  assert abs(g_gan - float(l['g_gan'])) < 1e-3 * abs(float(l['g_gan']))
+  assert abs(g_l1 - 10.0 * float(l['g_l1'])) < 1e-3 * abs(10.0 * float(l['g_l1']))
+  errs = {n.replace('generator/', '').replace('/conv2d_transpose', '').replace('/conv2d', ''):
+              round(_rel(eng.flat.G[n], ref[n]), 5) for n in O.g_names(P)}
+  assert max(errs.values()) < gtol, errs
+
+
+def test_train_loop_trajectory_tf32():
+  """Two reference `train_loop`s on the production path (TF32 tensor cores, the mode bench.py times):
+  the parameter UPDATES follow the oracle's TF1-Adam trajectory."""
+  O, P, eng, x, target, full, dmasks = _setup('auto')
+  g = torch.Generator().manual_seed(5)
+  x2 = x + torch.randn(x.shape, generator=g) * 0.01
+  t2 = target * 1.1
+  opt_d = O.TFAdam(O.d_names(P), P)
+  opt_g = O.TFAdam(O.g_names(P), P)
+  Pref = dict(P)
+  for it in range(2):
+    step = eng.train_loop((x.cuda(), target.cuda()), (x2.cuda(), t2.cuda()), dropout=dmasks)
+    O.train_step(Pref, opt_d, opt_g, (x, target), (x2, t2), O.SMALL, full, full)
+    assert step == it + 1
+  for n in P:
+    upd, ref = eng.P[n].cpu() - P[n], Pref[n] - P[n]
+    assert _rel(upd, ref) < 5e-2, (n, _rel(upd, ref))
+
+
+@pytest.mark.parametrize('overlap', ['1', '0'])
+def test_two_rank_nccl_train_loop_matches_accumulated_gradients(tmp_path, overlap):
+  """Real NCCL: two ranks run one data-parallel `train_loop` (one sample each, D all-reduce deferred
+  under the generator forward, G all-reduce in three buckets) and must land on the parameters a single
+  engine reaches by accumulating the two samples' gradients and applying Adam on their mean
+  (SURVEY 8(e) equivalence).  Skipped on a one-GPU box."""
+  import os
+  import subprocess
+  import sys
+  if torch.cuda.device_count() < 2:
+    pytest.skip('needs 2 GPUs')
+  from advoc_b200 import _native as N
+  from advoc_b200 import nets
+  from advoc_b200.train import TrainEngine
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  sys.path.insert(0, os.path.join(root, 'tests'))
+  import dp_worker
+  env = dict(os.environ)
+  env.update(DP_MATH='fp32', DP_OVERLAP=overlap)
+  r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+                      '--master-addr', '127.0.0.1', '--master-port', '29731', os.path.join(root, 'tests', 'dp_worker.py'),
+                      str(tmp_path)], cwd=root, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                     universal_newlines=True)
+  assert r.returncode == 0, r.stdout[-3000:]
+  got = [torch.load(os.path.join(str(tmp_path), 'rank%d.pt' % k)) for k in range(2)]
+  assert torch.equal(got[0]['p'], got[1]['p'])          # replicas stay in lock step
+  # single engine: accumulate the two samples' gradients, Adam on the mean, D first then G
+  eng = TrainEngine(nets.GenSpec(32, 5, (5, 4)), 32, nets.init_params(32, 32, 5, seed=0), 1, math=N.MATH_FP32)
+  f = eng.flat
+  data = [dp_worker.data(k) for k in range(2)]
+  lo, hi = f.dis_range()
+  acc = torch.zeros_like(f.g)
+  for x, tgt in data:
+    eng.d_step(x[0].cuda(), tgt[0].cuda(), dropout=None, apply=False)
+    acc[lo:hi] += f.g[lo:hi]
+  f.g[lo:hi] = acc[lo:hi] * 0.5
+  eng._adam(lo, hi, 1)
+  eng.refresh_weights('D')
+  lo, hi = f.gen_range()
+  for x, tgt in data:
+    eng.g_step(x[1].cuda(), tgt[1].cuda(), dropout=None, apply=False)
+    acc[lo:hi] += f.g[lo:hi]
+  f.g[lo:hi] = acc[lo:hi] * 0.5
+  eng._adam(lo, hi, 1)
+  p0 = TrainEngine(nets.GenSpec(32, 5, (5, 4)), 32, nets.init_params(32, 32, 5, seed=0), 1, math=N.MATH_FP32).flat.p.cpu()
+  upd_got, upd_want = got[0]['p'] - p0, f.p.cpu() - p0
+  assert _rel(got[0]['g'][lo:hi], acc[lo:hi].cpu()) < 1e-4      # all-reduced G gradients = the accumulated sum
+  assert _rel(upd_got, upd_want) < 1e-2
