@@ -47,6 +47,7 @@ struct alignas(64) TcParams {
   int osh, osw;        // output position stride (1 for conv, s for transposed conv)
   int Cn;              // produced channels (rows of B per tap)
   int kblocks;         // contraction channels / channels per 128-byte row (32 tf32, 64 fp16)
+  long total_tiles;    // M tiles (of the largest class) x classes x N tiles
   EpiDev epi;
   unsigned int* dbg;   // [0] != 0 after a barrier wait timed out
 };
@@ -59,7 +60,37 @@ struct SmemLayout {
 };
 
 // HALF: fp16 operands (kind::f16, 64 channels per 128-byte row) instead of tf32 (32 channels); the
-// byte layout of the ring, the descriptors and the four 32-byte K steps per row are the same
+// byte layout of the ring, the descriptors and the four 32-byte K steps per row are the same.
+//
+// PERSISTENT (round 2): the grid is one or two CTAs per SM and every CTA walks the tile list
+// t = blockIdx.x, blockIdx.x + gridDim.x, ...; the producer warp keeps streaming operand tiles across
+// tile boundaries and the accumulator is double-buffered in TMEM (2 x BN columns), so the epilogue of
+// tile i (TMEM -> registers -> global) overlaps the main loop of tile i + 1 and the pipeline never
+// drains between tiles.  (Round 1 ran one tile per CTA: with the K loops of the fp16 path only 16-64
+// ring slots long, pipeline fill + epilogue + TMEM alloc were a large share of every CTA's life:
+// profiles/r02c_ncu_fwd_f16.csv, tensor pipe 8-17 % active.)
+// Tile order: N tile fastest, then parity class, then M tile, so that the CTAs running at the same
+// time share their A tiles through L2.
+struct TcTile {
+  int n0, cls, iters;
+  long m0;
+  bool valid;
+};
+
+template <int BN>
+__device__ __forceinline__ TcTile tc_decode(const TcParams& p, long t, int n_ntiles) {
+  TcTile x;
+  const unsigned per_m = (unsigned)(n_ntiles * p.nclasses);
+  const unsigned m_tile = (unsigned)t / per_m;      // total tiles < 2^31 (checked on the host)
+  const unsigned rem = (unsigned)t - m_tile * per_m;
+  x.cls = (int)(rem / (unsigned)n_ntiles);
+  x.n0 = (int)(rem - (unsigned)x.cls * (unsigned)n_ntiles) * BN;
+  x.m0 = (long)m_tile * BM;
+  x.valid = x.m0 < (long)p.Nimg * p.Ah[x.cls] * p.Aw[x.cls];   // small classes have fewer M tiles
+  x.iters = p.ntaps[x.cls] * p.kblocks;
+  return x;
+}
+
 template <int BN, int STAGES, bool HALF>
 __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_constant__ TcParams p) {
   constexpr int BK = HALF ? 64 : 32;   // channels per k-block
@@ -67,37 +98,27 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[STAGES];
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
-  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_holder;
 
-  // CTAs that share an A tile (N tiles, then parity classes) are adjacent in launch order so
-  // the activations are fetched from HBM once and re-served from L2
   const int n_ntiles = p.Cn / BN;
-  const int n_tile = (int)(blockIdx.x % n_ntiles);
-  const int cls = (int)((blockIdx.x / n_ntiles) % p.nclasses);
-  const long m_tile = blockIdx.x / (n_ntiles * p.nclasses);
-  const int Ah = p.Ah[cls], Aw = p.Aw[cls];
-  const long Mc = (long)p.Nimg * Ah * Aw;
-  const long m0 = m_tile * BM;
-  if (m0 >= Mc) return;  // uniform per CTA, before any barrier or allocation
-  if (p.dbg && *reinterpret_cast<volatile unsigned int*>(p.dbg) != 0) return;  // aborted launch
-  const int n0 = n_tile * BN;
+  const long ntl = p.total_tiles;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // operand ring, 1024-byte aligned (SWIZZLE_128B atom)
   const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* ring_ptr = smem_raw + (ring - smem_u32(smem_raw));
-  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;   // two accumulators
 
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&p.tmA[cls]);
+    for (int c = 0; c < p.nclasses; ++c) prefetch_tmap(&p.tmA[c]);
     prefetch_tmap(&p.tmB);
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(&tmem_full_bar, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -111,36 +132,43 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_holder;
+  const bool aborted = p.dbg && *reinterpret_cast<volatile unsigned int*>(p.dbg) != 0;
 
-  const int iters = p.ntaps[cls] * p.kblocks;
-
-  if (warp == 0) {
+  if (aborted) {
+    // a previous launch timed out: do nothing (the host raises at its next sync point)
+  } else if (warp == 0) {
     // ===== TMA producer: warp-uniform loop, loads issued by one elected lane =====
-    const int a_w = (int)(m0 % Aw);
-    const long r = m0 / Aw;
-    const int a_h = (int)(r % Ah);
-    const int img = (int)(r / Ah);
-    const int cw = a_w * p.trav_w + p.base_w[cls];
-    const int ch = a_h * p.trav_h + p.base_h[cls];
     int stage = 0;
     uint32_t phase = 0;
-    int tap = 0, kb = 0;
-    for (int it = 0; it < iters; ++it) {
-      mbar_wait(&empty_bar[stage], phase ^ 1u, p.dbg, 1u);
-      uint8_t* a_dst = ring_ptr + stage * L::STAGE_BYTES;
-      uint8_t* b_dst = a_dst + L::A_BYTES;
-      const unsigned off = p.tap_off[cls][tap];
-      const int wrow = (int)p.tap_wrow[cls][tap] * p.Cn + n0;
-      __syncwarp();
-      if (elect_one()) {
-        mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-        tma_load_im2col_4d(&p.tmA[cls], &full_bar[stage], a_dst, kb * BK, cw, ch, img, (uint16_t)(off & 0xFF),
-                           (uint16_t)(off >> 8));
-        tma_load_2d(&p.tmB, &full_bar[stage], b_dst, kb * BK, wrow);
+    for (long t = blockIdx.x; t < ntl; t += gridDim.x) {
+      const TcTile tl = tc_decode<BN>(p, t, n_ntiles);
+      if (!tl.valid) continue;
+      const int cls = tl.cls;
+      const int Ah = p.Ah[cls], Aw = p.Aw[cls];
+      const int a_w = (int)(tl.m0 % Aw);
+      const long r = tl.m0 / Aw;
+      const int a_h = (int)(r % Ah);
+      const int img = (int)(r / Ah);
+      const int cw = a_w * p.trav_w + p.base_w[cls];
+      const int ch = a_h * p.trav_h + p.base_h[cls];
+      int tap = 0, kb = 0;
+      for (int it = 0; it < tl.iters; ++it) {
+        mbar_wait(&empty_bar[stage], phase ^ 1u, p.dbg, 1u);
+        uint8_t* a_dst = ring_ptr + stage * L::STAGE_BYTES;
+        uint8_t* b_dst = a_dst + L::A_BYTES;
+        const unsigned off = p.tap_off[cls][tap];
+        const int wrow = (int)p.tap_wrow[cls][tap] * p.Cn + tl.n0;
+        __syncwarp();
+        if (elect_one()) {
+          mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+          tma_load_im2col_4d(&p.tmA[cls], &full_bar[stage], a_dst, kb * BK, cw, ch, img, (uint16_t)(off & 0xFF),
+                             (uint16_t)(off >> 8));
+          tma_load_2d(&p.tmB, &full_bar[stage], b_dst, kb * BK, wrow);
+        }
+        __syncwarp();
+        if (++kb == p.kblocks) { kb = 0; ++tap; }
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
-      __syncwarp();
-      if (++kb == p.kblocks) { kb = 0; ++tap; }
-      if (++stage == STAGES) { stage = 0; phase ^= 1u; }
     }
   } else if (warp == 1) {
     // ===== MMA issuer: warp-uniform loop, tcgen05.mma issued by one elected lane (a plain
@@ -150,52 +178,76 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
     if (elect_one()) {   // one thread waits and issues; entered through elect.sync (see tc::elect_one)
       int stage = 0;
       uint32_t phase = 0;
-      for (int it = 0; it < iters; ++it) {
-        mbar_wait(&full_bar[stage], phase, p.dbg, 2u);
-        const uint32_t a_addr = ring + stage * L::STAGE_BYTES;
-        const uint64_t da = make_smem_desc(a_addr);
-        const uint64_t db = make_smem_desc(a_addr + L::A_BYTES);
+      uint32_t i = 0;   // tiles this CTA has started
+      for (long t = blockIdx.x; t < ntl; t += gridDim.x) {
+        const TcTile tl = tc_decode<BN>(p, t, n_ntiles);
+        if (!tl.valid) continue;
+        const uint32_t buf = i & 1u;
+        mbar_wait(&acc_empty[buf], ((i >> 1) & 1u) ^ 1u, p.dbg, 4u);   // epilogue drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * (uint32_t)BN;
+        for (int it = 0; it < tl.iters; ++it) {
+          mbar_wait(&full_bar[stage], phase, p.dbg, 2u);
+          const uint32_t a_addr = ring + stage * L::STAGE_BYTES;
+          const uint64_t da = make_smem_desc(a_addr);
+          const uint64_t db = make_smem_desc(a_addr + L::A_BYTES);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          // advance 32 bytes (= 2 x 16-byte units) along K inside the swizzle atom
-          umma_op<HALF>(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (it | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) {
+            // advance 32 bytes (= 2 x 16-byte units) along K inside the swizzle atom
+            umma_op<HALF>(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (it | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
-        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        umma_commit(&acc_full[buf]);       // accumulator complete -> epilogue
+        ++i;
       }
-      umma_commit(&tmem_full_bar);       // accumulator complete -> epilogue
     }
     __syncwarp();
   } else {
     // ===== epilogue: warp q may only touch TMEM lanes [32q, 32q+32) =====
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const long m = m0 + row;
-    const bool valid = m < Mc;
-    size_t pix = 0;
-    if (valid) {
-      const int a_w = (int)(m % Aw);
-      const long r = m / Aw;
-      const int a_h = (int)(r % Ah);
-      const long img = r / Ah;
-      pix = ((size_t)img * p.epi.Hs + (size_t)(a_h * p.osh + p.ph[cls])) * p.epi.Ws +
-            (size_t)(a_w * p.osw + p.pw[cls]);
-    }
-    mbar_wait(&tmem_full_bar, 0u, p.dbg, 3u);
-    tc_fence_after();
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      tmem_ld_wait();
+    uint32_t i = 0;
+    for (long t = blockIdx.x; t < ntl; t += gridDim.x) {
+      const TcTile tl = tc_decode<BN>(p, t, n_ntiles);
+      if (!tl.valid) continue;
+      const int cls = tl.cls;
+      const int Ah = p.Ah[cls], Aw = p.Aw[cls];
+      const long m = tl.m0 + row;
+      const bool valid = m < (long)p.Nimg * Ah * Aw;
+      size_t pix = 0;
       if (valid) {
+        const int a_w = (int)(m % Aw);
+        const long r = m / Aw;
+        const int a_h = (int)(r % Ah);
+        const long img = r / Ah;
+        pix = ((size_t)img * p.epi.Hs + (size_t)(a_h * p.osh + p.ph[cls])) * p.epi.Ws +
+              (size_t)(a_w * p.osw + p.pw[cls]);
+      }
+      const uint32_t buf = i & 1u;
+      mbar_wait(&acc_full[buf], (i >> 1) & 1u, p.dbg, 3u);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)BN + (uint32_t)c0, v);
+        tmem_ld_wait();
+        if (valid) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          epi_store_vec4(p.epi, pix, n0 + c0 + j,
-                     make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                 __uint_as_float(v[j + 3])));
+          for (int j = 0; j < 32; j += 4) {
+            epi_store_vec4(p.epi, pix, tl.n0 + c0 + j,
+                           make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                       __uint_as_float(v[j + 3])));
+          }
         }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[buf])) : "memory");
+      }
+      ++i;
     }
   }
 
@@ -237,10 +289,16 @@ int launch(const TcParams& p, int nclasses, long max_tiles, cudaStream_t st) {
                                           smem));
     configured = true;
   }
-  const long ctas = max_tiles * (p.Cn / BN) * nclasses;
-  ADVOC_REQUIRE(ctas < 2147483647L, ADVOC_BAD_SHAPE, "too many output tiles");
-  dim3 grid((unsigned)ctas, 1, 1);
-  conv_tc_kernel<BN, STAGES, HALF><<<grid, NUM_THREADS, smem, st>>>(p);
+  const long tiles = max_tiles * (p.Cn / BN) * nclasses;
+  ADVOC_REQUIRE(tiles < 2147483647L, ADVOC_BAD_SHAPE, "too many output tiles");
+  TcParams q = p;
+  q.total_tiles = tiles;
+  // persistent: as many CTAs as fit on the chip at once (two per SM while two rings and two pairs of
+  // accumulators fit: 2 x smem <= 227 KB and 2 x 2 x BN <= 512 TMEM columns)
+  const int per_sm = (2 * smem <= 220 * 1024 && 4 * BN <= 512) ? 2 : 1;
+  const long slots = (long)sm_count() * per_sm;
+  dim3 grid((unsigned)(tiles < slots ? tiles : slots), 1, 1);
+  conv_tc_kernel<BN, STAGES, HALF><<<grid, NUM_THREADS, smem, st>>>(q);
   count_launch();
   ADVOC_CHECK_CUDA(cudaGetLastError());
   return ADVOC_OK;

@@ -299,8 +299,8 @@ int deconv_one_tc(const advoc_conv_desc* d, const void* x, int ldx, const void* 
   static unsigned long long* prof = [] {
     unsigned long long* b = nullptr;
     if (getenv("ADVOC_ONE_PROFILE") == nullptr) return b;
-    if (cudaMalloc(&b, 256 * 8 * sizeof(unsigned long long)) != cudaSuccess) return (unsigned long long*)nullptr;
-    cudaMemset(b, 0, 256 * 8 * sizeof(unsigned long long));
+    if (cudaMalloc(&b, 512 * 8 * sizeof(unsigned long long)) != cudaSuccess) return (unsigned long long*)nullptr;
+    cudaMemset(b, 0, 512 * 8 * sizeof(unsigned long long));
     return b;
   }();
   p.prof = prof;
@@ -340,11 +340,11 @@ int deconv_one_tc(const advoc_conv_desc* d, const void* x, int ldx, const void* 
 
 }  // namespace advoc
 
-// Developer hook (ADVOC_ONE_PROFILE=1): per-CTA cycle counters of the last deconv_one_tc launch, [256][8] u64.
+// Developer hook (ADVOC_ONE_PROFILE=1): per-CTA cycle counters of the last deconv_one_tc launch, [512][8] u64.
 extern "C" __attribute__((visibility("default"))) int advoc_one_profile_read(unsigned long long* out) {
   using namespace advoc;
   ADVOC_REQUIRE(g_one_prof != nullptr && out != nullptr, ADVOC_UNSUPPORTED, "profiling is off (set ADVOC_ONE_PROFILE=1)");
-  ADVOC_CHECK_CUDA(cudaMemcpy(out, g_one_prof, 256 * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-  ADVOC_CHECK_CUDA(cudaMemset(g_one_prof, 0, 256 * 8 * sizeof(unsigned long long)));
+  ADVOC_CHECK_CUDA(cudaMemcpy(out, g_one_prof, 512 * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  ADVOC_CHECK_CUDA(cudaMemset(g_one_prof, 0, 512 * 8 * sizeof(unsigned long long)));
   return ADVOC_OK;
 }

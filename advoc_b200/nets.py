@@ -233,9 +233,10 @@ class Generator(object):
   def prepare(self):
     """Refresh the derived (packed / TF32-rounded) filter copies after the parameters changed
     and decide which stored activations must be TF32-rounded for their consumer."""
+    old = getattr(self, 'Wp', {})   # refreshed in place: captured CUDA graphs keep pointing at these copies
     self.Wp = {}
     for L in list(self.enc.values()) + list(self.dec.values()):
-      self.Wp[L.name] = _pack_for_tc(L, self.P[L.name + '/kernel'], self._ldx(L))
+      self.Wp[L.name] = _pack_for_tc(L, self.P[L.name + '/kernel'], self._ldx(L), old.get(L.name))
     n = self.spec.n_enc
     tc = lambda L: self.Wp[L.name] is not None
     # encoder_i writes E[i] (read by encoder_{i+1}) and Cat[i] (read by decoder_i)
@@ -326,7 +327,8 @@ class Discriminator(object):
       h, w = ho, wo
 
   def prepare(self):
-    self.Wp = {L.name: _pack_for_tc(L, self.P[L.name + '/kernel'], self.chans[i])
+    old = getattr(self, 'Wp', {})   # refreshed in place (fixed addresses for captured graphs)
+    self.Wp = {L.name: _pack_for_tc(L, self.P[L.name + '/kernel'], self.chans[i], old.get(L.name))
                for i, L in enumerate(self.layers)}
     self.round = [int(i + 1 < 5 and self.Wp[self.layers[i + 1].name] is not None) for i in range(5)]
     return self

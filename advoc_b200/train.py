@@ -72,16 +72,20 @@ class TrainEngine(object):
 
   def __init__(self, spec, ndf, params, batch, gan_weight=1.0, l1_weight=10.0, math=N.MATH_AUTO,
                lr=2e-4, beta1=0.5, beta2=0.999, eps=1e-8, process_group=None, world_size=1, rank=0,
-               base_seed=0, overlap=True):
+               base_seed=0, overlap=True, use_graphs=True):
     """`rank` / `base_seed` key the dropout masks (every replica and every step draws its own);
     `overlap`: under data parallelism the gradient all-reduces run asynchronously behind the compute
-    that does not depend on them (see train_loop)."""
+    that does not depend on them (see train_loop).  `use_graphs`: with dropout='rng' or None the
+    device work of d_step / g_step between two collectives is captured once and replayed as CUDA
+    graphs (130-170 launches per step otherwise pace the step from the host on the small model);
+    the Adam step size and the dropout counter live in device memory so the graphs follow them."""
     self.spec, self.ndf, self.B = spec, ndf, batch
     self.gan_weight, self.l1_weight = gan_weight, l1_weight
     self.lr, self.b1, self.b2, self.eps = lr, beta1, beta2, eps
     self.pg, self.world, self.rank = process_group, world_size, rank
     self.overlap = overlap
-    self.capture_launches = self.replayed_launches = 0    # launch accounting for bench.py (no graphs here)
+    self.use_graphs, self._graphs, self._graph_launches = use_graphs, {}, {}
+    self.capture_launches = self.replayed_launches = 0    # launch accounting for bench.py
     # splitmix64 of (base_seed, rank): the per-replica dropout stream; step k uses seed0 + k
     z = (base_seed * 0x100000001B3 + rank + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
     z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
@@ -101,9 +105,13 @@ class TrainEngine(object):
     self.cat_real = torch.zeros((batch, T, F, 2), **f32)   # [x, target]
     self.cat_fake = torch.zeros((batch, T, F, 2), **f32)   # [x, generated]
     self.g_out = torch.zeros((batch, T, F, 1), **f32)      # d loss / d generated
+    self.target_buf = torch.zeros((batch, T, F, 1), **f32)  # the L1 target (persistent: captured graphs read it)
     self.gCat = {k: torch.zeros_like(t) for k, t in self.G.Cat.items()}
     self.dz = [torch.zeros_like(t) for t in self.Dr.act]
     self.losses = torch.zeros(4, **f32)                    # d_loss, g_gan, g_l1, unused
+    self.dz_fake = torch.zeros_like(self.dz[4])
+    self.lr_t = torch.zeros(2, **f32)      # bias-corrected Adam step sizes (D, G) for advoc_adam_tf_step_dev
+    self.seed_d = torch.zeros(1, dtype=torch.int64, device=dev)   # dropout step counter (advoc_epilogue.d_seed)
     self.t_d, self.t_g = 0, 0
     self.rnd = 0 if math == N.MATH_FP32 else 1   # TF32-round stored gradients for tensor-core consumers
     self.step_count = 0
@@ -142,19 +150,23 @@ class TrainEngine(object):
     P = self.P
     if not hasattr(self, 'Wb'):
       self.Wb = {}
+    # every derived copy is refreshed IN PLACE (captured graphs keep pointing at it); the forward and
+    # the backward copy of a layer have different layouts, hence two tables
     if 'G' in which:
       self.G.prepare()
       for k, L in self.dec_b.items():      # deconv dgrad: conv over the big side
-        self.Wb[L.name] = nets._pack_for_tc(L, P[L.name + '/kernel'], L.desc.Cin)
+        self.Wb[L.name] = nets._pack_for_tc(L, P[L.name + '/kernel'], L.desc.Cin, self.Wb.get(L.name))
       for i, L in self.enc_t.items():      # conv dgrad: HWIO is already K-major, only round
-        self.Wb[L.name] = nets._pack_for_tc(L, P[L.name + '/kernel'], L.desc.Cout)
+        self.Wb[L.name] = nets._pack_for_tc(L, P[L.name + '/kernel'], L.desc.Cout, self.Wb.get(L.name))
     if 'D' in which:
       self.Dr.prepare()
       self.Df.Wp, self.Df.round = self.Dr.Wp, self.Dr.round
       for L in self.dis_t[1:]:
-        self.Wb[L.name] = nets._pack_for_tc(L, P[L.name + '/kernel'], L.desc.Cout)
+        self.Wb[L.name] = nets._pack_for_tc(L, P[L.name + '/kernel'], L.desc.Cout, self.Wb.get(L.name))
       k0 = P['discriminator/layer_1/conv2d/kernel']
-      self.w_sel = k0[:, :, 1:2, :].contiguous()   # [4,4,1,ndf]: filter slice of input channel 1
+      if not hasattr(self, 'w_sel'):
+        self.w_sel = torch.empty_like(k0[:, :, 1:2, :].contiguous())
+      self.w_sel.copy_(k0[:, :, 1:2, :])   # [4,4,1,ndf]: filter slice of input channel 1 (fixed address)
 
   def _wb(self, L):
     w = self.Wb.get(L.name)
@@ -201,10 +213,13 @@ class TrainEngine(object):
   # -------------------------------------------------------------------------------------------
   # generator backward (g_out holds d loss / d generated)
   # -------------------------------------------------------------------------------------------
-  def _g_backward(self, x_cat):
+  def _g_backward(self, x_cat, piece='all'):
+    """piece: 'all', or one of the three stretches between which a gradient bucket is complete and its
+    all-reduce can start (dec_8..5 + enc_8..5 hold 46 M of the regular model's 54 M
+    parameters): 'dec' (decoder_1..n), 'enc_hi' (encoder_n..split), 'enc_lo' (encoder_(split-1)..1)."""
     s, n, G = self.spec, self.spec.n_enc, self.G
     keep = 0.5
-    for k in range(1, n + 1):
+    for k in (range(1, n + 1) if piece in ('all', 'dec') else ()):
       L = self.dec_b[k]
       d = L.desc
       if k == 1:
@@ -219,12 +234,10 @@ class TrainEngine(object):
       ep = _epilogue(None, self.gCat[k], cc, 0, N.ACT_NONE, gate=cat, ld_gate=cc, gate_act=N.ACT_RELU,
                      gate_split=G.Dk[k], gate_scale0=scale0, round_tf32=self.rnd)
       self._run(L, dy, ld, co, self._wb(L), ep)
-    # decoder gradients are complete: their slice of the flat buffer goes out while the encoder
-    # backward runs (dec_8..5 + enc_8..5 hold 46 M of the regular model's 54 M parameters)
-    handles = []
-    if self._bucketed():
-      handles.append(self._allreduce_async(*self._bucket['dec']))
-    for i in range(n, 0, -1):
+    split = self._bucket_split
+    enc_range = {'all': range(n, 0, -1), 'dec': (), 'enc_hi': range(n, split - 1, -1),
+                 'enc_lo': range(split - 1, 0, -1)}[piece]
+    for i in enc_range:
       L = G.enc[i]
       d = L.desc
       dy, ld, co = self.gCat[i], self.gCat[i].shape[3], G.Dk[i]
@@ -240,11 +253,6 @@ class TrainEngine(object):
         ep = _epilogue(None, prev, prev.shape[3], G.Dk[i - 1], N.ACT_NONE, accumulate=1,
                        gate=G.E[i - 1], ld_gate=s.enc_ch[i - 2], gate_act=N.ACT_LRELU, round_tf32=self.rnd)
         self._run(Lt, dy, ld, co, self._wb(Lt), ep)
-      if self._bucketed() and i == self._bucket_split:
-        handles.append(self._allreduce_async(*self._bucket['enc_hi']))
-    if self._bucketed():
-      handles.append(self._allreduce_async(*self._bucket['enc_lo']))
-    return handles
 
   # -------------------------------------------------------------------------------------------
   # optimiser + collective
@@ -327,12 +335,41 @@ class TrainEngine(object):
     self.cat_real[..., 0:1].copy_(x)
     self.cat_real[..., 1:2].copy_(target)
     self.cat_fake[..., 0:1].copy_(x)
+    self.target_buf.copy_(target)
 
-  def _generate(self, dropout, seed):
+  # -------------------------------------------------------------------------------------------
+  # CUDA-graph replay of the device work between two collectives
+  # -------------------------------------------------------------------------------------------
+  def _replay(self, key, fn, graphable=True):
+    """Run `fn` (device work on persistent buffers only): eagerly the first time, then captured once
+    and replayed.  Host-side state (step counters, input staging, collectives) stays outside `fn`."""
+    if not (self.use_graphs and graphable):
+      return fn()
+    g = self._graphs.get(key)
+    if g is not None:
+      self.replayed_launches += self._graph_launches[key]
+      return g.replay()
+    fn()
+    torch.cuda.synchronize()
+    n0 = N.launch_count()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+      fn()
+    self._graph_launches[key] = N.launch_count() - n0
+    self.capture_launches += self._graph_launches[key]    # counted by the library, but only recorded
+    self._graphs[key] = g
+
+  def _generate(self, dropout):
+    """Generator forward into channel 1 of cat_fake.  dropout='rng' reads the step counter from device
+    memory (self.seed_d, set by the caller before the launch / replay)."""
     self._dropout_on = dropout is not None
     # encoder_1 reads x as channel 0 of the 2-channel buffer; decoder_1 writes channel 1
     return self.G.forward(self.cat_fake, out=self.cat_fake, out_ld=2, out_coff=1, dropout=dropout,
-                          seed=self.seed0 + seed, x_ld=2)
+                          seed_dev=self.seed_d if dropout == 'rng' else None, x_ld=2)
+
+  def _bump_seed(self):
+    self.step_count += 1
+    self.seed_d.fill_(self.seed0 + self.step_count)
 
   def _finish_d(self):
     """Second half of a deferred D update: wait for its all-reduce, Adam, refresh the packed filters."""
@@ -341,65 +378,98 @@ class TrainEngine(object):
     handles, lo, hi = self._pending_d
     self._pending_d = None
     self._wait(handles)
-    self.t_d += 1
-    self._adam(lo, hi, self.t_d)
-    self.refresh_weights('D')
+    self._apply('D', lo, hi)
+
+  def _apply(self, which, lo, hi):
+    """TF1-Adam on one network's slice + in-place refresh of its packed filter copies (one graph)."""
+    if which == 'D':
+      self.t_d += 1
+      t, slot = self.t_d, 0
+    else:
+      self.t_g += 1
+      t, slot = self.t_g, 1
+    self.lr_t[slot:slot + 1].fill_(self.lr * (1.0 - self.b2 ** t) ** 0.5 / (1.0 - self.b1 ** t))
+
+    def update():
+      f = self.flat
+      N.call('advoc_adam_tf_step_dev', _view_ptr(f.p, lo), _view_ptr(f.g, lo), _view_ptr(f.m, lo),
+             _view_ptr(f.v, lo), hi - lo, _view_ptr(self.lr_t, slot), self.b1, self.b2, self.eps,
+             1.0 / self.world, _stream())
+      self.refresh_weights(which)
+    self._replay('adam_' + which, update)
+
+  def _d_compute(self, dropout):
+    lo, hi = self.flat.dis_range()
+    self.flat.g[lo:hi].zero_()
+    self.losses[0:1].zero_()
+    self._generate(dropout)
+    p_real = self.Dr.forward(self.cat_real)
+    p_fake = self.Df.forward(self.cat_fake)
+    N.call('advoc_gan_logloss', _ptr(p_real), _ptr(p_fake), p_real.numel(), 0, 1.0, _ptr(self.losses),
+           _ptr(self.dz[4]), _ptr(self.dz_fake), _stream())
+    self._d_backward(self.Dr, self.cat_real, True, False)
+    self.dz[4].copy_(self.dz_fake)
+    self._d_backward(self.Df, self.cat_fake, True, False)
 
   def d_step(self, x, target, dropout='rng', apply=True, defer=False):
     """advoc_model.py:257 `D_train_op` on one minibatch.  defer: leave the all-reduce in flight and the
     optimiser update pending (train_loop finishes it under the next generator forward)."""
     self._finish_d()
-    self.step_count += 1
     lo, hi = self.flat.dis_range()
-    self.flat.g[lo:hi].zero_()
-    self.losses[0:1].zero_()
     self.load_batch(x, target)
-    self._generate(dropout, self.step_count)
-    p_real = self.Dr.forward(self.cat_real)
-    p_fake = self.Df.forward(self.cat_fake)
-    n = p_real.numel()
-    dz_fake = torch.empty_like(self.dz[4])
-    N.call('advoc_gan_logloss', _ptr(p_real), _ptr(p_fake), n, 0, 1.0, _ptr(self.losses),
-           _ptr(self.dz[4]), _ptr(dz_fake), _stream())
-    self._d_backward(self.Dr, self.cat_real, True, False)
-    self.dz[4].copy_(dz_fake)
-    self._d_backward(self.Df, self.cat_fake, True, False)
+    self._bump_seed()
+    graphable = dropout == 'rng' or dropout is None
+    self._replay(('d', dropout if graphable else None), lambda: self._d_compute(dropout), graphable)
     if apply and defer and self._bucketed():
       self._pending_d = ([self._allreduce_async(lo, hi)], lo, hi)
       return
     self._wait([self._allreduce_async(lo, hi)])
     if apply:
-      self.t_d += 1
-      self._adam(lo, hi, self.t_d)
-      self.refresh_weights('D')
+      self._apply('D', lo, hi)
 
-  def g_step(self, x, target, dropout='rng', apply=True):
-    """advoc_model.py:254-255 `G_train_op` on one minibatch (bumps the global step)."""
-    self.step_count += 1
+  def _g_forward(self, dropout):
     lo, hi = self.flat.gen_range()
     self.flat.g[lo:hi].zero_()
     self.losses[1:3].zero_()
-    self.load_batch(x, target)
-    self._generate(dropout, self.step_count)
-    n_out = self.g_out.numel()
-    N.call('advoc_l1_loss', _ptr(self.cat_fake), 2, 1, _ptr(target), n_out, self.l1_weight,
+    self._generate(dropout)
+    N.call('advoc_l1_loss', _ptr(self.cat_fake), 2, 1, _ptr(self.target_buf), self.g_out.numel(), self.l1_weight,
            _view_ptr(self.losses, 2), _ptr(self.g_out), 0, _stream())
+
+  def _g_through_d(self):
+    p_fake = self.Df.forward(self.cat_fake)
+    N.call('advoc_gan_logloss', None, _ptr(p_fake), p_fake.numel(), 1, self.gan_weight,
+           _view_ptr(self.losses, 1), None, _ptr(self.dz[4]), _stream())
+    self._d_backward(self.Df, self.cat_fake, False, True)
+
+  def g_step(self, x, target, dropout='rng', apply=True):
+    """advoc_model.py:254-255 `G_train_op` on one minibatch (bumps the global step)."""
+    lo, hi = self.flat.gen_range()
+    self.load_batch(x, target)
+    self._bump_seed()
+    graphable = dropout == 'rng' or dropout is None
+    mode = dropout if graphable else None
+    self._replay(('g_fwd', mode), lambda: self._g_forward(dropout), graphable)
     # a deferred D update (its all-reduce ran under the generator forward above) lands here: the
     # discriminator pass below goes through the already-updated D like the reference's (advoc_model.py:285-289)
     self._finish_d()
-    if self.gan_weight > 0:
-      p_fake = self.Df.forward(self.cat_fake)
-      N.call('advoc_gan_logloss', None, _ptr(p_fake), p_fake.numel(), 1, self.gan_weight,
-             _view_ptr(self.losses, 1), None, _ptr(self.dz[4]), _stream())
-      self._d_backward(self.Df, self.cat_fake, False, True)
-    handles = self._g_backward(self.cat_fake)
-    if not self._bucketed():
+    if self._bucketed():
+      # the backward pass is cut where a gradient bucket completes; the all-reduces between the pieces stay eager
+      if self.gan_weight > 0:
+        self._replay(('g_dis', mode), self._g_through_d, graphable)
+      handles = []
+      for piece in ('dec', 'enc_hi', 'enc_lo'):
+        self._replay(('g_bwd_' + piece, mode), lambda piece=piece: self._g_backward(self.cat_fake, piece), graphable)
+        handles.append(self._allreduce_async(*self._bucket[piece]))
+    else:
+      def rest():
+        if self.gan_weight > 0:
+          self._g_through_d()
+        self._g_backward(self.cat_fake, 'all')
+      self._replay(('g_bwd', mode), rest, graphable)
       handles = [self._allreduce_async(lo, hi)]
     self._wait(handles)
     if apply:
-      self.t_g += 1
-      self._adam(lo, hi, self.t_g)
-      self.refresh_weights('G')
+      self._apply('G', lo, hi)
     return self.t_g
 
   def train_loop(self, batch_d, batch_g, dropout='rng'):
