@@ -43,6 +43,7 @@ class Epilogue(C.Structure):
       ('gate_scale0', C.c_float), ('gate_scale1', C.c_float),
       ('d_seed', C.c_void_p),
       ('out0_dtype', C.c_int), ('out1_dtype', C.c_int),
+      ('out0_row_pad', C.c_int), ('reserved0', C.c_int),
   ]
 
 

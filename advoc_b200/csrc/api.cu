@@ -8,7 +8,7 @@
 
 // the ctypes mirror in advoc_b200/_native.py relies on these layouts (tests/test_boundary.py)
 static_assert(sizeof(advoc_conv_desc) == 56, "advoc_conv_desc layout");
-static_assert(sizeof(advoc_epilogue) == 144 && offsetof(advoc_epilogue, d_seed) == 128 &&
+static_assert(sizeof(advoc_epilogue) == 152 && offsetof(advoc_epilogue, out0_row_pad) == 144 && offsetof(advoc_epilogue, d_seed) == 128 &&
                   offsetof(advoc_epilogue, out0_dtype) == 136 && offsetof(advoc_epilogue, d_gate) == 96 &&
                   offsetof(advoc_epilogue, gate_scale1) == 124 && offsetof(advoc_epilogue, d_out0) == 24 &&
                   offsetof(advoc_epilogue, d_out1) == 40 &&
@@ -129,6 +129,11 @@ extern "C" int advoc_conv2d_fwd(const advoc_conv_desc* d, const void* d_xv, int 
   if (st) return st;
   const float* d_x = static_cast<const float*>(d_xv);   // half data when math == ADVOC_MATH_F16: only the
   const float* d_w = static_cast<const float*>(d_wv);   // tcgen05 kernels below ever see those pointers
+  if (ep->out0_row_pad != 0) {
+    ADVOC_REQUIRE(d->Cin <= 2 && d->math != ADVOC_MATH_F16, ADVOC_UNSUPPORTED,
+                  "out0_row_pad is only supported by the thin-input convolution");
+    return conv_fwd_simt(d, d_x, ld_x, d_w, ep, stream);
+  }
   if (d->math == ADVOC_MATH_FP32) return conv_fwd_simt(d, d_x, ld_x, d_w, ep, stream);
   const bool ok = conv_fwd_tc_eligible(d, ld_x);
   if (d->math == ADVOC_MATH_TF32 || d->math == ADVOC_MATH_F16 || ok) {
@@ -151,6 +156,7 @@ extern "C" int advoc_conv2d_transpose_fwd(const advoc_conv_desc* d, const void* 
   if (st) return st;
   const float* d_x = static_cast<const float*>(d_xv);
   const float* d_w = static_cast<const float*>(d_wv);
+  ADVOC_REQUIRE(ep->out0_row_pad == 0, ADVOC_UNSUPPORTED, "out0_row_pad is only supported by the thin-input convolution");
   if (d->math == ADVOC_MATH_FP32) return conv_transposed_simt(d, d_x, ld_x, d_w, ep, stream);
   if (deconv_one_tc_eligible(d, d_x, ld_x, ep)) return deconv_one_tc(d, d_x, ld_x, d_w, ep, stream);
   const bool ok = conv_transposed_tc_eligible(d, ld_x);

@@ -126,7 +126,10 @@ __device__ __forceinline__ float act_slope(int act, float alpha) {
   return act == ADVOC_ACT_LRELU ? alpha : (act == ADVOC_ACT_RELU ? 0.f : 1.f);
 }
 
-template <int CIN, int COUT, int KS = 4>
+// PPT = output pixels per thread.  With one pixel per thread the loop is bound by the shared-memory
+// pipe (every tap costs COUT/4 broadcast LDS.128 against COUT FMAs: both pipes full at once); two
+// pixels share each filter word, which makes the loop FMA-bound (r02: encoder_1 of the fp16 generator).
+template <int CIN, int COUT, int KS = 4, int PPT = 1>
 __global__ void __launch_bounds__(128) conv_thin_px_kernel(const ThinArgs<CIN> a) {
   __shared__ float4 ws4[KS * KS * CIN * COUT / 4];
   __shared__ float4 bs4[COUT / 4];
@@ -137,81 +140,129 @@ __global__ void __launch_bounds__(128) conv_thin_px_kernel(const ThinArgs<CIN> a
     bs4[threadIdx.x] = e.bias ? __ldg(reinterpret_cast<const float4*>(e.bias) + threadIdx.x)
                               : make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
-  const long pix = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  constexpr int PXB = 128 * PPT;     // pixels per block
   const unsigned pix_in_img = a.Ho * a.Wo;
-  const bool valid = pix < (long)a.N * pix_in_img;
-  float4 acc[COUT / 4];
-  if (valid) {
-  const unsigned img = (unsigned)(pix / pix_in_img);
-  const unsigned rem = (unsigned)(pix - (long)img * pix_in_img);
-  const int oh = rem / a.Wo, ow = rem - oh * a.Wo;
-  const float* xb = a.x + (size_t)img * a.H * a.W * a.ldx;
-  const int ih0 = oh * a.sh - a.pt, iw0 = ow * a.sw - a.pl;
+  const long npix = (long)a.N * pix_in_img;
+  const long pix0 = (long)blockIdx.x * PXB;
+  float4 acc[PPT][COUT / 4];
+  const float* row0[PPT];            // image base of each pixel
+  int ih0[PPT], iw0[PPT];
+  bool valid[PPT];
 #pragma unroll
-  for (int j = 0; j < COUT / 4; ++j) acc[j] = bs4[j];
+  for (int u = 0; u < PPT; ++u) {
+    const long pix = pix0 + threadIdx.x + 128 * u;     // pixel u of this thread: 128 apart, so that the
+    valid[u] = pix < npix;                              // threads of a warp read neighbouring input columns
+    const long pp = valid[u] ? pix : 0;
+    const unsigned img = (unsigned)(pp / pix_in_img);
+    const unsigned rem = (unsigned)(pp - (long)img * pix_in_img);
+    const int oh = rem / a.Wo, ow = rem - oh * a.Wo;
+    row0[u] = a.x + (size_t)img * a.H * a.W * a.ldx;
+    ih0[u] = oh * a.sh - a.pt;
+    iw0[u] = ow * a.sw - a.pl;
+#pragma unroll
+    for (int j = 0; j < COUT / 4; ++j) acc[u][j] = bs4[j];
+  }
 #pragma unroll
   for (int kh = 0; kh < KS; ++kh) {
-    const int ih = ih0 + kh;
-    if (ih < 0 || ih >= a.H) continue;
-    const float* row = xb + (size_t)ih * a.W * a.ldx;
 #pragma unroll
     for (int kw = 0; kw < KS; ++kw) {
-      const int iw = iw0 + kw;
-      if (iw < 0 || iw >= a.W) continue;
+      float xv[PPT][CIN];
+#pragma unroll
+      for (int u = 0; u < PPT; ++u) {
+        const int ih = ih0[u] + kh, iw = iw0[u] + kw;
+        const bool in = valid[u] && ih >= 0 && ih < a.H && iw >= 0 && iw < a.W;
+#pragma unroll
+        for (int c = 0; c < CIN; ++c)
+          xv[u][c] = in ? __ldg(row0[u] + ((size_t)ih * a.W + iw) * a.ldx + c) : 0.f;
+      }
 #pragma unroll
       for (int c = 0; c < CIN; ++c) {
-        const float xv = __ldg(row + iw * a.ldx + c);
         const float4* wp = ws4 + ((kh * KS + kw) * CIN + c) * (COUT / 4);
 #pragma unroll
         for (int j = 0; j < COUT / 4; ++j) {
           const float4 w = wp[j];
-          acc[j].x = fmaf(xv, w.x, acc[j].x);
-          acc[j].y = fmaf(xv, w.y, acc[j].y);
-          acc[j].z = fmaf(xv, w.z, acc[j].z);
-          acc[j].w = fmaf(xv, w.w, acc[j].w);
+#pragma unroll
+          for (int u = 0; u < PPT; ++u) {
+            acc[u][j].x = fmaf(xv[u][c], w.x, acc[u][j].x);
+            acc[u][j].y = fmaf(xv[u][c], w.y, acc[u][j].y);
+            acc[u][j].z = fmaf(xv[u][c], w.z, acc[u][j].z);
+            acc[u][j].w = fmaf(xv[u][c], w.w, acc[u][j].w);
+          }
         }
       }
     }
   }
-  }   // valid pixel
   // Stores: a thread-per-pixel store touches 32 different 128-byte lines per instruction.  Stage the
   // raw accumulators in shared memory (16-byte chunk j of pixel p at chunk j ^ (p & 7): conflict
-  // free both ways) and write them out cooperatively, 8 consecutive lanes per pixel row, so every
-  // store instruction covers whole lines; both activations are applied on the way out.
+  // free both ways) and write them out cooperatively, consecutive lanes along the channels of a
+  // pixel, so every store instruction covers whole lines; both activations are applied on the way out.
   {
-    __shared__ float4 stage[128 * (COUT / 4)];
+    __shared__ float4 stage[PXB * (COUT / 4)];
     constexpr int Q = COUT / 4;
     static_assert(Q == 8 || Q == 16, "staging layout assumes 32 or 64 output channels");
-    if (valid) {
 #pragma unroll
-      for (int j = 0; j < Q; ++j) stage[threadIdx.x * Q + (j ^ (threadIdx.x & 7))] = acc[j];
+    for (int u = 0; u < PPT; ++u) {
+      const int p = threadIdx.x + 128 * u;
+      if (valid[u]) {
+#pragma unroll
+        for (int j = 0; j < Q; ++j) stage[p * Q + (j ^ (p & 7))] = acc[u][j];
+      }
     }
     __syncthreads();
     const float s0 = act_slope(e.act0, e.alpha), s1 = act_slope(e.act1, e.alpha);
-    const long pix0 = (long)blockIdx.x * blockDim.x;
-    const long npix = (long)a.N * pix_in_img;
+    auto act4 = [](const float4& v, float s, float (&y)[4]) {
+      y[0] = v.x > 0.f ? v.x : s * v.x; y[1] = v.y > 0.f ? v.y : s * v.y;
+      y[2] = v.z > 0.f ? v.z : s * v.z; y[3] = v.w > 0.f ? v.w : s * v.w;
+    };
+    if (e.h0 && (!e.out1 || e.h1)) {
+      // fp16 destinations: eight channels (two staged chunks) per lane = one 16-byte store
+      constexpr int Q2 = Q / 2;
+      __half* o0 = reinterpret_cast<__half*>(e.out0);
+      __half* o1 = reinterpret_cast<__half*>(e.out1);
 #pragma unroll
-    for (int k = 0; k < Q; ++k) {
-      const int i = threadIdx.x + 128 * k;
-      const int p = i / Q, j = i % Q;
-      const long gp = pix0 + p;
-      if (gp >= npix) continue;
-      const float4 v = stage[p * Q + (j ^ (p & 7))];
-      float y[4] = {v.x > 0.f ? v.x : s0 * v.x, v.y > 0.f ? v.y : s0 * v.y,
-                    v.z > 0.f ? v.z : s0 * v.z, v.w > 0.f ? v.w : s0 * v.w};
-      if (e.round && !e.h0) {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) y[u] = round_tf32(y[u]);
-      }
-      store4(e.out0, e.h0, (size_t)gp * e.ld0 + e.coff0 + 4 * j, y);   // fp32 or fp16 destination
-      if (e.out1) {
-        float z[4] = {v.x > 0.f ? v.x : s1 * v.x, v.y > 0.f ? v.y : s1 * v.y,
-                      v.z > 0.f ? v.z : s1 * v.z, v.w > 0.f ? v.w : s1 * v.w};
-        if (e.round && !e.h1) {
-#pragma unroll
-          for (int u = 0; u < 4; ++u) z[u] = round_tf32(z[u]);
+      for (int k = 0; k < Q2 * PPT; ++k) {
+        const int i = threadIdx.x + 128 * k;
+        const int p = i / Q2, j = (i % Q2) * 2;
+        const long gp = pix0 + p;
+        if (gp >= npix) continue;
+        const float4 va = stage[p * Q + (j ^ (p & 7))], vb = stage[p * Q + ((j + 1) ^ (p & 7))];
+        float ya[4], yb[4];
+        act4(va, s0, ya); act4(vb, s0, yb);
+        const size_t gp0 = e.row_pad0 ? (size_t)gp + (size_t)(gp / a.Wo) * e.row_pad0 : (size_t)gp;
+        *reinterpret_cast<uint4*>(o0 + gp0 * e.ld0 + e.coff0 + 4 * j) =
+            make_uint4(pack_half2(ya[0], ya[1]), pack_half2(ya[2], ya[3]), pack_half2(yb[0], yb[1]), pack_half2(yb[2], yb[3]));
+        if (e.out1) {
+          act4(va, s1, ya); act4(vb, s1, yb);
+          *reinterpret_cast<uint4*>(o1 + (size_t)gp * e.ld1 + e.coff1 + 4 * j) =
+              make_uint4(pack_half2(ya[0], ya[1]), pack_half2(ya[2], ya[3]), pack_half2(yb[0], yb[1]), pack_half2(yb[2], yb[3]));
         }
-        store4(e.out1, e.h1, (size_t)gp * e.ld1 + e.coff1 + 4 * j, z);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < Q * PPT; ++k) {
+        const int i = threadIdx.x + 128 * k;
+        const int p = i / Q, j = i % Q;
+        const long gp = pix0 + p;
+        if (gp >= npix) continue;
+        const float4 v = stage[p * Q + (j ^ (p & 7))];
+        float y[4];
+        act4(v, s0, y);
+        if (e.round && !e.h0) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) y[u] = round_tf32(y[u]);
+        }
+        // fp32 or fp16 destination; rows of out0 may carry e.row_pad0 extra pixels
+        const size_t gp0 = e.row_pad0 ? (size_t)gp + (size_t)(gp / a.Wo) * e.row_pad0 : (size_t)gp;
+        store4(e.out0, e.h0, gp0 * e.ld0 + e.coff0 + 4 * j, y);
+        if (e.out1) {
+          float z[4];
+          act4(v, s1, z);
+          if (e.round && !e.h1) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) z[u] = round_tf32(z[u]);
+          }
+          store4(e.out1, e.h1, (size_t)gp * e.ld1 + e.coff1 + 4 * j, z);
+        }
       }
     }
   }
@@ -336,7 +387,7 @@ int conv_thin(const advoc_conv_desc* d, const float* x, int ldx, const float* w,
     if (d->Cin == 1) {
       ThinArgs<1> a = {x, w, d->N, d->H, d->W, ldx, d->Ho, d->Wo, d->Cout, d->sh, d->sw, d->pad_t, d->pad_l, e};
       if (d->kh == 5) conv_thin_px_kernel<1, 64, 5><<<blocks, 128, 0, s>>>(a);
-      else if (d->Cout == 32) conv_thin_px_kernel<1, 32><<<blocks, 128, 0, s>>>(a);
+      else if (d->Cout == 32) conv_thin_px_kernel<1, 32, 4, 2><<<(unsigned)((npix + 255) / 256), 128, 0, s>>>(a);
       else conv_thin_px_kernel<1, 64><<<blocks, 128, 0, s>>>(a);
     } else {
       ThinArgs<2> a = {x, w, d->N, d->H, d->W, ldx, d->Ho, d->Wo, d->Cout, d->sh, d->sw, d->pad_t, d->pad_l, e};
@@ -347,7 +398,8 @@ int conv_thin(const advoc_conv_desc* d, const float* x, int ldx, const float* w,
     ADVOC_CHECK_CUDA(cudaGetLastError());
     return ADVOC_OK;
   }
-  ADVOC_REQUIRE(!e.h0 && !e.h1, ADVOC_UNSUPPORTED, "fp16 destinations need the plain 32/64-channel thin conv");
+  ADVOC_REQUIRE(!e.h0 && !e.h1 && e.row_pad0 == 0, ADVOC_UNSUPPORTED,
+                "fp16 destinations / padded rows need the plain 32/64-channel thin conv");
   const int ppb = 256 / (d->Cout / 4);
   const long want = (npix + ppb - 1) / ppb;
   const int blocks = (int)(want < (long)sm_count() * 32 ? want : (long)sm_count() * 32);

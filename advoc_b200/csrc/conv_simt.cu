@@ -54,6 +54,8 @@ int lower_epilogue(const advoc_epilogue* ep, int Hs, int Wfull, int Cout, EpiDev
   ADVOC_REQUIRE((ep->out0_dtype == ADVOC_DT_F32 || ep->out0_dtype == ADVOC_DT_F16) &&
                     (ep->out1_dtype == ADVOC_DT_F32 || ep->out1_dtype == ADVOC_DT_F16),
                 ADVOC_BAD_ARG, "unknown output dtype");
+  ADVOC_REQUIRE(ep->out0_row_pad >= 0, ADVOC_BAD_ARG, "out0_row_pad must be >= 0");
+  e->row_pad0 = ep->out0_row_pad;
   e->h0 = ep->out0_dtype == ADVOC_DT_F16;
   e->h1 = ep->d_out1 != nullptr && ep->out1_dtype == ADVOC_DT_F16;
   if (e->h0 || e->h1)
@@ -212,6 +214,8 @@ int conv_to_one(const advoc_conv_desc* d, const float* x, int ldx, const float* 
 int conv_fwd_simt(const advoc_conv_desc* d, const float* x, int ldx, const float* w,
                   const advoc_epilogue* ep, void* stream) {
   if (ep && ep->d_out0 && conv_thin_eligible(d, ep)) return conv_thin(d, x, ldx, w, ep, stream);
+  ADVOC_REQUIRE(!ep || ep->out0_row_pad == 0, ADVOC_UNSUPPORTED,
+                "out0_row_pad is only supported by the thin-input convolution");
   if (ep && ep->d_out0 && conv_to_one_eligible(d, x, ldx, ep)) return conv_to_one(d, x, ldx, w, ep, stream);
   SimtArgs a = {};
   int st = lower_epilogue(ep, d->Ho, d->Wo, d->Cout, &a.epi);

@@ -27,6 +27,7 @@ struct EpiDev {
   // dropout counter in device memory (CUDA-graph replays draw fresh masks): see epi_seed()
   const unsigned long long* seed_ptr;
   int h0, h1;       // destination holds fp16 elements (ld / coff stay in elements); forward pass only
+  int row_pad0;     // out0 rows are Ws + row_pad0 pixels apart (thin-input convolution only)
 };
 
 // Seed of the counter-based dropout generator: the by-value seed, or -- when the caller keeps a

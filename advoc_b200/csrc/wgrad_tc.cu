@@ -11,9 +11,11 @@
 // canonical MN-major UMMA layout for 32-bit operands (4-pixel atoms 512 B apart, 32-channel
 // blocks BK*128 B apart).
 // The small side sits on the 128 TMEM lanes (M); the N axis is the concatenation (tap, big channel):
-// 16 boxes = 512 accumulator columns per CTA, so the small-side tile is fetched once for 16
-// tap/channel blocks.  Work = (M tile, N tile, pixel split); partial sums are added to dW with
-// fp32 atomics.
+// WNB boxes = 32 * WNB accumulator columns per CTA, so the small-side tile is fetched once for WNB
+// tap/channel blocks.  Work = (M tile, N tile, pixel split).  The pixel splits are reduced
+// DETERMINISTICALLY (round 2; round 1 used fp32 atomics): every split stores its partial tile to a
+// library-owned workspace [split][tap][cb][cs] and wgrad_reduce_kernel adds the splits to dW in split
+// order; a layer with a single split adds its tile to dW directly (one owner per element).
 #include "tc_ptx.cuh"
 
 #include <stdlib.h>
@@ -28,13 +30,17 @@ using namespace tc;
 
 constexpr int WM = 128;       // UMMA_M: small-side channels on the TMEM lanes
 constexpr int WBK = 16;       // pixels per pipeline stage (two K=8 steps)
-constexpr int WNB = 16;       // 32-channel blocks of the (tap, big-channel) axis per CTA = 512 TMEM columns
+// 32-channel blocks of the (tap, big-channel) axis per CTA.  Round 1 used 16 (512 TMEM columns, one
+// CTA per SM); ncu showed the kernel latency-bound that way (tensor pipe 20-23 % active, L2 8-13 %,
+// issue slots 5-8 %: profiles/r02k_ncu_full_wgrad_tc_regular.csv), so round 2 halves the tile to 8
+// blocks = 256 columns and 96 KB of ring and runs TWO CTAs per SM whose TMA latencies overlap.
+constexpr int WNB = 8;
 constexpr int WSTAGES = 4;
 constexpr int W_THREADS = 192;
 constexpr int BLK_BYTES = WBK * 128;                  // one [WBK pixels][32 channels] box
 constexpr int A_BYTES = (WM / 32) * BLK_BYTES;        // small side, 128 channels
-constexpr int B_BYTES = WNB * BLK_BYTES;              // big side, 16 (tap, channel-block) boxes
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;        // 40 KB
+constexpr int B_BYTES = WNB * BLK_BYTES;              // big side, WNB (tap, channel-block) boxes
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;        // 24 KB
 
 struct alignas(64) WgParams {
   CUtensorMap tmBig;    // im2col
@@ -46,6 +52,9 @@ struct alignas(64) WgParams {
   int mtiles, ntiles, kw;
   int Ho, Wo, sh, sw, lower_h, lower_w;
   long P, chunk;        // output pixels, pixels per split (multiple of WBK)
+  float* ws;            // partial tiles [nsplits][taps * Cb * Cs], or nullptr: accumulate into dw (see `atomic`)
+  long ws_stride;
+  int atomic;           // 1: fp32 atomics into dw (fallback when the workspace cannot be grown)
   unsigned int* dbg;
 };
 
@@ -70,7 +79,7 @@ constexpr uint32_t kIdescMN = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | 
 // D[cs, (tap, cb)] += sum_p small[p, cs] * big[p @ tap, cb]: the small-side tile is fetched once
 // per stage and shared by all 16 (tap, channel-block) boxes of the big side, which sit back to
 // back in smem so that ONE N=256 MMA spans eight of them (LBO = box size).
-__global__ void __launch_bounds__(W_THREADS) wgrad_tc_kernel(const __grid_constant__ WgParams p) {
+__global__ void __launch_bounds__(W_THREADS, 2) wgrad_tc_kernel(const __grid_constant__ WgParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[WSTAGES];
   __shared__ __align__(8) uint64_t empty_bar[WSTAGES];
@@ -81,6 +90,7 @@ __global__ void __launch_bounds__(W_THREADS) wgrad_tc_kernel(const __grid_consta
   unsigned id = blockIdx.x;
   const int nt = id % p.ntiles; id /= p.ntiles;
   const int mt = id % p.mtiles; id /= p.mtiles;
+  const unsigned split = id;
   const long p0 = (long)id * p.chunk;
   if (p0 >= p.P) return;
   const long p1 = p0 + p.chunk < p.P ? p0 + p.chunk : p.P;
@@ -92,7 +102,7 @@ __global__ void __launch_bounds__(W_THREADS) wgrad_tc_kernel(const __grid_consta
 
   const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* ring_ptr = smem_raw + (ring - smem_u32(smem_raw));
-  constexpr uint32_t TMEM_COLS = 512;
+  constexpr uint32_t TMEM_COLS = 32 * WNB;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.tmBig);
@@ -118,7 +128,7 @@ __global__ void __launch_bounds__(W_THREADS) wgrad_tc_kernel(const __grid_consta
   const uint32_t tmem_base = tmem_base_holder;
 
   if (warp == 0) {
-    // ===== TMA producer: 20 boxes per stage, one per lane (lanes 0-3 small side, 4-19 big side) =====
+    // ===== TMA producer: 12 boxes per stage, one per lane (lanes 0-3 small side, 4-11 big side) =====
     int my_c = 0;
     uint16_t my_kw = 0, my_kh = 0;
     if (lane < WM / 32) {
@@ -163,13 +173,11 @@ __global__ void __launch_bounds__(W_THREADS) wgrad_tc_kernel(const __grid_consta
         const uint32_t a_addr = ring + stage * STAGE_BYTES;
         const uint64_t da = make_mn_desc(a_addr, BLK_BYTES);
         const uint64_t db0 = make_mn_desc(a_addr + A_BYTES, BLK_BYTES);
-        const uint64_t db1 = make_mn_desc(a_addr + A_BYTES + 8 * BLK_BYTES, BLK_BYTES);
 #pragma unroll
         for (int k = 0; k < WBK / 8; ++k) {
-          // 8 pixels = 1024 bytes along K inside every box
+          // 8 pixels = 1024 bytes along K inside every box; one N = 256 MMA spans the 8 big-side boxes
           const uint32_t acc = (it | k) != 0 ? 1u : 0u;
           umma_tf32(tmem_base, da + (uint64_t)(64 * k), db0 + (uint64_t)(64 * k), kIdescMN, acc);
-          umma_tf32(tmem_base + 256u, da + (uint64_t)(64 * k), db1 + (uint64_t)(64 * k), kIdescMN, acc);
         }
         umma_commit(&empty_bar[stage]);
         if (++stage == WSTAGES) { stage = 0; phase ^= 1u; }
@@ -190,10 +198,16 @@ __global__ void __launch_bounds__(W_THREADS) wgrad_tc_kernel(const __grid_consta
       const int gb = gb0 + b;
       const int tap = gb / p.cbb, cblk = gb - tap * p.cbb;
       if (cs < p.Cs && gb < p.nboxes) {
+        float* dst = p.ws ? p.ws + (size_t)split * p.ws_stride : p.dw;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int cb = cblk * 32 + j;
-          if (cb < p.Cb) atomicAdd(p.dw + ((size_t)tap * p.Cb + cb) * p.Cs + cs, __uint_as_float(v[j]));
+          if (cb >= p.Cb) continue;
+          float* q = dst + ((size_t)tap * p.Cb + cb) * p.Cs + cs;   // 32 lanes = 32 consecutive cs: one 128-byte line
+          const float x = __uint_as_float(v[j]);
+          if (p.ws) *q = x;
+          else if (p.atomic) atomicAdd(q, x);
+          else *q += x;                                             // single split: this thread owns the element
         }
       }
     }
@@ -205,6 +219,43 @@ __global__ void __launch_bounds__(W_THREADS) wgrad_tc_kernel(const __grid_consta
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS)
                  : "memory");
   }
+}
+
+// dw[i] += sum over splits (in split order) of ws[s][i]
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw,
+                                                           long nelem4, int nsplits, long stride) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nelem4; i += (long)gridDim.x * blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int sp = 0; sp < nsplits; ++sp) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(ws + (size_t)sp * stride) + i);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    float4* d = reinterpret_cast<float4*>(dw) + i;
+    float4 o = *d;
+    o.x += acc.x; o.y += acc.y; o.z += acc.z; o.w += acc.w;
+    *d = o;
+  }
+}
+
+// Grow-only workspace for the split partials (one stream at a time uses the library's wgrad; the
+// partials of a launch are consumed by the reduce kernel queued right behind it).  Cannot grow while
+// the stream is being captured into a CUDA graph: the caller's eager warm-up pass sizes it.
+float* wgrad_workspace(size_t bytes, cudaStream_t st) {
+  static float* buf = nullptr;
+  static size_t cap = 0;
+  if (bytes <= cap) return buf;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  float* nb = nullptr;
+  const size_t want = bytes < ((size_t)64 << 20) ? ((size_t)64 << 20) : bytes + (bytes >> 2);
+  cudaDeviceSynchronize();                 // earlier launches may still read the old buffer
+  if (cudaMalloc(&nb, want) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (buf) cudaFree(buf);
+  buf = nb; cap = want;
+  return buf;
 }
 
 }  // namespace
@@ -241,10 +292,11 @@ int wgrad_tc(const advoc_conv_desc* d, const float* big, int ld_big, const float
   p.Ho = d->Ho; p.Wo = d->Wo; p.sh = d->sh; p.sw = d->sw; p.lower_h = lower_h; p.lower_w = lower_w;
   p.P = P;
   const long tiles = (long)p.mtiles * p.ntiles;
-  // two CTAs' worth of pixel splits per SM (measured: 1 leaves a tail, 3-4 only add atomics; the
-  // 512-column accumulators of two CTAs cannot co-reside, so this is load balance, not overlap)
-  static const long waves = getenv("ADVOC_WGRAD_WAVES") ? atol(getenv("ADVOC_WGRAD_WAVES")) : 2;
+  // pixel splits fill the chip's 2 x #SM CTA slots once; a layer that already has about that many
+  // (M, N) tiles runs unsplit (one owner per gradient element, no partials to write and reduce)
+  static const long waves = getenv("ADVOC_WGRAD_WAVES") ? atol(getenv("ADVOC_WGRAD_WAVES")) : 4;   // r02 sweep: 2 -> 1178, 3 -> 1242, 4 -> 1243, 6 -> 1233, 8 -> 1235 samples/s (regular step)
   long splits = ((long)sm_count() * waves + tiles - 1) / tiles;
+  if (tiles * 10 >= (long)sm_count() * waves * 7) splits = 1;
   const long max_splits = (P + 8 * WBK - 1) / (8 * WBK);
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
@@ -252,6 +304,16 @@ int wgrad_tc(const advoc_conv_desc* d, const float* big, int ld_big, const float
   splits = (P + p.chunk - 1) / p.chunk;
   const long ctas = tiles * splits;
   ADVOC_REQUIRE(ctas < 2147483647L, ADVOC_BAD_SHAPE, "too many wgrad CTAs");
+  cudaStream_t cst = reinterpret_cast<cudaStream_t>(stream);
+  const long nelem = (long)d->kh * d->kw * d->Cin * d->Cout;
+  static const bool force_atomic = getenv("ADVOC_WGRAD_ATOMIC") != nullptr;   // A/B switch (round-1 behaviour)
+  p.ws = nullptr; p.ws_stride = nelem; p.atomic = 0;
+  if (force_atomic) {
+    p.atomic = 1;
+  } else if (splits > 1) {
+    p.ws = (nelem % 4 == 0) ? wgrad_workspace((size_t)splits * nelem * sizeof(float), cst) : nullptr;
+    if (!p.ws) p.atomic = 1;               // workspace unavailable (capture in progress / odd size): atomics
+  }
   p.dbg = debug_word();
   constexpr int smem = WSTAGES * STAGE_BYTES + 1024;
   static bool configured = false;
@@ -259,9 +321,17 @@ int wgrad_tc(const advoc_conv_desc* d, const float* big, int ld_big, const float
     ADVOC_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  wgrad_tc_kernel<<<(unsigned)ctas, W_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  wgrad_tc_kernel<<<(unsigned)ctas, W_THREADS, smem, cst>>>(p);
   count_launch();
   ADVOC_CHECK_CUDA(cudaGetLastError());
+  if (p.ws) {
+    const long n4 = nelem / 4;
+    const long want = (n4 + 255) / 256;
+    const int blocks = (int)(want < (long)sm_count() * 8 ? want : (long)sm_count() * 8);
+    wgrad_reduce_kernel<<<blocks, 256, 0, cst>>>(p.ws, dw, n4, (int)splits, nelem);
+    count_launch();
+    ADVOC_CHECK_CUDA(cudaGetLastError());
+  }
   return ADVOC_OK;
 }
 

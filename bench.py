@@ -473,17 +473,18 @@ def _synthetic_mag(batch, seed):
   return (torch.randn(batch, T, 513, 1, generator=g).abs() * 0.1)
 
 
-def _train_engine(model_name, batch, world, rank, overlap=True):
+def _train_engine(model_name, batch, world, rank, overlap=True, use_graphs=True):
   from advoc_b200 import nets
   from advoc_b200.train import TrainEngine
   small = model_name == 'small'
   spec = nets.GenSpec(32 if small else 64, 5 if small else 8, (5, 4) if small else (8, 7, 6))
   ndf = 32 if small else 64
   params = nets.init_params(spec.ngf, ndf, spec.n_enc, seed=0)
-  return TrainEngine(spec, ndf, params, batch, world_size=world, rank=rank, overlap=overlap)
+  return TrainEngine(spec, ndf, params, batch, world_size=world, rank=rank, overlap=overlap, use_graphs=use_graphs)
 
 
-def measure_train_step(model_name, batch, world, rank, steps, warmup, barrier, with_e2e=True, overlap=True):
+def measure_train_step(model_name, batch, world, rank, steps, warmup, barrier, with_e2e=True, overlap=True,
+                       use_graphs=True):
   """Times the data-parallel G+D train step (advoc_model.py:285-289: D update on one minibatch, G update
   on the next), `batch` samples per GPU, the NCCL gradient all-reduces inside the timed region.  Returns
   a dict: samples/s over all ranks (max-over-ranks time), ms/step, the all-reduce time the compute
@@ -492,7 +493,7 @@ def measure_train_step(model_name, batch, world, rank, steps, warmup, barrier, w
   import torch.distributed as dist
   from advoc_b200 import _native as N
   from advoc_b200.model import SpectralUtil
-  eng = _train_engine(model_name, batch, world, rank, overlap)
+  eng = _train_engine(model_name, batch, world, rank, overlap, use_graphs)
   su = SpectralUtil()
   mags_h = [_synthetic_mag(batch, 100 + 2 * rank + i).pin_memory() for i in range(2)]
   mags_d = [m.cuda() for m in mags_h]
@@ -578,6 +579,7 @@ def measure_train_step(model_name, batch, world, rank, steps, warmup, barrier, w
                        'backward; exposed = time the compute stream waited') if (world > 1 and overlap) else
                       ('NCCL, not overlapped' if world > 1 else 'none (1 GPU)'),
          'tflops_per_gpu': tflops / world, 'launches_per_step': int(per_step),
+         'launch': 'CUDA-graph replay of the segments between collectives' if use_graphs else 'eager',
          'loss_values': [float(v) for v in eng.loss_values()]}
   if with_e2e:
     out['e2e'] = {'value': samples / (e2e_max * 1e-3), 'unit': 'samples/s', 'ms_per_step': e2e_max / steps,
@@ -605,7 +607,7 @@ def run_gpu_train(args):
 
   with ClockSampler(local) as clk:
     r = measure_train_step(args.model, args.batch, world, rank, args.steps, args.warmup, barrier,
-                           overlap=not args.no_overlap)
+                           overlap=not args.no_overlap, use_graphs=not args.no_graph)
   peaks = _peaks()
   tf32_peak = _tf32_peak()
   line = {

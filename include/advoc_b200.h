@@ -205,6 +205,12 @@ typedef struct advoc_epilogue {
   /* advoc_dtype of d_out0 / d_out1: ADVOC_DT_F16 stores IEEE half (round-to-nearest-even); ld / c_off
    * stay in elements.  Forward pass only (no gate / accumulate). */
   int out0_dtype, out1_dtype;
+  /* Extra (never written) pixels at the end of every image row of d_out0: pixel (h, w) of image b is
+   * stored at pixel index (b*Ho + h) * (Wo + out0_row_pad) + w.  The fp16 generator pads encoder_1's
+   * odd-width output by one zero pixel so that the next layer can read PAIRS of 32-channel pixels as
+   * 64-channel k-blocks (advoc_b200/nets.py).  Supported by the thin-input convolution only; 0 elsewhere. */
+  int out0_row_pad;
+  int reserved0;
 } advoc_epilogue;
 
 /* Re-pack a TF-layout filter [kh*kw, A, B] (A,B = Cin,Cout for conv; Cout,Cin for

@@ -99,14 +99,15 @@ def conv_same(x, kernel, bias, strides=(2, 2)):
   pt, pb = same_pads(xt.shape[2], kernel.shape[0], strides[0])
   pl, pr = same_pads(xt.shape[3], kernel.shape[1], strides[1])
   xt = F.pad(xt, (pl, pr, pt, pb))
-  y = F.conv2d(xt, kernel.permute(3, 2, 0, 1), bias, stride=strides)
+  # (.contiguous(): torch's float64 CPU conv backward insists on a contiguous weight gradient)
+  y = F.conv2d(xt, kernel.permute(3, 2, 0, 1).contiguous(), bias, stride=strides)
   return y.permute(0, 2, 3, 1)
 
 
 def deconv_same(x, kernel, bias, strides=(2, 2)):
   """tf.layers.conv2d_transpose(k=4, s=2, 'same'); kernel HWOI (advoc_model.py:65-69)."""
   xt = x.permute(0, 3, 1, 2)
-  y = F.conv_transpose2d(xt, kernel.permute(3, 2, 0, 1), bias, stride=strides, padding=1)
+  y = F.conv_transpose2d(xt, kernel.permute(3, 2, 0, 1).contiguous(), bias, stride=strides, padding=1)
   if strides[0] == 1:
     y = y[:, :, :-1, :]
   return y.permute(0, 2, 3, 1)
@@ -115,7 +116,7 @@ def deconv_same(x, kernel, bias, strides=(2, 2)):
 def discrim_conv(x, kernel, bias, stride):
   """tf.pad 1 + conv2d VALID (advoc_model.py:25-32)."""
   xt = F.pad(x.permute(0, 3, 1, 2), (1, 1, 1, 1))
-  y = F.conv2d(xt, kernel.permute(3, 2, 0, 1), bias, stride=stride)
+  y = F.conv2d(xt, kernel.permute(3, 2, 0, 1).contiguous(), bias, stride=stride)
   return y.permute(0, 2, 3, 1)
 
 

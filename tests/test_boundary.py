@@ -65,7 +65,8 @@ def test_struct_layouts_match_the_header():
   assert N.Epilogue.d_dropout_mask.offset == 64 and N.Epilogue.seed.offset == 80
   assert N.Epilogue.d_gate.offset == 96 and N.Epilogue.gate_scale1.offset == 124
   assert N.Epilogue.d_seed.offset == 128 and N.Epilogue.out0_dtype.offset == 136
-  assert C.sizeof(N.Epilogue) == 144
+  assert N.Epilogue.out0_row_pad.offset == 144
+  assert C.sizeof(N.Epilogue) == 152
 
 
 def _prototypes():

@@ -195,7 +195,8 @@ def _check_generator(G, P, x, spec_o, tol, n_enc):
   ref, layers = O.generator(P, x.cpu(), spec_o, return_layers=True)
   errs = {'out': _rel(out, ref)}
   for i in range(1, n_enc):
-    errs['E%d' % i] = _rel(G.E[i], O.lrelu(layers[i - 1]))
+    want = O.lrelu(layers[i - 1])
+    errs['E%d' % i] = _rel(G.E[i][:, :, :want.shape[2]], want)   # (the fp16 small generator pads E1's rows)
   errs['Cat%d' % n_enc] = _rel(G.Cat[n_enc], torch.relu(layers[n_enc - 1]))
   for k in range(n_enc - 1, 0, -1):
     dec = layers[n_enc + (n_enc - 1 - k)]          # output of decoder_{k+1}
@@ -237,6 +238,7 @@ def test_small_generator_forward_at_the_benchmarked_batch(math):
   else:
     assert any(h for _, _, h in inst), inst
     assert G.Cat[1].dtype == torch.float16 and G.Cat[4].dtype == torch.float16
+    assert G.pair2 is not None and G.E[1].dtype == torch.float16 and bool((G.E[1][:, :, -1] == 0).all())
 
 
 @pytest.mark.parametrize('math', ['auto', 'f16'])
