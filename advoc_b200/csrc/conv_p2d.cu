@@ -675,18 +675,31 @@ bool make_plan(const advoc_conv_desc* d, bool transposed, int Wstored, int n_out
 
 bool make_plan_uncached(const advoc_conv_desc* d, bool transposed, int Wstored, int n_out, bool tma_store, bool gate,
                         Plan* pl) {
-  static const int ctas_per_sm = getenv("ADVOC_P2D_CTAS") ? atoi(getenv("ADVOC_P2D_CTAS")) : 2;
-  if (ctas_per_sm >= 2) {
-    Plan two = *pl;
-    if (make_plan_budget(d, transposed, Wstored, n_out, tma_store, gate, &two, 106 * 1024, 256, 8 * 1024) &&
-        two.p.total_tiles >= 2L * sm_count()) {
-      two.ctas_per_sm = 2;
-      *pl = two;
-      return true;
-    }
+  static const int ctas_per_sm = getenv("ADVOC_P2D_CTAS") ? atoi(getenv("ADVOC_P2D_CTAS")) : 0;   // 0 = choose
+  Plan one = *pl, two = *pl;
+  const bool ok1 = make_plan_budget(d, transposed, Wstored, n_out, tma_store, gate, &one, 216 * 1024, 512, 32 * 1024);
+  const bool ok2 = ctas_per_sm != 1 &&
+                   make_plan_budget(d, transposed, Wstored, n_out, tma_store, gate, &two, 106 * 1024, 256, 8 * 1024) &&
+                   two.p.total_tiles >= 2L * sm_count();
+  bool use2 = ok2;
+  if (ok1 && ok2 && ctas_per_sm == 0) {
+    // Rounds of tiles each configuration needs; two co-resident CTAs share one SM's pipes, so a round of theirs
+    // lasts ~1.7x a single CTA's (measured r02: decoder_3, 640 tiles: 102 us as 3 rounds of pairs, 77 us as
+    // 5 single rounds with the larger filter slots; decoder_2 / encoder_2, 2464 tiles: 91 / 68 us paired,
+    // 100 / 79 us single).
+    const long slots = sm_count();
+    const double t1 = (double)((one.p.total_tiles + slots - 1) / slots);
+    const double t2 = 1.7 * (double)((two.p.total_tiles + 2 * slots - 1) / (2 * slots));
+    use2 = t2 < t1;
   }
-  pl->ctas_per_sm = 1;
-  return make_plan_budget(d, transposed, Wstored, n_out, tma_store, gate, pl, 216 * 1024, 512, 32 * 1024);
+  if (use2) {
+    two.ctas_per_sm = 2;
+    *pl = two;
+    return true;
+  }
+  one.ctas_per_sm = 1;
+  *pl = one;
+  return ok1;
 }
 
 bool make_plan_budget(const advoc_conv_desc* d, bool transposed, int Wstored, int n_out, bool tma_store, bool gate,

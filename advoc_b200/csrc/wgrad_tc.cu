@@ -29,18 +29,16 @@ namespace {
 using namespace tc;
 
 constexpr int WM = 128;       // UMMA_M: small-side channels on the TMEM lanes
-constexpr int WBK = 16;       // pixels per pipeline stage (two K=8 steps)
+// Pixels per pipeline stage (template WBK).  Every (channel block, WBK pixels) box is one TMA operation and
+// the kernel issues 12 of them per stage; with 2 KB boxes (WBK = 16, round 1) the per-operation cost of
+// the TMA unit, not bytes, paced the ring (ncu: 3.5 TB/s L2->SM at 22 % tensor activity, long-scoreboard
+// waits), so round 2 moves 32 or 64 pixels per box.
 // 32-channel blocks of the (tap, big-channel) axis per CTA.  Round 1 used 16 (512 TMEM columns, one
 // CTA per SM); ncu showed the kernel latency-bound that way (tensor pipe 20-23 % active, L2 8-13 %,
 // issue slots 5-8 %: profiles/r02k_ncu_full_wgrad_tc_regular.csv), so round 2 halves the tile to 8
 // blocks = 256 columns and 96 KB of ring and runs TWO CTAs per SM whose TMA latencies overlap.
 constexpr int WNB = 8;
-constexpr int WSTAGES = 4;
 constexpr int W_THREADS = 192;
-constexpr int BLK_BYTES = WBK * 128;                  // one [WBK pixels][32 channels] box
-constexpr int A_BYTES = (WM / 32) * BLK_BYTES;        // small side, 128 channels
-constexpr int B_BYTES = WNB * BLK_BYTES;              // big side, WNB (tap, channel-block) boxes
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;        // 24 KB
 
 struct alignas(64) WgParams {
   CUtensorMap tmBig;    // im2col
@@ -79,7 +77,12 @@ constexpr uint32_t kIdescMN = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | 
 // D[cs, (tap, cb)] += sum_p small[p, cs] * big[p @ tap, cb]: the small-side tile is fetched once
 // per stage and shared by all 16 (tap, channel-block) boxes of the big side, which sit back to
 // back in smem so that ONE N=256 MMA spans eight of them (LBO = box size).
+template <int WBK, int WSTAGES>
 __global__ void __launch_bounds__(W_THREADS, 2) wgrad_tc_kernel(const __grid_constant__ WgParams p) {
+  constexpr int BLK_BYTES = WBK * 128;                  // one [WBK pixels][32 channels] box
+  constexpr int A_BYTES = (WM / 32) * BLK_BYTES;        // small side, 128 channels
+  constexpr int B_BYTES = WNB * BLK_BYTES;              // big side, WNB (tap, channel-block) boxes
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[WSTAGES];
   __shared__ __align__(8) uint64_t empty_bar[WSTAGES];
@@ -94,7 +97,8 @@ __global__ void __launch_bounds__(W_THREADS, 2) wgrad_tc_kernel(const __grid_con
   const long p0 = (long)id * p.chunk;
   if (p0 >= p.P) return;
   const long p1 = p0 + p.chunk < p.P ? p0 + p.chunk : p.P;
-  const int iters = (int)((p1 - p0 + WBK - 1) / WBK);
+  const int iters = (int)((p1 - p0 + WBK - 1) / WBK);   // (the last stage may run past p1: TMA zero-fills rows beyond P,
+                                                        //  and chunk is a multiple of WBK so splits never overlap)
   if (p.dbg && *reinterpret_cast<volatile unsigned int*>(p.dbg) != 0) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = mt * WM;
@@ -267,8 +271,10 @@ bool wgrad_tc_eligible(const advoc_conv_desc* d, const float* big, int ld_big, c
          aligned16(small) && d->kh * d->kw <= 255 && d->pad_t <= 127 && d->pad_l <= 127 && cbb > 0;
 }
 
-int wgrad_tc(const advoc_conv_desc* d, const float* big, int ld_big, const float* small, int ld_small, float* dw,
-             void* stream) {
+template <int WBK, int WSTAGES>
+int wgrad_tc_impl(const advoc_conv_desc* d, const float* big, int ld_big, const float* small, int ld_small, float* dw,
+                  void* stream) {
+  constexpr int STAGE_BYTES = (WM / 32 + WNB) * WBK * 128;
   WgParams p = {};
   const long P = (long)d->N * d->Ho * d->Wo;
   if (P == 0) return ADVOC_OK;
@@ -318,10 +324,11 @@ int wgrad_tc(const advoc_conv_desc* d, const float* big, int ld_big, const float
   constexpr int smem = WSTAGES * STAGE_BYTES + 1024;
   static bool configured = false;
   if (!configured) {
-    ADVOC_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ADVOC_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<WBK, WSTAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          smem));
     configured = true;
   }
-  wgrad_tc_kernel<<<(unsigned)ctas, W_THREADS, smem, cst>>>(p);
+  wgrad_tc_kernel<WBK, WSTAGES><<<(unsigned)ctas, W_THREADS, smem, cst>>>(p);
   count_launch();
   ADVOC_CHECK_CUDA(cudaGetLastError());
   if (p.ws) {
@@ -333,6 +340,15 @@ int wgrad_tc(const advoc_conv_desc* d, const float* big, int ld_big, const float
     ADVOC_CHECK_CUDA(cudaGetLastError());
   }
   return ADVOC_OK;
+}
+
+int wgrad_tc(const advoc_conv_desc* d, const float* big, int ld_big, const float* small, int ld_small, float* dw,
+             void* stream) {
+  // pixels per TMA box / ring depth (two CTAs per SM up to 96 KB of ring): ADVOC_WGRAD_BK = 16 | 32 | 64
+  static const int bk = getenv("ADVOC_WGRAD_BK") ? atoi(getenv("ADVOC_WGRAD_BK")) : 32;   // r02: 16 -> 1247, 32 -> 1399, 64 -> 1370 samples/s
+  if (bk == 16) return wgrad_tc_impl<16, 4>(d, big, ld_big, small, ld_small, dw, stream);
+  if (bk == 64) return wgrad_tc_impl<64, 2>(d, big, ld_big, small, ld_small, dw, stream);
+  return wgrad_tc_impl<32, 2>(d, big, ld_big, small, ld_small, dw, stream);
 }
 
 }  // namespace advoc
