@@ -126,9 +126,10 @@ __device__ __forceinline__ float act_slope(int act, float alpha) {
   return act == ADVOC_ACT_LRELU ? alpha : (act == ADVOC_ACT_RELU ? 0.f : 1.f);
 }
 
-// PPT = output pixels per thread.  With one pixel per thread the loop is bound by the shared-memory
-// pipe (every tap costs COUT/4 broadcast LDS.128 against COUT FMAs: both pipes full at once); two
-// pixels share each filter word, which makes the loop FMA-bound (r02: encoder_1 of the fp16 generator).
+// PPT = output pixels per thread (two pixels share each filter word).  Measured r02: PPT = 2 changes nothing
+// with fp16 outputs (79 us) and costs 40 % with fp32 outputs (116 against 82 us: 140 registers, twice the
+// store instructions per thread) -- the kernel is bound by instruction issue (address / select / convert),
+// not by the filter reads -- so every launch uses PPT = 1; the parameter stays for the next attempt.
 template <int CIN, int COUT, int KS = 4, int PPT = 1>
 __global__ void __launch_bounds__(128) conv_thin_px_kernel(const ThinArgs<CIN> a) {
   __shared__ float4 ws4[KS * KS * CIN * COUT / 4];
@@ -387,7 +388,7 @@ int conv_thin(const advoc_conv_desc* d, const float* x, int ldx, const float* w,
     if (d->Cin == 1) {
       ThinArgs<1> a = {x, w, d->N, d->H, d->W, ldx, d->Ho, d->Wo, d->Cout, d->sh, d->sw, d->pad_t, d->pad_l, e};
       if (d->kh == 5) conv_thin_px_kernel<1, 64, 5><<<blocks, 128, 0, s>>>(a);
-      else if (d->Cout == 32) conv_thin_px_kernel<1, 32, 4, 2><<<(unsigned)((npix + 255) / 256), 128, 0, s>>>(a);
+      else if (d->Cout == 32) conv_thin_px_kernel<1, 32><<<blocks, 128, 0, s>>>(a);
       else conv_thin_px_kernel<1, 64><<<blocks, 128, 0, s>>>(a);
     } else {
       ThinArgs<2> a = {x, w, d->N, d->H, d->W, ldx, d->Ho, d->Wo, d->Cout, d->sh, d->sw, d->pad_t, d->pad_l, e};

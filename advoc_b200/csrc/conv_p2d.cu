@@ -943,6 +943,16 @@ bool conv_p2d_eligible(const advoc_conv_desc* d, int ldx, int transposed, int st
   static const long max_filter_kb = getenv("ADVOC_P2D_MAX_FILTER_KB") ? atol(getenv("ADVOC_P2D_MAX_FILTER_KB")) : 512;
   static const long min_tiles_per_sm =
       getenv("ADVOC_P2D_MIN_TILES_PER_SM") ? atol(getenv("ADVOC_P2D_MIN_TILES_PER_SM")) : 3;
+  // Round 2 (one CTA per SM when that needs fewer tile rounds, fp16 operands): a FORWARD convolution has one
+  // output class, so even an N = 256 tile keeps two accumulators in TMEM and the filter stream overlaps
+  // the epilogue -- the patch kernel then wins from one tile per SM on, filter-heavy or not (AdVoc-small
+  // encoder_4: 46 us against 56 on the per-tap kernel; regular encoder_3: 90 against 204, encoder_4: 96
+  // against 106).  A transposed convolution owns 4 x BN columns per tile (single-buffered from BN = 128):
+  // there the round-1 rule stands (regular decoder_5: 164 us here against 86 per tap).
+  static const long conv_max_filter_kb =
+      getenv("ADVOC_P2D_CONV_MAX_FILTER_KB") ? atol(getenv("ADVOC_P2D_CONV_MAX_FILTER_KB")) : 4096;
+  if (!transposed)
+    return pl.p.total_tiles >= sm_count() && (long)pl.filter_bytes_per_tile <= conv_max_filter_kb * 1024;
   return pl.p.total_tiles >= min_tiles_per_sm * sm_count() &&
          (long)pl.filter_bytes_per_tile <= max_filter_kb * 1024;
 }
