@@ -287,3 +287,97 @@ extern "C" __attribute__((visibility("default"))) int advoc_selftest_desc_shift(
   ADVOC_CHECK_CUDA(cudaDeviceSynchronize());
   return ADVOC_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// TMA operation-rate probe (round 2): how much does one cp.async.bulk.tensor cost as a function of its
+// box size?  One elected thread per CTA keeps `depth` 2-D tiled loads of {128 B x rows} in flight from an
+// L2-resident source into a ring of smem slots and times `reps` of them.  wgrad_tc (2 KB im2col boxes)
+// turned out to be paced by the operation count, not by bytes; this gives the curve.
+// ---------------------------------------------------------------------------------------------
+namespace advoc {
+namespace {
+using namespace tc;
+struct alignas(64) TmaProbeParams {
+  CUtensorMap tm;
+  unsigned long long* out;
+  int rows, reps, depth, src_rows, lanes;
+};
+__global__ void __launch_bounds__(64) tma_rate_probe(const __grid_constant__ TmaProbeParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[8 * 8];
+  const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* ring_ptr = smem_raw + (ring - smem_u32(smem_raw));
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 64; ++i) mbar_init(&bars[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    prefetch_tmap(&p.tm);
+  }
+  __syncthreads();
+  // `lanes` threads of warp 0 (1: entered through elect.sync) each run their own stream of loads
+  const bool active = p.lanes == 1 ? (threadIdx.x < 32 && elect_one()) : ((int)threadIdx.x < p.lanes);
+  if (active) {
+    const int me = p.lanes == 1 ? 0 : (int)threadIdx.x;
+    const uint32_t bytes = (uint32_t)p.rows * 128u;
+    const int nslots = p.depth;
+    const int span = p.src_rows / p.rows;             // boxes in this CTA's source window
+    const int row0 = (int)blockIdx.x * p.src_rows;
+    uint64_t* mybar = bars + me * 8;
+    uint8_t* myring = ring_ptr + (size_t)me * nslots * bytes;
+    if (p.depth == 1) {
+      // pure issue cost: 64 loads into distinct slots against ONE barrier, no waits in between
+      const int n = 64 * 1024 / (int)bytes < 64 ? 64 * 1024 / (int)bytes : 64;
+      const long long t0 = clock64();
+      mbar_expect_tx(&mybar[0], (uint32_t)n * bytes);
+      for (int i = 0; i < n; ++i)
+        tma_load_2d(&p.tm, &mybar[0], ring_ptr + (size_t)i * bytes, 0, row0 + (i % span) * p.rows);
+      const long long t1 = clock64();
+      mbar_wait(&mybar[0], 0u, nullptr, 0u);
+      const long long t2 = clock64();
+      p.out[blockIdx.x] = ((unsigned long long)(t1 - t0) << 32) | (unsigned long long)(t2 - t0);
+      return;
+    }
+    const long long t0 = clock64();
+    for (int i = 0; i < p.reps + nslots; ++i) {
+      const int s = i % nslots;
+      if (i >= nslots) mbar_wait(&mybar[s], (uint32_t)((i / nslots - 1) & 1), nullptr, 0u);
+      if (i < p.reps) {
+        mbar_expect_tx(&mybar[s], bytes);
+        tma_load_2d(&p.tm, &mybar[s], myring + (size_t)s * bytes, 0, row0 + ((i * p.lanes + me) % span) * p.rows);
+      }
+    }
+    if (me == 0) p.out[blockIdx.x] = (unsigned long long)(clock64() - t0);
+  }
+}
+}  // namespace
+}  // namespace advoc
+
+// h_out[ctas] u64: cycles each CTA needed for `reps` loads of {128 B x rows} with `depth` (<= 8) in flight.
+extern "C" __attribute__((visibility("default"))) int advoc_selftest_tma_rate(unsigned long long* h_out, int ctas,
+                                                                              int rows, int reps, int depth, int lanes) {
+  using namespace advoc;
+  ADVOC_REQUIRE(h_out && ctas > 0 && ctas <= 1024 && rows >= 8 && rows <= 256 && depth >= 1 && depth <= 8, ADVOC_BAD_ARG,
+                "bad arguments");
+  ADVOC_REQUIRE(lanes >= 1 && lanes <= 8 && (size_t)lanes * depth * rows * 128 <= 200 * 1024, ADVOC_BAD_ARG,
+                "ring does not fit");
+  TmaProbeParams p = {};
+  p.rows = rows; p.reps = reps; p.depth = depth; p.lanes = lanes;
+  p.src_rows = 4096;                                   // 512 KB of source per CTA: L2 resident after the first pass
+  float* src = nullptr;
+  const size_t total_rows = (size_t)ctas * p.src_rows;
+  ADVOC_CHECK_CUDA(cudaMalloc(&src, total_rows * 128));
+  ADVOC_CHECK_CUDA(cudaMemset(src, 0, total_rows * 128));
+  ADVOC_CHECK_CUDA(cudaMalloc(&p.out, ctas * sizeof(unsigned long long)));
+  int st = tc::encode_tiled2d(&p.tm, src, 32, (long)total_rows, 128, 32, rows);
+  if (st) return st;
+  const int smem = (depth == 1 ? 64 * 1024 : lanes * depth * rows * 128) + 1024;
+  ADVOC_CHECK_CUDA(cudaFuncSetAttribute(tma_rate_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024));
+  for (int pass = 0; pass < 2; ++pass) {               // first pass warms L2
+    tma_rate_probe<<<ctas, 64, smem>>>(p);
+    ADVOC_CHECK_CUDA(cudaGetLastError());
+    ADVOC_CHECK_CUDA(cudaDeviceSynchronize());
+  }
+  ADVOC_CHECK_CUDA(cudaMemcpy(h_out, p.out, ctas * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  cudaFree(src);
+  cudaFree(p.out);
+  return ADVOC_OK;
+}
