@@ -31,7 +31,7 @@ constexpr int BM = 128;        // UMMA_M (cta_group::1)
 constexpr int BK_BYTES = 128;  // one swizzle row of the K-major operands: 32 tf32 or 64 fp16 channels
 constexpr int MAX_CLASSES = 4;
 constexpr int MAX_TAPS = 25;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 224;   // warp 0: activation producer, 1: MMA issuer, 2-5: epilogue, 6: filter producer
 
 struct alignas(64) TcParams {
   CUtensorMap tmA[MAX_CLASSES];
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
     prefetch_tmap(&p.tmB);
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], 2);    // the activation producer and the filter producer each arrive with their bytes
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
@@ -136,8 +136,12 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
 
   if (aborted) {
     // a previous launch timed out: do nothing (the host raises at its next sync point)
-  } else if (warp == 0) {
-    // ===== TMA producer: warp-uniform loop, loads issued by one elected lane =====
+  } else if (warp == 0 || warp == 6) {
+    // ===== TMA producers: warp 0 streams the activation (im2col) tiles, warp 6 the filter tiles, each through
+    // one elected lane.  One thread spends ~540 cycles per {wait, expect_tx, issue} chain and ~150 more per extra
+    // TMA issue (profiles/r02r_tma_issue_probe.txt); with both loads on one thread a ring slot cost more issue
+    // time than the 192-512 tensor cycles it holds. =====
+    const bool filt = warp == 6;
     int stage = 0;
     uint32_t phase = 0;
     for (long t = blockIdx.x; t < ntl; t += gridDim.x) {
@@ -155,15 +159,18 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
       for (int it = 0; it < tl.iters; ++it) {
         mbar_wait(&empty_bar[stage], phase ^ 1u, p.dbg, 1u);
         uint8_t* a_dst = ring_ptr + stage * L::STAGE_BYTES;
-        uint8_t* b_dst = a_dst + L::A_BYTES;
         const unsigned off = p.tap_off[cls][tap];
         const int wrow = (int)p.tap_wrow[cls][tap] * p.Cn + tl.n0;
         __syncwarp();
         if (elect_one()) {
-          mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-          tma_load_im2col_4d(&p.tmA[cls], &full_bar[stage], a_dst, kb * BK, cw, ch, img, (uint16_t)(off & 0xFF),
-                             (uint16_t)(off >> 8));
-          tma_load_2d(&p.tmB, &full_bar[stage], b_dst, kb * BK, wrow);
+          if (filt) {
+            mbar_expect_tx(&full_bar[stage], L::B_BYTES);
+            tma_load_2d(&p.tmB, &full_bar[stage], a_dst + L::A_BYTES, kb * BK, wrow);
+          } else {
+            mbar_expect_tx(&full_bar[stage], L::A_BYTES);
+            tma_load_im2col_4d(&p.tmA[cls], &full_bar[stage], a_dst, kb * BK, cw, ch, img, (uint16_t)(off & 0xFF),
+                               (uint16_t)(off >> 8));
+          }
         }
         __syncwarp();
         if (++kb == p.kblocks) { kb = 0; ++tap; }

@@ -38,7 +38,8 @@ constexpr int WM = 128;       // UMMA_M: small-side channels on the TMEM lanes
 // issue slots 5-8 %: profiles/r02k_ncu_full_wgrad_tc_regular.csv), so round 2 halves the tile to 8
 // blocks = 256 columns and 96 KB of ring and runs TWO CTAs per SM whose TMA latencies overlap.
 constexpr int WNB = 8;
-constexpr int W_THREADS = 192;
+constexpr int W_NPROD = 2;        // TMA producer warps: warp 0 and warps 6 .. 4 + W_NPROD (r02: 1 -> 1420, 2 -> 1460, 4 -> 1465 samples/s)
+constexpr int W_THREADS = 192 + 32 * (W_NPROD - 1);   // + warp 1: MMA issuer, warps 2-5: epilogue
 
 struct alignas(64) WgParams {
   CUtensorMap tmBig;    // im2col
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(W_THREADS, 2) wgrad_tc_kernel(const __grid_con
     prefetch_tmap(&p.tmSmall);
 #pragma unroll
     for (int s = 0; s < WSTAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], W_NPROD);    // one arrival (+ its transaction bytes) per producer warp
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(&tmem_full_bar, 1);
@@ -131,19 +132,30 @@ __global__ void __launch_bounds__(W_THREADS, 2) wgrad_tc_kernel(const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_holder;
 
-  if (warp == 0) {
-    // ===== TMA producer: 12 boxes per stage, one per lane (lanes 0-3 small side, 4-11 big side) =====
+  if (warp == 0 || warp >= 6) {
+    // ===== TMA producers: the 12 boxes of a stage (4 small-side, 8 big-side) are split over W_NPROD warps -- issuing one TMA load costs its thread ~150 cycles and the lanes of one warp only partly
+    // overlap (profiles/r02r_tma_issue_probe.txt), so two warps halve the time a stage spends being issued =====
+    constexpr int PER_WARP = (WM / 32 + WNB) / W_NPROD;
+    static_assert(PER_WARP * W_NPROD == WM / 32 + WNB, "boxes must split evenly over the producer warps");
+    const int pw = warp == 0 ? 0 : warp - 5;
+    const int box = lane + PER_WARP * pw;          // box index of this lane (valid for lane < PER_WARP)
+    const bool mine = lane < PER_WARP;
+    const bool is_small = mine && box < WM / 32;
     int my_c = 0;
     uint16_t my_kw = 0, my_kh = 0;
-    if (lane < WM / 32) {
-      my_c = m0 + 32 * lane;
-    } else if (lane < WM / 32 + WNB) {
-      const int gb = gb0 + (lane - WM / 32);
+    bool have = mine;
+    if (is_small) {
+      my_c = m0 + 32 * box;
+    } else if (mine) {
+      const int gb = gb0 + (box - WM / 32);
+      have = gb < p.nboxes;                        // boxes of a partial last tile are not loaded
       const int tap = gb / p.cbb, cblk = gb - tap * p.cbb;
       my_c = 32 * cblk;
       my_kh = (uint16_t)(tap / p.kw);
       my_kw = (uint16_t)(tap - (tap / p.kw) * p.kw);
     }
+    const unsigned loaded = __ballot_sync(0xffffffffu, have);
+    const uint32_t my_bytes = (uint32_t)__popc(loaded) * BLK_BYTES;
     int stage = 0;
     uint32_t phase = 0;
     for (int it = 0; it < iters; ++it) {
@@ -154,14 +166,13 @@ __global__ void __launch_bounds__(W_THREADS, 2) wgrad_tc_kernel(const __grid_con
       const int img = (int)(r / p.Ho);
       if (lane == 0) {
         mbar_wait(&empty_bar[stage], phase ^ 1u, p.dbg, 11u);
-        const int nb = p.nboxes - gb0 < WNB ? p.nboxes - gb0 : WNB;   // boxes of a partial last tile are
-        mbar_expect_tx(&full_bar[stage], A_BYTES + nb * BLK_BYTES);   // not loaded (their columns are skipped)
+        mbar_expect_tx(&full_bar[stage], my_bytes);
       }
       __syncwarp();
-      uint8_t* dst = ring_ptr + stage * STAGE_BYTES + lane * BLK_BYTES;
-      if (lane < WM / 32) {
+      uint8_t* dst = ring_ptr + stage * STAGE_BYTES + box * BLK_BYTES;
+      if (is_small) {
         tma_load_2d(&p.tmSmall, &full_bar[stage], dst, my_c, (int)pix);
-      } else if (lane < WM / 32 + WNB && gb0 + (lane - WM / 32) < p.nboxes) {
+      } else if (have) {
         tma_load_im2col_4d(&p.tmBig, &full_bar[stage], dst, my_c, ow * p.sw + p.lower_w, oh * p.sh + p.lower_h,
                            img, my_kw, my_kh);
       }
