@@ -1,0 +1,361 @@
+// k4 convolution FROM ONE input channel on the tensor cores (generator encoder_1,
+// models/advoc/advoc_model.py:91-94: x [N, 256, 513, 1] -> [N, 128, 257, ngf], SAME, stride 2).
+//
+// The CUDA-core kernel for this layer (conv_direct.cu: one thread per output pixel) is bound by
+// instruction issue -- ~1840 warp instructions per 32 pixels, 70 % of the issue slots busy, the FMA pipe
+// 28 % (profiles/r02k_ncu_full_generator_forward.csv) -- not by the 150-270 MB it writes.  Here the
+// contraction over the 16 taps runs as tcgen05 MMAs (M = 128 pixels, N = Cout, K = 16) and the threads only
+// gather the im2col rows and convert / store the results:
+//   * producers (4 warps): thread m gathers the 16 taps of pixel m of the tile and writes row m of the
+//     K-major, 128B-swizzled A tile in shared memory (no TMA: one fp32 per tap has nothing to box);
+//   * the row holds the taps TWICE, as tf32 "hi" parts (chunks 0-3) and "lo" parts x - hi (chunks 4-7), and the
+//     filter sits in two resident B tiles [w_hi | w_hi] and [w_lo | 0]: six K = 8 MMAs per tile compute
+//     x_hi w_hi + x_lo w_hi + x_hi w_lo, i.e. the fp32 product to ~2^-21 -- encoder_1 stays as exact as the
+//     CUDA-core kernel it replaces (the 1e-3 parity budget of the stack has no room for a tf32 first layer:
+//     scripts emulation 7.9e-4 -> 8.6e-4 at the regular model's worst activation), and the tensor time of a
+//     K = 16 layer is negligible either way;
+//   * one MMA-issuing warp, accumulators double-buffered in TMEM, four epilogue warps (TMEM -> registers ->
+//     bias, one or two slope activations, fp32 / fp16 conversion -> 64-128 contiguous bytes per pixel).
+// Tiles are 8 x 16 output patches (4-D TMA stores clip at the image edge and honour padded rows).  Persistent
+// CTAs, two per SM.
+#include "epilogue.cuh"
+#include "tc_ptx.cuh"
+
+#include <stdlib.h>
+
+namespace advoc {
+
+int lower_epilogue(const advoc_epilogue* ep, int Hs, int Wfull, int Cout, EpiDev* out);
+
+namespace {
+
+using namespace tc;
+
+constexpr int I_TH = 8, I_TW = 16;     // output patch of a tile: 8 rows x 16 columns = the 128 GEMM rows
+constexpr int I_THREADS = 288;         // warps 0-3 gather producers, warp 4 MMA issuer, warps 5-8 epilogue
+constexpr uint32_t I_A_BYTES = 128 * 128;
+constexpr uint32_t I_STAGE_BYTES = 128 * 128;   // one staged output chunk: 128 pixels x <= 128 bytes
+
+struct alignas(64) OneInParams {
+  CUtensorMap tmO[2];   // output stores, box {CW channels, 16, 8, 1}
+  const float* x;
+  const float* w;   // HWIO [16][1][Cout]
+  int N, H, W, ldx, Ho, Wo, sh, sw, pt, pl;
+  int tiles_h, tiles_w, n_out, cw, out_half;
+  long tiles;
+  EpiDev epi;
+  unsigned int* dbg;
+};
+
+__device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void sts_v4u(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d_(const CUtensorMap* tm, uint32_t src, int c, int w, int h, int n) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tm)),
+               "r"(src), "r"(c), "r"(w), "r"(h), "r"(n)
+               : "memory");
+}
+
+struct OneTile { int img, oh0, ow0; };
+__device__ __forceinline__ OneTile one_tile(const OneInParams& p, long t) {
+  OneTile x;
+  unsigned s = (unsigned)t;                      // tiles < 2^31 (checked on the host)
+  x.ow0 = (int)(s % (unsigned)p.tiles_w) * I_TW;
+  s /= (unsigned)p.tiles_w;
+  x.oh0 = (int)(s % (unsigned)p.tiles_h) * I_TH;
+  x.img = (int)(s / (unsigned)p.tiles_h);
+  return x;
+}
+
+template <int COUT, int STAGES>
+__global__ void __launch_bounds__(I_THREADS, 2) conv_one_in_tc_kernel(const __grid_constant__ OneInParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t a_full[STAGES], a_empty[STAGES], acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_base_holder;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  constexpr uint32_t B_BYTES = COUT * 128;
+  const uint32_t b1 = ring + STAGES * I_A_BYTES, b2 = b1 + B_BYTES;
+  const uint32_t stage_base = b2 + B_BYTES;      // two staging buffers (out0, out1), 1024-byte aligned
+  constexpr uint32_t TMEM_COLS = 2 * COUT < 32 ? 32 : 2 * COUT;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&a_full[s], 4); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    prefetch_tmap(&p.tmO[0]);
+    if (p.n_out == 2) prefetch_tmap(&p.tmO[1]);
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(&tmem_base_holder)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // resident filter tiles, K-major rows of 128 B: B1[n] = [w_hi(16 taps) | w_hi(16 taps)], B2[n] = [w_lo | 0]
+  for (int i = threadIdx.x; i < COUT * 8; i += I_THREADS) {
+    const int n = i >> 3, c = i & 7;           // row, 16-byte chunk (4 K values)
+    float hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int tap = ((c & 3) << 2) + j;
+      const float v = __ldg(p.w + (size_t)tap * COUT + n);
+      hi[j] = round_tf32(v);
+      lo[j] = round_tf32(v - hi[j]);
+    }
+    const uint32_t off = (uint32_t)n * 128u + (((uint32_t)c ^ ((uint32_t)n & 7u)) << 4);
+    sts_v4(b1 + off, hi[0], hi[1], hi[2], hi[3]);
+    if (c < 4) sts_v4(b2 + off, lo[0], lo[1], lo[2], lo[3]);
+    else sts_v4(b2 + off, 0.f, 0.f, 0.f, 0.f);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_holder;
+  const bool aborted = p.dbg && *reinterpret_cast<volatile unsigned int*>(p.dbg) != 0;
+
+  if (aborted) {
+  } else if (warp < 4) {
+    // ===== gather producers: one output pixel (patch position r, c) per thread and tile; the 16 loads of the
+    // NEXT tile are issued before this tile's row is converted and written =====
+    const int m = (int)threadIdx.x;
+    const int r = m / I_TW, c = m % I_TW;
+    int stage = 0;
+    uint32_t phase = 0;
+    // (the kernel is bound by instruction issue, so the gather keeps one row pointer per filter row, immediate
+    // column offsets and precomputed row / column predicates: ~4 instructions per tap)
+    auto gather = [&](long t, float (&v)[16]) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = 0.f;
+      if (t >= p.tiles) return;
+      const OneTile tl = one_tile(p, t);
+      const int oh = tl.oh0 + r, ow = tl.ow0 + c;
+      if (oh >= p.Ho || ow >= p.Wo) return;
+      const int ih0 = oh * p.sh - p.pt, iw0 = ow * p.sw - p.pl;
+      const float* x00 = p.x + ((size_t)tl.img * p.H * p.W + (long)ih0 * p.W + iw0) * p.ldx;
+      bool cok[4];
+#pragma unroll
+      for (int kw = 0; kw < 4; ++kw) cok[kw] = (unsigned)(iw0 + kw) < (unsigned)p.W;
+      const long rstride = (long)p.W * p.ldx;
+#pragma unroll
+      for (int kh = 0; kh < 4; ++kh) {
+        const bool rok = (unsigned)(ih0 + kh) < (unsigned)p.H;
+        const float* xr = x00 + kh * rstride;
+#pragma unroll
+        for (int kw = 0; kw < 4; ++kw)
+          if (rok && cok[kw]) v[kh * 4 + kw] = __ldg(xr + kw * p.ldx);
+      }
+    };
+    float v[16], vn[16];
+    gather(blockIdx.x, v);
+    for (long t = blockIdx.x; t < p.tiles; t += gridDim.x) {
+      gather(t + gridDim.x, vn);
+      mbar_wait(&a_empty[stage], phase ^ 1u, p.dbg, 51u);
+      const uint32_t row = ring + (uint32_t)stage * I_A_BYTES + (uint32_t)m * 128u;
+      const uint32_t sx = (uint32_t)m & 7u;
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        float hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          hi[j] = round_tf32(v[4 * cc + j]);
+          lo[j] = round_tf32(v[4 * cc + j] - hi[j]);
+        }
+        sts_v4(row + (((uint32_t)cc ^ sx) << 4), hi[0], hi[1], hi[2], hi[3]);
+        sts_v4(row + (((uint32_t)(cc + 4) ^ sx) << 4), lo[0], lo[1], lo[2], lo[3]);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cta(&a_full[stage]);
+      if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = vn[j];
+    }
+  } else if (warp == 4) {
+    // ===== MMA issuer =====
+    constexpr uint32_t idesc = umma_idesc<false>(128, COUT);
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0, i = 0;
+      const uint64_t db1 = make_smem_desc(b1), db2 = make_smem_desc(b2);
+      for (long t = blockIdx.x; t < p.tiles; t += gridDim.x, ++i) {
+        const uint32_t buf = i & 1u;
+        mbar_wait(&acc_empty[buf], ((i >> 1) & 1u) ^ 1u, p.dbg, 52u);
+        mbar_wait(&a_full[stage], phase, p.dbg, 53u);
+        tc_fence_after();
+        const uint32_t d = tmem_base + buf * (uint32_t)COUT;
+        const uint64_t da = make_smem_desc(ring + (uint32_t)stage * I_A_BYTES);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)      // [x_hi | x_lo] . [w_hi | w_hi]
+          umma_tf32(d, da + (uint64_t)(2 * k), db1 + (uint64_t)(2 * k), idesc, k != 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 2; ++k)      // x_hi . w_lo
+          umma_tf32(d, da + (uint64_t)(2 * k), db2 + (uint64_t)(2 * k), idesc, 1u);
+        umma_commit(&a_empty[stage]);
+        umma_commit(&acc_full[buf]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue: warp w may only touch TMEM lanes [32 (w % 4), +32).  Rows are staged in swizzled shared
+    // memory (piece j of row m at j ^ sx: the pattern of the store tensor map) and leave through one TMA tensor
+    // store per destination and chunk: scattered per-thread stores kept the LSU 60 % busy on their own. =====
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const EpiDev& e = p.epi;
+    // none / relu / lrelu as y = max(v, s * v) with s = 1 / 0 / alpha (alpha <= 1): two instructions per value
+    const float s0 = e.act0 == ADVOC_ACT_LRELU ? e.alpha : (e.act0 == ADVOC_ACT_RELU ? 0.f : 1.f);
+    const float s1 = e.act1 == ADVOC_ACT_LRELU ? e.alpha : (e.act1 == ADVOC_ACT_RELU ? 0.f : 1.f);
+    const bool issuer = warp == 5 && lane == 0;
+    const int CW = p.cw;                                   // channels per staged chunk
+    const uint32_t row_bytes = (uint32_t)CW * (p.out_half ? 2u : 4u);   // 128 or 64
+    const uint32_t srow = stage_base + (uint32_t)m * row_bytes;
+    const uint32_t sx = row_bytes == 128u ? ((uint32_t)m & 7u) : (((uint32_t)m >> 1) & 3u);
+    uint32_t i = 0;
+    for (long t = blockIdx.x; t < p.tiles; t += gridDim.x, ++i) {
+      const uint32_t buf = i & 1u;
+      const OneTile tl = one_tile(p, t);
+      mbar_wait(&acc_full[buf], (i >> 1) & 1u, p.dbg, 54u);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < COUT; c0 += CW) {
+        if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging buffers free again
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll 1
+        for (int sub = 0; sub < CW; sub += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)COUT + (uint32_t)(c0 + sub), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            float x[8], y[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) x[u] = __uint_as_float(v[j + u]);
+            if (e.bias) {
+              const float4 ba = __ldg(reinterpret_cast<const float4*>(e.bias + c0 + sub + j));
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(e.bias + c0 + sub + j) + 1);
+              x[0] += ba.x; x[1] += ba.y; x[2] += ba.z; x[3] += ba.w;
+              x[4] += bb.x; x[5] += bb.y; x[6] += bb.z; x[7] += bb.w;
+            }
+#pragma unroll
+            for (int o = 0; o < 2; ++o) {
+              if (o == 1 && p.n_out != 2) break;
+#pragma unroll
+              for (int u = 0; u < 8; ++u) y[u] = fmaxf(x[u], (o == 0 ? s0 : s1) * x[u]);
+              const uint32_t dst = srow + (uint32_t)o * I_STAGE_BYTES;
+              if (p.out_half) {
+                const uint32_t piece = (uint32_t)(sub + j) >> 3;     // 8 halves = 16 bytes
+                sts_v4u(dst + ((piece ^ sx) << 4), pack_half2(y[0], y[1]), pack_half2(y[2], y[3]),
+                        pack_half2(y[4], y[5]), pack_half2(y[6], y[7]));
+              } else {
+                if (e.round) {
+#pragma unroll
+                  for (int u = 0; u < 8; ++u) y[u] = round_tf32(y[u]);
+                }
+                const uint32_t piece = (uint32_t)(sub + j) >> 2;     // 4 floats = 16 bytes
+                sts_v4(dst + ((piece ^ sx) << 4), y[0], y[1], y[2], y[3]);
+                sts_v4(dst + (((piece + 1u) ^ sx) << 4), y[4], y[5], y[6], y[7]);
+              }
+            }
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (issuer) {
+          tma_store_4d_(&p.tmO[0], stage_base, c0, tl.ow0, tl.oh0, tl.img);
+          if (p.n_out == 2) tma_store_4d_(&p.tmO[1], stage_base + I_STAGE_BYTES, c0, tl.ow0, tl.oh0, tl.img);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cta(&acc_empty[buf]);
+    }
+    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS)
+                 : "memory");
+  }
+}
+
+template <int COUT, int STAGES>
+int launch_one_in(const OneInParams& p, cudaStream_t st) {
+  constexpr int smem = STAGES * (int)I_A_BYTES + 2 * COUT * 128 + 2 * (int)I_STAGE_BYTES + 1024;
+  static bool configured = false;
+  if (!configured) {
+    ADVOC_CHECK_CUDA(cudaFuncSetAttribute(conv_one_in_tc_kernel<COUT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          smem));
+    configured = true;
+  }
+  const long slots = (long)sm_count() * 2;
+  const long ctas = p.tiles < slots ? p.tiles : slots;
+  conv_one_in_tc_kernel<COUT, STAGES><<<(unsigned)ctas, I_THREADS, smem, st>>>(p);
+  count_launch();
+  ADVOC_CHECK_CUDA(cudaGetLastError());
+  return ADVOC_OK;
+}
+
+}  // namespace
+
+// plain forward epilogue only: bias + none / relu / lrelu on one or two fp32 / fp16 outputs
+bool conv_one_in_tc_eligible(const advoc_conv_desc* d, const float* x, const float* w, const advoc_epilogue* ep) {
+  static const bool disabled = getenv("ADVOC_NO_ONE_IN_TC") != nullptr;   // A/B switch for benchmarking
+  auto slope = [](int a) { return a == ADVOC_ACT_NONE || a == ADVOC_ACT_LRELU || a == ADVOC_ACT_RELU; };
+  auto ok = [](const float* p, int ld, int co) { return aligned16(p) && ld % 8 == 0 && co % 8 == 0; };
+  return !disabled && d->math != ADVOC_MATH_FP32 && d->math != ADVOC_MATH_F16 && tc::tma_ok() && device_arch() == 100 &&
+         d->Cin == 1 && d->kh == 4 && d->kw == 4 && (d->Cout == 32 || d->Cout == 64 || d->Cout == 128) && x && w && ep &&
+         ep->d_out0 && !ep->d_gate && !ep->accumulate && ep->keep_prob >= 1.f && ep->store_w == 0 && slope(ep->act0) &&
+         ep->alpha >= 0.f && ep->alpha <= 1.f &&
+         slope(ep->act1) && (!ep->d_bias || aligned16(ep->d_bias)) && ok(ep->d_out0, ep->ld0, ep->c_off0) && (!ep->d_out1 || ok(ep->d_out1, ep->ld1, ep->c_off1)) &&
+         (!ep->d_out1 || ep->out0_dtype == ep->out1_dtype) &&      // the staged stores write one element type
+         (long)d->N * ((d->Ho + I_TH - 1) / I_TH) * ((d->Wo + I_TW - 1) / I_TW) < 2147483647L;
+}
+
+int conv_one_in_tc(const advoc_conv_desc* d, const float* x, int ldx, const float* w, const advoc_epilogue* ep,
+                   void* stream) {
+  OneInParams p = {};
+  int st = lower_epilogue(ep, d->Ho, d->Wo, d->Cout, &p.epi);
+  if (st) return st;
+  p.x = x; p.w = w; p.N = d->N; p.H = d->H; p.W = d->W; p.ldx = ldx; p.Ho = d->Ho; p.Wo = d->Wo;
+  p.sh = d->sh; p.sw = d->sw; p.pt = d->pad_t; p.pl = d->pad_l;
+  p.tiles_h = (d->Ho + I_TH - 1) / I_TH;
+  p.tiles_w = (d->Wo + I_TW - 1) / I_TW;
+  p.tiles = (long)d->N * p.tiles_h * p.tiles_w;
+  if (p.tiles == 0) return ADVOC_OK;
+  const EpiDev& e = p.epi;
+  p.n_out = e.out1 ? 2 : 1;
+  p.out_half = e.h0;
+  p.cw = e.h0 ? (d->Cout >= 64 ? 64 : 32) : 32;
+  const int es = e.h0 ? 2 : 4;
+  for (int o = 0; o < p.n_out; ++o) {
+    const long ld = o == 0 ? e.ld0 : e.ld1;
+    const long roww = (long)d->Wo + (o == 0 ? e.row_pad0 : 0);     // pixels per stored row of this destination
+    const char* base = reinterpret_cast<const char*>(o == 0 ? e.out0 : e.out1) + (size_t)(o == 0 ? e.coff0 : e.coff1) * es;
+    st = tc::encode_tiled4d(&p.tmO[o], base, d->Cout, d->Wo, d->Ho, d->N, ld, roww * ld, (long)d->Ho * roww * ld, p.cw,
+                            I_TW, I_TH, e.h0);
+    if (st) return st;
+  }
+  p.dbg = tc::debug_word();
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  switch (d->Cout) {
+    case 32: return launch_one_in<32, 3>(p, s);
+    case 64: return launch_one_in<64, 3>(p, s);
+    default: return launch_one_in<128, 2>(p, s);
+  }
+}
+
+}  // namespace advoc

@@ -34,6 +34,22 @@ def init(backend=None):
   return rank, local, world
 
 
+def bind_to_gpu_numa(local_rank):
+  """Pins the calling process to the CPU cores NVML reports as closest to its GPU, so that the pinned
+  host buffers it allocates afterwards (first touch) and its copy threads sit on that GPU's NUMA node.
+  With eight ranks streaming results to the host at once (infer.MelToMag.run_stream: 16.8 MB per 0.63 ms
+  each) unbound processes share one node's memory controllers.  Returns the number of cores bound to, or
+  0 when NVML / the affinity call is unavailable (nothing changes then)."""
+  try:
+    import pynvml
+    pynvml.nvmlInit()
+    h = pynvml.nvmlDeviceGetHandleByIndex(int(local_rank))
+    pynvml.nvmlDeviceSetCpuAffinity(h)
+    return len(os.sched_getaffinity(0))
+  except Exception:
+    return 0
+
+
 def shard_range(global_batch, world, rank):
   """Even split of the global minibatch; the reference's batch is a free parameter (no BN by
   default, advoc_model.py:21), so ranks only need equal shares for the mean to be exact."""

@@ -100,6 +100,8 @@ class _Conv(object):
     """Kernel that runs this layer (bench.py attributes time by it)."""
     k = N.lib().advoc_conv2d_kernel(C.byref(self.desc), self.ldx, 1 if self.kind == 'deconv' else 0,
                                     getattr(self, 'store_w', 0) or 0)
+    if k == 4:
+      return 'conv_one_in_tc_kernel/' + self.kind
     if k == 3:
       return 'deconv_one_tc_kernel/' + self.kind
     if k == 2:

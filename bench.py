@@ -186,8 +186,13 @@ def run_gpu(args):
   if not torch.cuda.is_available():
     raise RuntimeError('bench.py needs a GPU (the product path has no CPU fallback)')
   torch.cuda.set_device(local)
+  bound = 0
   if world > 1:
     dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    if not os.environ.get('ADVOC_NO_AFFINITY'):
+      # one process per GPU: keep each rank's pinned buffers and copy threads on its GPU's NUMA node
+      from advoc_b200 import dist as D
+      bound = D.bind_to_gpu_numa(local)
 
   def barrier():
     if world > 1:
@@ -273,6 +278,7 @@ def run_gpu(args):
               'd2h_bytes_per_step': int(eng.out_h.numel() * 4),
               'api': 'infer.MelToMag.run_stream (pinned host in / out, copies overlapped with the '
                      'neighbouring batches)',
+              'cpu_cores_bound_per_rank': bound,
               'serial_call_value': frames / (e2e_serial_ms * 1e-3),
               'serial_call_api': 'infer.MelToMag.__call__ (H2D, forward, D2H back to back)'},
       'gpu_launches': int(per_step * args.steps * 2),

@@ -308,7 +308,8 @@ ADVOC_API int advoc_conv2d_path(const advoc_conv_desc* d, int ld_x, int transpos
 
 /* Which kernel a forward call with this geometry launches: 0 CUDA-core fp32 (conv_simt.cu /
  * conv_direct.cu), 1 tcgen05 per-tap im2col kernel (conv_tc.cu), 2 tcgen05 persistent patch kernel
- * (conv_p2d.cu), 3 tcgen05 transposed conv to one channel (deconv_one_tc.cu).  store_w as in advoc_epilogue (0 = full width).  Host-side query, used by bench.py
+ * (conv_p2d.cu), 3 tcgen05 transposed conv to one channel (deconv_one_tc.cu), 4 tcgen05 conv from one channel
+ * (conv_one_in_tc.cu; taken when the epilogue is a plain forward one, else 0).  store_w as in advoc_epilogue (0 = full width).  Host-side query, used by bench.py
  * to attribute time to kernels.  replaces: nothing in the reference. */
 ADVOC_API int advoc_conv2d_kernel(const advoc_conv_desc* d, int ld_x, int transposed, int store_w);
 

@@ -380,3 +380,45 @@ def test_single_layers_fp16_operands(kernel):
   assert N.debug_flags() == 0
   assert L.kernel_family().startswith('deconv_one_tc')
   assert _rel(out, ref) < TOL
+
+
+@pytest.mark.parametrize('cout', [32, 64, 128])
+def test_one_input_channel_conv_on_tensor_cores(cout):
+  """encoder_1's geometry (one input channel, k4 s2 SAME, odd width) on conv_one_in_tc_kernel: the 3 x tf32
+  split keeps the products fp32-exact (<= 2e-6 against the oracle, where a single tf32 pass would be
+  3e-4), with fp32 + fp32, fp16 + fp16 (padded rows) and single-output epilogues."""
+  from advoc_b200 import _native as N
+  from advoc_b200 import nets
+  from oracle import nets_torch as O
+  g = torch.Generator().manual_seed(cout)
+  B, H, W = 3, 20, 37
+  x = torch.randn(B, H, W, 1, generator=g).abs() * 3.0
+  k = torch.randn(4, 4, 1, cout, generator=g) * 0.05
+  b = torch.randn(cout, generator=g) * 0.1
+  ref = O.conv_same(x, k, b, (2, 2))
+  ho, pt, _ = nets.same_pads(H, 4, 2)
+  wo, pl, _ = nets.same_pads(W, 4, 2)
+  L = nets._Conv('t', 'conv', nets._desc(B, H, W, 1, cout, 2, 2, pt, pl, ho, wo, N.MATH_AUTO))
+  xd, kd, bd = x.cuda(), k.cuda(), b.cuda()
+  # fp32 dual write into a wider buffer at a channel offset
+  y0 = torch.full((B, ho, wo, cout), float('nan'), device='cuda')
+  cat = torch.full((B, ho, wo, cout + 64), float('nan'), device='cuda')
+  L.run(xd, 1, kd, nets._epilogue(bd, y0, cout, 0, N.ACT_LRELU, cat, cout + 64, 64, N.ACT_RELU))
+  torch.cuda.synchronize()
+  assert N.debug_flags() == 0
+  assert L.kernel_family().startswith('conv_one_in_tc')
+  assert _rel(y0, O.lrelu(ref)) < 2e-6 and _rel(cat[..., 64:], torch.relu(ref)) < 2e-6
+  assert torch.isnan(cat[..., :64]).all()
+  # fp16 outputs, out0 with one padded pixel per row
+  h0 = torch.zeros((B, ho, wo + 1, cout), device='cuda', dtype=torch.float16)
+  h1 = torch.full((B, ho, wo, cout + 8), float('nan'), device='cuda', dtype=torch.float16)
+  L.run(xd, 1, kd, nets._epilogue(bd, h0, cout, 0, N.ACT_LRELU, h1, cout + 8, 8, N.ACT_RELU, row_pad0=1))
+  torch.cuda.synchronize()
+  assert N.debug_flags() == 0
+  assert _rel(h0[:, :, :wo].float(), O.lrelu(ref)) < 5e-4 and bool((h0[:, :, wo] == 0).all())
+  assert _rel(h1[..., 8:].float(), torch.relu(ref)) < 5e-4
+  # single fp32 output, no activation, no bias
+  y2 = torch.empty((B, ho, wo, cout), device='cuda')
+  L.run(xd, 1, kd, nets._epilogue(None, y2, cout, 0, N.ACT_NONE))
+  torch.cuda.synchronize()
+  assert _rel(y2, ref - b) < 2e-6
