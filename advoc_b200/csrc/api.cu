@@ -77,7 +77,10 @@ bool conv_p2d_eligible(const advoc_conv_desc* d, int ldx, int transposed, int st
 int conv_p2d(const advoc_conv_desc* d, int transposed, const void* x, int ldx, const void* w,
              const advoc_epilogue* ep, void* stream);
 bool tc_epilogue_ok(const advoc_epilogue* ep);
-bool conv_one_in_tc_eligible(const advoc_conv_desc* d, const float* x, const float* w, const advoc_epilogue* ep);
+bool conv_one_in_tc_eligible(const advoc_conv_desc* d, const float* x, int ldx, const float* w, const advoc_epilogue* ep);
+bool deconv_from_one_tc_eligible(const advoc_conv_desc* d, const float* x, const float* w, const advoc_epilogue* ep);
+int deconv_from_one_tc(const advoc_conv_desc* d, const float* x, int ldx, const float* w, const advoc_epilogue* ep,
+                       void* stream);
 int conv_one_in_tc(const advoc_conv_desc* d, const float* x, int ldx, const float* w, const advoc_epilogue* ep,
                    void* stream);
 int conv_tc_tile_n(const advoc_conv_desc* d, int transposed, int store_w);
@@ -133,7 +136,7 @@ extern "C" int advoc_conv2d_fwd(const advoc_conv_desc* d, const void* d_xv, int 
   if (st) return st;
   const float* d_x = static_cast<const float*>(d_xv);   // half data when math == ADVOC_MATH_F16: only the
   const float* d_w = static_cast<const float*>(d_wv);   // tcgen05 kernels below ever see those pointers
-  if (conv_one_in_tc_eligible(d, d_x, d_w, ep)) return conv_one_in_tc(d, d_x, ld_x, d_w, ep, stream);
+  if (conv_one_in_tc_eligible(d, d_x, ld_x, d_w, ep)) return conv_one_in_tc(d, d_x, ld_x, d_w, ep, stream);
   if (ep->out0_row_pad != 0) {
     ADVOC_REQUIRE(d->Cin <= 2 && d->math != ADVOC_MATH_F16, ADVOC_UNSUPPORTED,
                   "out0_row_pad is only supported by the thin-input convolution");
@@ -163,6 +166,7 @@ extern "C" int advoc_conv2d_transpose_fwd(const advoc_conv_desc* d, const void* 
   const float* d_w = static_cast<const float*>(d_wv);
   ADVOC_REQUIRE(ep->out0_row_pad == 0, ADVOC_UNSUPPORTED, "out0_row_pad is only supported by the thin-input convolution");
   if (d->math == ADVOC_MATH_FP32) return conv_transposed_simt(d, d_x, ld_x, d_w, ep, stream);
+  if (deconv_from_one_tc_eligible(d, d_x, d_w, ep)) return deconv_from_one_tc(d, d_x, ld_x, d_w, ep, stream);
   if (deconv_one_tc_eligible(d, d_x, ld_x, ep)) return deconv_one_tc(d, d_x, ld_x, d_w, ep, stream);
   const bool ok = conv_transposed_tc_eligible(d, ld_x);
   if (d->math == ADVOC_MATH_TF32 || d->math == ADVOC_MATH_F16 || ok) {
@@ -189,8 +193,8 @@ extern "C" int advoc_conv2d_path(const advoc_conv_desc* d, int ld_x, int transpo
 extern "C" int advoc_conv2d_kernel(const advoc_conv_desc* d, int ld_x, int transposed, int store_w) {
   // the one-input-channel forward conv runs on the tensor cores with fp32-exact (3 x tf32) products; it keeps
   // the TF-layout filter, so advoc_conv2d_path still reports ADVOC_MATH_FP32 for it (no packed copy)
-  if (d && !transposed && d->math != ADVOC_MATH_FP32 && d->math != ADVOC_MATH_F16 && d->Cin == 1 && d->kh == 4 &&
-      d->kw == 4 && (d->Cout == 32 || d->Cout == 64 || d->Cout == 128) && device_arch() == 100 &&
+  if (d && !transposed && d->math != ADVOC_MATH_FP32 && d->math != ADVOC_MATH_F16 && (d->Cin == 1 || d->Cin == 2) &&
+      d->kh == 4 && d->kw == 4 && (d->Cout == 32 || d->Cout == 64 || d->Cout % 128 == 0) && device_arch() == 100 &&
       getenv("ADVOC_NO_ONE_IN_TC") == nullptr)
     return 4;
   if (advoc_conv2d_path(d, ld_x, transposed) == ADVOC_MATH_FP32) return 0;

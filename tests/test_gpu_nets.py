@@ -422,3 +422,93 @@ def test_one_input_channel_conv_on_tensor_cores(cout):
   L.run(xd, 1, kd, nets._epilogue(None, y2, cout, 0, N.ACT_NONE))
   torch.cuda.synchronize()
   assert _rel(y2, ref - b) < 2e-6
+
+
+@pytest.mark.parametrize('cout', [32, 64])
+def test_two_input_channel_conv_on_tensor_cores(cout):
+  """Discriminator layer_1's geometry (two input channels, pad 1 + VALID k4 s2, odd width) on
+  conv_one_in_tc_kernel<.., MODE 1>: K = 32, hi / lo parts in two A tiles, fp32-exact products."""
+  from advoc_b200 import _native as N
+  from advoc_b200 import nets
+  from oracle import nets_torch as O
+  g = torch.Generator().manual_seed(100 + cout)
+  B, H, W = 3, 22, 45
+  x = torch.randn(B, H, W, 2, generator=g) * 2.0
+  k = torch.randn(4, 4, 2, cout, generator=g) * 0.05
+  b = torch.randn(cout, generator=g) * 0.1
+  ref = O.discrim_conv(x, k, b, 2)
+  ho, wo = (H + 2 - 4) // 2 + 1, (W + 2 - 4) // 2 + 1
+  assert tuple(ref.shape) == (B, ho, wo, cout)
+  L = nets._Conv('t', 'conv', nets._desc(B, H, W, 2, cout, 2, 2, 1, 1, ho, wo, N.MATH_AUTO))
+  xd, kd, bd = x.cuda(), k.cuda(), b.cuda()
+  y = torch.full((B, ho, wo, cout), float('nan'), device='cuda')
+  L.run(xd, 2, kd, nets._epilogue(bd, y, cout, 0, N.ACT_LRELU))
+  torch.cuda.synchronize()
+  assert N.debug_flags() == 0
+  assert L.kernel_family().startswith('conv_one_in_tc')
+  assert _rel(y, O.lrelu(ref)) < 2e-6
+  # fp16 destination with a channel offset
+  h = torch.full((B, ho, wo, cout + 8), float('nan'), device='cuda', dtype=torch.float16)
+  L.run(xd, 2, kd, nets._epilogue(bd, h, cout + 8, 8, N.ACT_RELU))
+  torch.cuda.synchronize()
+  assert _rel(h[..., 8:].float(), torch.relu(ref)) < 5e-4
+
+
+@pytest.mark.parametrize('cout,split', [(128, 64), (64, 0), (256, 128)])
+def test_one_input_channel_conv_backward_epilogue(cout, split):
+  """decoder_1's input gradient: a conv from the one-channel d loss / d generated to the concat gradient, gated
+  by relu' of the stored concat buffer with one scale per half (dropout 1 / keep on the decoder half);
+  Cout = 256 runs as two blockIdx.y chunks."""
+  from advoc_b200 import _native as N
+  from advoc_b200 import nets
+  from oracle import nets_torch as O
+  g = torch.Generator().manual_seed(7 + cout)
+  B, H, W = 2, 36, 50
+  x = torch.randn(B, H, W, 1, generator=g)
+  k = torch.randn(4, 4, 1, cout, generator=g) * 0.05
+  gate = torch.randn(B, H // 2, W // 2, cout + 8, generator=g)
+  ref = O.conv_same(x, k, torch.zeros(cout), (2, 2))
+  ho, pt, _ = nets.same_pads(H, 4, 2)
+  wo, pl, _ = nets.same_pads(W, 4, 2)
+  gs = gate[..., 8:]
+  scale = torch.where(torch.arange(cout) < split, torch.tensor(2.0), torch.tensor(0.5))
+  xd, kd, gd = x.cuda(), k.cuda(), gate.cuda()     # (kept alive: the epilogue holds raw pointers)
+  for act, neg in ((N.ACT_RELU, 0.0), (N.ACT_LRELU, 0.2)):
+    want = ref * torch.where(gs > 0, torch.tensor(1.0), torch.tensor(neg)) * scale
+    L = nets._Conv('t', 'conv', nets._desc(B, H, W, 1, cout, 2, 2, pt, pl, ho, wo, N.MATH_AUTO))
+    y = torch.full((B, ho, wo, cout + 16), float('nan'), device='cuda')
+    ep = nets._epilogue(None, y, cout + 16, 16, N.ACT_NONE, gate=gd, ld_gate=cout + 8, coff_gate=8,
+                        gate_act=act, gate_split=split, gate_scale0=2.0, gate_scale1=0.5)
+    L.run(xd, 1, kd, ep)
+    torch.cuda.synchronize()
+    assert N.debug_flags() == 0
+    assert _rel(y[..., 16:], want) < 2e-6
+    assert torch.isnan(y[..., :16]).all()
+
+
+@pytest.mark.parametrize('cin', [64, 256, 512])
+def test_transposed_conv_from_one_channel_on_tensor_cores(cin):
+  """Input gradient of the PatchGAN head (k4 s1, pad 1 + VALID, Cin -> 1): a stride-1 transposed conv from one
+  channel, gated by lrelu' of the stored layer_4 activation; checked against autograd of the oracle's conv."""
+  from advoc_b200 import _native as N
+  from advoc_b200 import nets
+  from oracle import nets_torch as O
+  g = torch.Generator().manual_seed(cin)
+  B, H, W = 2, 13, 21
+  a = torch.randn(B, H, W, cin, generator=g)                 # stored (post-lrelu) activation of layer_4
+  k = torch.randn(4, 4, cin, 1, generator=g) * 0.05
+  xin = a.clone().requires_grad_(True)
+  out = O.discrim_conv(xin, k, torch.zeros(1), 1)
+  ho, wo = H + 2 - 4 + 1, W + 2 - 4 + 1
+  assert tuple(out.shape) == (B, ho, wo, 1)
+  dy = torch.randn(B, ho, wo, 1, generator=g)
+  out.backward(dy)
+  want = xin.grad * torch.where(a > 0, torch.tensor(1.0), torch.tensor(0.2))
+  L = nets._Conv('t', 'deconv', nets._desc(B, H, W, cin, 1, 1, 1, 1, 1, ho, wo, N.MATH_AUTO))
+  y = torch.full((B, H, W, cin), float('nan'), device='cuda')
+  ad, dyd, kd = a.cuda(), dy.cuda(), k.cuda()      # (kept alive: the epilogue holds raw pointers)
+  ep = nets._epilogue(None, y, cin, 0, N.ACT_NONE, gate=ad, ld_gate=cin, gate_act=N.ACT_LRELU, round_tf32=0)
+  L.run(dyd, 1, kd, ep)
+  torch.cuda.synchronize()
+  assert N.debug_flags() == 0
+  assert _rel(y, want) < 2e-6
