@@ -10,6 +10,9 @@ int check_conv_desc(const advoc_conv_desc* d);
 bool wgrad_tc_eligible(const advoc_conv_desc* d, const float* big, int ld_big, const float* small, int ld_small);
 int wgrad_tc(const advoc_conv_desc* d, const float* big, int ld_big, const float* small, int ld_small, float* dw,
              void* stream);
+bool wgrad_thin_tc_eligible(const advoc_conv_desc* d, const float* big, int ld_big, const float* small, int ld_small);
+int wgrad_thin_tc(const advoc_conv_desc* d, const float* big, int ld_big, const float* small, int ld_small, float* dw,
+                  void* stream);
 int lower_epilogue(const advoc_epilogue* ep, int Hs, int Wfull, int Cout, EpiDev* out);
 
 namespace {
@@ -494,6 +497,8 @@ extern "C" int advoc_conv2d_wgrad(const advoc_conv_desc* d, const float* d_big, 
   if (M == 0) return ADVOC_OK;
   if (wgrad_tc_eligible(d, d_big, ld_big, d_small, ld_small))
     return wgrad_tc(d, d_big, ld_big, d_small, ld_small, d_dw, stream);
+  if (wgrad_thin_tc_eligible(d, d_big, ld_big, d_small, ld_small))
+    return wgrad_thin_tc(d, d_big, ld_big, d_small, ld_small, d_dw, stream);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const bool k4 = d->kh == 4 && d->kw == 4;
   if (d->kh == 5 && d->kw == 5 && d->Cin == 1 && d->Cout == 64 && d->sw <= 2 && ld_small % 4 == 0 && aligned16(d_small)) {

@@ -23,6 +23,7 @@
 namespace advoc {
 
 int check_conv_desc(const advoc_conv_desc* d);
+float* wgrad_workspace(size_t bytes, cudaStream_t st);   // shared with wgrad_thin_tc.cu
 
 namespace {
 
@@ -252,6 +253,8 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
   }
 }
 
+}  // namespace
+
 // Grow-only workspace for the split partials (one stream at a time uses the library's wgrad; the
 // partials of a launch are consumed by the reduce kernel queued right behind it).  Cannot grow while
 // the stream is being captured into a CUDA graph: the caller's eager warm-up pass sizes it.
@@ -272,8 +275,6 @@ float* wgrad_workspace(size_t bytes, cudaStream_t st) {
   buf = nb; cap = want;
   return buf;
 }
-
-}  // namespace
 
 bool wgrad_tc_eligible(const advoc_conv_desc* d, const float* big, int ld_big, const float* small, int ld_small) {
   const int cbb = (d->Cin + 31) / 32;

@@ -377,6 +377,10 @@ class Discriminator(object):
     self.Wp = {L.name: _pack_for_tc(L, self.P[L.name + '/kernel'], self.chans[i], old.get(L.name))
                for i, L in enumerate(self.layers)}
     self.round = [int(i + 1 < 5 and self.Wp[self.layers[i + 1].name] is not None) for i in range(5)]
+    # layer_4's activation is the TMA-fed tensor-core operand of the head's filter gradient
+    # (csrc/wgrad_thin_tc.cu), which would otherwise TRUNCATE it to tf32
+    if self.layers[4].desc.math != N.MATH_FP32 and self.round[2]:
+      self.round[3] = 1
     return self
 
   def _w(self, L):

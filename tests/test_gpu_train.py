@@ -262,3 +262,67 @@ def test_two_rank_nccl_train_loop_matches_accumulated_gradients(tmp_path, overla
   upd_got, upd_want = got[0]['p'] - p0, f.p.cpu() - p0
   assert _rel(got[0]['g'][lo:hi], acc[lo:hi].cpu()) < 1e-4      # all-reduced G gradients = the accumulated sum
   assert _rel(upd_got, upd_want) < 1e-2
+
+
+@pytest.mark.parametrize('cin,cout', [(1, 32), (1, 64), (1, 128), (1, 256), (2, 32), (2, 64), (2, 128)])
+def test_thin_filter_gradients_on_tensor_cores(cin, cout):
+  """wgrad_thin_tc_kernel (MODE 0 / 1): filter gradient of a conv from one / two input channels against torch's
+  conv2d weight gradient.  The thin side enters as hi + lo tf32 parts; the wide side is read by TMA and
+  truncated to tf32 by the tensor core, so with a tf32-representable dy the result is fp32-accurate.  Also
+  checks += semantics and run-to-run determinism."""
+  import ctypes as C
+  import torch.nn.functional as F
+  from advoc_b200 import _native as N
+  from advoc_b200.nets import _ptr, _stream
+  g = torch.Generator().manual_seed(cin * 1000 + cout)
+  B, H, W = 3, 52, 75
+  ho, wo = (H + 1 + 1 - 4) // 2 + 1, (W + 1 + 2 - 4) // 2 + 1
+  x = torch.randn(B, H, W, cin, generator=g)
+  dy = torch.randn(B, ho, wo, cout + 8, generator=g)
+  dy = (dy.view(torch.int32) & ~0x1FFF).view(torch.float32)        # tf32-representable
+  w = torch.zeros(4, 4, cin, cout, requires_grad=True)
+  xt = F.pad(x.permute(0, 3, 1, 2), (1, 2, 1, 2))
+  y = F.conv2d(xt.double(), w.double().permute(3, 2, 0, 1), stride=2)[:, :, :ho, :wo]
+  (ref,) = torch.autograd.grad(y, w, dy[..., 8:].double().permute(0, 3, 1, 2))
+  d = N.ConvDesc(B, H, W, cin, cout, 4, 4, 2, 2, 1, 1, ho, wo, N.MATH_AUTO)
+  xd, dyd = x.cuda().contiguous(), dy.cuda().contiguous()
+  base = torch.randn(4, 4, cin, cout, generator=g)
+  outs = []
+  for _ in range(2):
+    dw = base.cuda().clone()
+    n0 = N.launch_count()
+    N.call('advoc_conv2d_wgrad', C.byref(d), _ptr(xd), cin, _ptr(dyd[..., 8:]), cout + 8, _ptr(dw), _stream())
+    assert N.launch_count() - n0 == 2          # tensor-core kernel + ordered reduction of the partials
+    torch.cuda.synchronize()
+    assert N.debug_flags() == 0
+    outs.append(dw.cpu())
+  assert torch.equal(outs[0], outs[1])
+  assert _rel(outs[0] - base, ref.float()) < 1e-5
+
+
+@pytest.mark.parametrize('cin', [64, 256, 512])
+def test_to_one_channel_filter_gradient_on_tensor_cores(cin):
+  """wgrad_thin_tc_kernel MODE 2: filter gradient of the PatchGAN head (k4 s1 pad 1 VALID, Cin -> 1)."""
+  import ctypes as C
+  import torch.nn.functional as F
+  from advoc_b200 import _native as N
+  from advoc_b200.nets import _ptr, _stream
+  g = torch.Generator().manual_seed(cin)
+  B, H, W = 3, 19, 37
+  ho, wo = H + 2 - 4 + 1, W + 2 - 4 + 1
+  x = torch.randn(B, H, W, cin, generator=g)
+  x = (x.view(torch.int32) & ~0x1FFF).view(torch.float32)           # tf32-representable wide side
+  dy = torch.randn(B, ho, wo, 1, generator=g)
+  w = torch.zeros(1, cin, 4, 4, dtype=torch.float64, requires_grad=True)
+  y = F.conv2d(x.double().permute(0, 3, 1, 2).contiguous(), w, stride=1, padding=1)
+  (ref,) = torch.autograd.grad(y, w, dy.double().permute(0, 3, 1, 2).contiguous())
+  ref = ref.permute(2, 3, 1, 0)              # OIHW -> HWIO
+  d = N.ConvDesc(B, H, W, cin, 1, 4, 4, 1, 1, 1, 1, ho, wo, N.MATH_AUTO)
+  xd, dyd = x.cuda().contiguous(), dy.cuda().contiguous()
+  dw = torch.zeros(4, 4, cin, 1, device='cuda')
+  n0 = N.launch_count()
+  N.call('advoc_conv2d_wgrad', C.byref(d), _ptr(xd), cin, _ptr(dyd), 1, _ptr(dw), _stream())
+  assert N.launch_count() - n0 == 2
+  torch.cuda.synchronize()
+  assert N.debug_flags() == 0
+  assert _rel(dw, ref.float()) < 1e-5
