@@ -23,6 +23,8 @@
 
 namespace advoc {
 
+float* wgrad_workspace(size_t bytes, cudaStream_t st);   // wgrad_tc.cu: grow-only library workspace (one stream)
+
 namespace {
 
 using namespace tc;
@@ -47,7 +49,14 @@ struct alignas(64) TcParams {
   int osh, osw;        // output position stride (1 for conv, s for transposed conv)
   int Cn;              // produced channels (rows of B per tap)
   int kblocks;         // contraction channels / channels per 128-byte row (32 tf32, 64 fp16)
-  long total_tiles;    // M tiles (of the largest class) x classes x N tiles
+  long total_tiles;    // M tiles (of the largest class) x classes x N tiles x K splits
+  // split-K (round 2: the bottleneck layers of the regular model have 8-96 output tiles for 296 CTA slots and
+  // stream a 4-17 MB filter through them): every tile's tap / channel-block loop is cut into `ksplit` equal
+  // ranges run by different CTAs; each stores its raw fp32 accumulator to ws[split][stored pixel][channel] and
+  // splitk_finalize_kernel adds the splits in order and applies the epilogue.  1 = off.
+  int ksplit;
+  float* ws;
+  long ws_stride;
   EpiDev epi;
   unsigned int* dbg;   // [0] != 0 after a barrier wait timed out
 };
@@ -72,7 +81,7 @@ struct SmemLayout {
 // Tile order: N tile fastest, then parity class, then M tile, so that the CTAs running at the same
 // time share their A tiles through L2.
 struct TcTile {
-  int n0, cls, iters;
+  int n0, cls, iters, it0, ks;
   long m0;
   bool valid;
 };
@@ -80,14 +89,21 @@ struct TcTile {
 template <int BN>
 __device__ __forceinline__ TcTile tc_decode(const TcParams& p, long t, int n_ntiles) {
   TcTile x;
+  unsigned tt = (unsigned)t;                        // total tiles < 2^31 (checked on the host)
+  x.ks = 0;
+  if (p.ksplit > 1) {                               // K split fastest: the CTAs of one tile share its A tiles in L2
+    x.ks = (int)(tt % (unsigned)p.ksplit);
+    tt /= (unsigned)p.ksplit;
+  }
   const unsigned per_m = (unsigned)(n_ntiles * p.nclasses);
-  const unsigned m_tile = (unsigned)t / per_m;      // total tiles < 2^31 (checked on the host)
-  const unsigned rem = (unsigned)t - m_tile * per_m;
+  const unsigned m_tile = tt / per_m;
+  const unsigned rem = tt - m_tile * per_m;
   x.cls = (int)(rem / (unsigned)n_ntiles);
   x.n0 = (int)(rem - (unsigned)x.cls * (unsigned)n_ntiles) * BN;
   x.m0 = (long)m_tile * BM;
   x.valid = x.m0 < (long)p.Nimg * p.Ah[x.cls] * p.Aw[x.cls];   // small classes have fewer M tiles
-  x.iters = p.ntaps[x.cls] * p.kblocks;
+  x.iters = p.ntaps[x.cls] * p.kblocks / p.ksplit;   // ksplit divides every class's loop (host)
+  x.it0 = x.ks * x.iters;
   return x;
 }
 
@@ -155,7 +171,7 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
       const int img = (int)(r / Ah);
       const int cw = a_w * p.trav_w + p.base_w[cls];
       const int ch = a_h * p.trav_h + p.base_h[cls];
-      int tap = 0, kb = 0;
+      int tap = tl.it0 / p.kblocks, kb = tl.it0 - tap * p.kblocks;
       for (int it = 0; it < tl.iters; ++it) {
         mbar_wait(&empty_bar[stage], phase ^ 1u, p.dbg, 1u);
         uint8_t* a_dst = ring_ptr + stage * L::STAGE_BYTES;
@@ -240,7 +256,13 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)BN + (uint32_t)c0, v);
         tmem_ld_wait();
-        if (valid) {
+        if (valid && p.ksplit > 1) {
+          float4* dst = reinterpret_cast<float4*>(p.ws + (size_t)tl.ks * p.ws_stride + pix * p.Cn + tl.n0 + c0);
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            dst[j >> 2] = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                      __uint_as_float(v[j + 3]));
+        } else if (valid) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             epi_store_vec4(p.epi, pix, tl.n0 + c0 + j,
@@ -263,6 +285,23 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS)
                  : "memory");
+  }
+}
+
+// sum of the K splits (in split order: deterministic) + the layer's epilogue, four channels per thread
+__global__ void __launch_bounds__(256) splitk_finalize_kernel(const float* __restrict__ ws, long ws_stride, int ksplit,
+                                                              long npix, int Cn, const EpiDev e) {
+  const int quads = Cn >> 2;
+  const long total = npix * quads;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long pix = i / quads;
+    const int n = (int)(i - pix * quads) << 2;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < ksplit; ++s) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(ws + (size_t)s * ws_stride + (size_t)pix * Cn + n));
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    epi_store_vec4(e, (size_t)pix, n, acc);
   }
 }
 
@@ -296,18 +335,49 @@ int launch(const TcParams& p, int nclasses, long max_tiles, cudaStream_t st) {
                                           smem));
     configured = true;
   }
-  const long tiles = max_tiles * (p.Cn / BN) * nclasses;
+  long tiles = max_tiles * (p.Cn / BN) * nclasses;
   ADVOC_REQUIRE(tiles < 2147483647L, ADVOC_BAD_SHAPE, "too many output tiles");
   TcParams q = p;
-  q.total_tiles = tiles;
   // persistent: as many CTAs as fit on the chip at once (two per SM while two rings and two pairs of
   // accumulators fit: 2 x smem <= 227 KB and 2 x 2 x BN <= 512 TMEM columns)
   const int per_sm = (2 * smem <= 220 * 1024 && 4 * BN <= 512) ? 2 : 1;
   const long slots = (long)sm_count() * per_sm;
+  // split-K when the layer cannot fill half of the slots: the largest power of two that divides every class's
+  // loop, leaves >= 8 ring iterations per split and keeps tiles x splits within the slots
+  q.ksplit = 1;
+  static const bool no_split = getenv("ADVOC_TC_NO_SPLITK") != nullptr;   // A/B switch
+  const long npix = (long)p.Nimg * p.epi.Hs * p.epi.Ws;
+  if (!no_split && tiles * 2 <= slots) {
+    int ks = 1;
+    for (;;) {
+      const int next = ks * 2;
+      bool ok = tiles * next <= slots && (size_t)next * npix * p.Cn * sizeof(float) <= ((size_t)48 << 20);
+      for (int c = 0; c < nclasses && ok; ++c) {
+        const int total = p.ntaps[c] * p.kblocks;
+        ok = total % next == 0 && total / next >= 8;
+      }
+      if (!ok) break;
+      ks = next;
+    }
+    if (ks > 1) {
+      q.ws = wgrad_workspace((size_t)ks * npix * p.Cn * sizeof(float), st);
+      if (q.ws) { q.ksplit = ks; q.ws_stride = npix * p.Cn; }
+    }
+  }
+  tiles *= q.ksplit;
+  q.total_tiles = tiles;
   dim3 grid((unsigned)(tiles < slots ? tiles : slots), 1, 1);
   conv_tc_kernel<BN, STAGES, HALF><<<grid, NUM_THREADS, smem, st>>>(q);
   count_launch();
   ADVOC_CHECK_CUDA(cudaGetLastError());
+  if (q.ksplit > 1) {
+    const long work = npix * (p.Cn / 4);
+    const long blocks = (work + 255) / 256;
+    splitk_finalize_kernel<<<(unsigned)(blocks < 4L * sm_count() ? blocks : 4L * sm_count()), 256, 0, st>>>(
+        q.ws, q.ws_stride, q.ksplit, npix, p.Cn, p.epi);
+    count_launch();
+    ADVOC_CHECK_CUDA(cudaGetLastError());
+  }
   return ADVOC_OK;
 }
 

@@ -512,3 +512,59 @@ def test_transposed_conv_from_one_channel_on_tensor_cores(cin):
   torch.cuda.synchronize()
   assert N.debug_flags() == 0
   assert _rel(y, want) < 2e-6
+
+
+@pytest.mark.parametrize('math', ['auto', 'f16'])
+def test_bottleneck_layers_split_k(math):
+  """The regular model's bottleneck geometry (a handful of output tiles, 512-channel filters) on the per-tap
+  kernel with its tap / channel loop split over CTAs: partial accumulators to the workspace, then
+  splitk_finalize_kernel = ordered sum + the layer's epilogue (bias, activation, dual write, crop)."""
+  from advoc_b200 import _native as N
+  from advoc_b200 import nets
+  from oracle import nets_torch as O
+  half = math == 'f16'
+  m = N.MATH_F16 if half else N.MATH_AUTO
+  q = (lambda t: t.half().float()) if half else _tf32
+  adt = torch.float16 if half else torch.float32
+  g = torch.Generator().manual_seed(3)
+  B, H, W, Cin, Cout = 4, 2, 5, 512, 256
+  x = q(torch.randn(B, H, W, Cin, generator=g))       # exactly representable operands
+  k = torch.randn(4, 4, Cin, Cout, generator=g) * 0.02
+  b = torch.randn(Cout, generator=g) * 0.1
+  ref = O.conv_same(q(x), q(k), b, (2, 2))
+  ho, pt, _ = nets.same_pads(H, 4, 2)
+  wo, pl, _ = nets.same_pads(W, 4, 2)
+  L = nets._Conv('t', 'conv', nets._desc(B, H, W, Cin, Cout, 2, 2, pt, pl, ho, wo, m))
+  L.ldx = Cin
+  assert L.kernel_family().startswith('conv_tc')
+  y0 = torch.full((B, ho, wo, Cout), float('nan'), device='cuda', dtype=adt)
+  cat = torch.full((B, ho, wo, Cout + 64), float('nan'), device='cuda', dtype=adt)
+  bd, xd, kd = b.cuda(), x.cuda().to(adt), k.cuda()
+  wp = nets._pack_for_tc(L, kd, Cin)
+  ep = nets._epilogue(bd, y0, Cout, 0, N.ACT_LRELU, cat, Cout + 64, 64, N.ACT_RELU)
+  n0 = N.launch_count()
+  L.run(xd, Cin, wp, ep)
+  assert N.launch_count() - n0 == 2            # split-K kernel + finalize
+  torch.cuda.synchronize()
+  assert N.debug_flags() == 0
+  assert _rel(y0.float(), O.lrelu(ref)) < TOL
+  assert _rel(cat[..., 64:].float(), torch.relu(ref)) < TOL
+  assert torch.isnan(cat[..., :64].float()).all()
+  # transposed, cropped: decoder_8-like
+  H, W, Cin, Cout = 1, 3, 512, 256
+  x = q(torch.relu(torch.randn(B, H, W, Cin, generator=g)))
+  k = torch.randn(4, 4, Cout, Cin, generator=g) * 0.02
+  ref = torch.relu(O.deconv_same(q(x), q(k), b, (2, 2)))[:, :, :-1, :]
+  out = torch.full((B, 2 * H, 2 * W - 1, Cout + 32), float('nan'), device='cuda', dtype=adt)
+  L = nets._Conv('t', 'deconv', nets._desc(B, 2 * H, 2 * W, Cout, Cin, 2, 2, 1, 1, H, W, m))
+  L.ldx = Cin
+  assert L.kernel_family().startswith('conv_tc')
+  xd, kd = x.cuda().to(adt), k.cuda()
+  ep = nets._epilogue(bd, out, Cout + 32, 0, N.ACT_RELU, store_w=2 * W - 1)
+  n0 = N.launch_count()
+  L.run(xd, Cin, nets._pack_for_tc(L, kd, Cin), ep)
+  assert N.launch_count() - n0 == 2
+  torch.cuda.synchronize()
+  assert N.debug_flags() == 0
+  assert _rel(out[..., :Cout].float(), ref) < TOL
+  assert torch.isnan(out[..., Cout:].float()).all()
