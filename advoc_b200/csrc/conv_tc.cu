@@ -568,6 +568,115 @@ int conv_transposed_tc(const advoc_conv_desc* d, const void* x, int ldx, const v
   return run(p, nc, g, stream, half);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Convolution TO ONE channel (PatchGAN head, advoc_model.py:196-199) as a tensor-core GEMM + a gather:
+//   T[q][tap] = sum_c x[q][c] w[tap][c]        1x1 "convolution" to 32 channels on conv_tc_kernel (taps 0..15
+//                                               are the filter taps, the other rows of the packed filter are 0)
+//   y[p] = act(bias + sum_taps T[p s - pad + tap][tap])
+// The CUDA-core kernel it replaces (train.cu: conv_to_one_kernel, one warp per output pixel) re-reads every
+// input pixel once per tap through L2: 166 us for the 128 MB input of the regular model's head at B = 32.
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+__global__ void __launch_bounds__(256) pack_to_one_filter_kernel(const float* __restrict__ w, float* __restrict__ wq,
+                                                                 int taps, int Cin) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 32 * Cin) return;
+  const int n = i / Cin;
+  wq[i] = n < taps ? round_tf32(__ldg(w + i)) : 0.f;
+}
+
+struct GatherArgs {
+  const float* T;   // [N, H, W, 32]
+  int N, H, W, Ho, Wo, kh, kw, sh, sw, pt, pl;
+  EpiDev epi;
+};
+
+__global__ void __launch_bounds__(256) taps_gather_to_one_kernel(const GatherArgs a) {
+  const long npix = (long)a.N * a.Ho * a.Wo;
+  for (long pix = (long)blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += (long)gridDim.x * blockDim.x) {
+    const int ow = (int)(pix % a.Wo);
+    const long r = pix / a.Wo;
+    const int oh = (int)(r % a.Ho);
+    const long img = r / a.Ho;
+    float acc = 0.f;
+    for (int kh = 0; kh < a.kh; ++kh) {
+      const int ih = oh * a.sh - a.pt + kh;
+      if (ih < 0 || ih >= a.H) continue;
+      for (int kw = 0; kw < a.kw; ++kw) {
+        const int iw = ow * a.sw - a.pl + kw;
+        if (iw < 0 || iw >= a.W) continue;
+        acc += __ldg(a.T + (((size_t)img * a.H + ih) * a.W + iw) * 32 + kh * a.kw + kw);
+      }
+    }
+    epi_store(a.epi, (size_t)pix, 0, acc);
+  }
+}
+
+// grow-only scratch (T and the packed filter); cannot grow during a graph capture: the eager warm-up pass sizes it
+float* to_one_scratch(size_t bytes, cudaStream_t st) {
+  static float* buf = nullptr;
+  static size_t cap = 0;
+  if (bytes <= cap) return buf;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  float* nb = nullptr;
+  const size_t want = bytes + (bytes >> 2);
+  cudaDeviceSynchronize();
+  if (cudaMalloc(&nb, want) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (buf) cudaFree(buf);
+  buf = nb; cap = want;
+  return buf;
+}
+
+}  // namespace
+
+bool conv_to_one_tc_eligible(const advoc_conv_desc* d, const void* x, int ldx, const void* w, const advoc_epilogue* ep) {
+  static const bool disabled = getenv("ADVOC_NO_TO_ONE_TC") != nullptr;   // A/B switch
+  return !disabled && d->math != ADVOC_MATH_FP32 && d->math != ADVOC_MATH_F16 && d->Cout == 1 && d->kh * d->kw <= 32 &&
+         common_eligible(d->Cin, 32, ldx, 0) && aligned16(x) && aligned16(w) && ep && ep->d_out0 && !ep->d_out1 &&
+         !ep->d_gate && ep->keep_prob >= 1.f && ep->store_w == 0 && ep->out0_dtype == ADVOC_DT_F32 &&
+         ep->out0_row_pad == 0 && (long)d->N * d->H * d->W < 2147483647L / 32;
+}
+
+// returns ADVOC_UNSUPPORTED (without an error message) when the scratch cannot be grown right now: the
+// caller then takes the CUDA-core kernel
+int conv_to_one_tc(const advoc_conv_desc* d, const float* x, int ldx, const float* w, const advoc_epilogue* ep,
+                   void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const long pin = (long)d->N * d->H * d->W;
+  if (pin == 0 || (long)d->N * d->Ho * d->Wo == 0) return ADVOC_OK;
+  const size_t t_floats = (size_t)pin * 32, w_floats = (size_t)32 * d->Cin;
+  float* scratch = to_one_scratch((t_floats + w_floats) * sizeof(float), st);
+  if (!scratch) return ADVOC_UNSUPPORTED;
+  float* T = scratch;
+  float* wq = scratch + t_floats;
+  pack_to_one_filter_kernel<<<(32 * d->Cin + 255) / 256, 256, 0, st>>>(w, wq, d->kh * d->kw, d->Cin);
+  count_launch();
+  ADVOC_CHECK_CUDA(cudaGetLastError());
+  advoc_conv_desc d1 = *d;
+  d1.Cout = 32; d1.kh = 1; d1.kw = 1; d1.sh = 1; d1.sw = 1; d1.pad_t = 0; d1.pad_l = 0; d1.Ho = d->H; d1.Wo = d->W;
+  advoc_epilogue e1 = {};
+  e1.d_out0 = T; e1.ld0 = 32; e1.alpha = 0.f; e1.keep_prob = 1.f;
+  e1.gate_scale0 = e1.gate_scale1 = 1.f;
+  int rc = conv_fwd_tc(&d1, x, ldx, wq, &e1, stream);
+  if (rc) return rc;
+  GatherArgs g = {};
+  rc = lower_epilogue(ep, d->Ho, d->Wo, 1, &g.epi);
+  if (rc) return rc;
+  g.T = T; g.N = d->N; g.H = d->H; g.W = d->W; g.Ho = d->Ho; g.Wo = d->Wo; g.kh = d->kh; g.kw = d->kw;
+  g.sh = d->sh; g.sw = d->sw; g.pt = d->pad_t; g.pl = d->pad_l;
+  const long npix = (long)d->N * d->Ho * d->Wo;
+  const long blocks = (npix + 255) / 256;
+  taps_gather_to_one_kernel<<<(unsigned)(blocks < 8L * sm_count() ? blocks : 8L * sm_count()), 256, 0, st>>>(g);
+  count_launch();
+  ADVOC_CHECK_CUDA(cudaGetLastError());
+  return ADVOC_OK;
+}
+
 }  // namespace advoc
 
 extern "C" int advoc_debug_flags(unsigned int* out) {

@@ -301,6 +301,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ d
     const int cg = threadIdx.x % groups;
     if ((int)(threadIdx.x / groups) < ppb) {
       float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
       for (long p = (long)blockIdx.x * ppb + threadIdx.x / groups; p < pixels; p += (long)gridDim.x * ppb) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(dy + (size_t)p * ld + cg * 4));
         s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;

@@ -561,10 +561,38 @@ def test_bottleneck_layers_split_k(math):
   assert L.kernel_family().startswith('conv_tc')
   xd, kd = x.cuda().to(adt), k.cuda()
   ep = nets._epilogue(bd, out, Cout + 32, 0, N.ACT_RELU, store_w=2 * W - 1)
+  wp = nets._pack_for_tc(L, kd, Cin)
   n0 = N.launch_count()
-  L.run(xd, Cin, nets._pack_for_tc(L, kd, Cin), ep)
+  L.run(xd, Cin, wp, ep)
   assert N.launch_count() - n0 == 2
   torch.cuda.synchronize()
   assert N.debug_flags() == 0
   assert _rel(out[..., :Cout].float(), ref) < TOL
   assert torch.isnan(out[..., Cout:].float()).all()
+
+
+@pytest.mark.parametrize('cin', [256, 512])
+def test_conv_to_one_channel_on_tensor_cores(cin):
+  """PatchGAN head (k4 s1, pad 1 + VALID, Cin -> 1, bias + sigmoid) as a 1x1 tensor-core convolution to the 16
+  tap sums per input pixel + a gather (conv_tc.cu: conv_to_one_tc), fp32-accurate on
+  tf32-representable operands."""
+  from advoc_b200 import _native as N
+  from advoc_b200 import nets
+  from oracle import nets_torch as O
+  g = torch.Generator().manual_seed(cin + 1)
+  B, H, W = 3, 13, 21
+  x = _tf32(torch.randn(B, H, W, cin, generator=g))
+  k = _tf32(torch.randn(4, 4, cin, 1, generator=g) * 0.05)
+  b = torch.randn(1, generator=g) * 0.1
+  ref = torch.sigmoid(O.discrim_conv(x, k, b, 1))
+  ho, wo = H + 2 - 4 + 1, W + 2 - 4 + 1
+  L = nets._Conv('t', 'conv', nets._desc(B, H, W, cin, 1, 1, 1, 1, 1, ho, wo, N.MATH_AUTO))
+  xd, kd, bd = x.cuda(), k.cuda(), b.cuda()
+  y = torch.full((B, ho, wo, 1), float('nan'), device='cuda')
+  for _ in range(2):                  # the second call reuses the scratch
+    n0 = N.launch_count()
+    L.run(xd, cin, kd, nets._epilogue(bd, y, 1, 0, N.ACT_SIGMOID))
+    assert N.launch_count() - n0 in (3, 4)     # pack, 1x1 conv (+ split-K finalize at this tiny size), gather
+    torch.cuda.synchronize()
+    assert N.debug_flags() == 0
+    assert _rel(y, ref) < 1e-5
