@@ -200,8 +200,9 @@ extern "C" int advoc_conv2d_path(const advoc_conv_desc* d, int ld_x, int transpo
 extern "C" int advoc_conv2d_kernel(const advoc_conv_desc* d, int ld_x, int transposed, int store_w) {
   // the one-input-channel forward conv runs on the tensor cores with fp32-exact (3 x tf32) products; it keeps
   // the TF-layout filter, so advoc_conv2d_path still reports ADVOC_MATH_FP32 for it (no packed copy)
-  if (d && !transposed && d->math != ADVOC_MATH_FP32 && d->math != ADVOC_MATH_F16 && (d->Cin == 1 || d->Cin == 2) &&
-      d->kh == 4 && d->kw == 4 && (d->Cout == 32 || d->Cout == 64 || d->Cout % 128 == 0) && device_arch() == 100 &&
+  if (d && !transposed && d->math != ADVOC_MATH_FP32 && d->math != ADVOC_MATH_F16 &&
+      ((d->kh == 4 && d->kw == 4 && (d->Cin == 1 || d->Cin == 2)) || (d->kh == 5 && d->kw == 5 && d->Cin == 1)) &&
+      (d->Cout == 32 || d->Cout == 64 || d->Cout % 128 == 0) && device_arch() == 100 &&
       getenv("ADVOC_NO_ONE_IN_TC") == nullptr)
     return 4;
   if (advoc_conv2d_path(d, ld_x, transposed) == ADVOC_MATH_FP32) return 0;

@@ -47,7 +47,7 @@ constexpr int I_THREADS = 288;         // warps 0-3 gather producers, warp 4 MMA
 constexpr uint32_t I_A_BYTES = 128 * 128;
 constexpr uint32_t I_STAGE_BYTES = 128 * 128;   // one staged output chunk: 128 pixels x <= 128 bytes
 
-enum { M_CONV1 = 0, M_CONV2 = 1, M_TRANS1 = 2 };
+enum { M_CONV1 = 0, M_CONV2 = 1, M_TRANS1 = 2, M_CONV1_K5 = 3 };
 
 struct alignas(64) OneInParams {
   CUtensorMap tmO[2];   // output stores, box {CW channels, 16, 8, 1}
@@ -105,8 +105,10 @@ __device__ __forceinline__ void tma_load_4d_(const CUtensorMap* tm, uint64_t* ba
 template <int COUT, int STAGES, int MODE>
 __global__ void __launch_bounds__(I_THREADS, 2) conv_one_in_tc_kernel(const __grid_constant__ OneInParams p) {
   constexpr int CIN = MODE == M_CONV2 ? 2 : 1;
-  constexpr int KV = 16 * CIN;                   // K of the GEMM
-  constexpr uint32_t A_STAGE = (uint32_t)CIN * I_A_BYTES;   // K = 16: [hi | lo] in one tile; K = 32: hi tile, lo tile
+  constexpr int KS = MODE == M_CONV1_K5 ? 5 : 4;            // filter side (5: MelspecGAN conv_0, models/melspecgan/conv2d.py:182-184)
+  constexpr int KREAL = KS * KS * CIN;                      // taps x input channels
+  constexpr int KV = KREAL <= 16 ? 16 : 32;                 // K of the GEMM (25 -> 32: zero rows / columns)
+  constexpr uint32_t A_STAGE = (uint32_t)(KV / 16) * I_A_BYTES;   // K = 16: [hi | lo] in one tile; K = 32: hi tile, lo tile
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[STAGES], a_empty[STAGES], acc_full[2], acc_empty[2], gate_full[2];
   __shared__ uint32_t tmem_base_holder;
@@ -144,7 +146,7 @@ __global__ void __launch_bounds__(I_THREADS, 2) conv_one_in_tc_kernel(const __gr
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int k = KV == 16 ? (((c & 3) << 2) + j) : ((c << 2) + j);
-      const float v = __ldg(p.w + (size_t)k * p.ldw + n0 + n);
+      const float v = k < KREAL ? __ldg(p.w + (size_t)k * p.ldw + n0 + n) : 0.f;
       hi[j] = round_tf32(v);
       lo[j] = round_tf32(v - hi[j]);
     }
@@ -182,23 +184,23 @@ __global__ void __launch_bounds__(I_THREADS, 2) conv_one_in_tc_kernel(const __gr
       const int iw0 = MODE == M_TRANS1 ? ow + p.pl : ow * p.sw - p.pl;
       constexpr int DIR = MODE == M_TRANS1 ? -1 : 1;
       const float* x00 = p.x + ((size_t)tl.img * p.H * p.W + (long)ih0 * p.W + iw0) * p.ldx;
-      bool cok[4];
+      bool cok[KS];
 #pragma unroll
-      for (int kw = 0; kw < 4; ++kw) cok[kw] = (unsigned)(iw0 + DIR * kw) < (unsigned)p.W;
+      for (int kw = 0; kw < KS; ++kw) cok[kw] = (unsigned)(iw0 + DIR * kw) < (unsigned)p.W;
       const long rstride = (long)p.W * p.ldx;
 #pragma unroll
-      for (int kh = 0; kh < 4; ++kh) {
+      for (int kh = 0; kh < KS; ++kh) {
         const bool rok = (unsigned)(ih0 + DIR * kh) < (unsigned)p.H;
         const float* xr = x00 + DIR * kh * rstride;
 #pragma unroll
-        for (int kw = 0; kw < 4; ++kw) {
+        for (int kw = 0; kw < KS; ++kw) {
           if (rok && cok[kw]) {
             if (CIN == 1) {
-              v[kh * 4 + kw] = __ldg(xr + DIR * kw * p.ldx);
+              v[kh * KS + kw] = __ldg(xr + DIR * kw * p.ldx);
             } else {                        // two channels of a pixel: one 8-byte load (ldx even, x 8-byte aligned)
               const float2 xv = __ldg(reinterpret_cast<const float2*>(xr + kw * p.ldx));
-              v[(kh * 4 + kw) * CIN] = xv.x;
-              v[(kh * 4 + kw) * CIN + CIN - 1] = xv.y;
+              v[(kh * KS + kw) * CIN] = xv.x;
+              v[(kh * KS + kw) * CIN + CIN - 1] = xv.y;
             }
           }
         }
@@ -399,9 +401,9 @@ __global__ void __launch_bounds__(I_THREADS, 2) conv_one_in_tc_kernel(const __gr
 
 template <int COUT, int STAGES, int MODE>
 int launch_one_in(const OneInParams& p, int chunks, cudaStream_t st) {
-  constexpr int CIN = MODE == M_CONV2 ? 2 : 1;
-  constexpr int max_smem = STAGES * CIN * (int)I_A_BYTES + 2 * COUT * 128 + 2 * (int)I_STAGE_BYTES + 1024;
-  const int smem = STAGES * CIN * (int)I_A_BYTES + 2 * COUT * 128 + (p.has_gate ? 2 : p.n_out) * (int)I_STAGE_BYTES + 1024;
+  constexpr int ATILES = (MODE == M_CONV2 || MODE == M_CONV1_K5) ? 2 : 1;
+  constexpr int max_smem = STAGES * ATILES * (int)I_A_BYTES + 2 * COUT * 128 + 2 * (int)I_STAGE_BYTES + 1024;
+  const int smem = STAGES * ATILES * (int)I_A_BYTES + 2 * COUT * 128 + (p.has_gate ? 2 : p.n_out) * (int)I_STAGE_BYTES + 1024;
   static bool configured = false;
   if (!configured) {
     ADVOC_CHECK_CUDA(cudaFuncSetAttribute(conv_one_in_tc_kernel<COUT, STAGES, MODE>,
@@ -483,6 +485,13 @@ int run_one_in(int mode, int Nimg, int Hin, int Win, int Hp, int Wp, int C, int 
       default: return launch_one_in<128, 2, M_CONV2>(p, chunks, s);
     }
   }
+  if (mode == M_CONV1_K5) {
+    switch (cout) {
+      case 32: return launch_one_in<32, 2, M_CONV1_K5>(p, chunks, s);
+      case 64: return launch_one_in<64, 2, M_CONV1_K5>(p, chunks, s);
+      default: return launch_one_in<128, 2, M_CONV1_K5>(p, chunks, s);
+    }
+  }
   switch (cout) {
     case 32: return launch_one_in<32, 3, M_TRANS1>(p, chunks, s);
     case 64: return launch_one_in<64, 3, M_TRANS1>(p, chunks, s);
@@ -498,15 +507,16 @@ bool channels_fit(int C) { return C == 32 || C == 64 || (C >= 128 && C <= 1024 &
 // outputs) or backward epilogue (gate)
 bool conv_one_in_tc_eligible(const advoc_conv_desc* d, const float* x, int ldx, const float* w,
                              const advoc_epilogue* ep) {
-  return enabled() && d->math != ADVOC_MATH_FP32 && d->math != ADVOC_MATH_F16 && (d->Cin == 1 || d->Cin == 2) &&
-         d->kh == 4 && d->kw == 4 && channels_fit(d->Cout) && x && w && epilogue_fits(ep) &&
+  return enabled() && d->math != ADVOC_MATH_FP32 && d->math != ADVOC_MATH_F16 &&
+         ((d->kh == 4 && d->kw == 4 && (d->Cin == 1 || d->Cin == 2)) || (d->kh == 5 && d->kw == 5 && d->Cin == 1)) &&
+         channels_fit(d->Cout) && x && w && epilogue_fits(ep) &&
          (d->Cin == 1 || (ldx % 2 == 0 && (reinterpret_cast<uintptr_t>(x) & 7u) == 0)) &&
          (long)d->N * ((d->Ho + I_TH - 1) / I_TH) * ((d->Wo + I_TW - 1) / I_TW) < 2147483647L;
 }
 
 int conv_one_in_tc(const advoc_conv_desc* d, const float* x, int ldx, const float* w, const advoc_epilogue* ep,
                    void* stream) {
-  return run_one_in(d->Cin == 2 ? M_CONV2 : M_CONV1, d->N, d->H, d->W, d->Ho, d->Wo, d->Cout, d->sh, d->sw, d->pad_t,
+  return run_one_in(d->kh == 5 ? M_CONV1_K5 : (d->Cin == 2 ? M_CONV2 : M_CONV1), d->N, d->H, d->W, d->Ho, d->Wo, d->Cout, d->sh, d->sw, d->pad_t,
                     d->pad_l, x, ldx, w, ep, stream);
 }
 

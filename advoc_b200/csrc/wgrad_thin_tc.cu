@@ -40,7 +40,7 @@ constexpr int T_THREADS = 160;                  // warps 0-3: gather producers, 
 constexpr uint32_t T_BOX = T_BK * 128;          // one [128 pixels][32 channels] box
 constexpr int T_STAGES = 2;
 
-enum { W_CONV1 = 0, W_CONV2 = 1, W_TOONE = 2 };
+enum { W_CONV1 = 0, W_CONV2 = 1, W_TOONE = 2, W_CONV1_K5 = 3 };   // 3: 5x5 from one channel (MelspecGAN conv_0)
 
 struct alignas(64) ThinWgParams {
   CUtensorMap tmS;      // wide side as a [pixels, channels] matrix
@@ -74,7 +74,9 @@ __device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
 template <int MODE, int CB>
 __global__ void __launch_bounds__(T_THREADS, 1) wgrad_thin_tc_kernel(const __grid_constant__ ThinWgParams p) {
   constexpr int CIN = MODE == W_CONV2 ? 2 : 1;
-  constexpr int KV = 16 * CIN;
+  constexpr int KS = MODE == W_CONV1_K5 ? 5 : 4;
+  constexpr int KREAL = KS * KS * CIN;                      // rows of dW
+  constexpr int KV = KREAL <= 16 ? 16 : 32;                 // 25 -> 32: zero rows
   constexpr int NCOL = 2 * KV;                              // hi rows, lo rows
   constexpr uint32_t A_BYTES = 4 * T_BOX;                   // the MMA always spans 128 lanes (see the header)
   constexpr uint32_t BT_BYTES = NCOL * 128;                 // one warp's K-major tile: NCOL rows x 32 pixels
@@ -129,23 +131,23 @@ __global__ void __launch_bounds__(T_THREADS, 1) wgrad_thin_tc_kernel(const __gri
       const int iw0 = MODE == W_TOONE ? pw + p.pl : pw * p.sw - p.pl;
       constexpr int DIR = MODE == W_TOONE ? -1 : 1;
       const float* x00 = p.thin + ((size_t)img * p.Ht * p.Wt + (long)ih0 * p.Wt + iw0) * p.ldt;
-      bool cok[4];
+      bool cok[KS];
 #pragma unroll
-      for (int kw = 0; kw < 4; ++kw) cok[kw] = (unsigned)(iw0 + DIR * kw) < (unsigned)p.Wt;
+      for (int kw = 0; kw < KS; ++kw) cok[kw] = (unsigned)(iw0 + DIR * kw) < (unsigned)p.Wt;
       const long rstride = (long)p.Wt * p.ldt;
 #pragma unroll
-      for (int kh = 0; kh < 4; ++kh) {
+      for (int kh = 0; kh < KS; ++kh) {
         const bool rok = (unsigned)(ih0 + DIR * kh) < (unsigned)p.Ht;
         const float* xr = x00 + DIR * kh * rstride;
 #pragma unroll
-        for (int kw = 0; kw < 4; ++kw) {
+        for (int kw = 0; kw < KS; ++kw) {
           if (rok && cok[kw]) {
             if (CIN == 1) {
-              v[kh * 4 + kw] = __ldg(xr + DIR * kw * p.ldt);
+              v[kh * KS + kw] = __ldg(xr + DIR * kw * p.ldt);
             } else {
               const float2 xv = __ldg(reinterpret_cast<const float2*>(xr + kw * p.ldt));
-              v[(kh * 4 + kw) * CIN] = xv.x;
-              v[(kh * 4 + kw) * CIN + CIN - 1] = xv.y;
+              v[(kh * KS + kw) * CIN] = xv.x;
+              v[(kh * KS + kw) * CIN + CIN - 1] = xv.y;
             }
           }
         }
@@ -189,7 +191,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) wgrad_thin_tc_kernel(const __gri
     }
     // ===== epilogue: channel c = m0 + 32 warp + lane on TMEM lane 32 warp + lane =====
     const int c = m0 + warp * 32 + lane;
-    float* dst = p.ws + (size_t)blockIdx.x * KV * p.C;
+    float* dst = p.ws + (size_t)blockIdx.x * KREAL * p.C;
     if (iters > 0) {
       mbar_wait(&acc_bar, 0u, p.dbg, 63u);
       tc_fence_after();
@@ -205,7 +207,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) wgrad_thin_tc_kernel(const __gri
       }
       if (c < p.C && warp < CB) {
 #pragma unroll
-        for (int j = 0; j < KV; ++j) {
+        for (int j = 0; j < KREAL; ++j) {
           const float lo = KV == 16 ? __uint_as_float(a[(16 + j) & 31]) : __uint_as_float(b[j & 31]);
           dst[(size_t)j * p.C + c] = __uint_as_float(a[j]) + lo;
         }
@@ -267,8 +269,8 @@ __global__ void __launch_bounds__(256) wgrad_thin_reduce_kernel(const float* __r
 
 template <int MODE, int CB>
 int launch_thin_wg(const ThinWgParams& p, int splits, int chunks, float* dw, cudaStream_t st) {
-  constexpr int CIN = MODE == W_CONV2 ? 2 : 1;
-  constexpr int KV = 16 * CIN;
+  constexpr int KREAL = MODE == W_CONV1_K5 ? 25 : (MODE == W_CONV2 ? 32 : 16);
+  constexpr int KV = KREAL <= 16 ? 16 : 32;
   // the A descriptor always spans four boxes: keep what lies behind a narrower stage inside the allocation
   constexpr int smem = T_STAGES * (CB * (int)T_BOX + 4 * 2 * KV * 128) + (4 - CB) * (int)T_BOX + 1024;
   static bool configured = false;
@@ -279,7 +281,7 @@ int launch_thin_wg(const ThinWgParams& p, int splits, int chunks, float* dw, cud
   wgrad_thin_tc_kernel<MODE, CB><<<dim3((unsigned)splits, (unsigned)chunks), T_THREADS, smem, st>>>(p);
   count_launch();
   ADVOC_CHECK_CUDA(cudaGetLastError());
-  const int nelem = KV * p.C;
+  const int nelem = KREAL * p.C;
   wgrad_thin_reduce_kernel<<<(nelem + 31) / 32, 256, 0, st>>>(p.ws, dw, nelem, splits);
   count_launch();
   ADVOC_CHECK_CUDA(cudaGetLastError());
@@ -294,9 +296,10 @@ bool wide_ok(int C, const float* s, int ld) {
 
 bool wgrad_thin_tc_eligible(const advoc_conv_desc* d, const float* big, int ld_big, const float* small, int ld_small) {
   static const bool disabled = getenv("ADVOC_NO_THIN_WGRAD_TC") != nullptr;   // A/B switch
-  if (disabled || d->math == ADVOC_MATH_FP32 || !tc::tma_ok() || device_arch() != 100 || d->kh != 4 || d->kw != 4)
-    return false;
+  if (disabled || d->math == ADVOC_MATH_FP32 || !tc::tma_ok() || device_arch() != 100) return false;
   if ((long)d->N * d->H * d->W >= 2147483647L) return false;
+  if (d->kh == 5 && d->kw == 5) return d->Cin == 1 && wide_ok(d->Cout, small, ld_small);
+  if (d->kh != 4 || d->kw != 4) return false;
   if (d->Cin == 1 || d->Cin == 2)
     return wide_ok(d->Cout, small, ld_small) &&
            (d->Cin == 1 || (ld_big % 2 == 0 && (reinterpret_cast<uintptr_t>(big) & 7u) == 0));
@@ -307,7 +310,7 @@ int wgrad_thin_tc(const advoc_conv_desc* d, const float* big, int ld_big, const 
                   void* stream) {
   ThinWgParams p = {};
   const bool to_one = d->Cout == 1 && d->Cin > 2;
-  const int mode = to_one ? W_TOONE : (d->Cin == 2 ? W_CONV2 : W_CONV1);
+  const int mode = to_one ? W_TOONE : (d->kh == 5 ? W_CONV1_K5 : (d->Cin == 2 ? W_CONV2 : W_CONV1));
   const float* wide = to_one ? big : small;
   const int ldw = to_one ? ld_big : ld_small;
   p.C = to_one ? d->Cin : d->Cout;
@@ -329,7 +332,7 @@ int wgrad_thin_tc(const advoc_conv_desc* d, const float* big, int ld_big, const 
   p.chunk = ((p.P + splits - 1) / splits + T_BK - 1) / T_BK * T_BK;
   splits = (p.P + p.chunk - 1) / p.chunk;
   cudaStream_t cst = reinterpret_cast<cudaStream_t>(stream);
-  const size_t kv = mode == W_CONV2 ? 32 : 16;
+  const size_t kv = mode == W_CONV2 || mode == W_CONV1_K5 ? 32 : 16;
   p.ws = wgrad_workspace((size_t)splits * kv * p.C * sizeof(float), cst);
   ADVOC_REQUIRE(p.ws != nullptr, ADVOC_CUDA_ERROR, "wgrad workspace unavailable (first call inside a graph capture?)");
   p.dbg = tc::debug_word();
@@ -341,6 +344,7 @@ int wgrad_thin_tc(const advoc_conv_desc* d, const float* big, int ld_big, const 
   }
   if (mode == W_CONV1) { ADVOC_THIN_WG(W_CONV1) }
   if (mode == W_CONV2) { ADVOC_THIN_WG(W_CONV2) }
+  if (mode == W_CONV1_K5) { ADVOC_THIN_WG(W_CONV1_K5) }
   ADVOC_THIN_WG(W_TOONE)
 #undef ADVOC_THIN_WG
 }

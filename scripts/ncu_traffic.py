@@ -28,9 +28,9 @@ n_enc = 5 if model == 'small' else 8
 layers = (['generator/encoder_%d/conv2d' % i for i in range(1, n_enc + 1)] +
           ['generator/decoder_%d/conv2d_transpose' % k for k in range(n_enc, 0, -1)])
 conv = [r for r in body if re.search(r'conv_|deconv_', r[hdr.index('Kernel Name')])]
-# the capture window may start mid-forward: rotate so that it begins at encoder_1 (the thin-input conv)
+# the capture window may start mid-forward: rotate so that it begins at encoder_1 (the one-input-channel conv)
 conv = conv[-len(layers):]          # one whole forward (the last one captured)
-starts = [i for i, r in enumerate(conv) if 'conv_thin' in r[hdr.index('Kernel Name')]]
+starts = [i for i, r in enumerate(conv) if re.search(r'conv_thin|conv_one_in_tc', r[hdr.index('Kernel Name')])]
 if starts:
   conv = conv[starts[0]:] + conv[:starts[0]]
 assert len(conv) == len(layers), (len(conv), len(layers))

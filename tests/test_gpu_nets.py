@@ -596,3 +596,39 @@ def test_conv_to_one_channel_on_tensor_cores(cin):
     torch.cuda.synchronize()
     assert N.debug_flags() == 0
     assert _rel(y, ref) < 1e-5
+
+
+@pytest.mark.parametrize('cout', [64, 128])
+def test_5x5_one_input_channel_conv_on_tensor_cores(cout):
+  """MelspecGAN conv_0's geometry (5x5 s2 SAME from one channel, models/melspecgan/conv2d.py:182-184) on
+  conv_one_in_tc_kernel<.., MODE 3>: 25 taps padded to K = 32; plain forward and the gated epilogue the
+  gradient-penalty up-sweep uses."""
+  import torch.nn.functional as F
+  from advoc_b200 import _native as N
+  from advoc_b200 import nets
+  g = torch.Generator().manual_seed(500 + cout)
+  B, H, W = 3, 28, 41
+  x = torch.randn(B, H, W, 1, generator=g)
+  k = torch.randn(5, 5, 1, cout, generator=g) * 0.05
+  b = torch.randn(cout, generator=g) * 0.1
+  ho, pt, pb = nets.same_pads(H, 5, 2)
+  wo, pl, pr = nets.same_pads(W, 5, 2)
+  xt = F.pad(x.permute(0, 3, 1, 2).double(), (pl, pr, pt, pb))
+  ref = F.conv2d(xt, k.double().permute(3, 2, 0, 1), stride=2).permute(0, 2, 3, 1).float()
+  assert tuple(ref.shape) == (B, ho, wo, cout)
+  L = nets._Conv('t', 'conv', N.ConvDesc(B, H, W, 1, cout, 5, 5, 2, 2, pt, pl, ho, wo, N.MATH_AUTO))
+  xd, kd, bd = x.cuda(), k.cuda(), b.cuda()
+  y = torch.full((B, ho, wo, cout), float('nan'), device='cuda')
+  L.run(xd, 1, kd, nets._epilogue(bd, y, cout, 0, N.ACT_LRELU))
+  torch.cuda.synchronize()
+  assert N.debug_flags() == 0
+  assert L.kernel_family().startswith('conv_one_in_tc')
+  refb = ref + b
+  assert _rel(y, torch.where(refb > 0, refb, 0.2 * refb)) < 2e-6
+  gate = torch.randn(B, ho, wo, cout, generator=g)
+  gd = gate.cuda()
+  y2 = torch.full((B, ho, wo, cout), float('nan'), device='cuda')
+  L.run(xd, 1, kd, nets._epilogue(None, y2, cout, 0, N.ACT_NONE, gate=gd, ld_gate=cout, gate_act=N.ACT_LRELU))
+  torch.cuda.synchronize()
+  assert N.debug_flags() == 0
+  assert _rel(y2, ref * torch.where(gate > 0, torch.tensor(1.0), torch.tensor(0.2))) < 2e-6

@@ -264,29 +264,31 @@ def test_two_rank_nccl_train_loop_matches_accumulated_gradients(tmp_path, overla
   assert _rel(upd_got, upd_want) < 1e-2
 
 
-@pytest.mark.parametrize('cin,cout', [(1, 32), (1, 64), (1, 128), (1, 256), (2, 32), (2, 64), (2, 128)])
-def test_thin_filter_gradients_on_tensor_cores(cin, cout):
-  """wgrad_thin_tc_kernel (MODE 0 / 1): filter gradient of a conv from one / two input channels against torch's
-  conv2d weight gradient.  The thin side enters as hi + lo tf32 parts; the wide side is read by TMA and
-  truncated to tf32 by the tensor core, so with a tf32-representable dy the result is fp32-accurate.  Also
-  checks += semantics and run-to-run determinism."""
+@pytest.mark.parametrize('cin,cout,k', [(1, 32, 4), (1, 64, 4), (1, 128, 4), (1, 256, 4), (2, 32, 4), (2, 64, 4),
+                                        (2, 128, 4), (1, 64, 5), (1, 128, 5)])
+def test_thin_filter_gradients_on_tensor_cores(cin, cout, k):
+  """wgrad_thin_tc_kernel (MODE 0 / 1 / 3): filter gradient of a k4 conv from one / two input channels and of a
+  5x5 conv from one channel (MelspecGAN conv_0) against torch's conv2d weight gradient.  The thin side enters
+  as hi + lo tf32 parts; the wide side is read by TMA and truncated to tf32 by the tensor core, so with a
+  tf32-representable dy the result is fp32-accurate.  Also checks += semantics and run-to-run determinism."""
   import ctypes as C
   import torch.nn.functional as F
   from advoc_b200 import _native as N
   from advoc_b200.nets import _ptr, _stream
-  g = torch.Generator().manual_seed(cin * 1000 + cout)
+  g = torch.Generator().manual_seed(cin * 1000 + cout + k)
   B, H, W = 3, 52, 75
-  ho, wo = (H + 1 + 1 - 4) // 2 + 1, (W + 1 + 2 - 4) // 2 + 1
+  ho, wo = (H + 1 + (2 if k == 5 else 1) - k) // 2 + 1, (W + 1 + 2 - k) // 2 + 1
   x = torch.randn(B, H, W, cin, generator=g)
   dy = torch.randn(B, ho, wo, cout + 8, generator=g)
   dy = (dy.view(torch.int32) & ~0x1FFF).view(torch.float32)        # tf32-representable
-  w = torch.zeros(4, 4, cin, cout, requires_grad=True)
+  w = torch.zeros(cout, cin, k, k, dtype=torch.float64, requires_grad=True)
   xt = F.pad(x.permute(0, 3, 1, 2), (1, 2, 1, 2))
-  y = F.conv2d(xt.double(), w.double().permute(3, 2, 0, 1), stride=2)[:, :, :ho, :wo]
-  (ref,) = torch.autograd.grad(y, w, dy[..., 8:].double().permute(0, 3, 1, 2))
-  d = N.ConvDesc(B, H, W, cin, cout, 4, 4, 2, 2, 1, 1, ho, wo, N.MATH_AUTO)
+  y = F.conv2d(xt.double(), w, stride=2)[:, :, :ho, :wo]
+  (ref,) = torch.autograd.grad(y, w, dy[..., 8:].double().permute(0, 3, 1, 2).contiguous())
+  ref = ref.permute(2, 3, 1, 0)              # OIHW -> HWIO
+  d = N.ConvDesc(B, H, W, cin, cout, k, k, 2, 2, 1, 1, ho, wo, N.MATH_AUTO)
   xd, dyd = x.cuda().contiguous(), dy.cuda().contiguous()
-  base = torch.randn(4, 4, cin, cout, generator=g)
+  base = torch.randn(k, k, cin, cout, generator=g)
   outs = []
   for _ in range(2):
     dw = base.cuda().clone()
