@@ -73,14 +73,20 @@ __device__ __forceinline__ float apply_act(float v, int act, float alpha) {
   }
 }
 
-// Counter-based keep/drop decision shared by every kernel that applies dropout
-// (splitmix64 finaliser of seed ^ element index).  Deterministic, stateless.
+// Counter-based keep/drop decision shared by every kernel that applies dropout: a 32-bit multiply-xorshift
+// hash ("lowbias32" constants) of the element index, keyed by both halves of the seed.  Deterministic, stateless.
+// (Round 2: the splitmix64 finaliser used before cost ~30 instructions per element -- three 64-bit multiplies --
+// and made the epilogues of the dropout decoders the slowest stage of their kernels: 2000 warp instructions per
+// 32-column chunk in profiles/r02K_conv_tc_small_stall_samples.txt.)
 __device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t idx, float keep_prob) {
-  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (idx + 1);
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z = z ^ (z >> 31);
-  return (float)(uint32_t)(z >> 40) * (1.0f / 16777216.0f) < keep_prob;
+  uint32_t x = (uint32_t)idx * 0x9E3779B1u + (uint32_t)seed;
+  x ^= ((uint32_t)(idx >> 32) + (uint32_t)(seed >> 32)) * 0x85EBCA6Bu;
+  x ^= x >> 16;
+  x *= 0x21F0AAADu;
+  x ^= x >> 15;
+  x *= 0x735A2D97u;
+  x ^= x >> 15;
+  return (x >> 8) < (uint32_t)(keep_prob * 16777216.0f);
 }
 
 }  // namespace advoc

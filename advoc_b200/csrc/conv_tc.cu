@@ -232,6 +232,14 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
     const int q = warp & 3;
     const int row = q * 32 + lane;
     uint32_t i = 0;
+    // loop invariants of the epilogue (r02: with dropout on, reloading the seed word, re-dividing and hashing with
+    // 64-bit multiplies made this the slowest stage of the kernel: profiles/r02K_conv_tc_small_stall_samples.txt)
+    const uint64_t seed = p.epi.keep_prob < 1.f ? epi_seed(p.epi) : 0ull;
+    const float inv_keep = 1.f / p.epi.keep_prob;
+    const float* bias = p.epi.bias;
+    const bool plain = act_is_linear(p.epi.act0) && act_is_linear(p.epi.act1) && !p.epi.gate && !p.epi.accumulate &&
+                       !p.epi.mask;
+    const ActLin a0 = act_linear(p.epi.act0, p.epi.alpha), a1 = act_linear(p.epi.act1, p.epi.alpha);
     for (long t = blockIdx.x; t < ntl; t += gridDim.x) {
       const TcTile tl = tc_decode<BN>(p, t, n_ntiles);
       if (!tl.valid) continue;
@@ -254,7 +262,11 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t v[32];
+        float4 bv[8];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)BN + (uint32_t)c0, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)      // the chunk's 32 bias values, in flight together with the TMEM load
+          bv[j] = bias ? __ldg(reinterpret_cast<const float4*>(bias + tl.n0 + c0) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
         tmem_ld_wait();
         if (valid && p.ksplit > 1) {
           float4* dst = reinterpret_cast<float4*>(p.ws + (size_t)tl.ks * p.ws_stride + pix * p.Cn + tl.n0 + c0);
@@ -262,12 +274,72 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
           for (int j = 0; j < 32; j += 4)
             dst[j >> 2] = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
                                       __uint_as_float(v[j + 3]));
+        } else if (valid && plain) {
+          // forward fast path (bias + none / relu / lrelu [+ dropout] to one or two fp32 / fp16 destinations):
+          // 32 values of one pixel row, 16-byte stores
+          float x[32];
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b = bv[j >> 2];
+            x[j] = __uint_as_float(v[j]) + b.x; x[j + 1] = __uint_as_float(v[j + 1]) + b.y;
+            x[j + 2] = __uint_as_float(v[j + 2]) + b.z; x[j + 3] = __uint_as_float(v[j + 3]) + b.w;
+          }
+          const int n = tl.n0 + c0;
+          float sc[32];
+          if (p.epi.keep_prob < 1.f) {
+            const size_t idx = pix * p.epi.Cout + n;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sc[j] = dropout_keep(seed, idx + j, p.epi.keep_prob) ? inv_keep : 0.f;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sc[j] = 1.f;
+          }
+#pragma unroll
+          for (int o = 0; o < 2; ++o) {
+            if (o == 1 && !p.epi.out1) break;
+            const ActLin a = o == 0 ? a0 : a1;
+            float* base = o == 0 ? p.epi.out0 : p.epi.out1;
+            const size_t el = pix * (size_t)(o == 0 ? p.epi.ld0 : p.epi.ld1) + (size_t)((o == 0 ? p.epi.coff0 : p.epi.coff1) + n);
+            const bool half = o == 0 ? p.epi.h0 : p.epi.h1;
+            if (half) {
+              __half* dst = reinterpret_cast<__half*>(base) + el;
+              if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8)
+                  *reinterpret_cast<uint4*>(dst + j) =
+                      make_uint4(pack_half2(apply_lin(x[j], a) * sc[j], apply_lin(x[j + 1], a) * sc[j + 1]),
+                                 pack_half2(apply_lin(x[j + 2], a) * sc[j + 2], apply_lin(x[j + 3], a) * sc[j + 3]),
+                                 pack_half2(apply_lin(x[j + 4], a) * sc[j + 4], apply_lin(x[j + 5], a) * sc[j + 5]),
+                                 pack_half2(apply_lin(x[j + 6], a) * sc[j + 6], apply_lin(x[j + 7], a) * sc[j + 7]));
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                  *reinterpret_cast<uint2*>(dst + j) =
+                      make_uint2(pack_half2(apply_lin(x[j], a) * sc[j], apply_lin(x[j + 1], a) * sc[j + 1]),
+                                 pack_half2(apply_lin(x[j + 2], a) * sc[j + 2], apply_lin(x[j + 3], a) * sc[j + 3]));
+              }
+            } else {
+              float* dst = base + el;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float y[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  y[u] = apply_lin(x[j + u], a) * sc[j + u];
+                  if (p.epi.round) y[u] = round_tf32(y[u]);
+                }
+                *reinterpret_cast<float4*>(dst + j) = make_float4(y[0], y[1], y[2], y[3]);
+              }
+            }
+          }
         } else if (valid) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            epi_store_vec4(p.epi, pix, tl.n0 + c0 + j,
-                           make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                       __uint_as_float(v[j + 3])));
+            const float4 b = bv[j >> 2];
+            epi_store_vec4_core(p.epi, pix, tl.n0 + c0 + j,
+                                make_float4(__uint_as_float(v[j]) + b.x, __uint_as_float(v[j + 1]) + b.y,
+                                            __uint_as_float(v[j + 2]) + b.z, __uint_as_float(v[j + 3]) + b.w),
+                                seed, inv_keep);
           }
         }
       }

@@ -96,18 +96,26 @@ __device__ __forceinline__ void epi_store(const EpiDev& e, size_t pix, int n, fl
   }
 }
 
-// Four consecutive channels of one stored pixel (the vector form of epi_store).
+// Four consecutive channels of one stored pixel (the vector form of epi_store); `acc` already holds the bias,
+// `seed` = epi_seed(e) and `inv` = 1 / keep_prob come from the caller (loop-invariant: a kernel that calls this
+// 32 times per pixel row should not reload the seed word and re-divide every time).
+__device__ __forceinline__ void epi_store_vec4_core(const EpiDev& e, size_t pix, int n, float4 acc, uint64_t seed,
+                                                    float inv);
+
 __device__ __forceinline__ void epi_store_vec4(const EpiDev& e, size_t pix, int n, float4 acc) {
-  float v[4] = {acc.x, acc.y, acc.z, acc.w};
   if (e.bias) {
     const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + n));
-    v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+    acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
   }
+  epi_store_vec4_core(e, pix, n, acc, e.keep_prob < 1.f ? epi_seed(e) : 0ull, 1.f / e.keep_prob);
+}
+
+__device__ __forceinline__ void epi_store_vec4_core(const EpiDev& e, size_t pix, int n, float4 acc, uint64_t seed,
+                                                    float inv) {
+  float v[4] = {acc.x, acc.y, acc.z, acc.w};
   float sc[4] = {1.f, 1.f, 1.f, 1.f};
   if (e.keep_prob < 1.f) {
     const size_t idx = pix * e.Cout + n;
-    const float inv = 1.f / e.keep_prob;
-    const uint64_t seed = epi_seed(e);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const bool keep = e.mask ? (__ldg(e.mask + idx + j) != 0) : dropout_keep(seed, idx + j, e.keep_prob);
