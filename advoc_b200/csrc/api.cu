@@ -74,6 +74,7 @@ int conv_fwd_tc(const advoc_conv_desc* d, const void* x, int ldx, const void* w,
 int conv_transposed_tc(const advoc_conv_desc* d, const void* x, int ldx, const void* w,
                        const advoc_epilogue* ep, void* stream);
 bool conv_p2d_eligible(const advoc_conv_desc* d, int ldx, int transposed, int store_w);
+bool conv_p2d_preferred(const advoc_conv_desc* d, int ldx, int transposed, int store_w, const advoc_epilogue* ep);
 int conv_p2d(const advoc_conv_desc* d, int transposed, const void* x, int ldx, const void* w,
              const advoc_epilogue* ep, void* stream);
 bool tc_epilogue_ok(const advoc_epilogue* ep);
@@ -153,7 +154,7 @@ extern "C" int advoc_conv2d_fwd(const advoc_conv_desc* d, const void* d_xv, int 
   const bool ok = conv_fwd_tc_eligible(d, ld_x);
   if (d->math == ADVOC_MATH_TF32 || d->math == ADVOC_MATH_F16 || ok) {
     ADVOC_REQUIRE(ok, ADVOC_UNSUPPORTED, "conv shape not eligible for the tcgen05 path");
-    if (conv_p2d_eligible(d, ld_x, 0, 0)) {
+    if (conv_p2d_preferred(d, ld_x, 0, 0, ep)) {
       ADVOC_REQUIRE(aligned16(d_x) && aligned16(d_w), ADVOC_BAD_ALIGN, "x / w must be 16-byte aligned");
       ADVOC_REQUIRE(tc_epilogue_ok(ep), ADVOC_BAD_ALIGN,
                     "tcgen05 path needs 16-byte aligned outputs with ld and channel offset multiples of 4");
@@ -178,7 +179,7 @@ extern "C" int advoc_conv2d_transpose_fwd(const advoc_conv_desc* d, const void* 
   const bool ok = conv_transposed_tc_eligible(d, ld_x);
   if (d->math == ADVOC_MATH_TF32 || d->math == ADVOC_MATH_F16 || ok) {
     ADVOC_REQUIRE(ok, ADVOC_UNSUPPORTED, "conv_transpose shape not eligible for the tcgen05 path");
-    if (conv_p2d_eligible(d, ld_x, 1, ep->store_w)) {
+    if (conv_p2d_preferred(d, ld_x, 1, ep->store_w, ep)) {
       ADVOC_REQUIRE(aligned16(d_x) && aligned16(d_w), ADVOC_BAD_ALIGN, "x / w must be 16-byte aligned");
       ADVOC_REQUIRE(tc_epilogue_ok(ep), ADVOC_BAD_ALIGN,
                     "tcgen05 path needs 16-byte aligned outputs with ld and channel offset multiples of 4");
@@ -207,7 +208,7 @@ extern "C" int advoc_conv2d_kernel(const advoc_conv_desc* d, int ld_x, int trans
     return 4;
   if (advoc_conv2d_path(d, ld_x, transposed) == ADVOC_MATH_FP32) return 0;
   if (transposed && deconv_one_tc_geometry(d, ld_x)) return 3;
-  return conv_p2d_eligible(d, ld_x, transposed, store_w) ? 2 : 1;
+  return conv_p2d_preferred(d, ld_x, transposed, store_w, nullptr) ? 2 : 1;   // (a forward call: see conv_p2d_preferred)
 }
 
 extern "C" int advoc_conv2d_tile_n(const advoc_conv_desc* d, int ld_x, int transposed, int store_w) {

@@ -957,6 +957,20 @@ bool conv_p2d_eligible(const advoc_conv_desc* d, int ldx, int transposed, int st
          (long)pl.filter_bytes_per_tile <= max_filter_kb * 1024;
 }
 
+// Which of the two tcgen05 kernels a call takes.  Until the end of round 2 the patch kernel also ran the forward
+// layers conv_p2d_eligible admits; then the per-tap kernel's forward epilogue was rewritten (conv_tc.cu: stall
+// samples had shown its four epilogue warps, not the tensor pipe, pacing it) and it now wins or ties on every
+// forward layer of both generators (profiles/README.md, r02P: AdVoc-small 0.527 -> 0.466 ms, regular 1.167 -> 1.031 ms
+// with the patch kernel off).  The patch kernel keeps the BACKWARD epilogues -- gate tiles by TMA load, skip sums by
+// TMA reduce-add, which the per-tap kernel does element-wise (regular train step 1812 samples/s against 1761 without
+// it).  ep == nullptr asks about a forward call.  ADVOC_P2D_FORWARD restores the earlier routing for A/B runs.
+bool conv_p2d_preferred(const advoc_conv_desc* d, int ldx, int transposed, int store_w, const advoc_epilogue* ep) {
+  if (!conv_p2d_eligible(d, ldx, transposed, store_w)) return false;
+  static const bool force = getenv("ADVOC_P2D_FORCE") != nullptr;
+  static const bool forward_too = getenv("ADVOC_P2D_FORWARD") != nullptr;
+  return force || forward_too || (ep != nullptr && (ep->d_gate != nullptr || ep->accumulate != 0));
+}
+
 // N tile (template BN) of the patch-kernel launch for this geometry (host-side query)
 int conv_p2d_tile_n(const advoc_conv_desc* d, int transposed, int store_w) {
   Plan pl = {};

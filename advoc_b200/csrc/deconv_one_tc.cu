@@ -199,6 +199,11 @@ __global__ void __launch_bounds__(O_THREADS, KS == 4 ? 3 : 1) deconv_one_tc_kern
     long i = 0;
     unsigned long long w3 = 0;
     const long long ts = clock64();
+    // plain forward store: bias + none / relu / lrelu to one fp32 destination
+    const bool plain = act_is_linear(p.epi.act0) && p.epi.keep_prob >= 1.f && !p.epi.gate && !p.epi.accumulate &&
+                       !p.epi.out1 && !p.epi.h0 && !p.epi.round && !p.epi.mask;
+    const float bias0 = p.epi.bias ? __ldg(p.epi.bias) : 0.f;
+    const ActLin act0 = act_linear(p.epi.act0, p.epi.alpha);
     for (long t = blockIdx.x; t < ntl; t += gridDim.x, ++i) {
       const int buf = (int)(i & 1);
       const uint32_t use = (uint32_t)(i >> 1);
@@ -244,7 +249,8 @@ __global__ void __launch_bounds__(O_THREADS, KS == 4 ? 3 : 1) deconv_one_tc_kern
           }
         }
         const size_t pix = ((size_t)img * p.epi.Hs + (2 * ar + ph)) * p.epi.Ws + ow;
-        epi_store(p.epi, pix, 0, acc);
+        if (plain) p.epi.out0[pix * (size_t)p.epi.ld0 + p.epi.coff0] = apply_lin(acc + bias0, act0);   // (the col2im epilogue is instruction-bound: profiles/r02P)
+        else epi_store(p.epi, pix, 0, acc);
       }
     }
     if (p.prof && tid == 0) { p.prof[blockIdx.x * 8 + 5] = (unsigned long long)(clock64() - ts); p.prof[blockIdx.x * 8 + 6] = w3; }

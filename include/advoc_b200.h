@@ -306,7 +306,8 @@ ADVOC_API int advoc_adam_tf_step_dev(float* d_p, const float* d_g, float* d_m, f
  * advoc_conv2d_transpose_fwd.  Pure host logic. */
 ADVOC_API int advoc_conv2d_path(const advoc_conv_desc* d, int ld_x, int transposed);
 
-/* Which kernel a forward call with this geometry launches: 0 CUDA-core fp32 (conv_simt.cu /
+/* Which kernel a FORWARD call (no gate / accumulate in the epilogue) with this geometry launches -- input-gradient
+ * calls may take the patch kernel where a forward call takes the per-tap one: 0 CUDA-core fp32 (conv_simt.cu /
  * conv_direct.cu), 1 tcgen05 per-tap im2col kernel (conv_tc.cu), 2 tcgen05 persistent patch kernel
  * (conv_p2d.cu), 3 tcgen05 transposed conv to one channel (deconv_one_tc.cu), 4 tcgen05 conv from one channel
  * (conv_one_in_tc.cu; taken when the epilogue is a plain forward one, else 0).  store_w as in advoc_epilogue (0 = full width).  Host-side query, used by bench.py

@@ -230,9 +230,9 @@ def test_small_generator_forward_at_the_benchmarked_batch(math):
   inst = _instantiations(G)
   fams = {k for k, _, _ in inst}
   import os
-  if os.environ.get('ADVOC_NO_P2D') or os.environ.get('ADVOC_P2D_FORCE'):
+  if os.environ.get('ADVOC_NO_P2D') or os.environ.get('ADVOC_P2D_FORCE') or os.environ.get('ADVOC_NO_ONE_IN_TC'):
     return          # forced kernel choice (tests/test_gpu_forced_paths.py): the routing below does not apply
-  assert 'conv_p2d_kernel' in fams and 'deconv_one_tc_kernel' in fams, inst
+  assert 'conv_tc_kernel' in fams and 'deconv_one_tc_kernel' in fams and 'conv_one_in_tc_kernel' in fams, inst
   if math == 'auto':
     assert ('conv_tc_kernel', 128, False) in inst, inst
   else:
