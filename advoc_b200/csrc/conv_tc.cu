@@ -57,6 +57,12 @@ struct alignas(64) TcParams {
   int ksplit;
   float* ws;
   long ws_stride;
+  // merged parity classes (conv_tc_merged_kernel): shift s = (dh + 1) * 3 + (dw + 1) of the 3 x 3 neighbourhood
+  // feeds m_cnt[s] (class, tap) pairs: accumulator m_cls[s][j] (= 2 ph + pw) with filter tap m_wrow[s][j]
+  // the 9 entries are stored in ISSUE order (centre shift first: it reaches all four classes, so one N = 4 BN MMA
+  // initialises every accumulator); m_off = (dh + 1) << 2 | (dw + 1); m_span[s] = how many consecutive pairs of the
+  // entry form one MMA (their classes are adjacent accumulators and their filter tiles adjacent in the stage)
+  unsigned char m_cnt[9], m_cls[9][4], m_wrow[9][4], m_off[9], m_span[9];
   EpiDev epi;
   unsigned int* dbg;   // [0] != 0 after a barrier wait timed out
 };
@@ -67,6 +73,96 @@ struct SmemLayout {
   static constexpr int B_BYTES = BN * BK_BYTES;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 };
+
+// loop invariants of an epilogue (r02: with dropout on, reloading the seed word, re-dividing and hashing with 64-bit
+// multiplies made the epilogue the slowest stage of the kernel: profiles/r02K_conv_tc_small_stall_samples.txt)
+struct TcEpiInv {
+  uint64_t seed;
+  float inv_keep;
+  bool plain;       // bias + none / relu / lrelu [+ dropout] to one or two fp32 / fp16 destinations
+  ActLin a0, a1;
+};
+__device__ __forceinline__ TcEpiInv tc_epi_invariants(const EpiDev& e) {
+  TcEpiInv q;
+  q.seed = e.keep_prob < 1.f ? epi_seed(e) : 0ull;
+  q.inv_keep = 1.f / e.keep_prob;
+  q.plain = act_is_linear(e.act0) && act_is_linear(e.act1) && !e.gate && !e.accumulate && !e.mask;
+  q.a0 = act_linear(e.act0, e.alpha);
+  q.a1 = act_linear(e.act1, e.alpha);
+  return q;
+}
+
+// 32 consecutive channels [n, n + 32) of stored pixel `pix`: accumulator values v + bias values bv -> destination(s)
+__device__ __forceinline__ void tc_store_chunk(const EpiDev& e, const TcEpiInv& q, size_t pix, int n,
+                                               const uint32_t (&v)[32], const float4 (&bv)[8]) {
+  if (q.plain) {
+          // forward fast path (bias + none / relu / lrelu [+ dropout] to one or two fp32 / fp16 destinations):
+          // 32 values of one pixel row, 16-byte stores
+          float x[32];
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b = bv[j >> 2];
+            x[j] = __uint_as_float(v[j]) + b.x; x[j + 1] = __uint_as_float(v[j + 1]) + b.y;
+            x[j + 2] = __uint_as_float(v[j + 2]) + b.z; x[j + 3] = __uint_as_float(v[j + 3]) + b.w;
+          }
+          float sc[32];
+          if (e.keep_prob < 1.f) {
+            const size_t idx = pix * e.Cout + n;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sc[j] = dropout_keep(q.seed, idx + j, e.keep_prob) ? q.inv_keep : 0.f;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sc[j] = 1.f;
+          }
+#pragma unroll
+          for (int o = 0; o < 2; ++o) {
+            if (o == 1 && !e.out1) break;
+            const ActLin a = o == 0 ? q.a0 : q.a1;
+            float* base = o == 0 ? e.out0 : e.out1;
+            const size_t el = pix * (size_t)(o == 0 ? e.ld0 : e.ld1) + (size_t)((o == 0 ? e.coff0 : e.coff1) + n);
+            const bool half = o == 0 ? e.h0 : e.h1;
+            if (half) {
+              __half* dst = reinterpret_cast<__half*>(base) + el;
+              if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8)
+                  *reinterpret_cast<uint4*>(dst + j) =
+                      make_uint4(pack_half2(apply_lin(x[j], a) * sc[j], apply_lin(x[j + 1], a) * sc[j + 1]),
+                                 pack_half2(apply_lin(x[j + 2], a) * sc[j + 2], apply_lin(x[j + 3], a) * sc[j + 3]),
+                                 pack_half2(apply_lin(x[j + 4], a) * sc[j + 4], apply_lin(x[j + 5], a) * sc[j + 5]),
+                                 pack_half2(apply_lin(x[j + 6], a) * sc[j + 6], apply_lin(x[j + 7], a) * sc[j + 7]));
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                  *reinterpret_cast<uint2*>(dst + j) =
+                      make_uint2(pack_half2(apply_lin(x[j], a) * sc[j], apply_lin(x[j + 1], a) * sc[j + 1]),
+                                 pack_half2(apply_lin(x[j + 2], a) * sc[j + 2], apply_lin(x[j + 3], a) * sc[j + 3]));
+              }
+            } else {
+              float* dst = base + el;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float y[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  y[u] = apply_lin(x[j + u], a) * sc[j + u];
+                  if (e.round) y[u] = round_tf32(y[u]);
+                }
+                *reinterpret_cast<float4*>(dst + j) = make_float4(y[0], y[1], y[2], y[3]);
+              }
+            }
+          }
+  } else {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b = bv[j >> 2];
+            epi_store_vec4_core(e, pix, n + j,
+                                make_float4(__uint_as_float(v[j]) + b.x, __uint_as_float(v[j + 1]) + b.y,
+                                            __uint_as_float(v[j + 2]) + b.z, __uint_as_float(v[j + 3]) + b.w),
+                                q.seed, q.inv_keep);
+          }
+  }
+}
 
 // HALF: fp16 operands (kind::f16, 64 channels per 128-byte row) instead of tf32 (32 channels); the
 // byte layout of the ring, the descriptors and the four 32-byte K steps per row are the same.
@@ -234,12 +330,8 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
     uint32_t i = 0;
     // loop invariants of the epilogue (r02: with dropout on, reloading the seed word, re-dividing and hashing with
     // 64-bit multiplies made this the slowest stage of the kernel: profiles/r02K_conv_tc_small_stall_samples.txt)
-    const uint64_t seed = p.epi.keep_prob < 1.f ? epi_seed(p.epi) : 0ull;
-    const float inv_keep = 1.f / p.epi.keep_prob;
+    const TcEpiInv inv = tc_epi_invariants(p.epi);
     const float* bias = p.epi.bias;
-    const bool plain = act_is_linear(p.epi.act0) && act_is_linear(p.epi.act1) && !p.epi.gate && !p.epi.accumulate &&
-                       !p.epi.mask;
-    const ActLin a0 = act_linear(p.epi.act0, p.epi.alpha), a1 = act_linear(p.epi.act1, p.epi.alpha);
     for (long t = blockIdx.x; t < ntl; t += gridDim.x) {
       const TcTile tl = tc_decode<BN>(p, t, n_ntiles);
       if (!tl.valid) continue;
@@ -274,73 +366,8 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
           for (int j = 0; j < 32; j += 4)
             dst[j >> 2] = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
                                       __uint_as_float(v[j + 3]));
-        } else if (valid && plain) {
-          // forward fast path (bias + none / relu / lrelu [+ dropout] to one or two fp32 / fp16 destinations):
-          // 32 values of one pixel row, 16-byte stores
-          float x[32];
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b = bv[j >> 2];
-            x[j] = __uint_as_float(v[j]) + b.x; x[j + 1] = __uint_as_float(v[j + 1]) + b.y;
-            x[j + 2] = __uint_as_float(v[j + 2]) + b.z; x[j + 3] = __uint_as_float(v[j + 3]) + b.w;
-          }
-          const int n = tl.n0 + c0;
-          float sc[32];
-          if (p.epi.keep_prob < 1.f) {
-            const size_t idx = pix * p.epi.Cout + n;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) sc[j] = dropout_keep(seed, idx + j, p.epi.keep_prob) ? inv_keep : 0.f;
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) sc[j] = 1.f;
-          }
-#pragma unroll
-          for (int o = 0; o < 2; ++o) {
-            if (o == 1 && !p.epi.out1) break;
-            const ActLin a = o == 0 ? a0 : a1;
-            float* base = o == 0 ? p.epi.out0 : p.epi.out1;
-            const size_t el = pix * (size_t)(o == 0 ? p.epi.ld0 : p.epi.ld1) + (size_t)((o == 0 ? p.epi.coff0 : p.epi.coff1) + n);
-            const bool half = o == 0 ? p.epi.h0 : p.epi.h1;
-            if (half) {
-              __half* dst = reinterpret_cast<__half*>(base) + el;
-              if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 8)
-                  *reinterpret_cast<uint4*>(dst + j) =
-                      make_uint4(pack_half2(apply_lin(x[j], a) * sc[j], apply_lin(x[j + 1], a) * sc[j + 1]),
-                                 pack_half2(apply_lin(x[j + 2], a) * sc[j + 2], apply_lin(x[j + 3], a) * sc[j + 3]),
-                                 pack_half2(apply_lin(x[j + 4], a) * sc[j + 4], apply_lin(x[j + 5], a) * sc[j + 5]),
-                                 pack_half2(apply_lin(x[j + 6], a) * sc[j + 6], apply_lin(x[j + 7], a) * sc[j + 7]));
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                  *reinterpret_cast<uint2*>(dst + j) =
-                      make_uint2(pack_half2(apply_lin(x[j], a) * sc[j], apply_lin(x[j + 1], a) * sc[j + 1]),
-                                 pack_half2(apply_lin(x[j + 2], a) * sc[j + 2], apply_lin(x[j + 3], a) * sc[j + 3]));
-              }
-            } else {
-              float* dst = base + el;
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                float y[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  y[u] = apply_lin(x[j + u], a) * sc[j + u];
-                  if (p.epi.round) y[u] = round_tf32(y[u]);
-                }
-                *reinterpret_cast<float4*>(dst + j) = make_float4(y[0], y[1], y[2], y[3]);
-              }
-            }
-          }
         } else if (valid) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b = bv[j >> 2];
-            epi_store_vec4_core(p.epi, pix, tl.n0 + c0 + j,
-                                make_float4(__uint_as_float(v[j]) + b.x, __uint_as_float(v[j + 1]) + b.y,
-                                            __uint_as_float(v[j + 2]) + b.z, __uint_as_float(v[j + 3]) + b.w),
-                                seed, inv_keep);
-          }
+          tc_store_chunk(p.epi, inv, pix, tl.n0 + c0, v, bv);
         }
       }
       tc_fence_before();
@@ -358,6 +385,205 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS)
                  : "memory");
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k4 s2 transposed convolution with the FOUR PARITY CLASSES MERGED (round 2, end).  The per-class schedule above
+// fetches every input pixel once per (class, tap): 16 im2col tiles per 128 positions and k-block, and at N <= 64
+// that L2 -> SM stream paces the layer (AdVoc-small decoder_2 on the per-class schedule: 1.3 GB in 90 us).  Here a
+// tile is 128 positions (a, b) of the INPUT grid and owns all four outputs (2a + ph, 2b + pw): the nine shifted
+// views (a + dh, b + dw), dh, dw in {-1, 0, 1}, are fetched once each and every view feeds the 1, 2 or 4 (class,
+// tap) pairs that read it -- class (ph, pw) sees tap kh at dh = (ph + 1 - kh) / 2 -- into four accumulators that
+// sit side by side in TMEM.  9 A tiles + 16 filter tiles per k-block instead of 16 + 16.
+// ---------------------------------------------------------------------------------------------
+template <int BN, int STAGES, bool HALF>
+__global__ void __launch_bounds__(NUM_THREADS) conv_tc_merged_kernel(const __grid_constant__ TcParams p) {
+  constexpr int BK = HALF ? 64 : 32;
+  constexpr int A_BYTES = BM * BK_BYTES, B_BYTES = BN * BK_BYTES;
+  constexpr int STAGE_BYTES = A_BYTES + 4 * B_BYTES;
+  constexpr uint32_t ACC_COLS = 4 * BN;                       // four class accumulators
+  constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;                // double-buffered
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_base_holder;
+
+  const int n_ntiles = p.Cn / BN;
+  const long ntl = p.total_tiles;                             // M tiles x N tiles
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Ah = p.Ah[0], Aw = p.Aw[0];                       // the input-grid extent the tiles walk
+  const long Mtot = (long)p.Nimg * Ah * Aw;
+  const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* ring_ptr = smem_raw + (ring - smem_u32(smem_raw));
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.tmA[0]);
+    prefetch_tmap(&p.tmB);
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(&tmem_base_holder)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_holder;
+  const bool aborted = p.dbg && *reinterpret_cast<volatile unsigned int*>(p.dbg) != 0;
+
+  if (aborted) {
+  } else if (warp == 0 || warp == 6) {
+    // ===== TMA producers: warp 0 the nine shifted activation tiles, warp 6 the filter tiles of their pairs =====
+    const bool filt = warp == 6;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (long t = blockIdx.x; t < ntl; t += gridDim.x) {
+      const unsigned mt = (unsigned)t / (unsigned)n_ntiles;
+      const int n0 = (int)((unsigned)t - mt * (unsigned)n_ntiles) * BN;
+      const long m0 = (long)mt * BM;
+      const int b = (int)(m0 % Aw);
+      const long r = m0 / Aw;
+      const int a = (int)(r % Ah);
+      const int img = (int)(r / Ah);
+      for (int kb = 0; kb < p.kblocks; ++kb) {
+        for (int s = 0; s < 9; ++s) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u, p.dbg, 1u);
+          uint8_t* dst = ring_ptr + stage * STAGE_BYTES;
+          const int cnt = p.m_cnt[s];
+          __syncwarp();
+          if (elect_one()) {
+            if (filt) {
+              mbar_expect_tx(&full_bar[stage], (uint32_t)cnt * B_BYTES);
+              for (int j = 0; j < cnt; ++j)
+                tma_load_2d(&p.tmB, &full_bar[stage], dst + A_BYTES + j * B_BYTES, kb * BK, (int)p.m_wrow[s][j] * p.Cn + n0);
+            } else {
+              mbar_expect_tx(&full_bar[stage], A_BYTES);
+              tma_load_im2col_4d(&p.tmA[0], &full_bar[stage], dst, kb * BK, b + p.base_w[0], a + p.base_h[0], img,
+                                 (uint16_t)(p.m_off[s] & 3), (uint16_t)(p.m_off[s] >> 2));
+            }
+          }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = umma_idesc<HALF>(BM, BN);
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0, i = 0;
+      for (long t = blockIdx.x; t < ntl; t += gridDim.x, ++i) {
+        const uint32_t buf = i & 1u;
+        mbar_wait(&acc_empty[buf], ((i >> 1) & 1u) ^ 1u, p.dbg, 4u);
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + buf * ACC_COLS;
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          for (int s = 0; s < 9; ++s) {
+            mbar_wait(&full_bar[stage], phase, p.dbg, 2u);
+            const uint32_t a_addr = ring + stage * STAGE_BYTES;
+            const uint64_t da = make_smem_desc(a_addr);
+            const int cnt = p.m_cnt[s], span = p.m_span[s];
+            // (kb, s) = (0, 0) is the centre shift: one MMA over all four classes zeroes the accumulators
+            const uint32_t keep = (kb | s) != 0 ? 1u : 0u;
+            for (int j = 0; j < cnt; j += span) {
+              const uint32_t cls = p.m_cls[s][j];
+              const uint64_t db = make_smem_desc(a_addr + A_BYTES + j * B_BYTES);
+              const uint32_t idesc = span == 4 ? umma_idesc<HALF>(BM, 4 * BN)
+                                               : (span == 2 ? umma_idesc<HALF>(BM, 2 * BN) : umma_idesc<HALF>(BM, BN));
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_op<HALF>(d0 + cls * (uint32_t)BN, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                              (k != 0 || keep) ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          }
+        }
+        umma_commit(&acc_full[buf]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue: row = one input-grid position, four output pixels =====
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    uint32_t i = 0;
+    const TcEpiInv inv = tc_epi_invariants(p.epi);
+    const float* bias = p.epi.bias;
+    for (long t = blockIdx.x; t < ntl; t += gridDim.x, ++i) {
+      const unsigned mt = (unsigned)t / (unsigned)n_ntiles;
+      const int n0 = (int)((unsigned)t - mt * (unsigned)n_ntiles) * BN;
+      const long m = (long)mt * BM + row;
+      int a = 0, b = 0;
+      long img = 0;
+      if (m < Mtot) {
+        b = (int)(m % Aw);
+        const long r = m / Aw;
+        a = (int)(r % Ah);
+        img = r / Ah;
+      }
+      const uint32_t buf = i & 1u;
+      mbar_wait(&acc_full[buf], (i >> 1) & 1u, p.dbg, 3u);
+      tc_fence_after();
+#pragma unroll 1
+      for (int cls = 0; cls < 4; ++cls) {
+        const int oh = 2 * a + (cls >> 1), ow = 2 * b + (cls & 1);
+        const bool valid = m < Mtot && oh < p.epi.Hs && ow < p.epi.Ws;
+        const size_t pix = ((size_t)img * p.epi.Hs + (size_t)oh) * p.epi.Ws + (size_t)ow;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t v[32];
+          float4 bv[8];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS + (uint32_t)(cls * BN + c0), v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            bv[j] = bias ? __ldg(reinterpret_cast<const float4*>(bias + n0 + c0) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          tmem_ld_wait();
+          if (valid) tc_store_chunk(p.epi, inv, pix, n0 + c0, v, bv);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[buf])) : "memory");
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS)
+                 : "memory");
+  }
+}
+
+template <int BN, int STAGES, bool HALF>
+int launch_merged(const TcParams& p, long m_tiles, cudaStream_t st) {
+  constexpr int smem = STAGES * (BM * BK_BYTES + 4 * BN * BK_BYTES) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    ADVOC_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_merged_kernel<BN, STAGES, HALF>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  TcParams q = p;
+  q.ksplit = 1;
+  q.total_tiles = m_tiles * (p.Cn / BN);
+  ADVOC_REQUIRE(q.total_tiles < 2147483647L, ADVOC_BAD_SHAPE, "too many output tiles");
+  const int per_sm = (2 * smem <= 220 * 1024 && 2 * 8 * BN <= 512) ? 2 : 1;
+  const long slots = (long)sm_count() * per_sm;
+  conv_tc_merged_kernel<BN, STAGES, HALF><<<(unsigned)(q.total_tiles < slots ? q.total_tiles : slots), NUM_THREADS, smem, st>>>(q);
+  count_launch();
+  ADVOC_CHECK_CUDA(cudaGetLastError());
+  return ADVOC_OK;
 }
 
 // sum of the K splits (in split order: deterministic) + the layer's epilogue, four channels per thread
@@ -633,10 +859,56 @@ int conv_transposed_tc(const advoc_conv_desc* d, const void* x, int ldx, const v
       ++nc;
     }
   }
-  st = encode_B(&p.tmB, w, d->kh * d->kw * d->Cin, d->Cout, pick_bn(d->Cin, m_ctas_of(d->N, g, nc)), half);
-  if (st) return st;
+  const int bn = pick_bn(d->Cin, m_ctas_of(d->N, g, nc));
   p.Nimg = d->N; p.trav_h = 1; p.trav_w = 1; p.osh = d->sh; p.osw = d->sw;
   p.Cn = d->Cin; p.kblocks = d->Cout / bk_of(half);
+  // merged parity classes (conv_tc_merged_kernel) for the k4 s2 layers with narrow N tiles and many positions
+  static const bool no_merge = getenv("ADVOC_TC_NO_MERGE") != nullptr;   // A/B switch
+  // (r02R: BN = 64 needs all 512 TMEM columns = one CTA per SM and is slower than the per-class schedule: AdVoc-small
+  //  decoder_3 73 us against 54, regular decoder_2 235 against 196; BN = 32: decoder_2 81 against 91)
+  static const int merge_max_bn = getenv("ADVOC_TC_MERGE_MAX_BN") ? atoi(getenv("ADVOC_TC_MERGE_MAX_BN")) : 32;
+  const int mAh = (Hout + 1) / 2, mAw = (Wout + 1) / 2;
+  const long m_tiles = ((long)d->N * mAh * mAw + BM - 1) / BM;
+  if (!no_merge && nc == 4 && d->kh == 4 && d->kw == 4 && d->sh == 2 && d->sw == 2 && d->pad_t == 1 && d->pad_l == 1 &&
+      (bn == 32 || bn == 64) && bn <= merge_max_bn && m_tiles * (d->Cin / bn) >= 2L * sm_count() &&
+      mAh - 1 - d->Ho >= -128 && mAw - 1 - d->Wo >= -128 && mAh - 1 - d->Ho <= 127 && mAw - 1 - d->Wo <= 127) {
+    ClassGeom m = {};
+    m.Ah = mAh; m.Aw = mAw; m.lower_h = -1; m.lower_w = -1;
+    m.upper_h = mAh - 1 - d->Ho; m.upper_w = mAw - 1 - d->Wo;
+    st = encode_A(&p.tmA[0], x, d->N, d->Ho, d->Wo, ldx, d->Cout, m, 1, 1, half);
+    if (st) return st;
+    st = encode_B(&p.tmB, w, d->kh * d->kw * d->Cin, d->Cout, bn, half);
+    if (st) return st;
+    p.Ah[0] = mAh; p.Aw[0] = mAw; p.base_h[0] = -1; p.base_w[0] = -1;
+    // entry e of the issue order <- shift (dh, dw); the centre first
+    static const int order[9] = {4, 0, 1, 2, 3, 5, 6, 7, 8};
+    for (int e = 0; e < 9; ++e) {
+      const int s9 = order[e], dh = s9 / 3 - 1, dw = s9 % 3 - 1;
+      p.m_cnt[e] = 0;
+      p.m_off[e] = (unsigned char)(((dh + 1) << 2) | (dw + 1));
+      for (int ph = 0; ph < 2; ++ph)
+        for (int pw = 0; pw < 2; ++pw)
+          for (int kh = 0; kh < 4; ++kh)
+            for (int kw = 0; kw < 4; ++kw) {
+              if (((ph + 1 - kh) & 1) || ((pw + 1 - kw) & 1)) continue;     // tap of the other parity
+              if ((ph + 1 - kh) / 2 != dh || (pw + 1 - kw) / 2 != dw) continue;
+              const int j = p.m_cnt[e]++;
+              p.m_cls[e][j] = (unsigned char)(2 * ph + pw);
+              p.m_wrow[e][j] = (unsigned char)(kh * 4 + kw);
+            }
+      // pairs in class order: 4 pairs = classes 0..3, 2 pairs = classes (c, c + 1) when dw == 0, (c, c + 2) otherwise
+      p.m_span[e] = 1;
+      if (p.m_cnt[e] == 4) p.m_span[e] = 4;
+      else if (p.m_cnt[e] == 2 && p.m_cls[e][1] == p.m_cls[e][0] + 1) p.m_span[e] = 2;
+    }
+    p.dbg = debug_word();
+    p.nclasses = 1;
+    cudaStream_t cst = reinterpret_cast<cudaStream_t>(stream);
+    if (half) return bn == 32 ? launch_merged<32, 3, true>(p, m_tiles, cst) : launch_merged<64, 4, true>(p, m_tiles, cst);
+    return bn == 32 ? launch_merged<32, 3, false>(p, m_tiles, cst) : launch_merged<64, 4, false>(p, m_tiles, cst);
+  }
+  st = encode_B(&p.tmB, w, d->kh * d->kw * d->Cin, d->Cout, bn, half);
+  if (st) return st;
   return run(p, nc, g, stream, half);
 }
 

@@ -632,3 +632,36 @@ def test_5x5_one_input_channel_conv_on_tensor_cores(cout):
   torch.cuda.synchronize()
   assert N.debug_flags() == 0
   assert _rel(y2, ref * torch.where(gate > 0, torch.tensor(1.0), torch.tensor(0.2))) < 2e-6
+
+
+@pytest.mark.parametrize('math,cout', [('f16', 32), ('f16', 64), ('auto', 32), ('auto', 64)])
+def test_transposed_conv_merged_parity_classes(math, cout):
+  """conv_tc_merged_kernel: k4 s2 transposed convolution with the four output parity classes computed from nine
+  shared shifted views of the input tile (decoder_2 / decoder_3 geometry: many positions, 32 / 64 output
+  channels), cropped by one column, relu, written at a channel offset.  ADVOC_TC_NO_MERGE=1 in a child process
+  checks that the per-class schedule gives the same result."""
+  from advoc_b200 import _native as N
+  from advoc_b200 import nets
+  from oracle import nets_torch as O
+  half = math == 'f16'
+  m = N.MATH_F16 if half else N.MATH_AUTO
+  q = (lambda t: t.half().float()) if half else _tf32
+  adt = torch.float16 if half else torch.float32
+  g = torch.Generator().manual_seed(40 + cout)
+  B, H, W, Cin = 16, 64, 65, 64
+  x = q(torch.relu(torch.randn(B, H, W, Cin, generator=g)))
+  k = torch.randn(4, 4, cout, Cin, generator=g) * 0.05
+  b = torch.randn(cout, generator=g) * 0.1
+  ref = torch.relu(O.deconv_same(x, q(k), b, (2, 2)))[:, :, :-1, :]
+  out = torch.full((B, 2 * H, 2 * W - 1, cout + 32), float('nan'), device='cuda', dtype=adt)
+  L = nets._Conv('t', 'deconv', nets._desc(B, 2 * H, 2 * W, cout, Cin, 2, 2, 1, 1, H, W, m))
+  L.ldx = Cin
+  assert L.kernel_family().startswith('conv_tc')
+  xd, kd, bd = x.cuda().to(adt), k.cuda(), b.cuda()
+  wp = nets._pack_for_tc(L, kd, Cin)
+  ep = nets._epilogue(bd, out, cout + 32, 32, N.ACT_RELU, store_w=2 * W - 1)
+  L.run(xd, Cin, wp, ep)
+  torch.cuda.synchronize()
+  assert N.debug_flags() == 0
+  assert _rel(out[..., 32:].float(), ref) < TOL
+  assert torch.isnan(out[..., :32].float()).all()
