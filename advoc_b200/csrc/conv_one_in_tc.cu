@@ -172,6 +172,7 @@ __global__ void __launch_bounds__(I_THREADS, 2) conv_one_in_tc_kernel(const __gr
     uint32_t phase = 0;
     // (the kernel is bound by instruction issue, so the gather keeps one row pointer per filter row, immediate
     // column offsets and precomputed row / column predicates: ~4 instructions per tap)
+    const bool unit_ld = p.ldx == 1;      // inference: the lifted magnitude buffer [B, T, 513, 1] (immediate offsets)
     auto gather = [&](long t, float (&v)[KV]) {
 #pragma unroll
       for (int j = 0; j < KV; ++j) v[j] = 0.f;
@@ -196,7 +197,7 @@ __global__ void __launch_bounds__(I_THREADS, 2) conv_one_in_tc_kernel(const __gr
         for (int kw = 0; kw < KS; ++kw) {
           if (rok && cok[kw]) {
             if (CIN == 1) {
-              v[kh * KS + kw] = __ldg(xr + DIR * kw * p.ldx);
+              v[kh * KS + kw] = __ldg(unit_ld ? xr + DIR * kw : xr + DIR * kw * p.ldx);
             } else {                        // two channels of a pixel: one 8-byte load (ldx even, x 8-byte aligned)
               const float2 xv = __ldg(reinterpret_cast<const float2*>(xr + kw * p.ldx));
               v[(kh * KS + kw) * CIN] = xv.x;
@@ -218,8 +219,11 @@ __global__ void __launch_bounds__(I_THREADS, 2) conv_one_in_tc_kernel(const __gr
         float hi[4], lo[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          hi[j] = round_tf32(v[4 * cc + j]);
-          lo[j] = round_tf32(v[4 * cc + j] - hi[j]);
+          // hi = x truncated to tf32 (one LOP3), lo = x - hi exactly; the tensor core truncates lo itself.  (The
+          // round-to-nearest split used before cost 4 instructions per cvt.rna -- 128 of the producer's 440 warp
+          // instructions per tile, profiles/r02P -- and is no more accurate: both leave ~2^-21 of x.)
+          hi[j] = __uint_as_float(__float_as_uint(v[4 * cc + j]) & 0xFFFFE000u);
+          lo[j] = v[4 * cc + j] - hi[j];
         }
         if (KV == 16) {
           sts_v4(row + (((uint32_t)cc ^ sx) << 4), hi[0], hi[1], hi[2], hi[3]);
@@ -291,6 +295,7 @@ __global__ void __launch_bounds__(I_THREADS, 2) conv_one_in_tc_kernel(const __gr
     const int CW = p.cw;                                   // channels per staged chunk
     const uint32_t row_bytes = (uint32_t)CW * (p.out_half ? 2u : 4u);   // 128 or 64
     const uint32_t srow = stage_base + (uint32_t)m * row_bytes;
+    const bool dbl = row_bytes == 64u && !has_gate;
     const uint32_t sx = row_bytes == 128u ? ((uint32_t)m & 7u) : (((uint32_t)m >> 1) & 3u);
     uint32_t i = 0, g = 0;                                 // tile and chunk counters
     if (has_gate && issuer && (long)blockIdx.x < p.tiles) {
@@ -305,7 +310,14 @@ __global__ void __launch_bounds__(I_THREADS, 2) conv_one_in_tc_kernel(const __gr
       tc_fence_after();
 #pragma unroll 1
       for (int c0 = 0; c0 < COUT; c0 += CW, ++g) {
-        if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging buffers free again
+        // staging buffers free again.  64-byte rows (fp16, 32 channels) use half of a 16 KB slot, so the two halves
+        // alternate and only the store before the last one must have been read (the epilogue warps otherwise idle
+        // for the store's shared-memory read: 17-30 % of their samples in profiles/r02P)
+        if (issuer) {
+          if (dbl) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+        const uint32_t half_off = dbl ? (g & 1u) * (I_STAGE_BYTES / 2) : 0u;
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (has_gate) {
           if (issuer) {                                    // the NEXT chunk's gate tile, one chunk ahead
@@ -358,7 +370,7 @@ __global__ void __launch_bounds__(I_THREADS, 2) conv_one_in_tc_kernel(const __gr
               if (o == 1 && p.n_out != 2) break;
 #pragma unroll
               for (int u = 0; u < 8; ++u) y[u] = fmaxf(x[u], (o == 0 ? s0 : s1) * x[u]);
-              const uint32_t dst = srow + (uint32_t)o * I_STAGE_BYTES;
+              const uint32_t dst = srow + (uint32_t)o * I_STAGE_BYTES + half_off;
               if (p.out_half) {
                 const uint32_t piece = (uint32_t)(sub + j) >> 3;     // 8 halves = 16 bytes
                 sts_v4u(dst + ((piece ^ sx) << 4), pack_half2(y[0], y[1]), pack_half2(y[2], y[3]),
@@ -378,9 +390,10 @@ __global__ void __launch_bounds__(I_THREADS, 2) conv_one_in_tc_kernel(const __gr
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("bar.sync 2, 128;" ::: "memory");
         if (issuer) {
-          tma_store_4d_(&p.tmO[0], has_gate ? gate_base + (g & 1u) * I_STAGE_BYTES : stage_base, n0 + c0, tl.ow0, tl.oh0,
-                        tl.img);
-          if (p.n_out == 2) tma_store_4d_(&p.tmO[1], stage_base + I_STAGE_BYTES, n0 + c0, tl.ow0, tl.oh0, tl.img);
+          tma_store_4d_(&p.tmO[0], has_gate ? gate_base + (g & 1u) * I_STAGE_BYTES : stage_base + half_off, n0 + c0, tl.ow0,
+                        tl.oh0, tl.img);
+          if (p.n_out == 2)
+            tma_store_4d_(&p.tmO[1], stage_base + I_STAGE_BYTES + half_off, n0 + c0, tl.ow0, tl.oh0, tl.img);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }

@@ -176,8 +176,8 @@ __global__ void __launch_bounds__(T_THREADS, 1) wgrad_thin_tc_kernel(const __gri
       const uint32_t chunk = (uint32_t)lane >> 2;
 #pragma unroll
       for (int k = 0; k < KV; ++k) {
-        const float hi = round_tf32(v[k]);
-        const float lo = round_tf32(v[k] - hi);
+        const float hi = __uint_as_float(__float_as_uint(v[k]) & 0xFFFFE000u);   // truncated; lo = x - hi exactly, and
+        const float lo = v[k] - hi;                                               // the tensor core truncates lo itself
         const uint32_t off = ((chunk ^ ((uint32_t)k & 7u)) << 4) + col;
         sts_f32(tile + (uint32_t)k * 128u + off, hi);
         sts_f32(tile + (uint32_t)(KV + k) * 128u + off, lo);   // (KV + k) % 8 == k % 8
