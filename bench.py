@@ -465,8 +465,8 @@ def layer_roofline(eng, args, stream, flush):
             'peak_source': 'cuBLAS TF32 8192^3 measured in this run (the kernel computes in '
                            'kind::tf32); MEASURED_PEAKS.json bf16 burst = %.1f' % peaks['tensor'],
             'frac_of_bf16_peak': ach / peaks['tensor'],
-            'note': ('the per-tap kernel (conv_tc_kernel) is held below the tensor roofline by L2 delivery: ncu '
-                     'shows its deep layers at 81-100 % of the ~6300 B/clk L2 throughput cap '
+            'note': ('the per-tap kernel (conv_tc_kernel) fetches every input pixel once per filter tap through L2; '
+                     'with fp32 operands its wide layers run at 81-100 % of the ~6300 B/clk L2 throughput cap '
                      '(profiles/r01c_l2_delivery.txt)') if top.startswith('conv_tc') else None,
             'flops_per_launch': d['flops'] / n_launch, 'ms_per_launch': d['ms'] / n_launch,
             'share_of_step': d['ms'] / total, 'by_kernel': kernels, 'by_layer': layers}
