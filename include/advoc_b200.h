@@ -261,7 +261,9 @@ ADVOC_API int advoc_conv2d_transpose_fwd(const advoc_conv_desc* d, const void* d
  * TF layout HWIO; for a conv_transpose described by `d` (big side = its output) it is HWOI.
  *   d_dw[tap][cb][cs] += sum_{n,oh,ow} big[n, oh*sh-pad_t+kh, ow*sw-pad_l+kw, cb] * small[n,oh,ow,cs]
  * d_big [N,H,W,*] (pixel stride ld_big, Cin channels), d_small [N,Ho,Wo,*] (ld_small, Cout).
- * Accumulates with fp32 atomics across pixel splits (sum order is not fixed).
+ * Tensor-core paths (wgrad_tc.cu, wgrad_thin_tc.cu: every layer of the AdVoc / MelspecGAN nets unless the desc asks
+ * for ADVOC_MATH_FP32) reduce their pixel splits in a fixed order: bit-identical from run to run.  The CUDA-core
+ * fallbacks accumulate with fp32 atomics (sum order not fixed).
  * replaces: Conv2DBackpropFilter built by opt.minimize, advoc_model.py:254-257. */
 ADVOC_API int advoc_conv2d_wgrad(const advoc_conv_desc* d, const float* d_big, int ld_big,
                                  const float* d_small, int ld_small, float* d_dw, void* stream);
