@@ -103,7 +103,10 @@ __device__ __forceinline__ void tma_load_4d_(const CUtensorMap* tm, uint64_t* ba
 }
 
 template <int COUT, int STAGES, int MODE>
-__global__ void __launch_bounds__(I_THREADS, 2) conv_one_in_tc_kernel(const __grid_constant__ OneInParams p) {
+// (COUT = 32 from one channel -- AdVoc-small encoder_1 -- fits 72 registers and, with a two-slot ring, 73 KB of shared
+//  memory: three CTAs per SM for the latency chain gather -> MMA -> epilogue -> TMA store, profiles/README.md r02P)
+__global__ void __launch_bounds__(I_THREADS, (COUT == 32 && MODE == M_CONV1) ? 3 : 2)
+    conv_one_in_tc_kernel(const __grid_constant__ OneInParams p) {
   constexpr int CIN = MODE == M_CONV2 ? 2 : 1;
   constexpr int KS = MODE == M_CONV1_K5 ? 5 : 4;            // filter side (5: MelspecGAN conv_0, models/melspecgan/conv2d.py:182-184)
   constexpr int KREAL = KS * KS * CIN;                      // taps x input channels
@@ -423,7 +426,8 @@ int launch_one_in(const OneInParams& p, int chunks, cudaStream_t st) {
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     configured = true;
   }
-  const long slots = ((long)sm_count() * 2 + chunks - 1) / chunks;
+  const int per_sm = (COUT == 32 && MODE == M_CONV1 && 3 * (smem + 1024) <= 227 * 1024) ? 3 : 2;
+  const long slots = ((long)sm_count() * per_sm + chunks - 1) / chunks;
   const long ctas = p.tiles < slots ? p.tiles : slots;
   conv_one_in_tc_kernel<COUT, STAGES, MODE><<<dim3((unsigned)ctas, (unsigned)chunks), I_THREADS, smem, st>>>(p);
   count_launch();
@@ -486,7 +490,7 @@ int run_one_in(int mode, int Nimg, int Hin, int Win, int Hp, int Wp, int C, int 
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (mode == M_CONV1) {
     switch (cout) {
-      case 32: return launch_one_in<32, 3, M_CONV1>(p, chunks, s);
+      case 32: return launch_one_in<32, 2, M_CONV1>(p, chunks, s);
       case 64: return launch_one_in<64, 3, M_CONV1>(p, chunks, s);
       default: return launch_one_in<128, 2, M_CONV1>(p, chunks, s);
     }
