@@ -433,13 +433,15 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
 // tap) pairs that read it -- class (ph, pw) sees tap kh at dh = (ph + 1 - kh) / 2 -- into four accumulators that
 // sit side by side in TMEM.  9 A tiles + 16 filter tiles per k-block instead of 16 + 16.
 // ---------------------------------------------------------------------------------------------
-template <int BN, int STAGES, bool HALF>
+// ACC_BUFS = 1: single accumulator set (64-channel tiles: 256 TMEM columns, so that two CTAs still share an SM and
+// overlap each other's epilogues)
+template <int BN, int STAGES, bool HALF, int ACC_BUFS>
 __global__ void __launch_bounds__(NUM_THREADS) conv_tc_merged_kernel(const __grid_constant__ TcParams p) {
   constexpr int BK = HALF ? 64 : 32;
   constexpr int A_BYTES = BM * BK_BYTES, B_BYTES = BN * BK_BYTES;
   constexpr int STAGE_BYTES = A_BYTES + 4 * B_BYTES;
   constexpr uint32_t ACC_COLS = 4 * BN;                       // four class accumulators
-  constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;                // double-buffered
+  constexpr uint32_t TMEM_COLS = ACC_BUFS * ACC_COLS;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[STAGES];
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
@@ -517,8 +519,8 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_merged_kernel(const __gri
       int stage = 0;
       uint32_t phase = 0, i = 0;
       for (long t = blockIdx.x; t < ntl; t += gridDim.x, ++i) {
-        const uint32_t buf = i & 1u;
-        mbar_wait(&acc_empty[buf], ((i >> 1) & 1u) ^ 1u, p.dbg, 4u);
+        const uint32_t buf = i % ACC_BUFS, use = i / ACC_BUFS;
+        mbar_wait(&acc_empty[buf], (use & 1u) ^ 1u, p.dbg, 4u);
         tc_fence_after();
         const uint32_t d0 = tmem_base + buf * ACC_COLS;
         for (int kb = 0; kb < p.kblocks; ++kb) {
@@ -566,8 +568,8 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_merged_kernel(const __gri
         a = (int)(r % Ah);
         img = r / Ah;
       }
-      const uint32_t buf = i & 1u;
-      mbar_wait(&acc_full[buf], (i >> 1) & 1u, p.dbg, 3u);
+      const uint32_t buf = i % ACC_BUFS, use = i / ACC_BUFS;
+      mbar_wait(&acc_full[buf], use & 1u, p.dbg, 3u);
       tc_fence_after();
 #pragma unroll 1
       for (int cls = 0; cls < 4; ++cls) {
@@ -602,12 +604,12 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_merged_kernel(const __gri
   }
 }
 
-template <int BN, int STAGES, bool HALF>
+template <int BN, int STAGES, bool HALF, int ACC_BUFS>
 int launch_merged(const TcParams& p, long m_tiles, cudaStream_t st) {
   constexpr int smem = STAGES * (BM * BK_BYTES + 4 * BN * BK_BYTES) + 1024;
   static bool configured = false;
   if (!configured) {
-    ADVOC_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_merged_kernel<BN, STAGES, HALF>,
+    ADVOC_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_merged_kernel<BN, STAGES, HALF, ACC_BUFS>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
@@ -615,9 +617,9 @@ int launch_merged(const TcParams& p, long m_tiles, cudaStream_t st) {
   q.ksplit = 1;
   q.total_tiles = m_tiles * (p.Cn / BN);
   ADVOC_REQUIRE(q.total_tiles < 2147483647L, ADVOC_BAD_SHAPE, "too many output tiles");
-  const int per_sm = (2 * smem <= 220 * 1024 && 2 * 8 * BN <= 512) ? 2 : 1;
+  const int per_sm = (2 * smem <= 220 * 1024 && 2 * ACC_BUFS * 4 * BN <= 512) ? 2 : 1;
   const long slots = (long)sm_count() * per_sm;
-  conv_tc_merged_kernel<BN, STAGES, HALF><<<(unsigned)(q.total_tiles < slots ? q.total_tiles : slots), NUM_THREADS, smem, st>>>(q);
+  conv_tc_merged_kernel<BN, STAGES, HALF, ACC_BUFS><<<(unsigned)(q.total_tiles < slots ? q.total_tiles : slots), NUM_THREADS, smem, st>>>(q);
   count_launch();
   ADVOC_CHECK_CUDA(cudaGetLastError());
   return ADVOC_OK;
@@ -901,8 +903,9 @@ int conv_transposed_tc(const advoc_conv_desc* d, const void* x, int ldx, const v
   p.Cn = d->Cin; p.kblocks = d->Cout / bk_of(half);
   // merged parity classes (conv_tc_merged_kernel) for the k4 s2 layers with narrow N tiles and many positions
   static const bool no_merge = getenv("ADVOC_TC_NO_MERGE") != nullptr;   // A/B switch
-  // (r02R: BN = 64 needs all 512 TMEM columns = one CTA per SM and is slower than the per-class schedule: AdVoc-small
-  //  decoder_3 73 us against 54, regular decoder_2 235 against 196; BN = 32: decoder_2 81 against 91)
+  // (r02R-r02S: BN = 64 is slower than the per-class schedule both with two accumulator sets -- all 512 TMEM columns,
+  //  one CTA per SM: AdVoc-small decoder_3 64-73 us against 54, regular decoder_2 199-235 against 196 -- and with one
+  //  set at two CTAs per SM and a two-slot ring: 66 against 56, 213 against 193; BN = 32: decoder_2 71 against 91)
   static const int merge_max_bn = getenv("ADVOC_TC_MERGE_MAX_BN") ? atoi(getenv("ADVOC_TC_MERGE_MAX_BN")) : 32;
   const int mAh = (Hout + 1) / 2, mAw = (Wout + 1) / 2;
   const long m_tiles = ((long)d->N * mAh * mAw + BM - 1) / BM;
@@ -941,8 +944,8 @@ int conv_transposed_tc(const advoc_conv_desc* d, const void* x, int ldx, const v
     p.dbg = debug_word();
     p.nclasses = 1;
     cudaStream_t cst = reinterpret_cast<cudaStream_t>(stream);
-    if (half) return bn == 32 ? launch_merged<32, 3, true>(p, m_tiles, cst) : launch_merged<64, 4, true>(p, m_tiles, cst);
-    return bn == 32 ? launch_merged<32, 3, false>(p, m_tiles, cst) : launch_merged<64, 4, false>(p, m_tiles, cst);
+    if (half) return bn == 32 ? launch_merged<32, 3, true, 2>(p, m_tiles, cst) : launch_merged<64, 2, true, 1>(p, m_tiles, cst);
+    return bn == 32 ? launch_merged<32, 3, false, 2>(p, m_tiles, cst) : launch_merged<64, 2, false, 1>(p, m_tiles, cst);
   }
   st = encode_B(&p.tmB, w, d->kh * d->kw * d->Cin, d->Cout, bn, half);
   if (st) return st;
