@@ -1009,10 +1009,8 @@ float* to_one_scratch(size_t bytes, cudaStream_t st) {
   }
   float* nb = nullptr;
   const size_t want = bytes + (bytes >> 2);
-  cudaDeviceSynchronize();
   if (cudaMalloc(&nb, want) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-  if (buf) cudaFree(buf);
-  buf = nb; cap = want;
+  buf = nb; cap = want;          // (the outgrown buffer stays allocated: captured graphs may still point at it)
   return buf;
 }
 

@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
 
 }  // namespace
 
-// Grow-only workspace for the split partials (one stream at a time uses the library's wgrad; the
+// Grow-only workspace for the split partials (one stream at a time uses the library's wgrad / split-K convs; the
 // partials of a launch are consumed by the reduce kernel queued right behind it).  Cannot grow while
 // the stream is being captured into a CUDA graph: the caller's eager warm-up pass sizes it.
 float* wgrad_workspace(size_t bytes, cudaStream_t st) {
@@ -269,9 +269,10 @@ float* wgrad_workspace(size_t bytes, cudaStream_t st) {
   }
   float* nb = nullptr;
   const size_t want = bytes < ((size_t)64 << 20) ? ((size_t)64 << 20) : bytes + (bytes >> 2);
-  cudaDeviceSynchronize();                 // earlier launches may still read the old buffer
   if (cudaMalloc(&nb, want) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-  if (buf) cudaFree(buf);
+  // The outgrown buffer is NOT freed: CUDA graphs captured earlier (an inference engine's split-K layers, a train
+  // engine's filter gradients) keep launching kernels that point at it.  Growth happens a handful of times per
+  // process (sizes are per layer geometry), so the retired buffers cost at most a few hundred MB.
   buf = nb; cap = want;
   return buf;
 }

@@ -667,3 +667,45 @@ def test_transposed_conv_merged_parity_classes(math, cout):
   assert N.debug_flags() == 0
   assert _rel(out[..., 32:].float(), ref) < TOL
   assert torch.isnan(out[..., :32].float()).all()
+
+
+def test_captured_split_k_graph_survives_workspace_growth():
+  """A CUDA graph captured around a split-K layer keeps pointing at the library workspace it was captured with;
+  a later, larger request (here a 512 x 512-channel filter gradient: 5 splits x 16.8 MB) must not free that buffer
+  under the graph (csrc/wgrad_tc.cu: wgrad_workspace retires outgrown buffers instead of freeing them)."""
+  import ctypes as C
+  from advoc_b200 import _native as N
+  from advoc_b200 import nets
+  g = torch.Generator().manual_seed(9)
+  B, H, W, Cin, Cout = 4, 2, 5, 512, 256
+  x = _tf32(torch.randn(B, H, W, Cin, generator=g)).cuda()
+  k = (torch.randn(4, 4, Cin, Cout, generator=g) * 0.02).cuda()
+  ho, pt, _ = nets.same_pads(H, 4, 2)
+  wo, pl, _ = nets.same_pads(W, 4, 2)
+  L = nets._Conv('t', 'conv', nets._desc(B, H, W, Cin, Cout, 2, 2, pt, pl, ho, wo, N.MATH_AUTO))
+  wp = nets._pack_for_tc(L, k, Cin)
+  y = torch.zeros((B, ho, wo, Cout), device='cuda')
+  ep = nets._epilogue(None, y, Cout, 0, N.ACT_NONE)
+  n0 = N.launch_count()
+  L.run(x, Cin, wp, ep)                       # eager warm-up: sizes the workspace
+  assert N.launch_count() - n0 == 2          # split-K + finalize
+  torch.cuda.synchronize()
+  first = y.clone()
+  graph = torch.cuda.CUDAGraph()
+  with torch.cuda.graph(graph):
+    L.run(x, Cin, wp, ep)
+  # a request well beyond the 64 MB the workspace starts with
+  Bw, Hw = 4, 64
+  d = N.ConvDesc(Bw, Hw, Hw, 512, 512, 4, 4, 2, 2, 1, 1, Hw // 2, Hw // 2, N.MATH_AUTO)
+  big = torch.randn(Bw, Hw, Hw, 512, generator=g).cuda()
+  small = torch.randn(Bw, Hw // 2, Hw // 2, 512, generator=g).cuda()
+  dw = torch.zeros(4, 4, 512, 512, device='cuda')
+  N.call('advoc_conv2d_wgrad', C.byref(d), nets._ptr(big), 512, nets._ptr(small), 512, nets._ptr(dw), nets._stream())
+  torch.cuda.synchronize()
+  junk = [torch.randn(16 << 20, device='cuda') for _ in range(4)]     # would land in a freed workspace
+  y.zero_()
+  graph.replay()
+  torch.cuda.synchronize()
+  assert N.debug_flags() == 0
+  assert torch.equal(y, first)
+  del junk
