@@ -498,8 +498,10 @@ extern "C" int advoc_conv2d_wgrad(const advoc_conv_desc* d, const float* d_big, 
   if (M == 0) return ADVOC_OK;
   if (wgrad_tc_eligible(d, d_big, ld_big, d_small, ld_small))
     return wgrad_tc(d, d_big, ld_big, d_small, ld_small, d_dw, stream);
-  if (wgrad_thin_tc_eligible(d, d_big, ld_big, d_small, ld_small))
-    return wgrad_thin_tc(d, d_big, ld_big, d_small, ld_small, d_dw, stream);
+  if (wgrad_thin_tc_eligible(d, d_big, ld_big, d_small, ld_small)) {
+    st = wgrad_thin_tc(d, d_big, ld_big, d_small, ld_small, d_dw, stream);
+    if (st != ADVOC_UNSUPPORTED) return st;     // (no workspace during a graph capture: CUDA-core kernels below)
+  }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const bool k4 = d->kh == 4 && d->kw == 4;
   if (d->kh == 5 && d->kw == 5 && d->Cin == 1 && d->Cout == 64 && d->sw <= 2 && ld_small % 4 == 0 && aligned16(d_small)) {

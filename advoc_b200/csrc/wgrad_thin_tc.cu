@@ -334,7 +334,7 @@ int wgrad_thin_tc(const advoc_conv_desc* d, const float* big, int ld_big, const 
   cudaStream_t cst = reinterpret_cast<cudaStream_t>(stream);
   const size_t kv = mode == W_CONV2 || mode == W_CONV1_K5 ? 32 : 16;
   p.ws = wgrad_workspace((size_t)splits * kv * p.C * sizeof(float), cst);
-  ADVOC_REQUIRE(p.ws != nullptr, ADVOC_CUDA_ERROR, "wgrad workspace unavailable (first call inside a graph capture?)");
+  if (p.ws == nullptr) return ADVOC_UNSUPPORTED;   // workspace cannot grow inside a graph capture: the caller falls back
   p.dbg = tc::debug_word();
 #define ADVOC_THIN_WG(MODE)                                                     \
   switch (cb) {                                                                 \
